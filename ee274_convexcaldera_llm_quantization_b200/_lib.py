@@ -1,0 +1,137 @@
+"""ctypes binding of libcaldera_b200.so (the C ABI declared in include/caldera_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling
+into it without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcaldera_b200.so")
+
+CB_OK = 0
+CB_ERR_ARG, CB_ERR_BITS, CB_ERR_BLOCK, CB_ERR_WORKSPACE, CB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+CB_H_IDENTITY, CB_H_DIAG, CB_H_DENSE = 0, 1, 2
+
+
+class CalderaLibraryMissing(ImportError):
+    pass
+
+
+class cb_caldera_params(C.Structure):
+    _fields_ = [
+        ("compute_q", C.c_int32), ("compute_lr", C.c_int32),
+        ("q_bits", C.c_int32), ("l_bits", C.c_int32), ("r_bits", C.c_int32),
+        ("rank", C.c_int32), ("iters", C.c_int32), ("lplr_iters", C.c_int32),
+        ("aware", C.c_int32), ("n_order", C.c_int32), ("order", C.c_int32 * 8),
+        ("rand_svd", C.c_int32), ("sigma_reg", C.c_float), ("scale_w", C.c_int32),
+        ("global_scale_in", C.c_float), ("q_block", C.c_int64),
+        ("sketch_width", C.c_int32), ("power_iters", C.c_int32), ("warm_start", C.c_int32),
+        ("seed", C.c_uint64),
+    ]
+
+
+class cb_caldera_out(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in (
+        "Q", "L", "R", "Q_idxs", "Q_scale", "Q_packed", "L_idxs", "R_idxs", "L_scale", "R_scale",
+        "L_packed", "R_packed", "W_scaled", "errors", "scalars")]
+
+
+_SIGNATURES = {
+    "cb_version": (C.c_int, []),
+    "cb_status_string": (C.c_char_p, [C.c_int]),
+    "cb_kernel_launch_count": (C.c_int64, []),
+    "cb_quantize_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64,
+                                  C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cb_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
+    "cb_packed_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "cb_pack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cb_unpack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cb_hessian_probe": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cb_weighted_error": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cb_weighted_error_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "cb_lowrank_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                  C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cb_lowrank_init_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "cb_cholesky_inverse_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cb_jacobi_eigh_from_chol_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
+    "cb_sgemm_strided": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_int, C.c_void_p]),
+    "cb_caldera_layer_workspace_bytes": (C.c_size_t, [C.POINTER(cb_caldera_params), C.c_int64, C.c_int64, C.c_int]),
+    "cb_caldera_layer": (C.c_int, [C.POINTER(cb_caldera_params), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_int, C.POINTER(cb_caldera_out), C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library (cached).  Raises CalderaLibraryMissing if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CalderaLibraryMissing(
+            f"{LIB_PATH} is missing: build it with `python -m ee274_convexcaldera_llm_quantization_b200.build` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def status_string(status: int) -> str:
+    return load().cb_status_string(int(status)).decode()
+
+
+class CalderaRuntimeError(RuntimeError):
+    def __init__(self, status: int, where: str = ""):
+        self.status = status
+        super().__init__(f"{where}: libcaldera_b200 status {status} ({status_string(status)})")
+
+
+def check(status: int, where: str = "") -> None:
+    """Maps C status codes to the exception classes the reference raises."""
+    if status == CB_OK:
+        return
+    if status == CB_ERR_BITS:
+        raise AssertionError("Bit-width not supported!")
+    if status == CB_ERR_BLOCK:
+        raise ValueError(f"{where}: {status_string(status)}")
+    if status == CB_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{where}: {status_string(status)}")
+    if status == CB_ERR_ARG:
+        raise ValueError(f"{where}: {status_string(status)}")
+    raise CalderaRuntimeError(status, where)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must live on a CUDA device: this is the B200 path of the CALDERA hot loop and has no CPU "
+            "fallback (use the reference implementation for CPU runs)")

@@ -1,0 +1,241 @@
+"""Drop-in for RCR/caldera/decomposition/alg.py: `caldera()` on the B200 kernel library.
+
+The Python here only validates arguments, allocates outputs/workspace with torch and makes
+ONE call into `cb_caldera_layer` (csrc/driver.cu), which enqueues the whole alternating
+minimisation on the current CUDA stream.  The single host synchronisation per layer is
+the read-back of the error trajectory at the end.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .params import CalderaParams, CalderaDecomposition, QuantInfo  # noqa: F401  (re-exported like the reference)
+from .quantization import QuantizerFactory, LowMemoryQuantizer, AbstractQuantizer  # noqa: F401
+
+_ORDER_CODE = {"Q": 0, "LR": 1}
+
+
+def _resolve_device(device, W: torch.Tensor) -> torch.device:
+    dev = torch.device(device) if device is not None else W.device
+    if dev.type != "cuda":
+        raise RuntimeError(
+            "caldera(): the B200 path runs on CUDA devices only and has no CPU fallback "
+            f"(got device={device!r}); use the reference implementation for CPU runs")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _classify_hessian(H: Optional[torch.Tensor], n: int, dev: torch.device):
+    """Returns (h_kind, tensor-or-None).  A dense n x n H whose off-diagonal entries are all
+    zero (what main.py:163-165 builds with diag_embed) is routed to the diagonal path."""
+    if H is None:
+        return _lib.CB_H_IDENTITY, None
+    H = H.to(dev, torch.float32)
+    if H.dim() == 1:
+        if H.numel() != n:
+            raise ValueError(f"diagonal Hessian has {H.numel()} entries, expected {n}")
+        return _lib.CB_H_DIAG, H.contiguous()
+    if H.dim() != 2 or H.shape[0] != n or H.shape[1] != n:
+        raise ValueError(f"H must be ({n}, {n}) or ({n},), got {tuple(H.shape)}")
+    H = H.contiguous()
+    lib = _lib.load()
+    diag = torch.empty(n, dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.cb_hessian_probe(_lib.ptr(H), n, _lib.ptr(diag), _lib.ptr(flag), _lib.stream_ptr()),
+                   "hessian_probe")
+    if int(flag.item()) == 1:
+        return _lib.CB_H_DIAG, diag
+    return _lib.CB_H_DENSE, H
+
+
+def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Optional[float] = None,
+                  sketch_width: int = 0, power_iters: int = -1, warm_start: bool = True,
+                  seed: int = 0) -> _lib.cb_caldera_params:
+    order = list(quant_params.update_order)
+    for name in order:
+        if name not in _ORDER_CODE:
+            raise ValueError(f"update_order entries must be 'Q' or 'LR', got {name!r}")
+    if len(order) > 8:
+        raise ValueError("update_order longer than 8 entries is not supported")
+    p = _lib.cb_caldera_params()
+    p.compute_q = int(bool(quant_params.compute_quantized_component))
+    p.compute_lr = int(bool(quant_params.compute_low_rank_factors))
+    p.q_bits, p.l_bits, p.r_bits = int(quant_params.Q_bits), int(quant_params.L_bits), int(quant_params.R_bits)
+    p.rank = int(quant_params.rank)
+    p.iters = int(quant_params.iters)
+    p.lplr_iters = int(quant_params.lplr_iters)
+    p.aware = int(bool(quant_params.activation_aware_LR))
+    p.n_order = len(order)
+    for i, name in enumerate(order):
+        p.order[i] = _ORDER_CODE[name]
+    p.rand_svd = int(bool(quant_params.rand_svd))
+    p.sigma_reg = float(quant_params.sigma_reg)
+    p.scale_w = int(bool(scale_W))
+    p.global_scale_in = float(global_scale) if global_scale is not None else 0.0
+    p.q_block = 0          # quantize_matrix forces one block per tensor (alg.py:247)
+    p.sketch_width = int(sketch_width)
+    p.power_iters = int(power_iters)
+    p.warm_start = int(bool(warm_start))
+    p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return p
+
+
+def _check_factories(quant_params: CalderaParams):
+    for fac in (quant_params.quant_factory_Q, quant_params.quant_factory_LR):
+        method = str(getattr(fac, "method", "uniform")).lower()
+        if method != "uniform":
+            raise NotImplementedError(
+                f"Quantization method '{method}' not implemented in the B200 path "
+                "(the CALDERA hot path is pinned to method='uniform').")
+
+
+def caldera(
+    quant_params: CalderaParams,
+    W: torch.Tensor,
+    H: torch.Tensor = None,
+    device: str = "cuda",
+    use_tqdm: bool = True,
+    scale_W: bool = True,
+    *,
+    W_copy: str = "cpu",
+    global_scale: Optional[float] = None,
+    sketch_width: int = 0,
+    power_iters: int = -1,
+    warm_start: bool = True,
+    seed: int = 0,
+    return_packed: bool = True,
+):
+    """Runs CALDERA: decomposes W into Q + L R (alg.py:24-112), all arithmetic on `device`.
+
+    Positional/keyword arguments are the reference's.  `H` may additionally be a 1-D tensor
+    holding the diagonal of a diagonal Hessian.  Keyword-only extras (all optional):
+    W_copy   where CalderaDecomposition.W lives: "cpu" (reference behaviour, alg.py:81),
+             "device" or "none";
+    global_scale  inject the reference's global_scale instead of recomputing it;
+    sketch_width / power_iters / warm_start / seed  knobs of the randomized rank-r step;
+    return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed.
+    `use_tqdm` is accepted and ignored (the loop runs on the device).
+    """
+    if len(W.shape) != 2:
+        raise ValueError(f"Support only for 2D matrix, but your input has {len(W.shape)} dimensions.")
+    _check_factories(quant_params)
+    dev = _resolve_device(device, W)
+    lib = _lib.load()
+    m, n = int(W.shape[0]), int(W.shape[1])
+    r = int(quant_params.rank)
+    quant_factors = bool(quant_params.compute_low_rank_factors) and (quant_params.L_bits < 16 or quant_params.R_bits < 16)
+    if quant_params.compute_quantized_component:
+        assert quant_params.Q_bits in (2, 4, 8, 16), "Bit-width not supported!"
+    if quant_factors:
+        assert quant_params.L_bits in (2, 4, 8, 16) and quant_params.R_bits in (2, 4, 8, 16), "Bit-width not supported!"
+        if quant_params.lplr_iters < 1 and "LR" in quant_params.update_order and quant_params.iters > 0:
+            # the reference dereferences best_L_quant_out = None (alg.py:190)
+            raise AttributeError("'NoneType' object has no attribute 'A_idxs'")
+
+    with torch.cuda.device(dev):
+        Wd = W.to(dev, torch.float32, non_blocking=True).contiguous()
+        h_kind, Hd = _classify_hessian(H, n, dev)
+        p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed)
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        q_dtype = torch.int8 if quant_params.Q_bits <= 8 else torch.int16
+        l_dtype = torch.int8 if quant_params.L_bits <= 8 else torch.int16
+        r_dtype = torch.int8 if quant_params.R_bits <= 8 else torch.int16
+        nsteps = p.iters * p.n_order
+        Q = torch.empty((m, n), **f32)
+        L = torch.empty((m, r), **f32)
+        R = torch.empty((r, n), **f32)
+        small = torch.zeros(nsteps + 8 + 4, **f32)      # errors | scalars | Q/L/R scales
+        errors_d, scalars_d = small[:nsteps], small[nsteps:nsteps + 8]
+        Q_scale, L_scale, R_scale = (small[nsteps + 8 + i:nsteps + 9 + i] for i in range(3))
+        Q_idxs = torch.empty((1, m * n), dtype=q_dtype, device=dev) if p.compute_q else None
+        L_idxs = torch.empty((1, r * m), dtype=l_dtype, device=dev) if quant_factors else None
+        R_idxs = torch.empty((1, r * n), dtype=r_dtype, device=dev) if quant_factors else None
+        Q_packed = L_packed = R_packed = None
+        if return_packed and p.compute_q:
+            Q_packed = torch.empty(lib.cb_packed_bytes(m * n, p.q_bits), dtype=torch.uint8, device=dev)
+        if return_packed and quant_factors:
+            L_packed = torch.empty(lib.cb_packed_bytes(m * r, p.l_bits), dtype=torch.uint8, device=dev)
+            R_packed = torch.empty(lib.cb_packed_bytes(r * n, p.r_bits), dtype=torch.uint8, device=dev)
+        W_scaled = torch.empty((m, n), **f32) if (scale_W and W_copy != "none") else None
+
+        out = _lib.cb_caldera_out()
+        for name, t in (("Q", Q), ("L", L), ("R", R), ("Q_idxs", Q_idxs), ("Q_scale", Q_scale),
+                        ("Q_packed", Q_packed), ("L_idxs", L_idxs), ("R_idxs", R_idxs),
+                        ("L_scale", L_scale), ("R_scale", R_scale), ("L_packed", L_packed),
+                        ("R_packed", R_packed), ("W_scaled", W_scaled), ("errors", errors_d),
+                        ("scalars", scalars_d)):
+            setattr(out, name, None if t is None else t.data_ptr())
+
+        ws_bytes = lib.cb_caldera_layer_workspace_bytes(C.byref(p), m, n, h_kind)
+        if ws_bytes == 0:
+            # invalid parameters: let the layer call produce the precise status
+            ws_bytes = 256
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        st = lib.cb_caldera_layer(C.byref(p), _lib.ptr(Wd), m, n, _lib.ptr(Hd), h_kind, C.byref(out),
+                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        _lib.check(st, "caldera")
+        host = small.cpu()                                # the one synchronisation of the layer
+        del ws
+
+    errs = host[:nsteps].tolist()
+    scal = host[nsteps:nsteps + 8]
+    best_step = int(scal[2].item())
+    errors = {name: [] for name in quant_params.update_order}
+    k = 0
+    for _ in range(p.iters):
+        for name in quant_params.update_order:
+            errors[name].append(errs[k])
+            k += 1
+
+    taken = best_step >= 0
+    dec = CalderaDecomposition(Q=Q, L=L, R=R)
+    dec.scaleWH = None
+    dec.SU = torch.ones(n, **f32)
+    dec.SV = torch.ones(m, **f32)
+    if taken and p.compute_q:
+        dec.Q_idxs = Q_idxs
+        dec.Q_scale = Q_scale.reshape(1, 1)
+        dec.Q_packed = Q_packed
+    if taken and quant_factors:
+        dec.L_idxs, dec.R_idxs = L_idxs, R_idxs
+        dec.L_scale, dec.R_scale = L_scale.reshape(1, 1), R_scale.reshape(1, 1)
+        dec.L_packed, dec.R_packed = L_packed, R_packed
+    Wkeep = W_scaled if scale_W else Wd
+    if W_copy == "cpu":
+        dec.W = Wkeep.cpu()
+    elif W_copy == "device":
+        dec.W = Wkeep
+    else:
+        dec.W = None
+    dec.errors = errors
+    dec.global_scale = float(scal[0].item()) if scale_W else 1
+    dec.best_step = best_step
+    dec.device_stats = {"cholesky_retries": int(scal[6:7].view(torch.int32).item()),
+                        "jacobi_sweeps": int(scal[7:8].view(torch.int32).item())}
+    return dec
+
+
+def activation_aware_error(W: torch.Tensor, H: torch.Tensor, caldera_info: CalderaDecomposition, device: str):
+    """alg.py:286-302 for a decomposition held as dense tensors: sqrt(tr(E H E^T) / tr(W H W^T))."""
+    dev = _resolve_device(device, W)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        Wd = W.to(dev, torch.float32).contiguous()
+        m, n = Wd.shape
+        h_kind, Hd = _classify_hessian(H, n, dev)
+        What = (caldera_info.Q + caldera_info.L @ caldera_info.R) * caldera_info.global_scale
+        E = (What - Wd).contiguous()
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        _lib.check(lib.cb_weighted_error(_lib.ptr(E), m, n, None, 8, None, None, None, 0, _lib.ptr(Hd), h_kind,
+                                         _lib.ptr(acc[0:1]), None, None, 0, _lib.stream_ptr()), "weighted_error")
+        _lib.check(lib.cb_weighted_error(_lib.ptr(Wd), m, n, None, 8, None, None, None, 0, _lib.ptr(Hd), h_kind,
+                                         _lib.ptr(acc[1:2]), None, None, 0, _lib.stream_ptr()), "weighted_error")
+        num, den = acc.tolist()
+    return float((num / den) ** 0.5)

@@ -1,0 +1,130 @@
+// Shared device/host helpers for libcaldera_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/caldera_b200.h"
+
+namespace cb {
+
+// ---------------------------------------------------------------- launch bookkeeping
+extern long long g_launch_count;  // defined in api.cu
+inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (long long)n, __ATOMIC_RELAXED); }
+
+#define CB_CHECK_LAUNCH()                                         \
+  do {                                                            \
+    cb::note_launch();                                            \
+    cudaError_t e__ = cudaGetLastError();                         \
+    if (e__ != cudaSuccess) return CB_ERR_CUDA_BASE + (int)e__;   \
+  } while (0)
+
+#define CB_CUDA(call)                                             \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return CB_ERR_CUDA_BASE + (int)e__;   \
+  } while (0)
+
+#define CB_TRY(call)                   \
+  do {                                 \
+    int s__ = (call);                  \
+    if (s__ != CB_OK) return s__;      \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ int levels_of(int bits) { return (1 << (bits - 1)) - 1; }
+
+// Bit-exact restatement of the reference arithmetic (quantization.py:266, 95-96):
+// IEEE divide, IEEE multiply (no FMA contraction), round-half-even.
+__device__ __forceinline__ int quant_code(float x, float s, float lv) {
+  return __float2int_rn(__fmul_rn(__fdiv_rn(x, s), lv));
+}
+// quantization.py:105, 295
+__device__ __forceinline__ float dequant_val(int code, float s, float lv) {
+  return __fmul_rn(__fdiv_rn((float)code, lv), s);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide reductions; result valid in thread 0.  `red` is a 32-entry shared array.
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) v = warp_max(v);
+  __syncthreads();
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// max over non-negative floats via integer atomics (bit patterns of x >= 0 are ordered)
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// streaming 128-bit loads/stores (data touched once: do not pollute L1)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// counter-based RNG (splitmix64 finaliser) -> standard normal by Box-Muller
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float gaussian_from(uint64_t seed, uint64_t idx) {
+  uint64_t b = mix64(seed ^ mix64(idx));
+  float u1 = ((float)((b >> 40) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
+  float u2 = ((float)((b >> 8) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+}  // namespace cb

@@ -1,0 +1,451 @@
+// Host-side orchestration of one layer's decomposition: enqueues every stage of
+// caldera() (RCR/caldera/decomposition/alg.py:24-112) on one stream with no host
+// synchronisation.  Best-iterate selection (alg.py:105-107) and the LPLR inner best
+// (alg.py:184-188) are device-side flags consumed by predicated copies, and the error
+// trajectory is written to a device array the caller reads once at the end.
+#include <new>
+#include "common.cuh"
+#include "internal.h"
+
+namespace cb {
+
+// ---------------------------------------------------------------- workspace arena
+struct Arena {
+  uint8_t* base;
+  size_t off;
+  size_t cap;
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base == nullptr ? nullptr : reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+  bool ok() const { return base == nullptr || off <= cap; }
+};
+
+static inline int code_bytes(int bits) { return bits <= 8 ? 1 : 2; }
+static inline bool bits_ok(int b) { return b == 2 || b == 4 || b == 8 || b == 16; }
+
+// ---------------------------------------------------------------- rank-r factorisation
+struct LowrankBufs {
+  float *P, *Po, *Z, *Zo, *G, *Linv, *B, *work, *evals, *V;
+  int* status;  // [0] cholesky retries (max), [1] jacobi sweeps
+};
+
+static LowrankBufs plan_lowrank(Arena& a, int64_t m, int64_t n, int64_t q, float* Zo_persistent, int* status) {
+  LowrankBufs b;
+  b.P = a.take<float>(n * q);
+  b.Po = a.take<float>(n * q);
+  b.Z = a.take<float>(m * q);
+  b.Zo = Zo_persistent != nullptr ? Zo_persistent : a.take<float>(m * q);
+  b.G = a.take<float>(q * q);
+  b.Linv = a.take<float>(q * q);
+  b.B = a.take<float>(q * n);
+  b.work = a.take<float>(q * q);
+  b.evals = a.take<float>(q);
+  b.V = a.take<float>(q * q);
+  b.status = status;
+  return b;
+}
+
+// X (N x q) -> Xo (N x q) with orthonormal columns: CholeskyQR, G = X^T X = Lc Lc^T, Xo = X Lc^-T
+static int orthonormalize(const float* X, int64_t N, int64_t q, float* Xo, const LowrankBufs& b, cudaStream_t st) {
+  CB_TRY(sgemm(q, q, N, 1.f, X, 1, q, X, q, 1, b.G, q, 1, false, nullptr, st));
+  CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st));
+  CB_TRY(sgemm(N, q, q, 1.f, X, q, 1, b.Linv, 1, q, Xo, q, 1, false, nullptr, st));
+  return CB_OK;
+}
+
+// Y: m x n (already column-weighted when aware).  On exit L (m x r), R (r x n).
+static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t q, int niter, uint64_t seed,
+                        int aware, const float* inv_sqrt_h, bool warm_valid, float* L, float* R,
+                        const LowrankBufs& b, cudaStream_t st) {
+  if (!warm_valid) {
+    CB_TRY(fill_randn(b.P, n * q, seed, st));
+    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.P, q, 1, b.Z, q, 1, false, nullptr, st));
+    CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
+  }
+  for (int it = 0; it < niter; ++it) {
+    CB_TRY(sgemm(n, q, m, 1.f, Y, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));  // P = Y^T Zo
+    CB_TRY(orthonormalize(b.P, n, q, b.Po, b, st));
+    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.Po, q, 1, b.Z, q, 1, false, nullptr, st));  // Z = Y Po
+    CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
+  }
+  // second pass (CholeskyQR2) so the Rayleigh-Ritz basis is orthonormal to fp32 accuracy
+  CB_TRY(orthonormalize(b.Zo, m, q, b.Z, b, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
+  // B = Zo^T Y (q x n); G = B B^T; eigen-decomposition through the Cholesky factor
+  CB_TRY(sgemm(q, n, m, 1.f, b.Zo, 1, q, Y, n, 1, b.B, n, 1, false, nullptr, st));
+  CB_TRY(sgemm(q, q, n, 1.f, b.B, n, 1, b.B, 1, n, b.G, q, 1, false, nullptr, st));
+  CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
+  CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
+  // L = Zo V_r^T, R = V_r B (column-scaled by 1/sqrt(h) when aware: S V^T H^-1/2, alg.py:220-225)
+  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st));
+  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.B, n, 1, R, n, 1, false, aware ? inv_sqrt_h : nullptr, st));
+  if (!aware) {
+    // L = U sqrt(S), R = sqrt(S) V^T (alg.py:233-234); evals are squared singular values
+    CB_TRY(scale_cols(L, m, r, b.evals, 2, L, st));
+    CB_TRY(scale_rows(R, r, n, b.evals, 3, R, st));
+  }
+  return CB_OK;
+}
+
+__global__ void sqrt_vec_kernel(const float* in, int n, float* out) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = sqrtf(fmaxf(in[i], 0.f));
+}
+
+static int64_t default_sketch_width(const cb_caldera_params* p, int64_t m, int64_t n) {
+  const int64_t mn = m < n ? m : n;
+  int64_t q;
+  if (p->sketch_width > 0) q = p->sketch_width;
+  else if (p->rand_svd) q = 2 * (int64_t)p->rank;                               // alg.py:213
+  else q = (2 * (int64_t)p->rank > (int64_t)p->rank + 32) ? 2 * (int64_t)p->rank : (int64_t)p->rank + 32;
+  if (q > mn) q = mn;
+  if (q > 512) q = 512;
+  if (q < p->rank) q = p->rank;
+  return q;
+}
+
+// ---------------------------------------------------------------- layer plan
+struct LayerPlan {
+  double* dsc;     // [0] sumsq [1] den [2] num [3] num_inner
+  int* flags;      // [0] take_outer [1] take_inner [2] cholesky retries [3] jacobi sweeps
+  float* scalars;  // 8
+  float *h_eff, *sqrt_h, *inv_sqrt_h, *w_inner, *amax;
+  float* Ws;
+  void* codes_cur;
+  float* qscale_cur;
+  float *LRbuf, *Y, *RES, *Lcur, *Rcur, *Zwarm;
+  // LPLR
+  float *Rw, *Gs, *Linv, *Ginv, *Bl, *Br, *Ltmp, *Rtmp, *Lb, *Rb;
+  void *Lcodes_cur, *Rcodes_cur, *Lcodes_in, *Rcodes_in, *Lcodes_out;
+  float *Lscale_cur, *Rscale_cur, *Lscale_in, *Rscale_in;
+  LowrankBufs lr;
+  int64_t q;
+  bool quant_factors;
+};
+
+static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n, bool scale_w, LayerPlan& L) {
+  const int64_t r = p->rank;
+  L.quant_factors = p->compute_lr && (p->l_bits < 16 || p->r_bits < 16);
+  L.q = p->compute_lr ? default_sketch_width(p, m, n) : 0;
+  L.dsc = a.take<double>(4);
+  L.flags = a.take<int>(8);
+  L.scalars = a.take<float>(8);
+  L.h_eff = a.take<float>(n);
+  L.sqrt_h = a.take<float>(n);
+  L.inv_sqrt_h = a.take<float>(n);
+  L.w_inner = a.take<float>(n);
+  L.amax = a.take<float>(4);
+  L.Ws = scale_w ? a.take<float>(m * n) : nullptr;
+  L.codes_cur = p->compute_q ? (void*)a.take<uint8_t>(m * n * code_bytes(p->q_bits)) : nullptr;
+  L.qscale_cur = a.take<float>(4);
+  if (p->compute_lr) {
+    L.LRbuf = a.take<float>(m * n);
+    L.Y = a.take<float>(m * n);
+    L.RES = (L.quant_factors && p->aware) ? a.take<float>(m * n) : nullptr;
+    L.Lcur = a.take<float>(m * r);
+    L.Rcur = a.take<float>(r * n);
+    L.Zwarm = a.take<float>(m * L.q);
+    L.lr = plan_lowrank(a, m, n, L.q, L.Zwarm, nullptr);
+    if (L.quant_factors) {
+      L.Rw = a.take<float>(r * n);
+      L.Gs = a.take<float>(r * r);
+      L.Linv = a.take<float>(r * r);
+      L.Ginv = a.take<float>(r * r);
+      L.Bl = a.take<float>(m * r);
+      L.Br = a.take<float>(r * n);
+      L.Ltmp = a.take<float>(m * r);
+      L.Rtmp = a.take<float>(r * n);
+      L.Lb = a.take<float>(m * r);
+      L.Rb = a.take<float>(r * n);
+      L.Lcodes_cur = a.take<uint8_t>(m * r * code_bytes(p->l_bits));
+      L.Rcodes_cur = a.take<uint8_t>(r * n * code_bytes(p->r_bits));
+      L.Lcodes_in = a.take<uint8_t>(m * r * code_bytes(p->l_bits));
+      L.Rcodes_in = a.take<uint8_t>(r * n * code_bytes(p->r_bits));
+      L.Lcodes_out = a.take<uint8_t>(m * r * code_bytes(p->l_bits));
+      L.Lscale_cur = a.take<float>(4);
+      L.Rscale_cur = a.take<float>(4);
+      L.Lscale_in = a.take<float>(4);
+      L.Rscale_in = a.take<float>(4);
+    }
+  }
+  return a.ok() ? CB_OK : CB_ERR_WORKSPACE;
+}
+
+static int validate_params(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
+  if (p == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
+  if (p->n_order < 0 || p->n_order > 8 || p->iters < 0) return CB_ERR_ARG;
+  for (int i = 0; i < p->n_order; ++i)
+    if (p->order[i] != 0 && p->order[i] != 1) return CB_ERR_ARG;
+  if (p->compute_q && !bits_ok(p->q_bits)) return CB_ERR_BITS;
+  if (p->compute_lr) {
+    if (!bits_ok(p->l_bits) || !bits_ok(p->r_bits)) return CB_ERR_BITS;
+    if (p->rank < 1 || p->rank > m || p->rank > n) return CB_ERR_ARG;
+    if (p->rank > 512) return CB_ERR_UNSUPPORTED;
+    if ((p->l_bits < 16 || p->r_bits < 16) && p->lplr_iters < 1) return CB_ERR_ARG;
+  }
+  if (h_kind != CB_H_IDENTITY && h_kind != CB_H_DIAG && h_kind != CB_H_DENSE) return CB_ERR_ARG;
+  if (h_kind == CB_H_DENSE) return CB_ERR_UNSUPPORTED;
+  if (p->q_block != 0) return CB_ERR_UNSUPPORTED;
+  return CB_OK;
+}
+
+// whole-tensor quantise + dequantise (quantize_matrix, alg.py:245-250)
+static int quantize_whole(const float* x, int64_t rows, int64_t cols, int bits, void* codes, float* scale,
+                          float* deq, cudaStream_t st) {
+  return cb_quantize_f32(x, rows, cols, cols, 1, bits, 0, 1e-8f, codes, nullptr, scale, deq, (void*)st);
+}
+
+static int solve_spd_setup(float* G, int64_t r, float* Linv, float* Ginv, int* status, cudaStream_t st) {
+  CB_TRY(cholesky_inverse(G, (int)r, Linv, status, st));
+  // G^-1 = Linv^T Linv
+  CB_TRY(sgemm(r, r, r, 1.f, Linv, 1, r, Linv, r, 1, Ginv, r, 1, false, nullptr, st));
+  return CB_OK;
+}
+
+static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+  const int64_t r = p->rank;
+  const float* res = p->aware ? P.RES : P.Y;  // unweighted residual W - Q
+  for (int k = 0; k < p->lplr_iters; ++k) {
+    // ---- L update: weighted normal equations (alg.py:163 / :167)
+    const float* Rw = P.Rcur;
+    if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
+    CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st));     // R diag(h) R^T
+    CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st));        // res diag(h) R^T
+    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));  // alg.py:171-172
+    // ---- R update (alg.py:175)
+    CB_TRY(sgemm(r, r, m, 1.f, P.Lcur, 1, r, P.Lcur, r, 1, P.Gs, r, 1, false, nullptr, st));  // L^T L
+    CB_TRY(sgemm(r, n, m, 1.f, P.Lcur, 1, r, res, n, 1, P.Br, n, 1, false, nullptr, st));     // L^T res
+    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));  // alg.py:179-180
+    // ---- inner error ||(res - L R) H_sqrt||_F and best-so-far (alg.py:182-188)
+    CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+    CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
+    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
+    const int* f = P.flags + 1;
+    CB_TRY(copy_if(f, P.Lb, P.Lcur, sizeof(float) * m * r, st));
+    CB_TRY(copy_if(f, P.Rb, P.Rcur, sizeof(float) * r * n, st));
+    CB_TRY(copy_if(f, P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits), st));
+    CB_TRY(copy_if(f, P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits), st));
+    CB_TRY(copy_if(f, P.Lscale_in, P.Lscale_cur, sizeof(float), st));
+    CB_TRY(copy_if(f, P.Rscale_in, P.Rscale_cur, sizeof(float), st));
+  }
+  CB_CUDA(cudaMemcpyAsync(P.Lcur, P.Lb, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(P.Rcur, P.Rb, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  return CB_OK;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
+  if (validate_params(p, m, n, h_kind == CB_H_DENSE ? CB_H_DIAG : h_kind) != CB_OK) return 0;
+  Arena a{nullptr, 0, 0};
+  LayerPlan L{};
+  plan_layer(a, p, m, n, p->scale_w != 0, L);
+  return a.off + 256;
+}
+
+extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int64_t m, int64_t n, const float* h,
+                                int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes, void* stream) {
+  CB_TRY(validate_params(p, m, n, h_kind));
+  if (W == nullptr || out == nullptr || ws == nullptr) return CB_ERR_ARG;
+  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  if (out->Q == nullptr || out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr)
+    return CB_ERR_ARG;
+  if (p->compute_q && (out->Q_idxs == nullptr || out->Q_scale == nullptr)) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t r = p->compute_lr ? p->rank : 0;
+  const int64_t rr = p->rank;  // L/R outputs always have the parameter rank (alg.py:73-74)
+  const int64_t numel = m * n;
+  const bool scale_w = p->scale_w != 0;
+
+  Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+  LayerPlan P{};
+  CB_TRY(plan_layer(a, p, m, n, scale_w, P));
+  if (P.quant_factors && (out->L_idxs == nullptr || out->R_idxs == nullptr || out->L_scale == nullptr || out->R_scale == nullptr))
+    return CB_ERR_ARG;
+  if (p->compute_lr) P.lr.status = P.flags + 2;
+
+  // ---- initial state: Q = 0, L = 0, R = 0 (alg.py:71-75)
+  CB_CUDA(cudaMemsetAsync(P.dsc, 0, sizeof(double) * 4, st));
+  CB_CUDA(cudaMemsetAsync(P.flags, 0, sizeof(int) * 8, st));
+  CB_CUDA(cudaMemsetAsync(out->L, 0, sizeof(float) * m * rr, st));
+  CB_CUDA(cudaMemsetAsync(out->R, 0, sizeof(float) * rr * n, st));
+  if (p->compute_q) {
+    CB_CUDA(cudaMemsetAsync(out->Q_idxs, 0, (size_t)numel * code_bytes(p->q_bits), st));
+    CB_CUDA(cudaMemsetAsync(out->Q_scale, 0, sizeof(float), st));
+  }
+  if (p->iters * p->n_order > 0) CB_CUDA(cudaMemsetAsync(out->errors, 0, sizeof(float) * p->iters * p->n_order, st));
+  if (p->compute_lr) {
+    CB_CUDA(cudaMemsetAsync(P.Lcur, 0, sizeof(float) * m * r, st));
+    CB_CUDA(cudaMemsetAsync(P.Rcur, 0, sizeof(float) * r * n, st));
+  }
+  if (P.quant_factors) {
+    CB_CUDA(cudaMemsetAsync(P.Lcodes_out, 0, (size_t)m * r * code_bytes(p->l_bits), st));
+    CB_CUDA(cudaMemsetAsync(out->R_idxs, 0, (size_t)r * n * code_bytes(p->r_bits), st));
+  }
+
+  // ---- global scale, scaled W, error denominator, Hessian vectors
+  if (scale_w && !(p->global_scale_in > 0.f)) CB_TRY(sumsq(W, numel, P.dsc + 0, st));
+  CB_TRY(finalize_global_scale(P.dsc + 0, numel, p->global_scale_in, scale_w, P.scalars, st));
+  CB_TRY(prep_hessian_diag(h_kind == CB_H_DIAG ? h : nullptr, n, p->sigma_reg, p->aware, P.h_eff, P.sqrt_h,
+                           P.inv_sqrt_h, P.w_inner, nullptr, st));
+  CB_TRY(scale_and_den(W, P.Ws, m, n, P.scalars, P.h_eff, P.dsc + 1, st));
+  const float* Ws = scale_w ? P.Ws : W;
+  if (out->W_scaled != nullptr)
+    CB_CUDA(cudaMemcpyAsync(out->W_scaled, Ws, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
+
+  const int niter = p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 8);
+  bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false;
+  bool updated[8] = {false, false, false, false, false, false, false, false};
+  int step = 0;
+  for (int it = 0; it < p->iters; ++it) {
+    for (int oi = 0; oi < p->n_order; ++oi, ++step) {
+      const int which = p->order[oi];
+      bool num_ready = false;
+      if (which == 0 && p->compute_q) {
+        // ---- Q update (maybe_update_Q, alg.py:253-283)
+        const float* lrp = nullptr;
+        if (p->compute_lr && have_lr) {
+          if (!lrbuf_valid) CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+          lrbuf_valid = true;
+          lrp = P.LRbuf;
+        }
+        CB_TRY(resid_absmax(Ws, lrp, numel, P.amax, st));
+        CB_TRY(quant_err(Ws, lrp, P.h_eff, m, n, P.amax, 1e-8f, p->q_bits, P.codes_cur, P.qscale_cur, P.dsc + 2, st));
+        have_q = true;
+        num_ready = true;
+      } else if (which == 1 && p->compute_lr) {
+        // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
+        CB_TRY(form_y(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
+                      p->aware ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
+        CB_TRY(lowrank_core(P.Y, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
+                            warm_valid && p->warm_start, P.Lcur, P.Rcur, P.lr, st));
+        warm_valid = true;
+        if (P.quant_factors) CB_TRY(lplr_refine(p, P, m, n, st));
+        have_lr = true;
+        CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+        lrbuf_valid = true;
+      }
+      if (!num_ready) {
+        CB_TRY(err_accum(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
+                         (have_lr && lrbuf_valid) ? P.LRbuf : nullptr, P.h_eff, m, n, P.dsc + 2, st));
+      }
+      updated[oi] = true;
+      // `updated` is keyed by name in the reference (alg.py:91), so duplicates in update_order share a flag
+      bool all_updated = true;
+      for (int k = 0; k < p->n_order; ++k) {
+        bool u = false;
+        for (int j = 0; j < p->n_order; ++j) u = u || (updated[j] && p->order[j] == p->order[k]);
+        all_updated = all_updated && u;
+      }
+      CB_TRY(select_outer(P.dsc + 2, P.dsc + 1, out->errors, step, P.scalars, P.flags, all_updated ? 1 : 0, st));
+      // ---- best_decomp = deepcopy(curr_decomp) (alg.py:107), device side
+      const int* f = P.flags;
+      if (have_q) {
+        CB_TRY(copy_if(f, out->Q_idxs, P.codes_cur, (size_t)numel * code_bytes(p->q_bits), st));
+        CB_TRY(copy_if(f, out->Q_scale, P.qscale_cur, sizeof(float), st));
+      }
+      if (have_lr) {
+        CB_TRY(copy_if(f, out->L, P.Lcur, sizeof(float) * m * r, st));
+        CB_TRY(copy_if(f, out->R, P.Rcur, sizeof(float) * r * n, st));
+        if (P.quant_factors) {
+          CB_TRY(copy_if(f, P.Lcodes_out, P.Lcodes_in, (size_t)m * r * code_bytes(p->l_bits), st));
+          CB_TRY(copy_if(f, out->R_idxs, P.Rcodes_in, (size_t)r * n * code_bytes(p->r_bits), st));
+          CB_TRY(copy_if(f, out->L_scale, P.Lscale_in, sizeof(float), st));
+          CB_TRY(copy_if(f, out->R_scale, P.Rscale_in, sizeof(float), st));
+        }
+      }
+      // the Q update invalidates nothing; the LR update refreshed LRbuf above
+    }
+  }
+
+  // ---- materialise the best iterate
+  if (p->compute_q) {
+    CB_TRY(cb_dequantize_f32(out->Q_idxs, nullptr, out->Q_scale, numel, p->q_bits, 0, out->Q, stream));
+    if (out->Q_packed != nullptr) CB_TRY(cb_pack_codes(out->Q_idxs, numel, p->q_bits, out->Q_packed, stream));
+  } else {
+    CB_CUDA(cudaMemsetAsync(out->Q, 0, sizeof(float) * numel, st));
+  }
+  if (P.quant_factors) {
+    // L_idxs are the codes of L.T flattened (alg.py:171): transpose the (m x r) code matrix
+    CB_TRY(transpose_codes(P.Lcodes_out, m, r, code_bytes(p->l_bits), out->L_idxs, st));
+    if (out->L_packed != nullptr) CB_TRY(cb_pack_codes(out->L_idxs, m * r, p->l_bits, out->L_packed, stream));
+    if (out->R_packed != nullptr) CB_TRY(cb_pack_codes(out->R_idxs, r * n, p->r_bits, out->R_packed, stream));
+  }
+  // scalars: [0] global_scale [1] min_error [2] best_step [3] cholesky retries [4] jacobi sweeps
+  CB_CUDA(cudaMemcpyAsync(out->scalars, P.scalars, sizeof(float) * 8, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(out->scalars + 6, P.flags + 2, sizeof(int) * 2, cudaMemcpyDeviceToDevice, st));
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------- stand-alone stages (C ABI)
+extern "C" size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t q_width, int h_kind) {
+  if (m <= 0 || n <= 0 || r <= 0 || q_width < r || q_width > 512) return 0;
+  (void)h_kind;
+  Arena a{nullptr, 0, 0};
+  a.take<float>(4 * n);   // h vectors
+  a.take<float>(m * n);   // Y
+  a.take<int>(8);
+  plan_lowrank(a, m, n, q_width, nullptr, nullptr);
+  return a.off + 256;
+}
+
+extern "C" int cb_lowrank_init(const float* A, int64_t m, int64_t n, const float* h, int h_kind, int64_t r,
+                               int64_t q_width, int niter, uint64_t seed, int aware, float* L, float* R,
+                               float* sigma, void* ws, size_t ws_bytes, void* stream) {
+  if (A == nullptr || L == nullptr || R == nullptr || ws == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
+  if (r < 1 || r > m || r > n || q_width < r || q_width > m || q_width > n || niter < 0) return CB_ERR_ARG;
+  if (q_width > 512) return CB_ERR_UNSUPPORTED;
+  if (h_kind == CB_H_DENSE) return CB_ERR_UNSUPPORTED;
+  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+  float* hv = a.take<float>(4 * n);
+  float* Y = a.take<float>(m * n);
+  int* status = a.take<int>(8);
+  LowrankBufs b = plan_lowrank(a, m, n, q_width, nullptr, status);
+  if (!a.ok()) return CB_ERR_WORKSPACE;
+  CB_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 8, st));
+  CB_TRY(prep_hessian_diag(h_kind == CB_H_DIAG ? h : nullptr, n, 0.f, aware, hv, hv + n, hv + 2 * n, hv + 3 * n, nullptr, st));
+  CB_TRY(form_y(A, nullptr, 8, nullptr, aware ? hv + n : nullptr, m, n, Y, nullptr, st));
+  CB_TRY(lowrank_core(Y, m, n, r, q_width, niter, seed, aware, hv + 2 * n, false, L, R, b, st));
+  if (sigma != nullptr) {
+    sqrt_vec_kernel<<<1, 256, 0, st>>>(b.evals, (int)r, sigma);
+    CB_CHECK_LAUNCH();
+  }
+  return CB_OK;
+}
+
+extern "C" size_t cb_weighted_error_workspace_bytes(int64_t m, int64_t n, int64_t r, int h_kind) {
+  (void)h_kind;
+  if (m <= 0 || n <= 0) return 0;
+  return (r > 0 ? sizeof(float) * (size_t)m * n : 0) + 1024;
+}
+
+extern "C" int cb_weighted_error(const float* W, int64_t m, int64_t n, const void* q_codes, int q_bits,
+                                 const float* q_scale, const float* L, const float* R, int64_t r, const float* h,
+                                 int h_kind, double* out_num, double* out_den, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  if (W == nullptr || out_num == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
+  if (h_kind == CB_H_DENSE) return CB_ERR_UNSUPPORTED;
+  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  if (q_codes != nullptr && (!bits_ok(q_bits) || q_scale == nullptr)) return CB_ERR_BITS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* hw = h_kind == CB_H_DIAG ? h : nullptr;
+  float* LRbuf = nullptr;
+  if (L != nullptr && R != nullptr && r > 0) {
+    if (ws == nullptr || ws_bytes < sizeof(float) * (size_t)m * n) return CB_ERR_WORKSPACE;
+    LRbuf = reinterpret_cast<float*>(ws);
+    CB_TRY(sgemm(m, n, r, 1.f, L, r, 1, R, n, 1, LRbuf, n, 1, false, nullptr, st));
+  }
+  CB_TRY(err_accum(W, q_codes, q_codes != nullptr ? q_bits : 8, q_scale, LRbuf, hw, m, n, out_num, st));
+  if (out_den != nullptr) CB_TRY(err_accum(W, nullptr, 8, nullptr, nullptr, hw, m, n, out_den, st));
+  return CB_OK;
+}

@@ -1,0 +1,50 @@
+// Internal (non-ABI) interfaces shared between the translation units of libcaldera_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+// sgemm.cu -- C(i,j) = alpha * sum_k A(i,k) B(k,j) [* colscale[j]] (+ C), arbitrary strides
+int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
+          const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
+          bool accumulate, const float* colscale, cudaStream_t st);
+
+// smalldense.cu
+int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st);
+int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
+                          cudaStream_t st);
+
+// stages.cu -- fused element-wise stages of the outer loop (all asynchronous on `st`)
+struct HessianVecs {
+  const float* h;        // column weights of the error metric (n) or nullptr for all ones
+  const float* sqrt_h;   // sqrt(h) or nullptr
+  const float* inv_sqrt_h;
+  const float* w_inner;  // weights of the LPLR inner error: h (aware) or h^2 (not aware, alg.py:50)
+};
+
+int sumsq(const float* x, int64_t numel, double* out, cudaStream_t st);
+int finalize_global_scale(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars,
+                          cudaStream_t st);
+int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h,
+                  double* den, cudaStream_t st);
+int prep_hessian_diag(const float* h_in, int64_t n, float sigma_reg, int aware, float* h_eff, float* sqrt_h,
+                      float* inv_sqrt_h, float* w_inner, float* scratch, cudaStream_t st);
+int resid_absmax(const float* Ws, const float* LR, int64_t numel, float* amax, cudaStream_t st);
+int quant_err(const float* Ws, const float* LR, const float* h, int64_t m, int64_t n, const float* amax,
+              float eps, int bits, void* codes, float* qscale, double* num, cudaStream_t st);
+int form_y(const float* Ws, const void* codes, int bits, const float* qscale, const float* sqrt_h,
+           int64_t m, int64_t n, float* Y, float* RES, cudaStream_t st);
+int err_accum(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR,
+              const float* w, int64_t m, int64_t n, double* num, cudaStream_t st);
+int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags,
+                 int all_updated, cudaStream_t st);
+int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st);
+int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st);
+int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st);
+int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
+int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
+int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes, void* dst, cudaStream_t st);
+
+// quant.cu (C ABI, reused internally)
+}  // namespace cb

@@ -1,0 +1,454 @@
+// Block-wise abs-max uniform quantiser, dequantiser and the packed code format.
+//
+// Replaces LowMemoryQuantizer.quantize_block / dequantize_block (uniform branch),
+// RCR/caldera/utils/quantization.py:244-268, 290-307.  HBM-bound: every kernel here reads
+// its input once with 128-bit streaming loads, keeps the per-block abs-max / scale in
+// registers (warp-shuffle reduction over the lanes that share a block) and writes codes,
+// packed codes, scales and (optionally) the dequantised values from the same registers.
+//
+// Algorithmic bytes per element ("quantise/pack"): 4 (read) + bits/8 (packed)
+// + 4/block (scales) [+1 if int8 codes are requested, +4 if dequantised output is].
+#include "common.cuh"
+
+namespace cb {
+
+// ---------------------------------------------------------------- packing helpers
+template <int BITS> struct CodeT { using type = int8_t; };
+template <> struct CodeT<16> { using type = int16_t; };
+
+// ---------------------------------------------------------------- fast path
+// One warp handles tiles of 512 consecutive elements: 4 fully coalesced 512-byte loads
+// (lane l owns elements 4l..4l+3 of each 128-element chunk).  LPB = lanes per quantisation
+// block (block/4) for block in {32,64,128}; LPB == 0 means one scale for the whole tensor,
+// already reduced into scales[0] by absmax_fast_kernel.
+template <int BITS, int LPB>
+__global__ void __launch_bounds__(256)
+quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, float eps,
+                  void* __restrict__ codes, uint8_t* __restrict__ packed,
+                  float* __restrict__ scales, float* __restrict__ dequant) {
+  using code_t = typename CodeT<BITS>::type;
+  constexpr int LV = (1 << (BITS - 1)) - 1;
+  const float lv = (float)LV;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ntiles = (numel + 511) >> 9;
+  float s_whole = 0.f;
+  if (LPB == 0) s_whole = fmaxf(scales[0], eps);
+
+  for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+    const int64_t base = tile << 9;
+    float4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t idx = base + j * 128 + lane * 4;
+      ok[j] = idx < numel;
+      v[j] = ok[j] ? ld_stream4(x + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t idx = base + j * 128 + lane * 4;
+      float s;
+      if (LPB > 0) {
+        float a = fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+#pragma unroll
+        for (int o = LPB / 2; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        s = fmaxf(a, eps);
+        if (ok[j] && (lane % LPB) == 0) scales[idx / block] = s;
+      } else {
+        s = s_whole;
+      }
+      const int c0 = quant_code(v[j].x, s, lv), c1 = quant_code(v[j].y, s, lv);
+      const int c2 = quant_code(v[j].z, s, lv), c3 = quant_code(v[j].w, s, lv);
+      if (codes != nullptr && ok[j]) {
+        if (BITS <= 8) {
+          uint32_t w = (uint32_t)(uint8_t)(int8_t)c0 | ((uint32_t)(uint8_t)(int8_t)c1 << 8) |
+                       ((uint32_t)(uint8_t)(int8_t)c2 << 16) | ((uint32_t)(uint8_t)(int8_t)c3 << 24);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(codes) + idx) = w;
+        } else {
+          uint2 w;
+          w.x = (uint32_t)(uint16_t)(int16_t)c0 | ((uint32_t)(uint16_t)(int16_t)c1 << 16);
+          w.y = (uint32_t)(uint16_t)(int16_t)c2 | ((uint32_t)(uint16_t)(int16_t)c3 << 16);
+          *reinterpret_cast<uint2*>(reinterpret_cast<code_t*>(codes) + idx) = w;
+        }
+      }
+      if (dequant != nullptr && ok[j]) {
+        st_stream4(dequant + idx, make_float4(dequant_val(c0, s, lv), dequant_val(c1, s, lv),
+                                              dequant_val(c2, s, lv), dequant_val(c3, s, lv)));
+      }
+      if (packed != nullptr) {
+        if (BITS == 2) {
+          // byte = q0*64 + q1*16 + q2*4 + q3 (quantization.py:217-220), one byte per lane;
+          // four neighbouring lanes are gathered into one 32-bit store.
+          uint32_t b = (uint32_t)(((c0 + LV) << 6) | ((c1 + LV) << 4) | ((c2 + LV) << 2) | (c3 + LV));
+          uint32_t t = b | (__shfl_down_sync(0xffffffffu, b, 1) << 8);
+          uint32_t w = t | (__shfl_down_sync(0xffffffffu, t, 2) << 16);
+          if (ok[j] && (lane & 3) == 0) *reinterpret_cast<uint32_t*>(packed + (idx >> 2)) = w;
+        } else if (BITS == 4) {
+          // byte = q0*16 + q1 (quantization.py:152), two bytes per lane
+          uint32_t h = (uint32_t)(((c0 + LV) << 4) | (c1 + LV)) | ((uint32_t)(((c2 + LV) << 4) | (c3 + LV)) << 8);
+          uint32_t w = h | (__shfl_down_sync(0xffffffffu, h, 1) << 16);
+          if (ok[j] && (lane & 1) == 0) *reinterpret_cast<uint32_t*>(packed + (idx >> 1)) = w;
+        } else if (BITS == 8) {
+          uint32_t w = (uint32_t)(c0 + LV) | ((uint32_t)(c1 + LV) << 8) | ((uint32_t)(c2 + LV) << 16) |
+                       ((uint32_t)(c3 + LV) << 24);
+          if (ok[j]) *reinterpret_cast<uint32_t*>(packed + idx) = w;
+        } else {
+          // big-endian offset uint16
+          uint32_t s0 = (uint32_t)(c0 + LV), s1 = (uint32_t)(c1 + LV), s2 = (uint32_t)(c2 + LV), s3 = (uint32_t)(c3 + LV);
+          uint2 w;
+          w.x = (s0 >> 8) | ((s0 & 255u) << 8) | ((s1 >> 8) << 16) | ((s1 & 255u) << 24);
+          w.y = (s2 >> 8) | ((s2 & 255u) << 8) | ((s3 >> 8) << 16) | ((s3 & 255u) << 24);
+          if (ok[j]) *reinterpret_cast<uint2*>(packed + idx * 2) = w;
+        }
+      }
+    }
+  }
+}
+
+// whole-tensor abs-max, contiguous input, 128-bit loads; result atomically max-ed into *out
+__global__ void __launch_bounds__(256)
+absmax_fast_kernel(const float* __restrict__ x, int64_t numel, float* __restrict__ out) {
+  __shared__ float red[32];
+  float a = 0.f;
+  const int64_t n4 = numel >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 independent loads in flight per thread
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v0 = ld_stream4(x + 4 * i), v1 = ld_stream4(x + 4 * (i + stride));
+    float4 v2 = ld_stream4(x + 4 * (i + 2 * stride)), v3 = ld_stream4(x + 4 * (i + 3 * stride));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w))));
+  }
+  for (; i < n4; i += stride) {
+    float4 v0 = ld_stream4(x + 4 * i);
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+  }
+  a = block_max(a, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(out, a);
+}
+
+// ---------------------------------------------------------------- generic path
+// Any block size, any strides, any numel.  Scales must be zeroed first.
+__global__ void __launch_bounds__(256)
+absmax_generic_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t sr, int64_t sc,
+                      int64_t block, float* __restrict__ scales) {
+  const int64_t numel = rows * cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < numel; i0 += stride) {
+    const int64_t i = i0 + lane;
+    float a = 0.f;
+    int64_t b = -1;
+    if (i < numel) {
+      int64_t r = i / cols, c = i - r * cols;
+      a = fabsf(x[r * sr + c * sc]);
+      b = i / block;
+    }
+    // warp-aggregate when the whole warp falls into one block
+    const int64_t b_first = __shfl_sync(0xffffffffu, b, 0);
+    const bool same = __all_sync(0xffffffffu, b == b_first || b < 0);
+    if (same) {
+      a = warp_max(a);
+      if (lane == 0 && b_first >= 0) atomic_max_nonneg(scales + b_first, a);
+    } else if (b >= 0) {
+      atomic_max_nonneg(scales + b, a);
+    }
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+quant_generic_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t sr, int64_t sc,
+                     int64_t block, float eps, void* __restrict__ codes, uint8_t* __restrict__ packed,
+                     float* __restrict__ scales, float* __restrict__ dequant) {
+  using code_t = typename CodeT<BITS>::type;
+  constexpr int LV = (1 << (BITS - 1)) - 1;
+  constexpr int G = BITS == 2 ? 4 : (BITS == 4 ? 2 : 1);  // elements per packed byte (or per thread)
+  const float lv = (float)LV;
+  const int64_t numel = rows * cols;
+  const int64_t ngroups = (numel + G - 1) / G;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    uint32_t byte = 0;
+#pragma unroll
+    for (int e = 0; e < G; ++e) {
+      const int64_t i = g * G + e;
+      int sym = 0;
+      if (i < numel) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t b = i / block;
+        const float s = fmaxf(scales[b], eps);
+        if (i == b * block) scales[b] = s;  // idempotent clamp (max(max(a,eps),eps) == max(a,eps))
+        const int code = quant_code(x[r * sr + c * sc], s, lv);
+        if (codes != nullptr) reinterpret_cast<code_t*>(codes)[i] = (code_t)code;
+        if (dequant != nullptr) dequant[i] = dequant_val(code, s, lv);
+        sym = code + LV;
+      }
+      if (BITS <= 4) byte = (byte << BITS) | (uint32_t)sym;
+      else byte = (uint32_t)sym;
+    }
+    if (packed != nullptr) {
+      if (BITS <= 8) packed[g] = (uint8_t)byte;
+      else { packed[2 * g] = (uint8_t)(byte >> 8); packed[2 * g + 1] = (uint8_t)(byte & 255u); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- dequantise
+template <int BITS, bool PACKED>
+__device__ __forceinline__ int fetch_code(const void* codes, const uint8_t* packed, int64_t i) {
+  constexpr int LV = (1 << (BITS - 1)) - 1;
+  if (!PACKED) return (int)reinterpret_cast<const typename CodeT<BITS>::type*>(codes)[i];
+  if (BITS == 2) return (int)((packed[i >> 2] >> (2 * (3 - (int)(i & 3)))) & 3u) - LV;
+  if (BITS == 4) return (int)((packed[i >> 1] >> (4 * (1 - (int)(i & 1)))) & 15u) - LV;
+  if (BITS == 8) return (int)packed[i] - LV;
+  return (int)(((uint32_t)packed[2 * i] << 8) | packed[2 * i + 1]) - LV;
+}
+
+template <int BITS, bool PACKED>
+__global__ void __launch_bounds__(256)
+dequant_generic_kernel(const void* __restrict__ codes, const uint8_t* __restrict__ packed,
+                       const float* __restrict__ scales, int64_t numel, int64_t block,
+                       float* __restrict__ out) {
+  const float lv = (float)((1 << (BITS - 1)) - 1);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    out[i] = dequant_val(fetch_code<BITS, PACKED>(codes, packed, i), scales[i / block], lv);
+}
+
+// 16 elements per thread: one 32-bit word of 2-bit codes / two words of 4-bit codes /
+// one 128-bit word of int8 codes -> four 128-bit stores.  numel % 16 == 0, block % 16 == 0.
+template <int BITS, bool PACKED>
+__global__ void __launch_bounds__(256)
+dequant_fast_kernel(const void* __restrict__ codes, const uint8_t* __restrict__ packed,
+                    const float* __restrict__ scales, int64_t numel, int64_t block,
+                    float* __restrict__ out) {
+  constexpr int LV = (1 << (BITS - 1)) - 1;
+  const float lv = (float)LV;
+  const int64_t n16 = numel >> 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += stride) {
+    const int64_t i = t << 4;
+    const float s = scales[i / block];
+    int c[16];
+    if (PACKED && BITS == 2) {
+      uint32_t w = *reinterpret_cast<const uint32_t*>(packed + (i >> 2));
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint32_t byte = (w >> (8 * b)) & 255u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[4 * b + e] = (int)((byte >> (2 * (3 - e))) & 3u) - LV;
+      }
+    } else if (PACKED && BITS == 4) {
+      uint2 w = *reinterpret_cast<const uint2*>(packed + (i >> 1));
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        uint32_t byte = ((b < 4 ? w.x : w.y) >> (8 * (b & 3))) & 255u;
+        c[2 * b] = (int)(byte >> 4) - LV;
+        c[2 * b + 1] = (int)(byte & 15u) - LV;
+      }
+    } else {
+      // int8 codes (or offset bytes when PACKED && BITS == 8)
+      uint4 w = *reinterpret_cast<const uint4*>(PACKED ? (const void*)(packed + i)
+                                                       : (const void*)(reinterpret_cast<const int8_t*>(codes) + i));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        uint32_t byte = (ww[b >> 2] >> (8 * (b & 3))) & 255u;
+        c[b] = PACKED ? (int)byte - LV : (int)(int8_t)byte;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      st_stream4(out + i + 4 * k, make_float4(dequant_val(c[4 * k], s, lv), dequant_val(c[4 * k + 1], s, lv),
+                                              dequant_val(c[4 * k + 2], s, lv), dequant_val(c[4 * k + 3], s, lv)));
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+pack_kernel(const void* __restrict__ codes, int64_t numel, uint8_t* __restrict__ packed) {
+  using code_t = typename CodeT<BITS>::type;
+  constexpr int LV = (1 << (BITS - 1)) - 1;
+  constexpr int G = BITS == 2 ? 4 : (BITS == 4 ? 2 : 1);
+  const int64_t ngroups = (numel + G - 1) / G;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const code_t* c = reinterpret_cast<const code_t*>(codes);
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    uint32_t byte = 0;
+#pragma unroll
+    for (int e = 0; e < G; ++e) {
+      const int64_t i = g * G + e;
+      const int sym = i < numel ? (int)c[i] + LV : 0;
+      if (BITS <= 4) byte = (byte << BITS) | (uint32_t)sym;
+      else byte = (uint32_t)sym;
+    }
+    if (BITS <= 8) packed[g] = (uint8_t)byte;
+    else { packed[2 * g] = (uint8_t)(byte >> 8); packed[2 * g + 1] = (uint8_t)(byte & 255u); }
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+unpack_kernel(const uint8_t* __restrict__ packed, int64_t numel, void* __restrict__ codes) {
+  using code_t = typename CodeT<BITS>::type;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    reinterpret_cast<code_t*>(codes)[i] = (code_t)fetch_code<BITS, true>(nullptr, packed, i);
+}
+
+// ---------------------------------------------------------------- host dispatch
+static bool bits_ok(int bits) { return bits == 2 || bits == 4 || bits == 8 || bits == 16; }
+
+template <int BITS>
+static int quantize_bits(const float* x, int64_t rows, int64_t cols, int64_t sr, int64_t sc, int64_t block,
+                         float eps, void* codes, uint8_t* packed, float* scales, float* dequant,
+                         cudaStream_t st) {
+  const int64_t numel = rows * cols;
+  const bool whole = (block == numel);
+  const bool contiguous = (sc == 1 && sr == cols) || (rows == 1 && sc == 1);
+  const bool fast = contiguous && aligned16(x) && (numel % 16 == 0) &&
+                    (codes == nullptr || aligned16(codes)) && (packed == nullptr || aligned16(packed)) &&
+                    (dequant == nullptr || aligned16(dequant)) &&
+                    (whole || block == 32 || block == 64 || block == 128);
+  if (fast) {
+    const int grid = grid_for((numel + 511) / 512, 8, 8);  // 8 warps per CTA, one 512-element tile per warp-iteration
+    if (whole) {
+      CB_CUDA(cudaMemsetAsync(scales, 0, sizeof(float), st));
+      absmax_fast_kernel<<<grid_for(numel / 4, 256 * 4, 8), 256, 0, st>>>(x, numel, scales);
+      CB_CHECK_LAUNCH();
+      quant_fast_kernel<BITS, 0><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+    } else if (block == 32) {
+      quant_fast_kernel<BITS, 8><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+    } else if (block == 64) {
+      quant_fast_kernel<BITS, 16><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+    } else {
+      quant_fast_kernel<BITS, 32><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+    }
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+  }
+  CB_CUDA(cudaMemsetAsync(scales, 0, sizeof(float) * (size_t)(numel / block), st));
+  absmax_generic_kernel<<<grid_for(numel, 256, 8), 256, 0, st>>>(x, rows, cols, sr, sc, block, scales);
+  CB_CHECK_LAUNCH();
+  constexpr int G = BITS == 2 ? 4 : (BITS == 4 ? 2 : 1);
+  quant_generic_kernel<BITS><<<grid_for((numel + G - 1) / G, 256, 8), 256, 0, st>>>(
+      x, rows, cols, sr, sc, block, eps, codes, packed, scales, dequant);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+__global__ void clamp_scale_kernel(float* s, float eps) { s[0] = fmaxf(s[0], eps); }
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" size_t cb_packed_bytes(int64_t numel, int bits) {
+  if (numel < 0) return 0;
+  switch (bits) {
+    case 2: return (size_t)((numel + 3) / 4);
+    case 4: return (size_t)((numel + 1) / 2);
+    case 8: return (size_t)numel;
+    case 16: return (size_t)numel * 2;
+    default: return 0;
+  }
+}
+
+extern "C" int cb_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t stride_r, int64_t stride_c,
+                               int bits, int64_t block, float eps, void* codes, uint8_t* packed,
+                               float* scales, float* dequant, void* stream) {
+  if (!bits_ok(bits)) return CB_ERR_BITS;
+  if (rows < 0 || cols < 0) return CB_ERR_ARG;
+  const int64_t numel = rows * cols;
+  if (numel == 0) return CB_OK;
+  if (x == nullptr || scales == nullptr) return CB_ERR_ARG;
+  if (block == 0) block = numel;
+  if (block < 0 || numel % block != 0) return CB_ERR_BLOCK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (bits) {
+    case 2: rc = quantize_bits<2>(x, rows, cols, stride_r, stride_c, block, eps, codes, packed, scales, dequant, st); break;
+    case 4: rc = quantize_bits<4>(x, rows, cols, stride_r, stride_c, block, eps, codes, packed, scales, dequant, st); break;
+    case 8: rc = quantize_bits<8>(x, rows, cols, stride_r, stride_c, block, eps, codes, packed, scales, dequant, st); break;
+    default: rc = quantize_bits<16>(x, rows, cols, stride_r, stride_c, block, eps, codes, packed, scales, dequant, st); break;
+  }
+  if (rc != CB_OK) return rc;
+  if (block == numel) {
+    // whole-tensor mode: publish the clamped scale max(absmax, eps)
+    clamp_scale_kernel<<<1, 1, 0, st>>>(scales, eps);
+    CB_CHECK_LAUNCH();
+  }
+  return CB_OK;
+}
+
+template <int BITS>
+static int dequant_bits(const void* codes, const uint8_t* packed, const float* scales, int64_t numel,
+                        int64_t block, float* out, cudaStream_t st) {
+  const bool fast = (BITS <= 8) && (numel % 16 == 0) && (block % 16 == 0) && aligned16(out) &&
+                    (packed != nullptr ? aligned16(packed) : aligned16(codes));
+  if (fast) {
+    const int grid = grid_for(numel / 16, 256, 8);
+    if (packed != nullptr) dequant_fast_kernel<BITS, true><<<grid, 256, 0, st>>>(codes, packed, scales, numel, block, out);
+    else dequant_fast_kernel<BITS, false><<<grid, 256, 0, st>>>(codes, packed, scales, numel, block, out);
+  } else {
+    const int grid = grid_for(numel, 256, 8);
+    if (packed != nullptr) dequant_generic_kernel<BITS, true><<<grid, 256, 0, st>>>(codes, packed, scales, numel, block, out);
+    else dequant_generic_kernel<BITS, false><<<grid, 256, 0, st>>>(codes, packed, scales, numel, block, out);
+  }
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" int cb_dequantize_f32(const void* codes, const uint8_t* packed, const float* scales,
+                                 int64_t numel, int bits, int64_t block, float* out, void* stream) {
+  if (!bits_ok(bits)) return CB_ERR_BITS;
+  if ((codes == nullptr) == (packed == nullptr) || scales == nullptr || out == nullptr || numel < 0) return CB_ERR_ARG;
+  if (numel == 0) return CB_OK;
+  if (block == 0) block = numel;
+  if (block < 0 || numel % block != 0) return CB_ERR_BLOCK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bits) {
+    case 2: return dequant_bits<2>(codes, packed, scales, numel, block, out, st);
+    case 4: return dequant_bits<4>(codes, packed, scales, numel, block, out, st);
+    case 8: return dequant_bits<8>(codes, packed, scales, numel, block, out, st);
+    default: return dequant_bits<16>(codes, packed, scales, numel, block, out, st);
+  }
+}
+
+extern "C" int cb_pack_codes(const void* codes, int64_t numel, int bits, uint8_t* packed, void* stream) {
+  if (!bits_ok(bits)) return CB_ERR_BITS;
+  if (codes == nullptr || packed == nullptr || numel < 0) return CB_ERR_ARG;
+  if (numel == 0) return CB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(numel, 256, 8);
+  switch (bits) {
+    case 2: pack_kernel<2><<<grid, 256, 0, st>>>(codes, numel, packed); break;
+    case 4: pack_kernel<4><<<grid, 256, 0, st>>>(codes, numel, packed); break;
+    case 8: pack_kernel<8><<<grid, 256, 0, st>>>(codes, numel, packed); break;
+    default: pack_kernel<16><<<grid, 256, 0, st>>>(codes, numel, packed); break;
+  }
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" int cb_unpack_codes(const uint8_t* packed, int64_t numel, int bits, void* codes, void* stream) {
+  if (!bits_ok(bits)) return CB_ERR_BITS;
+  if (codes == nullptr || packed == nullptr || numel < 0) return CB_ERR_ARG;
+  if (numel == 0) return CB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(numel, 256, 8);
+  switch (bits) {
+    case 2: unpack_kernel<2><<<grid, 256, 0, st>>>(packed, numel, codes); break;
+    case 4: unpack_kernel<4><<<grid, 256, 0, st>>>(packed, numel, codes); break;
+    case 8: unpack_kernel<8><<<grid, 256, 0, st>>>(packed, numel, codes); break;
+    default: unpack_kernel<16><<<grid, 256, 0, st>>>(packed, numel, codes); break;
+  }
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}

@@ -1,0 +1,496 @@
+// Fused element-wise stages of the CALDERA outer loop.
+//
+// Every kernel here makes exactly one pass over an m x n operand with 128-bit accesses and
+// folds in everything the reference does in separate torch ops around it:
+//   scale_and_den    W / global_scale           + denominator  sum_j h_j W_ij^2   (alg.py:42, 298)
+//   resid_absmax     residual = W - L R         + abs-max for the whole-tensor scale (alg.py:262, quantization.py:262)
+//   quant_err        quantise + dequantise      + error numerator sum_j h_j (res - Q)^2 (alg.py:280-283, 298)
+//   form_y           residual = W - Q           + column weighting by sqrt(h)  (alg.py:124, 211)
+//   err_accum        E = W - Q - L R            + sum_j w_j E_ij^2              (alg.py:182, 298)
+// For a diagonal Hessian tr(E H E^T) == sum_ij h_j E_ij^2, which is what replaces the
+// reference's four dense products per error evaluation.
+#include "common.cuh"
+#include "internal.h"
+
+namespace cb {
+
+// ---------------------------------------------------------------- vector helpers
+template <int VEC> struct FVec;
+template <> struct FVec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void load_stream(const float* p) { float4 t = ld_stream4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct FVec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = *p; }
+  __device__ __forceinline__ void load_stream(const float* p) { v[0] = *p; }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+
+template <int VEC, typename code_t>
+__device__ __forceinline__ void load_codes(const code_t* p, int (&c)[VEC]) {
+  if (VEC == 4 && sizeof(code_t) == 1) {
+    uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) c[k] = (int)(int8_t)((w >> (8 * k)) & 255u);
+  } else if (VEC == 4) {
+    uint2 w = *reinterpret_cast<const uint2*>(p);
+    c[0] = (int)(int16_t)(w.x & 0xFFFFu); c[1 % VEC] = (int)(int16_t)(w.x >> 16);
+    c[2 % VEC] = (int)(int16_t)(w.y & 0xFFFFu); c[3 % VEC] = (int)(int16_t)(w.y >> 16);
+  } else {
+    c[0] = (int)p[0];
+  }
+}
+template <int VEC, typename code_t>
+__device__ __forceinline__ void store_codes(code_t* p, const int (&c)[VEC]) {
+  if (VEC == 4 && sizeof(code_t) == 1) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) w |= (uint32_t)(uint8_t)(int8_t)c[k] << (8 * k);
+    *reinterpret_cast<uint32_t*>(p) = w;
+  } else if (VEC == 4) {
+    uint2 w;
+    w.x = (uint32_t)(uint16_t)(int16_t)c[0] | ((uint32_t)(uint16_t)(int16_t)c[1 % VEC] << 16);
+    w.y = (uint32_t)(uint16_t)(int16_t)c[2 % VEC] | ((uint32_t)(uint16_t)(int16_t)c[3 % VEC] << 16);
+    *reinterpret_cast<uint2*>(p) = w;
+  } else {
+    p[0] = (code_t)c[0];
+  }
+}
+
+static inline bool can_vec4(int64_t n, std::initializer_list<const void*> ptrs16) {
+  if (n % 4 != 0) return false;
+  for (const void* p : ptrs16)
+    if (p != nullptr && !aligned16(p)) return false;
+  return true;
+}
+
+#define CB_GRID_STRIDE_CHUNKS(VEC, numel)                                                 \
+  const int64_t nchunk__ = (numel) / (VEC);                                               \
+  const int64_t stride__ = (int64_t)gridDim.x * blockDim.x;                               \
+  for (int64_t ch__ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch__ < nchunk__; ch__ += stride__)
+
+// ---------------------------------------------------------------- global scale
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t numel, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float part = 0.f;
+  int cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const float v = x[i];
+    part = fmaf(v, v, part);
+    if (++cnt == 64) { acc += (double)part; part = 0.f; cnt = 0; }
+  }
+  acc += (double)part;
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+__global__ void finalize_gs_kernel(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars) {
+  // alg.py:38-41: W.square().mean().sqrt().item(), fp32
+  float gs = 1.f;
+  if (scale_w) gs = gs_in > 0.f ? gs_in : sqrtf((float)(sumsq[0] / (double)numel));
+  scalars[0] = gs;
+  scalars[1] = __int_as_float(0x7f800000);  // min_error = +inf
+  scalars[2] = -1.f;                        // best step
+  scalars[3] = 0.f; scalars[4] = 0.f; scalars[5] = __int_as_float(0x7f800000); scalars[6] = 0.f; scalars[7] = 0.f;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+scale_den_kernel(const float* __restrict__ W, float* __restrict__ Ws, int64_t numel, int64_t n,
+                 const float* __restrict__ gs_ptr, const float* __restrict__ h, double* __restrict__ den) {
+  __shared__ double red[32];
+  const float gs = gs_ptr[0];
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = i % n;
+    FVec<VEC> w, hv;
+    w.load_stream(W + i);
+    if (h != nullptr) hv.load(h + j);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      w.v[k] = __fdiv_rn(w.v[k], gs);  // alg.py:42, true division
+      part = fmaf((h != nullptr ? hv.v[k] : 1.f) * w.v[k], w.v[k], part);
+    }
+    if (Ws != nullptr) w.store(Ws + i);
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(den, acc);
+}
+
+// ---------------------------------------------------------------- diagonal Hessian prep
+__global__ void __launch_bounds__(1024)
+prep_h_kernel(const float* __restrict__ h_in, int n, float sigma_reg, int aware, float* __restrict__ h_eff,
+              float* __restrict__ sqrt_h, float* __restrict__ inv_sqrt_h, float* __restrict__ w_inner) {
+  __shared__ float red[32];
+  __shared__ float s_shift;
+  float mn = __int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mn = fminf(mn, h_in != nullptr ? h_in[i] : 1.f);
+  // block min via max of negatives
+  float neg = -mn;
+  neg = warp_max(neg);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = neg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float best = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmaxf(best, red[w]);
+    const float lo = -best;
+    // alg.py:59-63: shift the spectrum up to sigma_reg (aware branch only)
+    s_shift = (aware && lo < sigma_reg) ? (sigma_reg - lo) : 0.f;
+  }
+  __syncthreads();
+  const float shift = s_shift;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float h = (h_in != nullptr ? h_in[i] : 1.f) + shift;
+    h_eff[i] = h;
+    if (aware) {
+      const float sh = sqrtf(h);
+      sqrt_h[i] = sh;
+      inv_sqrt_h[i] = __fdiv_rn(1.f, sh);
+      w_inner[i] = h;
+    } else {
+      sqrt_h[i] = 1.f;
+      inv_sqrt_h[i] = 1.f;
+      w_inner[i] = h * h;  // H_sqrt := H when not activation aware (alg.py:50)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hessian_probe_kernel(const float* __restrict__ H, int64_t n, float* __restrict__ diag, int* __restrict__ offdiag_count) {
+  const int64_t total = n * n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int cnt = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / n, j = e - i * n;
+    const float v = H[e];
+    if (i == j) diag[i] = v;
+    else if (v != 0.f) ++cnt;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt > 0) atomicAdd(offdiag_count, cnt);
+}
+__global__ void probe_finish_kernel(int* flag) { flag[0] = (flag[0] == 0) ? 1 : 0; }
+
+// ---------------------------------------------------------------- Q update
+template <int VEC>
+__global__ void __launch_bounds__(256)
+resid_absmax_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, int64_t numel, float* __restrict__ amax) {
+  __shared__ float red[32];
+  float a = 0.f;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> w, p;
+    w.load(Ws + i);
+    if (LR != nullptr) p.load_stream(LR + i);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) a = fmaxf(a, fabsf(LR != nullptr ? w.v[k] - p.v[k] : w.v[k]));
+  }
+  a = block_max(a, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(amax, a);
+}
+
+template <int VEC, typename code_t>
+__global__ void __launch_bounds__(256)
+quant_err_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, const float* __restrict__ h,
+                 int64_t numel, int64_t n, const float* __restrict__ amax, float eps, float lv,
+                 code_t* __restrict__ codes, float* __restrict__ qscale, double* __restrict__ num) {
+  __shared__ double red[32];
+  const float s = fmaxf(amax[0], eps);
+  if (blockIdx.x == 0 && threadIdx.x == 0) qscale[0] = s;
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = i % n;
+    FVec<VEC> w, p, hv;
+    w.load(Ws + i);
+    if (LR != nullptr) p.load_stream(LR + i);
+    if (h != nullptr) hv.load(h + j);
+    int c[VEC];
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float res = LR != nullptr ? w.v[k] - p.v[k] : w.v[k];
+      c[k] = quant_code(res, s, lv);
+      const float e = res - dequant_val(c[k], s, lv);
+      part = fmaf((h != nullptr ? hv.v[k] : 1.f) * e, e, part);
+    }
+    store_codes<VEC, code_t>(codes + i, c);
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(num, acc);
+}
+
+// ---------------------------------------------------------------- LR update inputs / error
+template <int VEC, typename code_t>
+__global__ void __launch_bounds__(256)
+form_y_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
+              float lv, const float* __restrict__ sqrt_h, int64_t numel, int64_t n,
+              float* __restrict__ Y, float* __restrict__ RES) {
+  const float s = codes != nullptr ? qscale[0] : 0.f;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = i % n;
+    FVec<VEC> w, sh, y;
+    w.load(Ws + i);
+    if (sqrt_h != nullptr) sh.load(sqrt_h + j);
+    int c[VEC];
+    if (codes != nullptr) load_codes<VEC, code_t>(codes + i, c);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      if (codes != nullptr) w.v[k] = w.v[k] - dequant_val(c[k], s, lv);
+      y.v[k] = sqrt_h != nullptr ? w.v[k] * sh.v[k] : w.v[k];
+    }
+    if (Y != nullptr) y.store(Y + i);
+    if (RES != nullptr) w.store(RES + i);
+  }
+}
+
+template <int VEC, typename code_t>
+__global__ void __launch_bounds__(256)
+err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
+           float lv, const float* __restrict__ LR, const float* __restrict__ wcol, int64_t numel, int64_t n,
+           double* __restrict__ num) {
+  __shared__ double red[32];
+  const float s = codes != nullptr ? qscale[0] : 0.f;
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = i % n;
+    FVec<VEC> w, p, hv;
+    w.load(Ws + i);
+    if (LR != nullptr) p.load_stream(LR + i);
+    if (wcol != nullptr) hv.load(wcol + j);
+    int c[VEC];
+    if (codes != nullptr) load_codes<VEC, code_t>(codes + i, c);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float e = w.v[k];
+      if (codes != nullptr) e -= dequant_val(c[k], s, lv);
+      if (LR != nullptr) e -= p.v[k];
+      part = fmaf((wcol != nullptr ? hv.v[k] : 1.f) * e, e, part);
+    }
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(num, acc);
+}
+
+// ---------------------------------------------------------------- selection / bookkeeping
+__global__ void select_outer_kernel(double* num, const double* den, float* errors, int step, float* scalars,
+                                    int* flags, int all_updated) {
+  // alg.py:104-107: strict '<' and only once every component has been updated
+  const float err = (float)sqrt(num[0] / den[0]);
+  errors[step] = err;
+  const int take = (err < scalars[1]) && all_updated;
+  flags[0] = take;
+  if (take) { scalars[1] = err; scalars[2] = (float)step; }
+  num[0] = 0.0;
+}
+__global__ void select_inner_kernel(double* num, float* scalars, int* flags, int first) {
+  // alg.py:182-188
+  const float err = (float)sqrt(num[0]);
+  const float best = first ? __int_as_float(0x7f800000) : scalars[5];
+  const int take = err < best;
+  flags[1] = take;
+  if (take) scalars[5] = err; else if (first) scalars[5] = best;
+  num[0] = 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+copy_if_kernel(const int* __restrict__ flag, uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes, int vec_ok) {
+  if (flag != nullptr && flag[0] == 0) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const size_t n16 = bytes >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = t0; i < n16; i += stride) d4[i] = s4[i];
+    for (size_t i = (n16 << 4) + t0; i < bytes; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = t0; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ p, int64_t count, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    p[i] = gaussian_from(seed, (uint64_t)i);
+}
+
+// mode 0: multiply by v, 1: divide by v, 2: multiply by sqrt(sqrt(v)), 3: divide by sqrt(sqrt(v))
+// (modes 2/3 take squared singular values, i.e. eigenvalues of the Gram matrix)
+__device__ __forceinline__ float apply_mode(float x, float v, int mode) {
+  switch (mode) {
+    case 0: return x * v;
+    case 1: return __fdiv_rn(x, v);
+    case 2: return x * sqrtf(sqrtf(fmaxf(v, 0.f)));
+    default: { const float d = sqrtf(sqrtf(fmaxf(v, 0.f))); return d > 0.f ? __fdiv_rn(x, d) : 0.f; }
+  }
+}
+__global__ void __launch_bounds__(256)
+scale_cols_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, const float* __restrict__ v, int mode, float* __restrict__ out) {
+  const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = apply_mode(X[i], v[i % cols], mode);
+}
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, const float* __restrict__ v, int mode, float* __restrict__ out) {
+  const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = apply_mode(X[i], v[i / cols], mode);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ src, int64_t rows, int64_t cols, T* __restrict__ dst) {
+  __shared__ T tile[32][33];
+  const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t r = by + k, c = bx + tx;
+    if (r < rows && c < cols) tile[k][tx] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t c = bx + k, r = by + tx;  // dst is cols x rows
+    if (r < rows && c < cols) dst[c * rows + r] = tile[tx][k];
+  }
+}
+
+// ---------------------------------------------------------------- host wrappers
+int sumsq(const float* x, int64_t numel, double* out, cudaStream_t st) {
+  sumsq_kernel<<<grid_for(numel, 256 * 8, 4), 256, 0, st>>>(x, numel, out);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int finalize_global_scale(const double* ss, int64_t numel, float gs_in, int scale_w, float* scalars, cudaStream_t st) {
+  finalize_gs_kernel<<<1, 1, 0, st>>>(ss, numel, gs_in, scale_w, scalars);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h, double* den, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {W, Ws, h}))
+    scale_den_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den);
+  else
+    scale_den_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int prep_hessian_diag(const float* h_in, int64_t n, float sigma_reg, int aware, float* h_eff, float* sqrt_h,
+                      float* inv_sqrt_h, float* w_inner, float*, cudaStream_t st) {
+  prep_h_kernel<<<1, 1024, 0, st>>>(h_in, (int)n, sigma_reg, aware, h_eff, sqrt_h, inv_sqrt_h, w_inner);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int resid_absmax(const float* Ws, const float* LR, int64_t numel, float* amax, cudaStream_t st) {
+  CB_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
+  if (can_vec4(numel, {Ws, LR}))
+    resid_absmax_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(Ws, LR, numel, amax);
+  else
+    resid_absmax_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(Ws, LR, numel, amax);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int quant_err(const float* Ws, const float* LR, const float* h, int64_t m, int64_t n, const float* amax, float eps,
+              int bits, void* codes, float* qscale, double* num, cudaStream_t st) {
+  const int64_t numel = m * n;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  const bool v4 = can_vec4(n, {Ws, LR, h, codes});
+#define CB_QE(VEC, T, G)                                                                                       \
+  quant_err_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, LR, h, numel, n, amax, eps, lv, reinterpret_cast<T*>(codes), \
+                                              qscale, num)
+  if (bits <= 8) { if (v4) CB_QE(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_QE(1, int8_t, grid_for(numel, 256 * 4, 8)); }
+  else { if (v4) CB_QE(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_QE(1, int16_t, grid_for(numel, 256 * 4, 8)); }
+#undef CB_QE
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int form_y(const float* Ws, const void* codes, int bits, const float* qscale, const float* sqrt_h, int64_t m,
+           int64_t n, float* Y, float* RES, cudaStream_t st) {
+  const int64_t numel = m * n;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  const bool v4 = can_vec4(n, {Ws, codes, sqrt_h, Y, RES});
+#define CB_FY(VEC, T, G) \
+  form_y_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, sqrt_h, numel, n, Y, RES)
+  if (bits <= 8) { if (v4) CB_FY(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_FY(1, int8_t, grid_for(numel, 256 * 4, 8)); }
+  else { if (v4) CB_FY(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_FY(1, int16_t, grid_for(numel, 256 * 4, 8)); }
+#undef CB_FY
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int err_accum(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR, const float* w,
+              int64_t m, int64_t n, double* num, cudaStream_t st) {
+  const int64_t numel = m * n;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  const bool v4 = can_vec4(n, {Ws, codes, LR, w});
+#define CB_ER(VEC, T, G) \
+  err_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num)
+  if (bits <= 8) { if (v4) CB_ER(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int8_t, grid_for(numel, 256 * 4, 8)); }
+  else { if (v4) CB_ER(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int16_t, grid_for(numel, 256 * 4, 8)); }
+#undef CB_ER
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags, int all_updated, cudaStream_t st) {
+  select_outer_kernel<<<1, 1, 0, st>>>(num, den, errors, step, scalars, flags, all_updated);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st) {
+  select_inner_kernel<<<1, 1, 0, st>>>(num, scalars, flags, first);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return CB_OK;
+  const int vec_ok = aligned16(dst) && aligned16(src);
+  copy_if_kernel<<<grid_for((int64_t)(bytes / 16 + 1), 256 * 4, 4), 256, 0, st>>>(
+      flag, reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(src), bytes, vec_ok);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st) {
+  randn_kernel<<<grid_for(count, 256 * 4, 4), 256, 0, st>>>(p, count, seed);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st) {
+  scale_cols_kernel<<<grid_for(rows * cols, 256 * 4, 4), 256, 0, st>>>(X, rows, cols, v, mode, out);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st) {
+  scale_rows_kernel<<<grid_for(rows * cols, 256 * 4, 4), 256, 0, st>>>(X, rows, cols, v, mode, out);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes, void* dst, cudaStream_t st) {
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  if (elem_bytes == 1) transpose_kernel<int8_t><<<grid, 256, 0, st>>>((const int8_t*)src, rows, cols, (int8_t*)dst);
+  else if (elem_bytes == 2) transpose_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)src, rows, cols, (int16_t*)dst);
+  else transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)src, rows, cols, (float*)dst);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+}  // namespace cb
+
+extern "C" int cb_hessian_probe(const float* H, int64_t n, float* diag, int* is_diag, void* stream) {
+  if (H == nullptr || diag == nullptr || is_diag == nullptr || n <= 0) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_CUDA(cudaMemsetAsync(is_diag, 0, sizeof(int), st));
+  cb::hessian_probe_kernel<<<cb::grid_for(n * n, 256 * 8, 4), 256, 0, st>>>(H, n, diag, is_diag);
+  CB_CHECK_LAUNCH();
+  cb::probe_finish_kernel<<<1, 1, 0, st>>>(is_diag);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}

@@ -1,0 +1,138 @@
+"""Drop-in for RCR/caldera/utils/quantization.py (uniform method) on libcaldera_b200.
+
+Same names, constructor arguments, return conventions and exceptions as the reference's
+`LowMemoryQuantizer` / `QuantizerFactory` (quantization.py:18-37, 244-319).  The uniform
+method runs in the sm_100a kernels of csrc/quant.cu; the codebook methods (nf4/nf2/bbint*)
+are outside the hot path and raise NotImplementedError at call time.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import List
+
+import torch
+
+from . import _lib
+
+_BITWIDTHS = [2, 4, 8, 16]
+_QUANTIZER_METHODS = ["uniform", "nf4", "nf2", "bbint4", "bbint2"]
+
+
+class AbstractQuantizer(ABC):
+    @abstractmethod
+    def quantize_block(self, weight): ...
+
+    @abstractmethod
+    def dequantize_block(self, weight_quant, weight_params, weight_shape): ...
+
+
+class LowMemoryQuantizer(AbstractQuantizer):
+    """quantization.py:18.  `quantize_block` returns (codes, scales, shape) with codes
+    int8 (bits<=8) / int16 of shape (numel/block, block) and scales fp32 (numel/block, 1)."""
+
+    def __init__(self, num_bits: int = 2, method: str = "uniform", block_size: int = 64):
+        self.num_bits = num_bits
+        assert self.num_bits in _BITWIDTHS, "Bit-width not supported!"
+        self.method = method.lower()
+        if self.method not in _QUANTIZER_METHODS:
+            raise NotImplementedError(f"Quantization method '{self.method}' not supported yet.")
+        self.block_size = block_size
+        # same constructor-time checks as quantization.py:36-37, 42-43, 53-54
+        if self.method == "nf4" and self.num_bits != 4:
+            raise ValueError("NF4 quantization supports only 4 bits.")
+        if self.method == "nf2" and self.num_bits != 2:
+            raise ValueError("NF2 quantization supports only 2 bits.")
+        if self.method == "bbint4" and self.num_bits != 4:
+            raise ValueError("bbint4 quantization supports only 4 bits.")
+
+    # -- helpers -----------------------------------------------------------------
+    def _check_method(self, what):
+        if self.method != "uniform":
+            raise NotImplementedError(
+                f"{what} method '{self.method}' not implemented in the B200 path "
+                "(only method='uniform' is on the CALDERA hot path).")
+
+    def quantize_block(self, weight: torch.Tensor, epsilon: float = 1e-8, return_packed: bool = False):
+        """quantization.py:244-288.  With return_packed=True a fourth value, the packed
+        uint8 code stream (MSB-first, offset binary), is appended."""
+        if len(weight.shape) != 2:
+            raise ValueError(f"Support only for 2D matrix, but your input has {len(weight.shape)} dimensions.")
+        total = weight.shape[0] * weight.shape[1]
+        if total % self.block_size != 0:
+            raise ValueError(
+                f"Weight with shape {weight.shape[0]} x {weight.shape[1]} "
+                f"is not divisible by block size {self.block_size}")
+        self._check_method("Quantization")
+        _lib.require_cuda(weight, "weight")
+        lib = _lib.load()
+        w = weight if weight.dtype == torch.float32 else weight.float()
+        nblk = total // self.block_size
+        cdtype = torch.int8 if self.num_bits <= 8 else torch.int16
+        codes = torch.empty((nblk, self.block_size), dtype=cdtype, device=w.device)
+        scales = torch.empty((nblk, 1), dtype=torch.float32, device=w.device)
+        packed = None
+        if return_packed:
+            packed = torch.empty(lib.cb_packed_bytes(total, self.num_bits), dtype=torch.uint8, device=w.device)
+        with torch.cuda.device(w.device):
+            st = lib.cb_quantize_f32(_lib.ptr(w), w.shape[0], w.shape[1], w.stride(0), w.stride(1),
+                                     self.num_bits, self.block_size, float(epsilon), _lib.ptr(codes),
+                                     _lib.ptr(packed), _lib.ptr(scales), None, _lib.stream_ptr())
+        _lib.check(st, "quantize_block")
+        if return_packed:
+            return codes, scales, weight.shape, packed
+        return codes, scales, weight.shape
+
+    def dequantize_block(self, weight_quant: torch.Tensor, weight_params, weight_shape: List[int]):
+        """quantization.py:290-307.  `weight_quant` may be the int8/int16 codes or the packed
+        uint8 stream produced with return_packed=True."""
+        self._check_method("Dequantization")
+        _lib.require_cuda(weight_quant, "weight_quant")
+        lib = _lib.load()
+        numel = 1
+        for s in weight_shape:
+            numel *= int(s)
+        scales = weight_params.contiguous().float()
+        out = torch.empty(numel, dtype=torch.float32, device=weight_quant.device)
+        q = weight_quant.contiguous()
+        is_packed = q.dtype == torch.uint8
+        with torch.cuda.device(q.device):
+            st = lib.cb_dequantize_f32(None if is_packed else _lib.ptr(q), _lib.ptr(q) if is_packed else None,
+                                       _lib.ptr(scales), numel, self.num_bits, numel // scales.numel(),
+                                       _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(st, "dequantize_block")
+        return out.reshape(tuple(weight_shape))
+
+
+class QuantizerFactory:
+    """quantization.py:310-319."""
+
+    def __init__(self, method="uniform", block_size=64):
+        self.method = method
+        self.block_size = block_size
+
+    def get_quantizer(self, num_bits, device="cpu"):
+        return LowMemoryQuantizer(num_bits=num_bits, method=self.method, block_size=self.block_size)
+
+    def __str__(self):
+        return f"QuantizerFactory(method={self.method}, block_size={self.block_size})"
+
+
+def pack_codes(codes: torch.Tensor, num_bits: int) -> torch.Tensor:
+    """int8/int16 codes -> packed uint8 stream (layout in include/caldera_b200.h)."""
+    _lib.require_cuda(codes, "codes")
+    lib = _lib.load()
+    c = codes.contiguous()
+    out = torch.empty(lib.cb_packed_bytes(c.numel(), num_bits), dtype=torch.uint8, device=c.device)
+    with torch.cuda.device(c.device):
+        _lib.check(lib.cb_pack_codes(_lib.ptr(c), c.numel(), num_bits, _lib.ptr(out), _lib.stream_ptr()), "pack_codes")
+    return out
+
+
+def unpack_codes(packed: torch.Tensor, num_bits: int, numel: int) -> torch.Tensor:
+    _lib.require_cuda(packed, "packed")
+    lib = _lib.load()
+    out = torch.empty(numel, dtype=torch.int8 if num_bits <= 8 else torch.int16, device=packed.device)
+    with torch.cuda.device(packed.device):
+        _lib.check(lib.cb_unpack_codes(_lib.ptr(packed.contiguous()), numel, num_bits, _lib.ptr(out),
+                                       _lib.stream_ptr()), "unpack_codes")
+    return out

@@ -1,0 +1,192 @@
+/*
+ * caldera_b200.h -- C ABI of libcaldera_b200.so (sm_100a CUDA kernels for the CALDERA
+ * per-layer decomposition hot path).
+ *
+ * Every entry point takes raw DEVICE pointers, plain sizes and a cudaStream_t passed as
+ * void*.  Nothing here allocates persistent device memory: outputs and scratch are owned
+ * by the caller (size from the *_workspace_bytes() queries).  All calls are asynchronous
+ * on `stream` unless stated otherwise.  Return value: 0 = ok, <0 = bad argument (the
+ * Python shim raises the reference's exception class before launching), >0 = CUDA runtime
+ * error (1000 + cudaError_t) or numerical failure.
+ *
+ * Reference interfaces replaced (RCR = /root/reference/rank-constrained-regression-main/src):
+ *   cb_quantize_f32        LowMemoryQuantizer.quantize_block, uniform branch
+ *                          RCR/caldera/utils/quantization.py:244-268 (+ :93-101)
+ *   cb_dequantize_f32      LowMemoryQuantizer.dequantize_block, uniform branch
+ *                          RCR/caldera/utils/quantization.py:290-295, 103-105, 306-307
+ *   cb_pack_codes / cb_unpack_codes
+ *                          new packed format; bit order of quantization.py:152, 217-220
+ *   cb_caldera_layer       caldera()                 RCR/caldera/decomposition/alg.py:24-112
+ *                          (maybe_update_Q :253-283, update_LR :128-198, LR_init :201-235,
+ *                           quantize_matrix :245-250, activation_aware_error :286-302)
+ *   cb_lowrank_init        LR_init                   RCR/caldera/decomposition/alg.py:201-235
+ *   cb_weighted_error      activation_aware_error    RCR/caldera/decomposition/alg.py:286-302
+ *   cb_convex_prox_layer   solve_convex_optimization + low_rank_factorization +
+ *                          quantize_residual + compute_certificates
+ *                          RCR/convex_caldera/decomposition/convex_caldera.py:128-419
+ */
+#ifndef CALDERA_B200_H
+#define CALDERA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_VERSION 100
+
+/* status codes */
+#define CB_OK 0
+#define CB_ERR_ARG (-1)          /* null pointer, negative size, bad enum           */
+#define CB_ERR_BITS (-2)         /* bits not in {2,4,8,16}            -> AssertionError */
+#define CB_ERR_BLOCK (-3)        /* numel % block != 0                -> ValueError     */
+#define CB_ERR_WORKSPACE (-4)    /* workspace too small                                 */
+#define CB_ERR_UNSUPPORTED (-5)  /* valid in the reference, not built here              */
+#define CB_ERR_CUDA_BASE 1000    /* 1000 + cudaError_t                                  */
+#define CB_ERR_NUMERIC 2000      /* e.g. Cholesky breakdown that the ridge retry could not fix */
+
+int cb_version(void);
+/* Human-readable text for a status code (static storage). */
+const char* cb_status_string(int status);
+/* Number of kernels this library has launched in this process (all streams). */
+int64_t cb_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------- quantiser */
+
+/* Block-wise abs-max uniform quantiser.
+ *   x        rows x cols fp32, element (r,c) at x[r*stride_r + c*stride_c] (any strides;
+ *            the reference quantises the non-contiguous view L.T, alg.py:171)
+ *   bits     2, 4, 8 or 16;  levels = 2^(bits-1) - 1
+ *   block    elements per block in row-major flattened order; 0 = one block (whole tensor)
+ *   eps      scale floor (reference: 1e-8)
+ *   codes    optional out, int8 (bits<=8) or int16 (bits==16), numel entries, row-major
+ *   packed   optional out, cb_packed_bytes(numel,bits) bytes, offset-binary MSB-first
+ *   scales   out, numel/block fp32
+ *   dequant  optional out, numel fp32 row-major: (code/levels)*scale
+ * Per element: s = max(absmax(block), eps); code = rint((x / s) * levels)  (IEEE divide,
+ * IEEE multiply, round-half-even) -- bit-exact with the reference.
+ */
+int cb_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t stride_r, int64_t stride_c,
+                    int bits, int64_t block, float eps,
+                    void* codes, uint8_t* packed, float* scales, float* dequant, void* stream);
+
+/* Inverse: out[i] = (code[i] / levels) * scales[i / block].  Exactly one of codes/packed
+ * must be non-null. */
+int cb_dequantize_f32(const void* codes, const uint8_t* packed, const float* scales,
+                      int64_t numel, int bits, int64_t block, float* out, void* stream);
+
+size_t cb_packed_bytes(int64_t numel, int bits);
+int cb_pack_codes(const void* codes, int64_t numel, int bits, uint8_t* packed, void* stream);
+int cb_unpack_codes(const uint8_t* packed, int64_t numel, int bits, void* codes, void* stream);
+
+/* ------------------------------------------------------------------------- stages */
+
+/* kind of the Hessian argument */
+#define CB_H_IDENTITY 0   /* h == NULL                                   */
+#define CB_H_DIAG 1       /* h = n fp32 diagonal entries                 */
+#define CB_H_DENSE 2      /* h = n x n fp32 row-major symmetric matrix   */
+
+/* Scans an n x n matrix: *is_diag (device int) = 1 when every off-diagonal entry of
+ * (H + H^T)/2 is exactly zero; diag[n] receives the diagonal.  Lets callers that pass
+ * torch.diag_embed(h) (main.py:163-165) take the diagonal fast path. */
+int cb_hessian_probe(const float* H, int64_t n, float* diag, int* is_diag, void* stream);
+
+/* num = sum_ij w_j * (W - Q - L R)_ij^2 and den = sum_ij w_j * W_ij^2 accumulated into
+ * the device doubles out_num / out_den (caller zeroes them).  Q given as codes + scale
+ * (or NULL for Q = 0); L (m x r), R (r x n) may be NULL for LR = 0.  For CB_H_DENSE the
+ * weights are the full quadratic form tr(E H E^T). */
+int cb_weighted_error(const float* W, int64_t m, int64_t n,
+                      const void* q_codes, int q_bits, const float* q_scale,
+                      const float* L, const float* R, int64_t r,
+                      const float* h, int h_kind,
+                      double* out_num, double* out_den, void* ws, size_t ws_bytes, void* stream);
+size_t cb_weighted_error_workspace_bytes(int64_t m, int64_t n, int64_t r, int h_kind);
+
+/* Rank-r factors minimising ||(A - L R) H^(1/2)||_F (LR_init, alg.py:201-235) by
+ * randomized subspace iteration with oversampled width q_width, `niter` power iterations,
+ * CholeskyQR re-orthonormalisation and a Rayleigh-Ritz step (one-sided Jacobi).
+ *   aware != 0: L has orthonormal columns, R = L^T A           (== U_r, S_r V_r^T H^(-1/2))
+ *   aware == 0: L = U_r sqrt(S_r), R = sqrt(S_r) V_r^T of A itself (H ignored)
+ *   warm: optional q_width x m fp32 basis from a previous call (in/out), NULL = Gaussian start
+ */
+int cb_lowrank_init(const float* A, int64_t m, int64_t n, const float* h, int h_kind,
+                    int64_t r, int64_t q_width, int niter, uint64_t seed, int aware,
+                    float* L, float* R, float* sigma /* r, optional */,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t q_width, int h_kind);
+
+/* Small dense helpers (exported for tests and for callers that build their own loops). */
+/* G (q x q, symmetric, row-major, destroyed) -> Lc in the lower triangle of G and
+ * Linv = Lc^-1 (q x q lower triangular, may be NULL).  On breakdown the factorisation is
+ * retried on G + ridge*mean(diag)*I with ridge = 1e-6, 1e-4, 1e-2 and *status gets the
+ * number of retries (device int, may be NULL). */
+int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream);
+/* Eigen-decomposition of the SPD matrix G = Lc Lc^T from its Cholesky factor by one-sided
+ * Jacobi on Lc's columns.  evals[q] descending, evecs row k = k-th eigenvector.
+ * work: q*q floats. */
+int cb_jacobi_eigh_from_chol_f32(const float* Lc, int64_t q, float* evals, float* evecs,
+                                 float* work, int* sweeps, void* stream);
+/* C = alpha * op(A) op(B) (+ C) with arbitrary element strides: A(i,k) = A[i*a_rs + k*a_cs],
+ * B(k,j) = B[k*b_rs + j*b_cs], C(i,j) = C[i*c_rs + j*c_cs].  fp32 SIMT kernel: the path for
+ * shapes the tcgen05 tiles do not cover and the in-library reference for them. */
+int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha,
+                     const float* A, int64_t a_rs, int64_t a_cs,
+                     const float* B, int64_t b_rs, int64_t b_cs,
+                     float* C, int64_t c_rs, int64_t c_cs, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------- fused driver */
+
+typedef struct cb_caldera_params {
+  int32_t compute_q;        /* CalderaParams.compute_quantized_component */
+  int32_t compute_lr;       /* CalderaParams.compute_low_rank_factors    */
+  int32_t q_bits, l_bits, r_bits;
+  int32_t rank;
+  int32_t iters;
+  int32_t lplr_iters;
+  int32_t aware;            /* activation_aware_LR                        */
+  int32_t n_order;          /* len(update_order), <= 8                    */
+  int32_t order[8];         /* 0 = "Q", 1 = "LR"                          */
+  int32_t rand_svd;         /* 1: q=2r, niter=2 like torch.svd_lowrank; 0: accurate mode */
+  float sigma_reg;
+  int32_t scale_w;          /* caldera(..., scale_W=)                     */
+  float global_scale_in;    /* >0: use this instead of computing sqrt(mean(W^2)) */
+  int64_t q_block;          /* 0 = whole-tensor scale (reference semantics, alg.py:247);
+                               >0 = per-block scales (opt-in extension)   */
+  int32_t sketch_width;     /* 0 = default (2*rank)                       */
+  int32_t power_iters;      /* <0 = default (2 if rand_svd else 8)        */
+  int32_t warm_start;       /* reuse the previous outer iteration's basis */
+  uint64_t seed;
+} cb_caldera_params;
+
+typedef struct cb_caldera_out {
+  /* all device pointers, caller-allocated */
+  float* Q;            /* m x n fp32, best iterate (scaled space)                  */
+  float* L;            /* m x r                                                     */
+  float* R;            /* r x n                                                     */
+  void* Q_idxs;        /* int8/int16 m*n codes of the best iterate                  */
+  float* Q_scale;      /* numel/q_block (or 1) scales                               */
+  uint8_t* Q_packed;   /* optional, cb_packed_bytes(m*n, q_bits)                    */
+  void* L_idxs;        /* int8/int16, r*m, order of (L^T).flatten(); only if l_bits<16 or r_bits<16 */
+  void* R_idxs;        /* int8/int16, r*n                                           */
+  float* L_scale;      /* 1 */
+  float* R_scale;      /* 1 */
+  uint8_t* L_packed;   /* optional */
+  uint8_t* R_packed;   /* optional */
+  float* W_scaled;     /* optional m x n: W / global_scale (CalderaDecomposition.W) */
+  float* errors;       /* iters * n_order floats, in sub-step order                 */
+  float* scalars;      /* 8 floats: [0]=global_scale [1]=min_error [2]=best_step
+                          [3]=cholesky retries [4]=jacobi sweeps (last) [5..7] reserved */
+} cb_caldera_out;
+
+size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind);
+/* Whole per-layer decomposition, enqueued on `stream` with no host synchronisation. */
+int cb_caldera_layer(const cb_caldera_params* p, const float* W, int64_t m, int64_t n,
+                     const float* h, int h_kind, const cb_caldera_out* out,
+                     void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALDERA_B200_H */

@@ -1,0 +1,208 @@
+"""GPU parity of caldera() (cb_caldera_layer) against golden runs of the reference, the
+numpy oracle, and size-independent properties at the BASELINE shape.
+
+Tolerances (see DESIGN.md "Parity"): integer codes and scales are bit-exact wherever the
+quantiser input is bit-identical (iterate 0 with the reference's global_scale injected);
+the Hessian-weighted relative error of the returned iterate is within 1e-3 relative of the
+reference (north_star); the rest of the trajectory is path dependent (the 2-bit Q update is
+discontinuous) and is compared with a looser bound."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import caldera_oracle as orc
+from src.caldera.utils.dataclasses import CalderaParams
+from src.caldera.utils.quantization import QuantizerFactory, unpack_codes
+from src.caldera.decomposition.alg import caldera
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "caldera_*.npz")))
+IDS = [os.path.basename(p)[8:-4] for p in FILES]
+
+
+def _load(path):
+    z = np.load(path)
+    kw = json.loads(str(z["params"]))
+    H = None
+    if "H" in z:
+        H = torch.from_numpy(z["H"])
+    elif "h" in z:
+        H = torch.diag(torch.from_numpy(z["h"]))      # dense diag_embed, as main.py:165 passes it
+    return z, kw, H
+
+
+def _params(kw):
+    return CalderaParams(quant_factory_Q=QuantizerFactory(method="uniform", block_size=64),
+                         quant_factory_LR=QuantizerFactory(method="uniform", block_size=64), **kw)
+
+
+def _weighted_error_torch(W, h, Q, L, R):
+    E = (Q + L @ R - W).double()
+    hd = torch.ones(W.shape[1], dtype=torch.float64, device=W.device) if h is None else h.double()
+    return float(((E * E * hd[None, :]).sum() / (W.double() ** 2 * hd[None, :]).sum()).sqrt())
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_golden(path):
+    z, kw, H = _load(path)
+    p = _params(kw)
+    if "H" in z:
+        with pytest.raises(NotImplementedError):
+            caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False, scale_W=bool(z["scale_W"]))
+        pytest.skip("dense (non-diagonal) Hessian: not built yet")
+    scale_W = bool(z["scale_W"])
+    gs = float(z["global_scale"]) if scale_W else None
+    d = caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False, scale_W=scale_W, global_scale=gs)
+    m, n = z["W"].shape
+    # ---- structure (alg.py:71-81, 108-111)
+    assert d.Q.shape == (m, n) and d.L.shape == (m, p.rank) and d.R.shape == (p.rank, n)
+    assert d.Q.dtype == d.L.dtype == d.R.dtype == torch.float32 and d.Q.is_cuda
+    assert d.W.device.type == "cpu" and d.W.shape == (m, n)
+    assert set(d.errors) == set(p.update_order)
+    assert isinstance(d.global_scale, float) or d.global_scale == 1
+    if scale_W:
+        assert abs(d.global_scale - float(z["global_scale"])) <= 1e-7 * float(z["global_scale"])
+    quantised = p.compute_low_rank_factors and (p.L_bits < 16 or p.R_bits < 16)
+    # ---- trajectories
+    ref_all, got_all = [], []
+    for k in p.update_order:
+        ref, got = z[f"errors_{k}"], np.array(d.errors[k])
+        assert got.shape == ref.shape and np.isfinite(got).all()
+        ref_all.append(ref)
+        got_all.append(got)
+        loose = 3e-2 if (quantised or p.rand_svd) else 5e-3
+        np.testing.assert_allclose(got, ref, rtol=loose)
+    ref_all, got_all = np.concatenate(ref_all), np.concatenate(got_all)
+    # first sub-step: quantiser input (or SVD input) is bit-identical to the reference's
+    first = p.update_order[0]
+    np.testing.assert_allclose(d.errors[first][0], z[f"errors_{first}"][0], rtol=2e-5 if first == "Q" else 1e-3)
+    # ---- the returned (best) iterate: north_star tolerance 1e-3 relative
+    order = p.update_order
+    k = len(order)
+    seq_ref = [float(z[f"errors_{order[s % k]}"][s // k]) for s in range(p.iters * k)]
+    seq_got = [d.errors[order[s % k]][s // k] for s in range(p.iters * k)]
+    ref_best, got_best = min(seq_ref[k - 1:]), min(seq_got[k - 1:])   # strict arg-min once all updated (alg.py:105)
+    tol = 1e-3 if not (quantised or p.rand_svd) else 2e-2
+    assert abs(got_best - ref_best) <= tol * ref_best, (got_best, ref_best)
+    # ---- self consistency: the error reported for the returned iterate is the error of the returned tensors
+    h = None if H is None else torch.diagonal(H).to(DEV)
+    if kw.get("sigma_reg", 0) and p.activation_aware_LR and h is not None and float(h.min()) < kw["sigma_reg"]:
+        h = h + (kw["sigma_reg"] - float(h.min()))
+    consistent = _weighted_error_torch(d.W.to(DEV), h, d.Q, d.L, d.R)
+    assert d.best_step == int(np.argmin(seq_got[k - 1:])) + k - 1
+    np.testing.assert_allclose(consistent, seq_got[d.best_step], rtol=2e-5)
+    # ---- codes
+    if p.compute_quantized_component:
+        assert d.Q_idxs.shape == (1, m * n) and d.Q_idxs.dtype == torch.int8
+        assert d.Q_scale.shape == (1, 1)
+        lv = 2 ** (p.Q_bits - 1) - 1
+        assert torch.equal(d.Q, ((d.Q_idxs.float() / lv) * d.Q_scale).reshape(m, n))
+        assert torch.equal(unpack_codes(d.Q_packed, p.Q_bits, m * n), d.Q_idxs.reshape(-1))
+        if "Q_idxs" in z and not quantised and not p.rand_svd:
+            match = float((d.Q_idxs.cpu().numpy() == z["Q_idxs"]).mean())
+            assert match > 0.99, match
+    if quantised:
+        assert d.L_idxs.shape == (1, p.rank * m) and d.R_idxs.shape == (1, p.rank * n)
+        lvl, lvr = 2 ** (p.L_bits - 1) - 1, 2 ** (p.R_bits - 1) - 1
+        Lq = ((d.L_idxs.float() / lvl) * d.L_scale).reshape(p.rank, m).T     # codes of L.T (alg.py:171)
+        Rq = ((d.R_idxs.float() / lvr) * d.R_scale).reshape(p.rank, n)
+        assert torch.equal(Lq.contiguous(), d.L) and torch.equal(Rq, d.R)
+        assert int(d.L_idxs.abs().max()) == lvl and int(d.R_idxs.abs().max()) == lvr
+
+
+def test_iterate0_codes_bit_exact():
+    """Q-first, one sub-step: residual == W exactly, so codes and scale must equal the reference's."""
+    z, kw, H = _load(os.path.join(GOLDEN, "caldera_q_only.npz"))
+    p = _params(kw)
+    d = caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False, global_scale=float(z["global_scale"]))
+    np.testing.assert_array_equal(d.Q_idxs.cpu().numpy(), z["Q_idxs"])
+    np.testing.assert_array_equal(d.Q_scale.cpu().numpy(), z["Q_scale"])
+    np.testing.assert_array_equal(d.Q.cpu().numpy(), z["Q"])
+    np.testing.assert_array_equal(d.W.numpy(), z["W_scaled"])
+    np.testing.assert_allclose(d.errors["Q"], z["errors_Q"], rtol=2e-6)
+    # independently computed global_scale: within an ulp or two of torch's reduction
+    d2 = caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False)
+    assert abs(d2.global_scale - float(z["global_scale"])) <= 2.5e-7 * float(z["global_scale"])
+
+
+def test_h_forms_agree():
+    """None / 1-D diagonal / dense diag_embed Hessians take the same device path."""
+    g = torch.Generator().manual_seed(5)
+    W = 0.02 * torch.randn(128, 192, generator=g)
+    h = 0.5 + torch.rand(192, generator=g)
+    p = _params(dict(Q_bits=2, L_bits=16, R_bits=16, rank=8, iters=2, update_order=["Q", "LR"]))
+    a = caldera(p, W, h, device=DEV, use_tqdm=False, seed=3)
+    b = caldera(p, W.to(DEV), torch.diag(h).to(DEV), device=DEV, use_tqdm=False, seed=3)
+    assert a.errors == b.errors and torch.equal(a.Q_idxs, b.Q_idxs) and torch.equal(a.L, b.L)
+    c = caldera(p, W, None, device=DEV, use_tqdm=False, seed=3)
+    e = caldera(p, W, torch.ones(192), device=DEV, use_tqdm=False, seed=3)
+    assert c.errors == e.errors
+
+
+def test_error_conventions_gpu():
+    W = torch.randn(64, 64)
+    with pytest.raises(AttributeError):
+        caldera(_params(dict(L_bits=4, R_bits=4, rank=4, iters=1, lplr_iters=0, update_order=["Q", "LR"])),
+                W, device=DEV, use_tqdm=False)
+    with pytest.raises(AssertionError):
+        caldera(_params(dict(Q_bits=3, rank=4, iters=1, update_order=["Q"])), W, device=DEV, use_tqdm=False)
+    # update_order == [] (the dataclass default): nothing runs, zeros come back (dataclasses.py:48-57)
+    d = caldera(_params(dict(rank=4, iters=2)), W, device=DEV, use_tqdm=False)
+    assert d.errors == {} and float(d.Q.abs().max()) == 0 and float(d.L.abs().max()) == 0
+    assert d.Q_idxs is None and d.Q_scale == 1
+
+
+@pytest.mark.parametrize("lbits", [16, 4])
+def test_vs_oracle_medium(lbits):
+    g = torch.Generator().manual_seed(77)
+    m, n, r = 320, 448, 24
+    W = 0.02 * torch.randn(m, n, generator=g)
+    h = torch.exp(0.8 * torch.randn(n, generator=g))
+    kw = dict(Q_bits=4, L_bits=lbits, R_bits=lbits, rank=r, iters=3, lplr_iters=3, update_order=["LR", "Q"])
+    ref = orc.caldera_oracle(orc.OracleParams(**kw), W.numpy(), h.numpy())
+    d = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, global_scale=ref.global_scale)
+    np.testing.assert_allclose(d.errors["LR"][0], ref.errors["LR"][0], rtol=1e-3 if lbits == 16 else 2e-2)
+    best_ref = min(ref.errors["Q"])
+    best_got = min(d.errors["Q"])
+    assert abs(best_got - best_ref) <= (1e-3 if lbits == 16 else 2e-2) * best_ref
+
+
+@pytest.mark.parametrize("cfg", ["c2_lr16", "c4_lr4"])
+def test_full_size_properties(cfg):
+    """BASELINE config 2 shape (4096 x 4096, rank 128, Q 2-bit): invariants that need no CPU oracle."""
+    m = n = 4096
+    r = 128
+    g = torch.Generator().manual_seed(1000)
+    W = 0.02 * torch.randn(m, n, generator=g)
+    h = 0.5 + torch.rand(n, generator=g)
+    lb = 16 if cfg == "c2_lr16" else 4
+    kw = dict(Q_bits=2, L_bits=lb, R_bits=lb, rank=r, iters=2 if lb == 4 else 3, lplr_iters=2,
+              update_order=["Q", "LR"])
+    d = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, W_copy="device")
+    eq, elr = d.errors["Q"], d.errors["LR"]
+    assert 0.97 < eq[0] < 0.995            # survey probe: first-Q error 0.987 at 4096^2
+    assert elr[0] < eq[0] and min(elr) < 0.95
+    assert d.best_step >= 1
+    hd = h.to(DEV)
+    consistent = _weighted_error_torch(d.W, hd, d.Q, d.L, d.R)
+    seq = [x for pair in zip(eq, elr) for x in pair]
+    np.testing.assert_allclose(consistent, seq[d.best_step], rtol=1e-5)
+    assert abs(consistent - min(seq[1:])) < 1e-6
+    assert torch.equal(d.Q, ((d.Q_idxs.float() / 1) * d.Q_scale).reshape(m, n))
+    assert torch.equal(unpack_codes(d.Q_packed, 2, m * n), d.Q_idxs.reshape(-1))
+    # rank-r optimality of the first LR step against the exact spectrum (torch SVD on the GPU)
+    if lb == 16:
+        Wd = d.W
+        amax = Wd.abs().max()
+        Q0 = torch.round(Wd / amax) * amax
+        S = torch.linalg.svdvals(((Wd - Q0) * hd.sqrt()[None, :]).double())
+        opt = float(((S[r:] ** 2).sum() / ((Wd.double() ** 2) * hd[None, :].double()).sum()).sqrt())
+        assert elr[0] <= opt * (1 + 1e-3), (elr[0], opt)
+        assert float((d.L.T @ d.L - torch.eye(r, device=DEV)).abs().max()) < 1e-3 or d.best_step != 1
