@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- decomposition throughput of the CALDERA hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): decomposed matrices / s at 4096 x 4096, rank 128, 2-bit Q
+(config[1]: L/R 16-bit, activation aware, 5 outer iterations, update_order Q,LR).
+One step = one full caldera() decomposition of one synthetic layer.
+
+  value     matrices/s with inputs resident in HBM (cb_caldera_layer enqueued back to back,
+            CUDA-event timed, max over ranks)
+  e2e       the same through the public API with HOST (pinned) inputs: H2D of W and h, the
+            decomposition, D2H of the packed result, all inside the timed region
+  roofline  the dominant kernel, timed alone with CUDA events at the workload's shape
+  cpu_baseline  the numpy port of the reference (oracle/) on the host cores, bounded sample
+
+`--impl reference` times the oracle port only (the Python reference cannot travel to the
+GPU box) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M = N = 4096
+RANK = 128
+ITERS = 5
+WORKLOAD = "llama2-7b q_proj 4096x4096, rank 128, Q 2-bit, L/R 16-bit, activation-aware, iters=5, order Q,LR"
+METRIC = "decomp matrices/sec (4096x4096, rank-128, 2-bit Q)"
+UNIT = "matrices/s"
+
+
+def synth_layer(idx, m=M, n=N):
+    """SURVEY.md section 8d synthetic inputs: per-layer seeded W ~ 0.02 N(0,1), h = 0.5 + U(0,1)."""
+    import torch
+    g = torch.Generator().manual_seed(1000 + idx)
+    W = 0.02 * torch.randn(m, n, generator=g, dtype=torch.float32)
+    h = 0.5 + torch.rand(n, generator=g, dtype=torch.float32)
+    return W, h
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(threads=None):
+    """One outer iteration (Q update + LR update, exact SVD, four-product error evaluation)
+    of the workload's layer with the numpy port of the reference; scaled linearly to ITERS."""
+    import numpy as np
+    from oracle import caldera_oracle as orc
+    W, h = synth_layer(0)
+    p = orc.OracleParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=1, update_order=["Q", "LR"])
+    t0 = time.perf_counter()
+    d = orc.caldera_oracle(p, W.numpy(), np.diag(h.numpy()))
+    dt = time.perf_counter() - t0
+    return dt, d
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    times = []
+    budget = 240.0
+    t_start = time.perf_counter()
+    if args.warmup > 0:
+        cpu_reference_sample()      # one warm-up sample is enough for a ~10 s CPU step
+    for _ in range(max(args.steps, 1)):
+        dt, _ = cpu_reference_sample()
+        times.append(dt)
+        if time.perf_counter() - t_start + dt > budget:
+            break
+    per_iter = sum(times) / len(times)
+    value = 1.0 / (per_iter * ITERS)
+    sample = (f"{len(times)} sample(s) of 1 outer iteration (Q+LR, exact SVD) of one {M}x{N} layer, "
+              f"{per_iter:.2f} s each, scaled x{ITERS} iterations")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_iter * ITERS * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "steps_measured": len(times)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def time_kernel(fn, iters=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def roofline_probes(dev, peaks):
+    """Dominant kernel classes timed alone (CUDA events on the launching stream) at the
+    workload's shapes.  Inputs (64 MiB W, 192 MiB rotating) exceed nothing smaller than L2,
+    so three tensors are rotated to defeat the 126 MB L2."""
+    import torch
+    from ee274_convexcaldera_llm_quantization_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    xs = [0.02 * torch.randn(M, N, device=dev) for _ in range(3)]
+    numel = M * N
+    # (a) quantise + pack, 2-bit, block 64 (the direct LowMemoryQuantizer path)
+    packed = torch.empty(numel // 4, dtype=torch.uint8, device=dev)
+    scales = torch.empty(numel // 64, device=dev)
+    k = [0]
+
+    def quant():
+        x = xs[k[0] % 3]
+        k[0] += 1
+        lib.cb_quantize_f32(_lib.ptr(x), M, N, N, 1, 2, 64, 1e-8, None, _lib.ptr(packed), _lib.ptr(scales), None,
+                            _lib.stream_ptr())
+    t = time_kernel(quant)
+    bytes_q = 4 * numel + numel // 4 + 4 * numel // 64
+    out["quantize_pack_b2_bs64"] = {"bound": "hbm", "achieved": bytes_q / t / 1e9, "peak": peaks["hbm_gbs"],
+                                    "unit": "GB/s", "frac": bytes_q / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                    "seconds": t, "algorithmic_bytes": bytes_q}
+    # (b) sketch contraction Z = Y P (m x n) x (n x q), the dominant kernel of the LR update
+    q = 2 * RANK
+    P = torch.randn(N, q, device=dev)
+    Z = torch.empty(M, q, device=dev)
+
+    def sketch():
+        x = xs[k[0] % 3]
+        k[0] += 1
+        lib.cb_sgemm_strided(M, q, N, 1.0, _lib.ptr(x), N, 1, _lib.ptr(P), q, 1, _lib.ptr(Z), q, 1, 0,
+                             _lib.stream_ptr())
+    t = time_kernel(sketch, iters=10)
+    flops = 2.0 * M * N * q
+    out["sketch_gemm_fp32"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"],
+                               "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                               "seconds": t, "algorithmic_flops": flops}
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ee274_convexcaldera_llm_quantization_b200 import _lib
+    from ee274_convexcaldera_llm_quantization_b200.alg import make_c_params, caldera
+    from ee274_convexcaldera_llm_quantization_b200.runner import CalderaLayerRunner
+    from src.caldera.utils.dataclasses import CalderaParams
+    from src.caldera.utils.quantization import QuantizerFactory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    fac = QuantizerFactory(method="uniform", block_size=64)
+    qp = CalderaParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=ITERS, lplr_iters=5,
+                       activation_aware_LR=True, update_order=["Q", "LR"], quant_factory_Q=fac,
+                       quant_factory_LR=fac, rand_svd=False, sigma_reg=0)
+    cp = make_c_params(qp, True, seed=1000 + rank)
+
+    # synthetic layers: distinct per rank (weak scaling: per-GPU work is fixed), pinned on the host
+    npool = 3
+    host_layers = []
+    for i in range(npool):
+        W, h = synth_layer(rank * npool + i)
+        host_layers.append((W.pin_memory(), h.pin_memory()))
+    dev_layers = [(W.to(dev), h.to(dev)) for W, h in host_layers]
+    runner = CalderaLayerRunner(cp, M, N, _lib.CB_H_DIAG, dev, want_packed=True, want_w_scaled=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        W, h = dev_layers[i % npool]
+        runner.enqueue(W, h)
+
+    # ---- resident timing (value)
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cb_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    launches = lib.cb_kernel_launch_count() - launches0
+    secs = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    errs = runner.read_small()[:runner.nsteps].tolist()
+
+    # ---- end-to-end timing through the public API, host buffers in, packed result out
+    out_host = {"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
+                "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
+
+    def step_e2e(i):
+        W, h = host_layers[i % npool]
+        d = caldera(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank)
+        out_host["Q_packed"].copy_(d.Q_packed, non_blocking=True)
+        out_host["L"].copy_(d.L, non_blocking=True)
+        out_host["R"].copy_(d.R, non_blocking=True)
+        return d
+    e2e_steps = max(1, min(args.steps, 10))
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_secs = time.perf_counter() - t0
+    barrier()
+
+    tmax = torch.tensor([secs, e2e_secs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    secs, e2e_secs = (float(x) for x in tmax.tolist())
+    h2d = M * N * 4 + N * 4
+    d2h = M * N // 4 + (M + N) * RANK * 4 + runner.small.numel() * 4
+
+    if rank == 0:
+        value = world * args.steps / secs
+        e2e_value = world * e2e_steps / e2e_secs
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "l2": "per-step working set ~400 MiB > 126 MB L2; 3 layers rotated",
+                           "parallelism": f"layer-sharded x{world}, no data-path collective",
+                           "sketch_width": 2 * RANK, "power_iters": 8, "peaks": peaks["source"]},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "errors_last_layer": [round(e, 6) for e in errs]}
+        if world == 1:
+            probes = roofline_probes(dev, peaks)
+            dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_fp32")
+            line["roofline"] = {k: probes[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+            line["roofline"]["kernel"] = dominant
+            line["roofline_all"] = probes
+            if not args.no_cpu:
+                cores = host_threads()
+                dt, _ = cpu_reference_sample()
+                v = 1.0 / (dt * ITERS)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"1 outer iteration (Q+LR, exact SVD, 4-product error) of one "
+                                                  f"{M}x{N} layer with the numpy port: {dt:.2f} s, scaled x{ITERS}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@ import torch
 from . import _lib
 from .params import CalderaParams, CalderaDecomposition, QuantInfo  # noqa: F401  (re-exported like the reference)
 from .quantization import QuantizerFactory, LowMemoryQuantizer, AbstractQuantizer  # noqa: F401
+from .runner import CalderaLayerRunner
 
 _ORDER_CODE = {"Q": 0, "LR": 1}
 
@@ -144,48 +145,20 @@ def caldera(
         p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed)
 
         f32 = dict(dtype=torch.float32, device=dev)
-        q_dtype = torch.int8 if quant_params.Q_bits <= 8 else torch.int16
-        l_dtype = torch.int8 if quant_params.L_bits <= 8 else torch.int16
-        r_dtype = torch.int8 if quant_params.R_bits <= 8 else torch.int16
-        nsteps = p.iters * p.n_order
-        Q = torch.empty((m, n), **f32)
-        L = torch.empty((m, r), **f32)
-        R = torch.empty((r, n), **f32)
-        small = torch.zeros(nsteps + 8 + 4, **f32)      # errors | scalars | Q/L/R scales
-        errors_d, scalars_d = small[:nsteps], small[nsteps:nsteps + 8]
-        Q_scale, L_scale, R_scale = (small[nsteps + 8 + i:nsteps + 9 + i] for i in range(3))
-        Q_idxs = torch.empty((1, m * n), dtype=q_dtype, device=dev) if p.compute_q else None
-        L_idxs = torch.empty((1, r * m), dtype=l_dtype, device=dev) if quant_factors else None
-        R_idxs = torch.empty((1, r * n), dtype=r_dtype, device=dev) if quant_factors else None
-        Q_packed = L_packed = R_packed = None
-        if return_packed and p.compute_q:
-            Q_packed = torch.empty(lib.cb_packed_bytes(m * n, p.q_bits), dtype=torch.uint8, device=dev)
-        if return_packed and quant_factors:
-            L_packed = torch.empty(lib.cb_packed_bytes(m * r, p.l_bits), dtype=torch.uint8, device=dev)
-            R_packed = torch.empty(lib.cb_packed_bytes(r * n, p.r_bits), dtype=torch.uint8, device=dev)
-        W_scaled = torch.empty((m, n), **f32) if (scale_W and W_copy != "none") else None
-
-        out = _lib.cb_caldera_out()
-        for name, t in (("Q", Q), ("L", L), ("R", R), ("Q_idxs", Q_idxs), ("Q_scale", Q_scale),
-                        ("Q_packed", Q_packed), ("L_idxs", L_idxs), ("R_idxs", R_idxs),
-                        ("L_scale", L_scale), ("R_scale", R_scale), ("L_packed", L_packed),
-                        ("R_packed", R_packed), ("W_scaled", W_scaled), ("errors", errors_d),
-                        ("scalars", scalars_d)):
-            setattr(out, name, None if t is None else t.data_ptr())
-
-        ws_bytes = lib.cb_caldera_layer_workspace_bytes(C.byref(p), m, n, h_kind)
-        if ws_bytes == 0:
-            # invalid parameters: let the layer call produce the precise status
-            ws_bytes = 256
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        st = lib.cb_caldera_layer(C.byref(p), _lib.ptr(Wd), m, n, _lib.ptr(Hd), h_kind, C.byref(out),
-                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        _lib.check(st, "caldera")
-        host = small.cpu()                                # the one synchronisation of the layer
-        del ws
+        run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
+                                 want_w_scaled=(W_copy != "none"))
+        run.enqueue(Wd, Hd)
+        host = run.read_small()                           # the one synchronisation of the layer
+        nsteps = run.nsteps
+        Q, L, R = run.Q, run.L, run.R
+        Q_idxs, L_idxs, R_idxs = run.Q_idxs, run.L_idxs, run.R_idxs
+        Q_packed, L_packed, R_packed = run.Q_packed, run.L_packed, run.R_packed
+        Q_scale, L_scale, R_scale = run.Q_scale, run.L_scale, run.R_scale
+        W_scaled = run.W_scaled
+        run.ws = None                                     # release the workspace
 
     errs = host[:nsteps].tolist()
-    scal = host[nsteps:nsteps + 8]
+    scal = host[run.nerr_pad:run.nerr_pad + 8]
     best_step = int(scal[2].item())
     errors = {name: [] for name in quant_params.update_order}
     k = 0
@@ -201,11 +174,11 @@ def caldera(
     dec.SV = torch.ones(m, **f32)
     if taken and p.compute_q:
         dec.Q_idxs = Q_idxs
-        dec.Q_scale = Q_scale.reshape(1, 1)
+        dec.Q_scale = Q_scale.clone().reshape(1, 1)
         dec.Q_packed = Q_packed
     if taken and quant_factors:
         dec.L_idxs, dec.R_idxs = L_idxs, R_idxs
-        dec.L_scale, dec.R_scale = L_scale.reshape(1, 1), R_scale.reshape(1, 1)
+        dec.L_scale, dec.R_scale = L_scale.clone().reshape(1, 1), R_scale.clone().reshape(1, 1)
         dec.L_packed, dec.R_packed = L_packed, R_packed
     Wkeep = W_scaled if scale_W else Wd
     if W_copy == "cpu":
