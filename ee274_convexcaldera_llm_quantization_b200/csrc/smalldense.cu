@@ -278,7 +278,8 @@ jacobi_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, fl
         if (fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
           const float zeta = (be - al) / (2.f * ga);
           const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          const float c = rsqrtf(1.f + tt * tt), sn = c * tt;
+          // IEEE sqrt/divide: rsqrtf's 2-ulp bias accumulates over ~q rotations per vector per sweep
+          const float c = __fdiv_rn(1.f, __fsqrt_rn(fmaf(tt, tt, 1.f))), sn = c * tt;
 #pragma unroll
           for (int k = 0; k < JMAXV; ++k) {
             const int i = lane + 32 * k;
@@ -316,7 +317,7 @@ jacobi_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, fl
   __syncthreads();
   for (int v = warp; v < q; v += nwarps) {
     const float lam = s_lam[v];
-    const float inv = lam > 0.f ? rsqrtf(lam) : 0.f;
+    const float inv = lam > 0.f ? __fdiv_rn(1.f, __fsqrt_rn(lam)) : 0.f;
     const int rk = s_rank[v];
     for (int i = lane; i < q; i += 32) evecs[(size_t)rk * q + i] = work[(size_t)v * q + i] * inv;
     if (lane == 0) evals[rk] = lam;

@@ -53,8 +53,9 @@ class CalderaLayerRunner:
                      "L_packed", "R_packed", "W_scaled"):
             t = getattr(self, name)
             setattr(self.out, name, None if t is None else t.data_ptr())
-        self.out.errors = self.errors_d.data_ptr()
-        self.out.scalars = self.scalars_d.data_ptr()
+        # raw addresses: data_ptr() of an empty slice (update_order == []) is null
+        self.out.errors = self.small.data_ptr()
+        self.out.scalars = self.small.data_ptr() + 4 * self.nerr_pad
 
     def enqueue(self, W: torch.Tensor, h: Optional[torch.Tensor]) -> None:
         """Asynchronous: enqueues the whole layer on the current stream of `device`."""

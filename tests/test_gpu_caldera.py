@@ -23,6 +23,12 @@ from src.caldera.decomposition.alg import caldera
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
+
+def _tdiv(x, lv):
+    """True IEEE division on the GPU (torch turns tensor / python_scalar into a multiply by the
+    reciprocal on CUDA, which is not what the CPU reference computes)."""
+    return x / torch.full((), float(lv), device=x.device)
+
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "caldera_*.npz")))
 IDS = [os.path.basename(p)[8:-4] for p in FILES]
 
@@ -103,7 +109,7 @@ def test_golden(path):
         assert d.Q_idxs.shape == (1, m * n) and d.Q_idxs.dtype == torch.int8
         assert d.Q_scale.shape == (1, 1)
         lv = 2 ** (p.Q_bits - 1) - 1
-        assert torch.equal(d.Q, ((d.Q_idxs.float() / lv) * d.Q_scale).reshape(m, n))
+        assert torch.equal(d.Q, (_tdiv(d.Q_idxs.float(), lv) * d.Q_scale).reshape(m, n))
         assert torch.equal(unpack_codes(d.Q_packed, p.Q_bits, m * n), d.Q_idxs.reshape(-1))
         if "Q_idxs" in z and not quantised and not p.rand_svd:
             match = float((d.Q_idxs.cpu().numpy() == z["Q_idxs"]).mean())
@@ -111,8 +117,8 @@ def test_golden(path):
     if quantised:
         assert d.L_idxs.shape == (1, p.rank * m) and d.R_idxs.shape == (1, p.rank * n)
         lvl, lvr = 2 ** (p.L_bits - 1) - 1, 2 ** (p.R_bits - 1) - 1
-        Lq = ((d.L_idxs.float() / lvl) * d.L_scale).reshape(p.rank, m).T     # codes of L.T (alg.py:171)
-        Rq = ((d.R_idxs.float() / lvr) * d.R_scale).reshape(p.rank, n)
+        Lq = (_tdiv(d.L_idxs.float(), lvl) * d.L_scale).reshape(p.rank, m).T     # codes of L.T (alg.py:171)
+        Rq = (_tdiv(d.R_idxs.float(), lvr) * d.R_scale).reshape(p.rank, n)
         assert torch.equal(Lq.contiguous(), d.L) and torch.equal(Rq, d.R)
         assert int(d.L_idxs.abs().max()) == lvl and int(d.R_idxs.abs().max()) == lvr
 
@@ -195,7 +201,7 @@ def test_full_size_properties(cfg):
     seq = [x for pair in zip(eq, elr) for x in pair]
     np.testing.assert_allclose(consistent, seq[d.best_step], rtol=1e-5)
     assert abs(consistent - min(seq[1:])) < 1e-6
-    assert torch.equal(d.Q, ((d.Q_idxs.float() / 1) * d.Q_scale).reshape(m, n))
+    assert torch.equal(d.Q, (_tdiv(d.Q_idxs.float(), 1) * d.Q_scale).reshape(m, n))
     assert torch.equal(unpack_codes(d.Q_packed, 2, m * n), d.Q_idxs.reshape(-1))
     # rank-r optimality of the first LR step against the exact spectrum (torch SVD on the GPU)
     if lb == 16:

@@ -19,6 +19,12 @@ _QNAMES = [str(n) for n in _QZ["names"]]
 DEV = "cuda"
 
 
+def _tdiv(x, lv):
+    """True IEEE division on the GPU (torch turns tensor / python_scalar into a multiply by the
+    reciprocal on CUDA, which is not what the CPU reference computes)."""
+    return x / torch.full((), float(lv), device=x.device)
+
+
 def _quant(x_t, bits, bs, packed=True):
     q = QuantizerFactory(method="uniform", block_size=bs).get_quantizer(bits)
     return q, q.quantize_block(x_t, return_packed=packed)
@@ -99,7 +105,7 @@ def test_full_size_properties(bits, bs):
     want = torch.round((x.reshape(-1, block) / amax) * lv).to(codes.dtype)
     assert torch.equal(codes, want)
     deq = q.dequantize_block(packed, scales, shape)
-    assert torch.equal(deq, ((want.float() / lv) * amax).reshape(m, n))
+    assert torch.equal(deq, (_tdiv(want.float(), lv) * amax).reshape(m, n))
     # error bound and idempotence: re-quantising the dequantised tensor reproduces the codes
     assert float((x - deq).abs().max()) <= float(amax.max()) / (2 * lv) * (1 + 1e-5)
     _, (codes2, scales2, _, packed2) = _quant(deq, bits, block)
