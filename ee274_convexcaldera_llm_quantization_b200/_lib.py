@@ -65,6 +65,10 @@ _SIGNATURES = {
     "cb_sgemm_strided": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_int, C.c_void_p]),
+    "cb_gemm_bf16_tn": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "cb_convert_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cb_caldera_layer_workspace_bytes": (C.c_size_t, [C.POINTER(cb_caldera_params), C.c_int64, C.c_int64, C.c_int]),
     "cb_caldera_layer": (C.c_int, [C.POINTER(cb_caldera_params), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_int, C.POINTER(cb_caldera_out), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -100,6 +100,9 @@ static int64_t default_sketch_width(const cb_caldera_params* p, int64_t m, int64
   if (p->sketch_width > 0) q = p->sketch_width;
   else if (p->rand_svd) q = 2 * (int64_t)p->rank;                               // alg.py:213
   else q = (2 * (int64_t)p->rank > (int64_t)p->rank + 32) ? 2 * (int64_t)p->rank : (int64_t)p->rank + 32;
+  // the shared-memory Rayleigh-Ritz solver (smalldense.cu) holds q <= 224 columns; prefer it
+  // whenever that still leaves >= 32 columns of oversampling
+  if (p->sketch_width <= 0 && q > 224 && (int64_t)p->rank + 32 <= 224) q = 224;
   if (q > mn) q = mn;
   if (q > 512) q = 512;
   if (q < p->rank) q = p->rank;

@@ -40,31 +40,43 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
       s.Di[i][j] = 0.f;
     }
     __syncthreads();
-    // 2. warp 0 factorises it (lane = row) and inverts the factor (lane = column)
+    // 2. warp 0 factorises it and inverts the factor, entirely in registers: lane i owns
+    //    row i of the block (a[c], fully unrolled so indexing is static) and column i of the inverse
     if (warp == 0) {
-      for (int j = 0; j < nb; ++j) {
-        float d = s.D[j][j];
-        if (!(d > 0.f) || !isfinite(d)) { if (lane == 0) s.fail = 1; d = 1.f; }
+      float a[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = s.D[lane][c];
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float d = __shfl_sync(0xffffffffu, a[j], j);
+        if (j < nb && (!(d > 0.f) || !isfinite(d))) { bad = true; d = 1.f; }
+        if (j >= nb) d = 1.f;
         const float sd = sqrtf(d), inv = 1.f / sd;
-        float lij = 0.f;
-        __syncwarp();
-        if (lane == j) s.D[j][j] = sd;
-        if (lane > j && lane < nb) { lij = s.D[lane][j] * inv; s.D[lane][j] = lij; }
-        __syncwarp();
-        if (lane > j && lane < nb)
-          for (int c = j + 1; c <= lane; ++c) s.D[lane][c] -= lij * s.D[c][j];
-        __syncwarp();
+        const float lij = (lane > j) ? a[j] * inv : (lane == j ? sd : 0.f);
+        a[j] = (lane >= j) ? lij : 0.f;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) {
+          const float lcj = __shfl_sync(0xffffffffu, lij, c);   // L[c][j]
+          if (lane >= c) a[c] = fmaf(-lij, lcj, a[c]);
+        }
       }
-      // inverse: column `lane` by forward substitution, loops kept warp-uniform
-      if (lane < nb) s.Di[lane][lane] = 1.f / s.D[lane][lane];
+      if (bad && lane == 0) s.fail = 1;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s.D[lane][c] = a[c];       // row `lane` of the factor
       __syncwarp();
-      for (int i = 1; i < nb; ++i) {
-        float acc = 0.f;
-        for (int k = 0; k < i; ++k)
-          if (k >= lane) acc += s.D[i][k] * s.Di[k][lane];
-        if (lane < i) s.Di[i][lane] = -acc / s.D[i][i];
-        __syncwarp();
+      // inverse X = L^-1, lane = column: x_i = (delta_ic - sum_{k<i} L[i][k] x_k) / L[i][i];
+      // L is read back from shared memory (broadcast) so only x[] stays in registers
+      float x[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        float acc = (lane == i) ? 1.f : 0.f;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fmaf(-s.D[i][k], x[k], acc);
+        x[i] = (lane <= i) ? acc / s.D[i][i] : 0.f;
       }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s.Di[c][lane] = x[c];      // column `lane` of the inverse
     }
     __syncthreads();
     // write the factor back, publish the inverse block
@@ -139,7 +151,20 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
 }
 
 // Linv = Lc^-1 by block forward substitution; diagonal blocks already hold their inverses.
-__device__ void tri_inverse(const float* G, int q, float* Linv, CholSmem& s) {
+// Block columns are independent, so up to 8 "chains" of 128 threads each walk one block
+// column at a time (chain c takes columns c and nblk-1-c, which balances the triangular
+// work); every 32x32x32 block product is staged through chain-private shared tiles.
+//   X[i][j] = -Dinv_i * sum_{k=j}^{i-1} L[i][k] X[k][j]
+struct ChainTiles {
+  float Lt[NB][NB + 1];   // L[i][k] tile, later the partial sum S
+  float Xt[NB][NB + 4];   // X[k][j] tile, later Dinv_i (16-byte aligned rows)
+};
+
+__device__ __forceinline__ void chain_sync(int chain) {
+  asm volatile("bar.sync %0, 128;" ::"r"(chain + 1) : "memory");
+}
+
+__device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tiles) {
   const int tid = threadIdx.x;
   const int nblk = (q + NB - 1) / NB;
   // strict upper triangle and not-yet-computed blocks start at zero
@@ -148,35 +173,71 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, CholSmem& s) {
     if ((i / NB) != (j / NB) || j > i) Linv[e] = 0.f;
   }
   __syncthreads();
-  for (int bi = 1; bi < nblk; ++bi) {
-    const int r0 = bi * NB, nbi = min(NB, q - r0), W = r0;  // W columns to the left
-    // stage L[bi, 0:W] as Lrow[i][k] in Pt (NB x (TMAXR+4)) and Di_bi in Di
-    for (int e = tid; e < nbi * W; e += blockDim.x) {
-      const int i = e / W, k = e - i * W;
-      s.Pt[i][k] = G[(size_t)(r0 + i) * q + k];
+  const int chain = tid >> 7, ct = tid & 127;
+  const int nchains = min(8, (nblk + 1) / 2);
+  if (chain < nchains) {
+    ChainTiles& T = tiles[chain];
+    const int orow = ct >> 2, oc0 = (ct & 3) * 8;     // this thread's 1 x 8 strip of a 32 x 32 block
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int jj = chain; jj < (nblk + 1) / 2; jj += nchains) {
+        const int j = pass == 0 ? jj : nblk - 1 - jj;
+        if (pass == 1 && j == jj) continue;            // middle column handled in pass 0
+        for (int i = j + 1; i < nblk; ++i) {
+          float acc[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+          for (int k = j; k < i; ++k) {
+            chain_sync(chain);
+            for (int e = ct; e < NB * NB; e += 128) {
+              const int r = e >> 5, c = e & 31;
+              const int gr = i * NB + r, gc = k * NB + c;
+              T.Lt[r][c] = (gr < q && gc < q) ? G[(size_t)gr * q + gc] : 0.f;
+              const int xr = k * NB + r, xc = j * NB + c;
+              T.Xt[r][c] = (xr < q && xc < q) ? Linv[(size_t)xr * q + xc] : 0.f;
+            }
+            chain_sync(chain);
+#pragma unroll 8
+            for (int kk = 0; kk < NB; ++kk) {
+              const float l = T.Lt[orow][kk];
+              const float4 x0 = *reinterpret_cast<const float4*>(&T.Xt[kk][oc0]);
+              const float4 x1 = *reinterpret_cast<const float4*>(&T.Xt[kk][oc0 + 4]);
+              acc[0] = fmaf(l, x0.x, acc[0]); acc[1] = fmaf(l, x0.y, acc[1]);
+              acc[2] = fmaf(l, x0.z, acc[2]); acc[3] = fmaf(l, x0.w, acc[3]);
+              acc[4] = fmaf(l, x1.x, acc[4]); acc[5] = fmaf(l, x1.y, acc[5]);
+              acc[6] = fmaf(l, x1.z, acc[6]); acc[7] = fmaf(l, x1.w, acc[7]);
+            }
+          }
+          // X[i][j] = -Dinv_i * S
+          chain_sync(chain);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) T.Lt[orow][oc0 + c] = acc[c];
+          for (int e = ct; e < NB * NB; e += 128) {
+            const int r = e >> 5, c = e & 31;
+            const int gr = i * NB + r, gc = i * NB + c;
+            T.Xt[r][c] = (gr < q && gc < q && c <= r) ? Linv[(size_t)gr * q + gc] : 0.f;
+          }
+          chain_sync(chain);
+          float out[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) out[c] = 0.f;
+          for (int kk = 0; kk <= orow; ++kk) {
+            const float d = T.Xt[orow][kk];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) out[c] = fmaf(d, T.Lt[kk][oc0 + c], out[c]);
+          }
+          const int gr = i * NB + orow;
+          if (gr < q) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int gc = j * NB + oc0 + c;
+              if (gc < q) Linv[(size_t)gr * q + gc] = -out[c];
+            }
+          }
+        }
+      }
     }
-    {
-      const int i = tid >> 5, j = tid & 31;
-      s.Di[i][j] = (i < nbi && j <= i) ? Linv[(size_t)(r0 + i) * q + r0 + j] : 0.f;
-    }
-    __syncthreads();
-    // S[i][col] = sum_{k = blockstart(col)}^{W-1} Lrow[i][k] * Linv[k][col]; staged in Praw (as [col][i])
-    for (int e = tid; e < nbi * W; e += blockDim.x) {
-      const int i = e / W, col = e - i * W;
-      float acc = 0.f;
-      for (int k = (col / NB) * NB; k < W; ++k) acc = fmaf(s.Pt[i][k], Linv[(size_t)k * q + col], acc);
-      s.Praw[col][i] = acc;
-    }
-    __syncthreads();
-    // Linv[bi][col] = -Di_bi * S
-    for (int e = tid; e < nbi * W; e += blockDim.x) {
-      const int i = e / W, col = e - i * W;
-      float acc = 0.f;
-      for (int k = 0; k <= i; ++k) acc = fmaf(s.Di[i][k], s.Praw[col][k], acc);
-      Linv[(size_t)(r0 + i) * q + col] = -acc;
-    }
-    __syncthreads();
   }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024, 1)
@@ -212,7 +273,7 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
     ++retries;
     __syncthreads();
   }
-  if (Linv != nullptr) tri_inverse(G, q, Linv, s);
+  if (Linv != nullptr) tri_inverse(G, q, Linv, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }
 
@@ -325,10 +386,127 @@ jacobi_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, fl
   if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
 }
 
+// Shared-memory variant for q <= 224 (q % 4 == 0): the q x q working matrix (<= 204 KB) lives
+// in shared memory for the whole solve, so a round costs one pass of shared-memory traffic
+// instead of a round trip to L2.  512 threads = 64 groups of 8 lanes; a group owns one
+// column pair at a time and keeps both columns in registers between the dot products and
+// the rotation (one load + one store per element and round).
+constexpr int JS_QMAX = 224;
+constexpr int JS_THREADS = 512;
+constexpr int JS_V4 = JS_QMAX / 32;   // float4 per lane and vector
+
+__global__ void __launch_bounds__(JS_THREADS, 1)
+jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, float* __restrict__ evecs,
+                   int* __restrict__ sweeps_out, int max_sweeps, float tol) {
+  extern __shared__ __align__(16) float js_smem[];
+  const int stride = q + 4;
+  float* V = js_smem;                       // V[v * stride + i] = component i of vector v
+  float* s_lam = V + (size_t)q * stride;    // q
+  int* s_rank = reinterpret_cast<int*>(s_lam + q);
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JS_THREADS >> 5;
+  const int g = tid >> 3, gl = tid & 7, ngroups = JS_THREADS >> 3;
+  for (int e = tid; e < q * q; e += JS_THREADS) {
+    const int i = e / q, v = e - i * q;
+    V[v * stride + i] = (i >= v) ? Lc[e] : 0.f;
+  }
+  __syncthreads();
+  const int qe = q + (q & 1);
+  const int npairs = qe >> 1;
+  const int nv4 = (q + 31) >> 5;            // float4 per lane (8 lanes x 4 floats = 32 elements per step)
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    for (int t = 0; t < qe - 1; ++t) {
+      for (int pi = g; pi < npairs; pi += ngroups) {
+        int a, b;
+        if (pi == 0) { a = qe - 1; b = t; }
+        else { a = (t + pi) % (qe - 1); b = (t - pi + (qe - 1)) % (qe - 1); }
+        const bool live = (a < q && b < q);
+        float4* xa = reinterpret_cast<float4*>(V + (size_t)(live ? a : 0) * stride);
+        float4* xb = reinterpret_cast<float4*>(V + (size_t)(live ? b : 0) * stride);
+        float4 x[JS_V4], y[JS_V4];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int k = 0; k < JS_V4; ++k) {
+          const int i4 = gl + 8 * k;         // float4 index; element 4*i4
+          if (k < nv4 && 4 * i4 < q && live) { x[k] = xa[i4]; y[k] = xb[i4]; }
+          else { x[k] = make_float4(0.f, 0.f, 0.f, 0.f); y[k] = x[k]; }
+          al = fmaf(x[k].x, x[k].x, al); al = fmaf(x[k].y, x[k].y, al); al = fmaf(x[k].z, x[k].z, al); al = fmaf(x[k].w, x[k].w, al);
+          be = fmaf(y[k].x, y[k].x, be); be = fmaf(y[k].y, y[k].y, be); be = fmaf(y[k].z, y[k].z, be); be = fmaf(y[k].w, y[k].w, be);
+          ga = fmaf(x[k].x, y[k].x, ga); ga = fmaf(x[k].y, y[k].y, ga); ga = fmaf(x[k].z, y[k].z, ga); ga = fmaf(x[k].w, y[k].w, ga);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        if (live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
+          const float zeta = (be - al) / (2.f * ga);
+          const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+          const float c = __fdiv_rn(1.f, __fsqrt_rn(fmaf(tt, tt, 1.f))), sn = c * tt;
+#pragma unroll
+          for (int k = 0; k < JS_V4; ++k) {
+            const int i4 = gl + 8 * k;
+            if (k < nv4 && 4 * i4 < q) {
+              xa[i4] = make_float4(c * x[k].x - sn * y[k].x, c * x[k].y - sn * y[k].y, c * x[k].z - sn * y[k].z, c * x[k].w - sn * y[k].w);
+              xb[i4] = make_float4(sn * x[k].x + c * y[k].x, sn * x[k].y + c * y[k].y, sn * x[k].z + c * y[k].z, sn * x[k].w + c * y[k].w);
+            }
+          }
+          if (gl == 0) atomicAdd(&s_rot, 1);
+        }
+      }
+      __syncthreads();
+    }
+    const int rot = s_rot;
+    __syncthreads();
+    if (rot == 0) { ++sweep; break; }
+  }
+  for (int v = warp; v < q; v += nwarps) {
+    float acc = 0.f;
+    for (int i = lane; i < q; i += 32) { const float z = V[v * stride + i]; acc = fmaf(z, z, acc); }
+    acc = warp_sum(acc);
+    if (lane == 0) s_lam[v] = acc;
+  }
+  __syncthreads();
+  for (int v = tid; v < q; v += JS_THREADS) {
+    const float lv = s_lam[v];
+    int rk = 0;
+    for (int u = 0; u < q; ++u) {
+      const float lu = s_lam[u];
+      rk += (lu > lv) || (lu == lv && u < v);
+    }
+    s_rank[v] = rk;
+  }
+  __syncthreads();
+  for (int v = warp; v < q; v += nwarps) {
+    const float lam = s_lam[v];
+    const float inv = lam > 0.f ? __fdiv_rn(1.f, __fsqrt_rn(lam)) : 0.f;
+    const int rk = s_rank[v];
+    for (int i = lane; i < q; i += 32) evecs[(size_t)rk * q + i] = V[v * stride + i] * inv;
+    if (lane == 0) evals[rk] = lam;
+  }
+  if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
+}
+
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
                           cudaStream_t st) {
   if (Lc == nullptr || evals == nullptr || evecs == nullptr || work == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
+  if (q <= JS_QMAX && q % 4 == 0) {
+    const size_t smem = ((size_t)q * (q + 4) + 2 * (size_t)q) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CB_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(((size_t)JS_QMAX * (JS_QMAX + 4) + 2 * JS_QMAX) * sizeof(float))));
+      attr_set = true;
+    }
+    jacobi_smem_kernel<<<1, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, 1e-6f);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+  }
   jacobi_kernel<<<1, 1024, 0, st>>>(Lc, q, evals, evecs, work, sweeps, 30, 1e-6f);
   CB_CHECK_LAUNCH();
   return CB_OK;

@@ -136,6 +136,19 @@ int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha,
                      const float* B, int64_t b_rs, int64_t b_cs,
                      float* C, int64_t c_rs, int64_t c_cs, int accumulate, void* stream);
 
+/* C (M x N fp32, ldc) = alpha * A (M x K) * B (N x K)^T with bf16 operands, both K-major
+ * (lda, ldb in elements, multiples of 8), fp32 accumulation in tensor memory: the
+ * tcgen05 / TMEM / TMA contraction kernel (csrc/gemm_tc.cu).  splitk <= 0 picks the K split
+ * that fills the machine.  *error_flag (device int, may be NULL) is set if the in-kernel
+ * pipeline watchdog fired.  Exported for validation against cb_sgemm_strided. */
+int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
+                    const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int* error_flag,
+                    void* stream);
+/* fp32 (rows x cols, ldx) -> bf16 copy Y (ldy) and/or transposed copy Yt (cols x rows, ldyt),
+ * optionally scaling column c by colscale[c] first. */
+int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
+                    void* Yt_bf16, int64_t ldyt, const float* colscale, void* stream);
+
 /* ------------------------------------------------------------------------- fused driver */
 
 typedef struct cb_caldera_params {
@@ -177,7 +190,8 @@ typedef struct cb_caldera_out {
   float* W_scaled;     /* optional m x n: W / global_scale (CalderaDecomposition.W) */
   float* errors;       /* iters * n_order floats, in sub-step order                 */
   float* scalars;      /* 8 floats: [0]=global_scale [1]=min_error [2]=best_step
-                          [3]=cholesky retries [4]=jacobi sweeps (last) [5..7] reserved */
+                          [5]=LPLR inner best error; [6],[7] hold int32 bit patterns: cholesky
+                          ridge retries (max over the layer) and jacobi sweeps (last solve) */
 } cb_caldera_out;
 
 size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind);

@@ -45,6 +45,9 @@ run.enqueue(*layers[1])
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 torch.cuda.profiler.stop()
-errs = run.read_small()[:run.nsteps].tolist()
+small = run.read_small()
+errs = small[:run.nsteps].tolist()
+stats = small[run.nerr_pad + 6:run.nerr_pad + 8].view(torch.int32).tolist()
 print(f"layer {a.m}x{a.n} r={a.rank} lbits={a.lbits}: {dt * 1e3:.2f} ms, "
-      f"{_lib.load().cb_kernel_launch_count() - n0} launches, errors {[round(e, 5) for e in errs]}")
+      f"{_lib.load().cb_kernel_launch_count() - n0} launches, chol_retries={stats[0]} jacobi_sweeps={stats[1]}, "
+      f"errors {[round(e, 5) for e in errs]}")

@@ -1,0 +1,58 @@
+"""The tcgen05/TMEM/TMA GEMM (csrc/gemm_tc.cu) against torch on bf16-rounded operands."""
+import pytest
+import torch
+
+from ee274_convexcaldera_llm_quantization_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(M, N, K, splitk, lda=None, ldb=None, alpha=1.0):
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + 3 * N + 7 * K + splitk)
+    lda = lda or (K + 7) // 8 * 8
+    ldb = ldb or (K + 7) // 8 * 8
+    A = torch.zeros(M, lda, device=DEV, dtype=torch.bfloat16)
+    B = torch.zeros(N, ldb, device=DEV, dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    B[:, :K] = torch.randn(N, K, generator=g, device=DEV).bfloat16()
+    if lda > K:
+        A[:, K:] = 7.0      # padding beyond K must never be read (TMA tensor map is K wide)
+    if ldb > K:
+        B[:, K:] = -5.0
+    C = torch.full((M, N), float("nan"), device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    st = lib.cb_gemm_bf16_tn(M, N, K, alpha, _lib.ptr(A), lda, _lib.ptr(B), ldb, _lib.ptr(C), N, splitk,
+                             _lib.ptr(flag), _lib.stream_ptr())
+    _lib.check(st, "gemm_bf16_tn")
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0, "pipeline watchdog fired"
+    ref = alpha * (A[:, :K].double() @ B[:, :K].double().T)
+    err = float((C.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    return err
+
+
+@pytest.mark.parametrize("M,N,K,splitk", [
+    (128, 64, 64, 1), (128, 128, 128, 1), (128, 256, 256, 1), (256, 256, 4096, 1), (256, 256, 4096, 0),
+    (256, 4096, 4096, 0), (4096, 256, 4096, 0), (4096, 224, 4096, 0), (224, 224, 4096, 0), (128, 4096, 224, 1),
+    (100, 72, 200, 1), (1000, 333, 777, 3), (4096, 4096, 128, 1), (37, 53, 29, 1)])
+def test_gemm_tc_matches_torch(M, N, K, splitk):
+    err = _run(M, N, K, splitk)
+    assert err < 2e-5, err
+
+
+def test_gemm_tc_alpha_and_ld():
+    assert _run(256, 192, 320, 1, lda=384, ldb=512, alpha=-0.5) < 2e-5
+
+
+def test_convert_bf16():
+    lib = _lib.load()
+    X = torch.randn(300, 200, device=DEV)
+    s = torch.rand(200, device=DEV) + 0.5
+    Y = torch.empty(300, 200, device=DEV, dtype=torch.bfloat16)
+    Yt = torch.empty(200, 304, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.cb_convert_bf16(_lib.ptr(X), 300, 200, 200, _lib.ptr(Y), 200, _lib.ptr(Yt), 304, _lib.ptr(s),
+                                   _lib.stream_ptr()), "convert")
+    ref = (X * s[None, :]).bfloat16()
+    assert torch.equal(Y, ref) and torch.equal(Yt[:, :300], ref.T)
