@@ -29,7 +29,7 @@ class cb_caldera_params(C.Structure):
         ("rand_svd", C.c_int32), ("sigma_reg", C.c_float), ("scale_w", C.c_int32),
         ("global_scale_in", C.c_float), ("q_block", C.c_int64),
         ("sketch_width", C.c_int32), ("power_iters", C.c_int32), ("warm_start", C.c_int32),
-        ("seed", C.c_uint64),
+        ("use_tensor_cores", C.c_int32), ("seed", C.c_uint64),
     ]
 
 

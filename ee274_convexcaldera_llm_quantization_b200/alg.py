@@ -57,7 +57,7 @@ def _classify_hessian(H: Optional[torch.Tensor], n: int, dev: torch.device):
 
 def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Optional[float] = None,
                   sketch_width: int = 0, power_iters: int = -1, warm_start: bool = True,
-                  seed: int = 0) -> _lib.cb_caldera_params:
+                  seed: int = 0, use_tensor_cores: bool = True) -> _lib.cb_caldera_params:
     order = list(quant_params.update_order)
     for name in order:
         if name not in _ORDER_CODE:
@@ -83,6 +83,7 @@ def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Opti
     p.sketch_width = int(sketch_width)
     p.power_iters = int(power_iters)
     p.warm_start = int(bool(warm_start))
+    p.use_tensor_cores = int(bool(use_tensor_cores))
     p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return p
 
@@ -111,6 +112,7 @@ def caldera(
     warm_start: bool = True,
     seed: int = 0,
     return_packed: bool = True,
+    use_tensor_cores: bool = True,
 ):
     """Runs CALDERA: decomposes W into Q + L R (alg.py:24-112), all arithmetic on `device`.
 
@@ -120,6 +122,7 @@ def caldera(
              "device" or "none";
     global_scale  inject the reference's global_scale instead of recomputing it;
     sketch_width / power_iters / warm_start / seed  knobs of the randomized rank-r step;
+    use_tensor_cores  bf16 tcgen05 contractions for aligned shapes (default) or fp32 SIMT everywhere;
     return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed.
     `use_tqdm` is accepted and ignored (the loop runs on the device).
     """
@@ -142,7 +145,8 @@ def caldera(
     with torch.cuda.device(dev):
         Wd = W.to(dev, torch.float32, non_blocking=True).contiguous()
         h_kind, Hd = _classify_hessian(H, n, dev)
-        p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed)
+        p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed,
+                          use_tensor_cores)
 
         f32 = dict(dtype=torch.float32, device=dev)
         run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
@@ -190,8 +194,10 @@ def caldera(
     dec.errors = errors
     dec.global_scale = float(scal[0].item()) if scale_W else 1
     dec.best_step = best_step
-    dec.device_stats = {"cholesky_retries": int(scal[6:7].view(torch.int32).item()),
-                        "jacobi_sweeps": int(scal[7:8].view(torch.int32).item())}
+    stats = scal[5:8].view(torch.int32).tolist()
+    dec.device_stats = {"cholesky_retries": stats[0], "jacobi_sweeps": stats[1], "tc_watchdog": stats[2]}
+    if stats[2] != 0:
+        raise _lib.CalderaRuntimeError(2001, "caldera: tcgen05 pipeline watchdog fired")
     return dec
 
 

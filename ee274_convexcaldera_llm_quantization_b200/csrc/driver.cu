@@ -90,6 +90,97 @@ static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t
   return CB_OK;
 }
 
+// ---------------------------------------------------------------- tensor-core variant
+// Same algorithm with every large contraction on the tcgen05 kernel (gemm_tc.cu).  All
+// operands are bf16 and K-major, so each intermediate is kept in the orientation(s) its
+// consumers contract over: "t" buffers are (q x long), plain ones (long x q).  Gram
+// matrices, Cholesky factors and the Rayleigh-Ritz eigenproblem stay in fp32.
+typedef __nv_bfloat16 bf16;
+struct LowrankTcBufs {
+  bf16 *Yb, *Ytb;                 // m x n, n x m
+  bf16 *Ptb, *Pb, *Potb;          // q x n, n x q, q x n
+  bf16 *Ztb, *Zb, *Zotb, *Zob;    // q x m, m x q, q x m (persistent for warm starts), m x q
+  bf16 *Linvb, *Bb, *Btb, *Vb;    // q x q, q x n, n x q, q x q
+  float *G, *Linv, *work, *evals, *V;
+  int* status;                    // [0] cholesky retries, [1] jacobi sweeps, [2] gemm watchdog
+};
+
+static bool lowrank_tc_usable(int64_t m, int64_t n, int64_t r, int64_t q) {
+  return m % 8 == 0 && n % 8 == 0 && q % 8 == 0 && r % 8 == 0 && m >= 256 && n >= 256 && q >= 16;
+}
+
+static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, int* status) {
+  LowrankTcBufs b;
+  b.Yb = a.take<bf16>(m * n); b.Ytb = a.take<bf16>(n * m);
+  b.Ptb = a.take<bf16>(q * n); b.Pb = a.take<bf16>(n * q); b.Potb = a.take<bf16>(q * n);
+  b.Ztb = a.take<bf16>(q * m); b.Zb = a.take<bf16>(m * q); b.Zotb = a.take<bf16>(q * m); b.Zob = a.take<bf16>(m * q);
+  b.Linvb = a.take<bf16>(q * q); b.Bb = a.take<bf16>(q * n); b.Btb = a.take<bf16>(n * q); b.Vb = a.take<bf16>(q * q);
+  b.G = a.take<float>(q * q); b.Linv = a.take<float>(q * q); b.work = a.take<float>(q * q);
+  b.evals = a.take<float>(q); b.V = a.take<float>(q * q);
+  b.status = status;
+  return b;
+}
+
+__global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p, int64_t count, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    p[i] = __float2bfloat16_rn(gaussian_from(seed, (uint64_t)i));
+}
+
+// Xt (q x N) and X (N x q) hold the same raw sketch; writes the orthonormalised sketch as
+// Xot (q x N) and/or Xo (N x q).
+static int orthonormalize_tc(const bf16* Xt, const bf16* X, int64_t N, int64_t q, bf16* Xot, bf16* Xo,
+                             const LowrankTcBufs& b, cudaStream_t st) {
+  int* wd = b.status != nullptr ? b.status + 2 : nullptr;
+  CB_CUDA(cudaMemsetAsync(b.G, 0, sizeof(float) * q * q, st));
+  CB_TRY(gemm_tc(q, q, N, 1.f, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+  CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st));
+  CB_TRY(to_bf16(b.Linv, q, q, q, b.Linvb, q, nullptr, 0, nullptr, st));
+  // Xot[q, N] = Linv[q, K=q] * X[N, K=q]^T
+  CB_TRY(gemm_tc(q, N, q, 1.f, b.Linvb, q, X, q, nullptr, 0, Xot, N, Xo, q, nullptr, nullptr, 1, wd, nullptr, st));
+  return CB_OK;
+}
+
+static int lowrank_core_tc(int64_t m, int64_t n, int64_t r, int64_t q, int niter, uint64_t seed, int aware,
+                           const float* inv_sqrt_h, bool warm_valid, float* L, float* R, bf16* Lb, bf16* Rtb,
+                           const LowrankTcBufs& b, cudaStream_t st) {
+  int* wd = b.status != nullptr ? b.status + 2 : nullptr;
+  if (!warm_valid) {
+    randn_bf16_kernel<<<grid_for(q * n, 256 * 4, 4), 256, 0, st>>>(b.Ptb, q * n, seed);
+    CB_CHECK_LAUNCH();
+    // Zt[q, m] = Pt[q, K=n] * Y[m, K=n]^T
+    CB_TRY(gemm_tc(q, m, n, 1.f, b.Ptb, n, b.Yb, n, nullptr, 0, b.Ztb, m, b.Zb, q, nullptr, nullptr, 1, wd, nullptr, st));
+    CB_TRY(orthonormalize_tc(b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  }
+  for (int it = 0; it < niter; ++it) {
+    // Pt[q, n] = Zot[q, K=m] * Yt[n, K=m]^T
+    CB_TRY(gemm_tc(q, n, m, 1.f, b.Zotb, m, b.Ytb, m, nullptr, 0, b.Ptb, n, b.Pb, q, nullptr, nullptr, 1, wd, nullptr, st));
+    CB_TRY(orthonormalize_tc(b.Ptb, b.Pb, n, q, b.Potb, nullptr, b, st));
+    CB_TRY(gemm_tc(q, m, n, 1.f, b.Potb, n, b.Yb, n, nullptr, 0, b.Ztb, m, b.Zb, q, nullptr, nullptr, 1, wd, nullptr, st));
+    CB_TRY(orthonormalize_tc(b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  }
+  // CholeskyQR2 on the (bf16-rounded) basis itself
+  CB_CUDA(cudaMemcpyAsync(b.Ztb, b.Zotb, sizeof(bf16) * q * m, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zb, b.Zob, sizeof(bf16) * q * m, cudaMemcpyDeviceToDevice, st));
+  CB_TRY(orthonormalize_tc(b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  // B[q, n] = Zot[q, K=m] * Yt[n, K=m]^T  (bf16 in both orientations); G = B B^T in fp32
+  CB_TRY(gemm_tc(q, n, m, 1.f, b.Zotb, m, b.Ytb, m, nullptr, 0, b.Bb, n, b.Btb, q, nullptr, nullptr, 1, wd, nullptr, st));
+  CB_CUDA(cudaMemsetAsync(b.G, 0, sizeof(float) * q * q, st));
+  CB_TRY(gemm_tc(q, q, n, 1.f, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+  CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
+  CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
+  CB_TRY(to_bf16(b.V, q, q, q, b.Vb, q, nullptr, 0, nullptr, st));
+  // L[m, r] = Zo[m, K=q] * V_r[r, K=q]^T ;  R[r, n] = V_r[r, K=q] * Bt[n, K=q]^T (col-scaled by 1/sqrt(h))
+  CB_TRY(gemm_tc(m, r, q, 1.f, b.Zob, q, b.Vb, q, L, r, aware ? Lb : nullptr, r, nullptr, 0, nullptr, nullptr, 1, wd, nullptr, st));
+  CB_TRY(gemm_tc(r, n, q, 1.f, b.Vb, q, b.Btb, q, R, n, nullptr, 0, aware ? Rtb : nullptr, r, aware ? inv_sqrt_h : nullptr,
+                 nullptr, 1, wd, nullptr, st));
+  if (!aware) {
+    CB_TRY(scale_cols(L, m, r, b.evals, 2, L, st));
+    CB_TRY(scale_rows(R, r, n, b.evals, 3, R, st));
+  }
+  return CB_OK;
+}
+
 __global__ void sqrt_vec_kernel(const float* in, int n, float* out) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = sqrtf(fmaxf(in[i], 0.f));
 }
@@ -124,8 +215,11 @@ struct LayerPlan {
   void *Lcodes_cur, *Rcodes_cur, *Lcodes_in, *Rcodes_in, *Lcodes_out;
   float *Lscale_cur, *Rscale_cur, *Lscale_in, *Rscale_in;
   LowrankBufs lr;
+  LowrankTcBufs tc;
+  bf16 *Lb16, *Rtb16;   // bf16 copies of L (m x r) and R^T (n x r) for the tensor-core L R product
   int64_t q;
   bool quant_factors;
+  bool use_tc;
 };
 
 static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n, bool scale_w, LayerPlan& L) {
@@ -151,6 +245,12 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
     L.Rcur = a.take<float>(r * n);
     L.Zwarm = a.take<float>(m * L.q);
     L.lr = plan_lowrank(a, m, n, L.q, L.Zwarm, nullptr);
+    L.use_tc = p->use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, L.q);
+    if (L.use_tc) {
+      L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr);
+      L.Lb16 = a.take<bf16>(m * r);
+      L.Rtb16 = a.take<bf16>(n * r);
+    }
     if (L.quant_factors) {
       L.Rw = a.take<float>(r * n);
       L.Gs = a.take<float>(r * r);
@@ -205,6 +305,17 @@ static int solve_spd_setup(float* G, int64_t r, float* Linv, float* Ginv, int* s
   // G^-1 = Linv^T Linv
   CB_TRY(sgemm(r, r, r, 1.f, Linv, 1, r, Linv, r, 1, Ginv, r, 1, false, nullptr, st));
   return CB_OK;
+}
+
+// LRbuf = L R (m x n fp32): tensor cores when the shape allows, SIMT otherwise
+static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
+  if (P.use_tc) {
+    CB_TRY(to_bf16(P.Lcur, m, r, r, P.Lb16, r, nullptr, 0, nullptr, st));
+    CB_TRY(to_bf16(P.Rcur, r, n, n, nullptr, 0, P.Rtb16, r, nullptr, st));
+    return gemm_tc(m, n, r, 1.f, P.Lb16, r, P.Rtb16, r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
+                   P.flags + 4, nullptr, st);
+  }
+  return sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st);
 }
 
 static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
@@ -273,7 +384,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   CB_TRY(plan_layer(a, p, m, n, scale_w, P));
   if (P.quant_factors && (out->L_idxs == nullptr || out->R_idxs == nullptr || out->L_scale == nullptr || out->R_scale == nullptr))
     return CB_ERR_ARG;
-  if (p->compute_lr) P.lr.status = P.flags + 2;
+  if (p->compute_lr) { P.lr.status = P.flags + 2; P.tc.status = P.flags + 2; }
 
   // ---- initial state: Q = 0, L = 0, R = 0 (alg.py:71-75)
   CB_CUDA(cudaMemsetAsync(P.dsc, 0, sizeof(double) * 4, st));
@@ -316,7 +427,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         // ---- Q update (maybe_update_Q, alg.py:253-283)
         const float* lrp = nullptr;
         if (p->compute_lr && have_lr) {
-          if (!lrbuf_valid) CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+          if (!lrbuf_valid) CB_TRY(lr_product(P, m, n, r, st));
           lrbuf_valid = true;
           lrp = P.LRbuf;
         }
@@ -328,12 +439,18 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
         CB_TRY(form_y(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
                       p->aware ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
-        CB_TRY(lowrank_core(P.Y, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
-                            warm_valid && p->warm_start, P.Lcur, P.Rcur, P.lr, st));
+        if (P.use_tc) {
+          CB_TRY(to_bf16(P.Y, m, n, n, P.tc.Yb, n, P.tc.Ytb, m, nullptr, st));
+          CB_TRY(lowrank_core_tc(m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
+                                 warm_valid && p->warm_start, P.Lcur, P.Rcur, nullptr, nullptr, P.tc, st));
+        } else {
+          CB_TRY(lowrank_core(P.Y, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
+                              warm_valid && p->warm_start, P.Lcur, P.Rcur, P.lr, st));
+        }
         warm_valid = true;
         if (P.quant_factors) CB_TRY(lplr_refine(p, P, m, n, st));
         have_lr = true;
-        CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+        CB_TRY(lr_product(P, m, n, r, st));
         lrbuf_valid = true;
       }
       if (!num_ready) {
@@ -382,9 +499,10 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
     if (out->L_packed != nullptr) CB_TRY(cb_pack_codes(out->L_idxs, m * r, p->l_bits, out->L_packed, stream));
     if (out->R_packed != nullptr) CB_TRY(cb_pack_codes(out->R_idxs, r * n, p->r_bits, out->R_packed, stream));
   }
-  // scalars: [0] global_scale [1] min_error [2] best_step [3] cholesky retries [4] jacobi sweeps
+  // scalars: [0] global_scale [1] min_error [2] best_step; [5..7] int32 bit patterns:
+  // cholesky ridge retries, jacobi sweeps of the last solve, tensor-core pipeline watchdog
   CB_CUDA(cudaMemcpyAsync(out->scalars, P.scalars, sizeof(float) * 8, cudaMemcpyDeviceToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(out->scalars + 6, P.flags + 2, sizeof(int) * 2, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(out->scalars + 5, P.flags + 2, sizeof(int) * 3, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 

@@ -335,9 +335,15 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
             int* error_flag, int* splits_used, cudaStream_t st) {
   if (!gemm_tc_supported(M, N, K, A, lda, B, ldb)) return CB_ERR_UNSUPPORTED;
-  const int bn = (N >= 192) ? 256 : (N >= 96 ? 128 : 64);
+  // largest N tile that still yields >= ~0.8 waves of CTAs; otherwise the smallest tile
+  // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
-  const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  const int64_t mt = (M + TC_BM - 1) / TC_BM;
+  int bn = 64;
+  if (N >= 192 && mt * ((N + 255) / 256) >= 120) bn = 256;
+  else if (N >= 96 && mt * ((N + 127) / 128) >= 120) bn = 128;
+  else if (N >= 192 && splitk == 1 && mt * ((N + 63) / 64) < 32) bn = 256;   // tiny grids: fewer, fatter CTAs
+  const int64_t tiles = mt * ((N + bn - 1) / bn);
   int splits = splitk;
   if (splits <= 0) {
     splits = 1;

@@ -1,6 +1,7 @@
 // Internal (non-ABI) interfaces shared between the translation units of libcaldera_b200.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace cb {
@@ -45,6 +46,15 @@ int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st);
 int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes, void* dst, cudaStream_t st);
+
+// gemm_tc.cu -- tcgen05 path: C[M,N] (+)= alpha * A[M,K] * B[N,K]^T, bf16 K-major operands
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);
+int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A, int64_t lda,
+            const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, __nv_bfloat16* Cb, int64_t ldcb,
+            __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
+            int* error_flag, int* splits_used, cudaStream_t st);
+int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
+            __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st);
 
 // quant.cu (C ABI, reused internally)
 }  // namespace cb

@@ -32,8 +32,8 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
   for (int k0 = 0; k0 < q; k0 += NB) {
     const int nb = min(NB, q - k0);
     // 1. diagonal block -> shared
-    {
-      const int i = tid >> 5, j = tid & 31;
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+      const int i = e >> 5, j = e & 31;
       float v = 0.f;
       if (i < nb && j <= i) v = G[(size_t)(k0 + i) * q + k0 + j];
       s.D[i][j] = v;
@@ -55,10 +55,13 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
         const float sd = sqrtf(d), inv = 1.f / sd;
         const float lij = (lane > j) ? a[j] * inv : (lane == j ? sd : 0.f);
         a[j] = (lane >= j) ? lij : 0.f;
+        // constant trip counts on both loops so the unroller resolves every index statically
 #pragma unroll
-        for (int c = j + 1; c < NB; ++c) {
-          const float lcj = __shfl_sync(0xffffffffu, lij, c);   // L[c][j]
-          if (lane >= c) a[c] = fmaf(-lij, lcj, a[c]);
+        for (int c = 0; c < NB; ++c) {
+          if (c > j) {
+            const float lcj = __shfl_sync(0xffffffffu, lij, c);   // L[c][j]
+            if (lane >= c) a[c] = fmaf(-lij, lcj, a[c]);
+          }
         }
       }
       if (bad && lane == 0) s.fail = 1;
@@ -72,7 +75,8 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
       for (int i = 0; i < NB; ++i) {
         float acc = (lane == i) ? 1.f : 0.f;
 #pragma unroll
-        for (int k = 0; k < i; ++k) acc = fmaf(-s.D[i][k], x[k], acc);
+        for (int k = 0; k < NB; ++k)
+          if (k < i) acc = fmaf(-s.D[i][k], x[k], acc);
         x[i] = (lane <= i) ? acc / s.D[i][i] : 0.f;
       }
 #pragma unroll
@@ -80,8 +84,8 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
     }
     __syncthreads();
     // write the factor back, publish the inverse block
-    {
-      const int i = tid >> 5, j = tid & 31;
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+      const int i = e >> 5, j = e & 31;
       if (i < nb && j <= i) {
         G[(size_t)(k0 + i) * q + k0 + j] = s.D[i][j];
         if (Linv != nullptr) Linv[(size_t)(k0 + i) * q + k0 + j] = s.Di[i][j];
@@ -174,7 +178,7 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tile
   }
   __syncthreads();
   const int chain = tid >> 7, ct = tid & 127;
-  const int nchains = min(8, (nblk + 1) / 2);
+  const int nchains = min((int)(blockDim.x >> 7), (nblk + 1) / 2);
   if (chain < nchains) {
     ChainTiles& T = tiles[chain];
     const int orow = ct >> 2, oc0 = (ct & 3) * 8;     // this thread's 1 x 8 strip of a 32 x 32 block
@@ -240,7 +244,9 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tile
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024, 1)
+constexpr int CHOL_THREADS = 512;   // 128 registers/thread: the 32x32 diagonal factor lives in registers
+
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
@@ -255,7 +261,7 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
   }
   __syncthreads();
   int retries = 0;
-  const float ridges[3] = {1e-6f, 1e-4f, 1e-2f};
+
   while (true) {
     chol_factor(G, q, Linv, s);
     __syncthreads();
@@ -263,7 +269,7 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
     __syncthreads();
     if (!failed || retries >= 3) { if (failed) retries = 99; break; }
     // restore the lower triangle from the untouched upper one, add a ridge, retry
-    const float ridge = ridges[retries] * fmaxf(s.mean_diag, 1e-30f);
+    const float ridge = (retries == 0 ? 1e-6f : (retries == 1 ? 1e-4f : 1e-2f)) * fmaxf(s.mean_diag, 1e-30f);
     for (int e = tid; e < q * q; e += blockDim.x) {
       const int i = e / q, j = e - i * q;
       if (j < i) G[e] = G[(size_t)j * q + i];
@@ -285,7 +291,7 @@ int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st)
     CB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
     attr_set = true;
   }
-  chol_inv_kernel<<<1, 1024, sizeof(CholSmem), st>>>(G, q, Linv, status);
+  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, status);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -419,11 +425,13 @@ jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ eval
     if (tid == 0) s_rot = 0;
     __syncthreads();
     for (int t = 0; t < qe - 1; ++t) {
-      for (int pi = g; pi < npairs; pi += ngroups) {
-        int a, b;
+      // trip count is uniform across the CTA: the group shuffles below use the full warp mask
+      for (int pbase = 0; pbase < npairs; pbase += ngroups) {
+        const int pi = pbase + g;
+        int a = 0, b = 0;
         if (pi == 0) { a = qe - 1; b = t; }
-        else { a = (t + pi) % (qe - 1); b = (t - pi + (qe - 1)) % (qe - 1); }
-        const bool live = (a < q && b < q);
+        else if (pi < npairs) { a = (t + pi) % (qe - 1); b = (t - pi + (qe - 1)) % (qe - 1); }
+        const bool live = (pi < npairs && a < q && b < q);
         float4* xa = reinterpret_cast<float4*>(V + (size_t)(live ? a : 0) * stride);
         float4* xb = reinterpret_cast<float4*>(V + (size_t)(live ? b : 0) * stride);
         float4 x[JS_V4], y[JS_V4];

@@ -170,6 +170,8 @@ typedef struct cb_caldera_params {
   int32_t sketch_width;     /* 0 = default (2*rank)                       */
   int32_t power_iters;      /* <0 = default (2 if rand_svd else 8)        */
   int32_t warm_start;       /* reuse the previous outer iteration's basis */
+  int32_t use_tensor_cores; /* 1: bf16 tcgen05 contractions where the shape allows (dims % 8 == 0,
+                               m, n >= 256); 0: fp32 SIMT contractions everywhere        */
   uint64_t seed;
 } cb_caldera_params;
 
@@ -190,8 +192,8 @@ typedef struct cb_caldera_out {
   float* W_scaled;     /* optional m x n: W / global_scale (CalderaDecomposition.W) */
   float* errors;       /* iters * n_order floats, in sub-step order                 */
   float* scalars;      /* 8 floats: [0]=global_scale [1]=min_error [2]=best_step
-                          [5]=LPLR inner best error; [6],[7] hold int32 bit patterns: cholesky
-                          ridge retries (max over the layer) and jacobi sweeps (last solve) */
+                          [5],[6],[7] hold int32 bit patterns: cholesky ridge retries (max over
+                          the layer), jacobi sweeps (last solve), tcgen05 pipeline watchdog */
 } cb_caldera_out;
 
 size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind);

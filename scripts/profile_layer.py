@@ -26,13 +26,14 @@ ap.add_argument("--rank", type=int, default=128)
 ap.add_argument("--lbits", type=int, default=16)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warm", type=int, default=1)
+ap.add_argument("--no-tc", action="store_true")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 qp = CalderaParams(Q_bits=2, L_bits=a.lbits, R_bits=a.lbits, rank=a.rank, iters=a.iters, lplr_iters=5,
                    update_order=["Q", "LR"])
-cp = make_c_params(qp, True, seed=1000)
+cp = make_c_params(qp, True, seed=1000, use_tensor_cores=not a.no_tc)
 run = CalderaLayerRunner(cp, a.m, a.n, _lib.CB_H_DIAG, dev, want_w_scaled=False)
 layers = [tuple(t.to(dev) for t in synth_layer(i, a.m, a.n)) for i in range(2)]
 for i in range(a.warm):
@@ -47,7 +48,7 @@ dt = time.perf_counter() - t0
 torch.cuda.profiler.stop()
 small = run.read_small()
 errs = small[:run.nsteps].tolist()
-stats = small[run.nerr_pad + 6:run.nerr_pad + 8].view(torch.int32).tolist()
+stats = small[run.nerr_pad + 5:run.nerr_pad + 8].view(torch.int32).tolist()
 print(f"layer {a.m}x{a.n} r={a.rank} lbits={a.lbits}: {dt * 1e3:.2f} ms, "
-      f"{_lib.load().cb_kernel_launch_count() - n0} launches, chol_retries={stats[0]} jacobi_sweeps={stats[1]}, "
+      f"{_lib.load().cb_kernel_launch_count() - n0} launches, chol_retries={stats[0]} jacobi_sweeps={stats[1]} tc_watchdog={stats[2]}, "
       f"errors {[round(e, 5) for e in errs]}")

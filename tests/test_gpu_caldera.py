@@ -212,3 +212,22 @@ def test_full_size_properties(cfg):
         opt = float(((S[r:] ** 2).sum() / ((Wd.double() ** 2) * hd[None, :].double()).sum()).sqrt())
         assert elr[0] <= opt * (1 + 1e-3), (elr[0], opt)
         assert float((d.L.T @ d.L - torch.eye(r, device=DEV)).abs().max()) < 1e-3 or d.best_step != 1
+
+
+def test_tensor_core_path_agrees_with_simt():
+    """bf16 tcgen05 contractions vs fp32 SIMT contractions on the same layer (aligned shape)."""
+    g = torch.Generator().manual_seed(11)
+    m, n, r = 1024, 768, 32
+    W = 0.02 * torch.randn(m, n, generator=g)
+    h = torch.exp(0.5 * torch.randn(n, generator=g))
+    kw = dict(Q_bits=4, L_bits=16, R_bits=16, rank=r, iters=3, update_order=["Q", "LR"])
+    a = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=5, use_tensor_cores=True)
+    b = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=5, use_tensor_cores=False)
+    assert a.device_stats["tc_watchdog"] == 0
+    assert a.errors["Q"][0] == b.errors["Q"][0]                     # no contraction involved yet
+    np.testing.assert_allclose(a.errors["LR"], b.errors["LR"], rtol=2e-3)
+    np.testing.assert_allclose(min(a.errors["LR"]), min(b.errors["LR"]), rtol=1e-3)
+    hd = h.to(DEV)
+    np.testing.assert_allclose(_weighted_error_torch(a.W.to(DEV), hd, a.Q, a.L, a.R),
+                               [e for pair in zip(a.errors["Q"], a.errors["LR"]) for e in pair][a.best_step],
+                               rtol=5e-5)
