@@ -87,6 +87,10 @@ static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t
     CB_TRY(scale_cols(L, m, r, b.evals, 2, L, st));
     CB_TRY(scale_rows(R, r, n, b.evals, 3, R, st));
   }
+  // leave the basis rotated into its Ritz vectors (sorted): the next warm-started solve then
+  // sees a nearly diagonal projected matrix and the Jacobi step converges in 2-3 sweeps
+  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 
@@ -178,6 +182,11 @@ static int lowrank_core_tc(int64_t m, int64_t n, int64_t r, int64_t q, int niter
     CB_TRY(scale_cols(L, m, r, b.evals, 2, L, st));
     CB_TRY(scale_rows(R, r, n, b.evals, 3, R, st));
   }
+  // rotate the stored basis into its Ritz vectors for the next warm start:
+  // Zrot[m, q] = Zo[m, K=q] * V[q, K=q]^T, written in both orientations
+  CB_TRY(gemm_tc(m, q, q, 1.f, b.Zob, q, b.Vb, q, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, nullptr, 1, wd, nullptr, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zob, b.Zb, sizeof(bf16) * m * q, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zotb, b.Ztb, sizeof(bf16) * m * q, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 
@@ -248,8 +257,8 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
     L.use_tc = p->use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, L.q);
     if (L.use_tc) {
       L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr);
-      L.Lb16 = a.take<bf16>(m * r);
-      L.Rtb16 = a.take<bf16>(n * r);
+      L.Lb16 = a.take<bf16>(3 * m * r);
+      L.Rtb16 = a.take<bf16>(3 * n * r);
     }
     if (L.quant_factors) {
       L.Rw = a.take<float>(r * n);
@@ -307,12 +316,39 @@ static int solve_spd_setup(float* G, int64_t r, float* Linv, float* Ginv, int* s
   return CB_OK;
 }
 
-// LRbuf = L R (m x n fp32): tensor cores when the shape allows, SIMT otherwise
+// LRbuf = L R (m x n fp32): tensor cores when the shape allows, SIMT otherwise.  The factors
+// are split into bf16 hi + lo parts and contracted as one K = 3r GEMM
+//   [Lh | Lh | Ll] [Rh | Rl | Rh]^T = Lh Rh + Lh Rl + Ll Rh
+// so the product carries ~16 mantissa bits: the residual W - L R that the Q update quantises
+// and the reported error then agree with the fp32 factors that are returned.
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int transpose, int second_is_lo,
+              bf16* __restrict__ out /* rows_out x 3*inner */) {
+  // transpose == 0: X is rows x cols, out row i = [hi(i,:) | (lo or hi)(i,:) | (hi or lo)(i,:)] with inner = cols
+  // transpose == 1: X is rows x cols, out row j (of cols) built from column j, inner = rows
+  const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t inner = transpose ? rows : cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / cols, j = e - i * cols;
+    const float v = X[e];
+    const bf16 hi = __float2bfloat16_rn(v);
+    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int64_t orow = transpose ? j : i, ok = transpose ? i : j;
+    bf16* o = out + orow * 3 * inner + ok;
+    o[0] = hi;
+    o[inner] = second_is_lo ? lo : hi;
+    o[2 * inner] = second_is_lo ? hi : lo;
+  }
+}
+
 static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
   if (P.use_tc) {
-    CB_TRY(to_bf16(P.Lcur, m, r, r, P.Lb16, r, nullptr, 0, nullptr, st));
-    CB_TRY(to_bf16(P.Rcur, r, n, n, nullptr, 0, P.Rtb16, r, nullptr, st));
-    return gemm_tc(m, n, r, 1.f, P.Lb16, r, P.Rtb16, r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
+    // A' = [Lh | Lh | Ll] (m x 3r),  B' = [Rh^T | Rl^T | Rh^T] (n x 3r)
+    split3_kernel<<<grid_for(m * r, 256 * 4, 4), 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16);
+    CB_CHECK_LAUNCH();
+    split3_kernel<<<grid_for(r * n, 256 * 4, 4), 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16);
+    CB_CHECK_LAUNCH();
+    return gemm_tc(m, n, 3 * r, 1.f, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
                    P.flags + 4, nullptr, st);
   }
   return sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st);

@@ -21,6 +21,7 @@ struct CholSmem {
   float Praw[TMAXR][NB + 1];       // panel rows before the triangular solve (row-major)
   float Pt[NB][TMAXR + 4];         // solved panel, transposed: Pt[c][row]
   float diag0[QMAX];               // backup of the diagonal for the ridge retry
+  float rdiag[NB];                 // reciprocal diagonal of the current 32 x 32 factor
   int fail;
   float mean_diag;
 };
@@ -50,9 +51,10 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         float d = __shfl_sync(0xffffffffu, a[j], j);
-        if (j < nb && (!(d > 0.f) || !isfinite(d))) { bad = true; d = 1.f; }
         if (j >= nb) d = 1.f;
-        const float sd = sqrtf(d), inv = 1.f / sd;
+        if (!(d > 0.f) || d > 3.0e38f) { bad = true; d = 1.f; }   // non-positive, NaN or inf pivot
+        const float inv = rsqrtf(d), sd = d * inv;                   // 2-ulp rsqrt is ample for a Gram factor
+        if (lane == 0) s.rdiag[j] = inv;                              // 1 / L[j][j]
         const float lij = (lane > j) ? a[j] * inv : (lane == j ? sd : 0.f);
         a[j] = (lane >= j) ? lij : 0.f;
         // constant trip counts on both loops so the unroller resolves every index statically
@@ -77,7 +79,7 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
 #pragma unroll
         for (int k = 0; k < NB; ++k)
           if (k < i) acc = fmaf(-s.D[i][k], x[k], acc);
-        x[i] = (lane <= i) ? acc / s.D[i][i] : 0.f;
+        x[i] = (lane <= i) ? acc * s.rdiag[i] : 0.f;
       }
 #pragma unroll
       for (int c = 0; c < NB; ++c) s.Di[c][lane] = x[c];      // column `lane` of the inverse
@@ -255,9 +257,10 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
   for (int i = tid; i < q; i += blockDim.x) { s.diag0[i] = G[(size_t)i * q + i]; }
   if (tid == 0) s.fail = 0;
   __syncthreads();
-  if (tid == 0) {
-    for (int i = 0; i < q; ++i) dsum += (double)s.diag0[i];
-    s.mean_diag = (float)(dsum / (double)q);
+  if (tid < 32) {
+    for (int i = tid; i < q; i += 32) dsum += (double)s.diag0[i];
+    dsum = warp_sum(dsum);
+    if (tid == 0) s.mean_diag = (float)(dsum / (double)q);
   }
   __syncthreads();
   int retries = 0;
@@ -499,6 +502,10 @@ jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ eval
   if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
 }
 
+// A column pair is rotated while |<x,y>| > tol * |x| |y|.  The captured energy of the
+// Rayleigh-Ritz step is second order in the residual coupling, so 3e-5 leaves it exact to fp32.
+constexpr float kJacobiTol = 3e-5f;
+
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
                           cudaStream_t st) {
   if (Lc == nullptr || evals == nullptr || evecs == nullptr || work == nullptr || q <= 0) return CB_ERR_ARG;
@@ -511,11 +518,11 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
                                    (int)(((size_t)JS_QMAX * (JS_QMAX + 4) + 2 * JS_QMAX) * sizeof(float))));
       attr_set = true;
     }
-    jacobi_smem_kernel<<<1, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, 1e-6f);
+    jacobi_smem_kernel<<<1, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, kJacobiTol);
     CB_CHECK_LAUNCH();
     return CB_OK;
   }
-  jacobi_kernel<<<1, 1024, 0, st>>>(Lc, q, evals, evecs, work, sweeps, 30, 1e-6f);
+  jacobi_kernel<<<1, 1024, 0, st>>>(Lc, q, evals, evecs, work, sweeps, 30, kJacobiTol);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
