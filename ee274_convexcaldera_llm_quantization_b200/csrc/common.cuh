@@ -51,9 +51,44 @@ __device__ __forceinline__ int levels_of(int bits) { return (1 << (bits - 1)) - 
 __device__ __forceinline__ int quant_code(float x, float s, float lv) {
   return __float2int_rn(__fmul_rn(__fdiv_rn(x, s), lv));
 }
+
+// The same correctly rounded quotient x / s with the reciprocal hoisted out of the element
+// loop (one scale serves a whole block).  Markstein's theorem: with y = RN(1/s) and q within
+// one ulp of x/s, RN(q + (x - s q) y) == RN(x / s) when the remainder is formed exactly
+// (FMA), unless the significand of s is all ones.  Two correction steps bring the first
+// estimate RN(x y) (< 1.5 ulp) inside that hypothesis.  `ScaleRecip::exact` is false for the
+// excluded significand and for scales whose reciprocal or remainders could leave the normal
+// range; those (block-uniform, rare) cases take the plain IEEE divide.
+struct ScaleRecip {
+  float s, y;
+  bool exact;
+};
+__device__ __forceinline__ ScaleRecip make_scale_recip(float s) {
+  ScaleRecip r;
+  r.s = s;
+  r.y = __frcp_rn(s);
+  r.exact = (s > 1e-18f) && (s < 1e18f) && ((__float_as_uint(s) & 0x7FFFFFu) != 0x7FFFFFu);
+  return r;
+}
+__device__ __forceinline__ float div_by_scale(float x, const ScaleRecip& r) {
+  if (!r.exact) return __fdiv_rn(x, r.s);   // uniform over the block that shares the scale
+  // |x| so small that a remainder would be subnormal (inexact) gives |x / s| < 1e-12 here, far
+  // below every code boundary, so its last bits cannot change a code
+  const float q0 = __fmul_rn(x, r.y);
+  const float q1 = fmaf(fmaf(-q0, r.s, x), r.y, q0);
+  return fmaf(fmaf(-q1, r.s, x), r.y, q1);
+}
+__device__ __forceinline__ int quant_code(float x, const ScaleRecip& r, float lv) {
+  return __float2int_rn(__fmul_rn(div_by_scale(x, r), lv));
+}
 // quantization.py:105, 295
 __device__ __forceinline__ float dequant_val(int code, float s, float lv) {
   return __fmul_rn(__fdiv_rn((float)code, lv), s);
+}
+// same value with the reciprocal of the level count hoisted (lv = 2^(b-1) - 1 never has an
+// all-ones significand, so the exact path always applies)
+__device__ __forceinline__ float dequant_val(int code, float s, const ScaleRecip& lvr) {
+  return __fmul_rn(div_by_scale((float)code, lvr), s);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

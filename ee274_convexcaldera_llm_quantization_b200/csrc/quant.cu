@@ -33,8 +33,10 @@ quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, flo
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t ntiles = (numel + 511) >> 9;
-  float s_whole = 0.f;
-  if (LPB == 0) s_whole = fmaxf(scales[0], eps);
+  constexpr int BLOCK = LPB * 4;            // elements per quantisation block (compile time)
+  const ScaleRecip lvr = make_scale_recip(lv);
+  ScaleRecip whole = make_scale_recip(1.f);
+  if (LPB == 0) whole = make_scale_recip(fmaxf(scales[0], eps));
 
   for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
     const int64_t base = tile << 9;
@@ -49,18 +51,17 @@ quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, flo
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t idx = base + j * 128 + lane * 4;
-      float s;
+      ScaleRecip sr = whole;
       if (LPB > 0) {
         float a = fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
 #pragma unroll
         for (int o = LPB / 2; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        s = fmaxf(a, eps);
-        if (ok[j] && (lane % LPB) == 0) scales[idx / block] = s;
-      } else {
-        s = s_whole;
+        sr = make_scale_recip(fmaxf(a, eps));
+        if (ok[j] && (lane % (LPB > 0 ? LPB : 1)) == 0) scales[idx / (BLOCK > 0 ? BLOCK : 1)] = sr.s;
       }
-      const int c0 = quant_code(v[j].x, s, lv), c1 = quant_code(v[j].y, s, lv);
-      const int c2 = quant_code(v[j].z, s, lv), c3 = quant_code(v[j].w, s, lv);
+      const float s = sr.s;
+      const int c0 = quant_code(v[j].x, sr, lv), c1 = quant_code(v[j].y, sr, lv);
+      const int c2 = quant_code(v[j].z, sr, lv), c3 = quant_code(v[j].w, sr, lv);
       if (codes != nullptr && ok[j]) {
         if (BITS <= 8) {
           uint32_t w = (uint32_t)(uint8_t)(int8_t)c0 | ((uint32_t)(uint8_t)(int8_t)c1 << 8) |
@@ -74,8 +75,8 @@ quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, flo
         }
       }
       if (dequant != nullptr && ok[j]) {
-        st_stream4(dequant + idx, make_float4(dequant_val(c0, s, lv), dequant_val(c1, s, lv),
-                                              dequant_val(c2, s, lv), dequant_val(c3, s, lv)));
+        st_stream4(dequant + idx, make_float4(dequant_val(c0, s, lvr), dequant_val(c1, s, lvr),
+                                              dequant_val(c2, s, lvr), dequant_val(c3, s, lvr)));
       }
       if (packed != nullptr) {
         if (BITS == 2) {
@@ -229,7 +230,7 @@ dequant_fast_kernel(const void* __restrict__ codes, const uint8_t* __restrict__ 
                     const float* __restrict__ scales, int64_t numel, int64_t block,
                     float* __restrict__ out) {
   constexpr int LV = (1 << (BITS - 1)) - 1;
-  const float lv = (float)LV;
+  const ScaleRecip lv = make_scale_recip((float)LV);
   const int64_t n16 = numel >> 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += stride) {

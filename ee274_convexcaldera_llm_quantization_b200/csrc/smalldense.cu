@@ -346,10 +346,12 @@ jacobi_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, fl
         }
         al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
         if (fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
-          const float zeta = (be - al) / (2.f * ga);
-          const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          // IEEE sqrt/divide: rsqrtf's 2-ulp bias accumulates over ~q rotations per vector per sweep
-          const float c = __fdiv_rn(1.f, __fsqrt_rn(fmaf(tt, tt, 1.f))), sn = c * tt;
+          // rotation parameters in fp64: c and s are then rounded independently, so c^2 + s^2 - 1
+          // has no systematic sign and column norms do not drift over the ~q rotations per sweep
+          const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
+          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cd = 1.0 / sqrt(1.0 + tt * tt);
+          const float c = (float)cd, sn = (float)(cd * tt);
 #pragma unroll
           for (int k = 0; k < JMAXV; ++k) {
             const int i = lane + 32 * k;
@@ -455,9 +457,12 @@ jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ eval
           ga += __shfl_xor_sync(0xffffffffu, ga, o);
         }
         if (live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
-          const float zeta = (be - al) / (2.f * ga);
-          const float tt = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-          const float c = __fdiv_rn(1.f, __fsqrt_rn(fmaf(tt, tt, 1.f))), sn = c * tt;
+          // rotation parameters in fp64: c and s are then rounded independently, so c^2 + s^2 - 1
+          // has no systematic sign and column norms do not drift over the ~q rotations per sweep
+          const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
+          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cd = 1.0 / sqrt(1.0 + tt * tt);
+          const float c = (float)cd, sn = (float)(cd * tt);
 #pragma unroll
           for (int k = 0; k < JS_V4; ++k) {
             const int i4 = gl + 8 * k;

