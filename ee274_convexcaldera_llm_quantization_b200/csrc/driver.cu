@@ -226,13 +226,18 @@ struct LayerPlan {
   LowrankBufs lr;
   LowrankTcBufs tc;
   bf16 *Lb16, *Rtb16;   // bf16 copies of L (m x r) and R^T (n x r) for the tensor-core L R product
+  // dense (non-diagonal) Hessian
+  float *Hs, *Ebuf, *Tbuf, *HP, *HRt;
   int64_t q;
   bool quant_factors;
   bool use_tc;
+  bool dense;
 };
 
-static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n, bool scale_w, LayerPlan& L) {
+static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n, bool scale_w, int h_kind,
+                      LayerPlan& L) {
   const int64_t r = p->rank;
+  L.dense = (h_kind == CB_H_DENSE);
   L.quant_factors = p->compute_lr && (p->l_bits < 16 || p->r_bits < 16);
   L.q = p->compute_lr ? default_sketch_width(p, m, n) : 0;
   L.dsc = a.take<double>(4);
@@ -249,12 +254,12 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
   if (p->compute_lr) {
     L.LRbuf = a.take<float>(m * n);
     L.Y = a.take<float>(m * n);
-    L.RES = (L.quant_factors && p->aware) ? a.take<float>(m * n) : nullptr;
+    L.RES = (L.quant_factors && p->aware && !L.dense) ? a.take<float>(m * n) : nullptr;
     L.Lcur = a.take<float>(m * r);
     L.Rcur = a.take<float>(r * n);
     L.Zwarm = a.take<float>(m * L.q);
     L.lr = plan_lowrank(a, m, n, L.q, L.Zwarm, nullptr);
-    L.use_tc = p->use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, L.q);
+    L.use_tc = p->use_tensor_cores != 0 && !L.dense && lowrank_tc_usable(m, n, r, L.q);
     if (L.use_tc) {
       L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr);
       L.Lb16 = a.take<bf16>(3 * m * r);
@@ -282,6 +287,15 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
       L.Rscale_in = a.take<float>(4);
     }
   }
+  if (L.dense) {
+    L.Hs = a.take<float>(n * n);
+    L.Ebuf = a.take<float>(m * n);
+    L.Tbuf = a.take<float>(m * n);
+    if (p->compute_lr) {
+      L.HP = a.take<float>(n * L.q);
+      L.HRt = a.take<float>(n * r);
+    }
+  }
   return a.ok() ? CB_OK : CB_ERR_WORKSPACE;
 }
 
@@ -298,7 +312,7 @@ static int validate_params(const cb_caldera_params* p, int64_t m, int64_t n, int
     if ((p->l_bits < 16 || p->r_bits < 16) && p->lplr_iters < 1) return CB_ERR_ARG;
   }
   if (h_kind != CB_H_IDENTITY && h_kind != CB_H_DIAG && h_kind != CB_H_DENSE) return CB_ERR_ARG;
-  if (h_kind == CB_H_DENSE) return CB_ERR_UNSUPPORTED;
+  if (h_kind == CB_H_DENSE && p->aware && p->sigma_reg > 0.f) return CB_ERR_UNSUPPORTED;  // needs lambda_min(H)
   if (p->q_block != 0) return CB_ERR_UNSUPPORTED;
   return CB_OK;
 }
@@ -314,6 +328,55 @@ static int solve_spd_setup(float* G, int64_t r, float* Linv, float* Ginv, int* s
   // G^-1 = Linv^T Linv
   CB_TRY(sgemm(r, r, r, 1.f, Linv, 1, r, Linv, r, 1, Ginv, r, 1, false, nullptr, st));
   return CB_OK;
+}
+
+// ---------------------------------------------------------------- dense Hessian
+// For a general symmetric H the weighted problem min ||(res - L R) H^(1/2)||_F needs no square
+// root of H at all: the left singular vectors of res H^(1/2) are the eigenvectors of
+// A = res H res^T, so the subspace iteration applies A as three products
+//   P = res^T Z,   HP = H P,   Z' = res HP
+// (P is re-orthonormalised in between, which does not change the span), Rayleigh-Ritz uses
+// G = P^T H P with P = res^T Zo, and R = L^T res = V_r P^T (alg.py:210-225 with V V^T = I).
+static int lowrank_core_dense(const float* res, const float* Hs, int64_t m, int64_t n, int64_t r, int64_t q,
+                              int niter, uint64_t seed, bool warm_valid, float* L, float* R, float* HP,
+                              const LowrankBufs& b, cudaStream_t st) {
+  if (!warm_valid) {
+    CB_TRY(fill_randn(b.P, n * q, seed, st));
+    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st));
+    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st));
+    CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
+  }
+  for (int it = 0; it < niter; ++it) {
+    CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));   // P = res^T Zo
+    CB_TRY(orthonormalize(b.P, n, q, b.Po, b, st));
+    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.Po, q, 1, HP, q, 1, false, nullptr, st));     // HP = H Po
+    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st));     // Z = res HP
+    CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
+  }
+  CB_TRY(orthonormalize(b.Zo, m, q, b.Z, b, st));
+  CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
+  CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));     // P = res^T Zo
+  CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st));
+  CB_TRY(sgemm(q, q, n, 1.f, b.P, 1, q, HP, q, 1, b.G, q, 1, false, nullptr, st));       // G = P^T H P
+  CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
+  CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
+  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st));       // L = Zo V_r^T
+  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.P, 1, q, R, n, 1, false, nullptr, st));        // R = V_r P^T
+  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st));     // Ritz rotation (warm start)
+  CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
+  return CB_OK;
+}
+
+// out += tr(E H E^T) (squared == false) or ||E H||_F^2 (squared == true), E = A - Q - LR
+static int dense_quadratic(const LayerPlan& P, const float* A, const void* codes, int bits, const float* qscale,
+                           const float* LR, int64_t m, int64_t n, bool squared, double* out, cudaStream_t st) {
+  const float* E = A;
+  if (codes != nullptr || LR != nullptr) {
+    CB_TRY(form_e(A, codes, bits, qscale, LR, m, n, P.Ebuf, st));
+    E = P.Ebuf;
+  }
+  CB_TRY(sgemm(m, n, n, 1.f, E, n, 1, P.Hs, n, 1, P.Tbuf, n, 1, false, nullptr, st));
+  return dot_accum(P.Tbuf, squared ? P.Tbuf : E, m * n, out, st);
 }
 
 // LRbuf = L R (m x n fp32): tensor cores when the shape allows, SIMT otherwise.  The factors
@@ -356,13 +419,19 @@ static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaS
 
 static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
   const int64_t r = p->rank;
-  const float* res = p->aware ? P.RES : P.Y;  // unweighted residual W - Q
+  const float* res = (p->aware && !P.dense) ? P.RES : P.Y;  // unweighted residual W - Q
   for (int k = 0; k < p->lplr_iters; ++k) {
     // ---- L update: weighted normal equations (alg.py:163 / :167)
-    const float* Rw = P.Rcur;
-    if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
-    CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st));     // R diag(h) R^T
-    CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st));        // res diag(h) R^T
+    if (P.dense && p->aware) {
+      CB_TRY(sgemm(n, r, n, 1.f, P.Hs, n, 1, P.Rcur, 1, n, P.HRt, r, 1, false, nullptr, st));   // H R^T
+      CB_TRY(sgemm(r, r, n, 1.f, P.Rcur, n, 1, P.HRt, r, 1, P.Gs, r, 1, false, nullptr, st));   // R H R^T
+      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, P.HRt, r, 1, P.Bl, r, 1, false, nullptr, st));      // res H R^T
+    } else {
+      const float* Rw = P.Rcur;
+      if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
+      CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st));     // R diag(h) R^T
+      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st));        // res diag(h) R^T
+    }
     CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
     CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st));
     CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));  // alg.py:171-172
@@ -374,7 +443,8 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
     CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));  // alg.py:179-180
     // ---- inner error ||(res - L R) H_sqrt||_F and best-so-far (alg.py:182-188)
     CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
-    CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
+    if (P.dense) CB_TRY(dense_quadratic(P, res, nullptr, 8, nullptr, P.LRbuf, m, n, !p->aware, P.dsc + 3, st));
+    else CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
     CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
     const int* f = P.flags + 1;
     CB_TRY(copy_if(f, P.Lb, P.Lcur, sizeof(float) * m * r, st));
@@ -394,10 +464,10 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
 using namespace cb;
 
 extern "C" size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
-  if (validate_params(p, m, n, h_kind == CB_H_DENSE ? CB_H_DIAG : h_kind) != CB_OK) return 0;
+  if (validate_params(p, m, n, h_kind) != CB_OK) return 0;
   Arena a{nullptr, 0, 0};
   LayerPlan L{};
-  plan_layer(a, p, m, n, p->scale_w != 0, L);
+  plan_layer(a, p, m, n, p->scale_w != 0, h_kind, L);
   return a.off + 256;
 }
 
@@ -405,7 +475,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
                                 int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes, void* stream) {
   CB_TRY(validate_params(p, m, n, h_kind));
   if (W == nullptr || out == nullptr || ws == nullptr) return CB_ERR_ARG;
-  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  if ((h_kind == CB_H_DIAG || h_kind == CB_H_DENSE) && h == nullptr) return CB_ERR_ARG;
   if (out->Q == nullptr || out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr)
     return CB_ERR_ARG;
   if (p->compute_q && (out->Q_idxs == nullptr || out->Q_scale == nullptr)) return CB_ERR_ARG;
@@ -417,7 +487,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
 
   Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
   LayerPlan P{};
-  CB_TRY(plan_layer(a, p, m, n, scale_w, P));
+  CB_TRY(plan_layer(a, p, m, n, scale_w, h_kind, P));
   if (P.quant_factors && (out->L_idxs == nullptr || out->R_idxs == nullptr || out->L_scale == nullptr || out->R_scale == nullptr))
     return CB_ERR_ARG;
   if (p->compute_lr) { P.lr.status = P.flags + 2; P.tc.status = P.flags + 2; }
@@ -448,6 +518,13 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
                            P.inv_sqrt_h, P.w_inner, nullptr, st));
   CB_TRY(scale_and_den(W, P.Ws, m, n, P.scalars, P.h_eff, P.dsc + 1, st));
   const float* Ws = scale_w ? P.Ws : W;
+  if (P.dense) {
+    // alg.py:54 symmetrises only in the activation-aware branch; otherwise H is used as given
+    if (p->aware) CB_TRY(symmetrize(h, n, P.Hs, st));
+    else CB_CUDA(cudaMemcpyAsync(P.Hs, h, sizeof(float) * n * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemsetAsync(P.dsc + 1, 0, sizeof(double), st));
+    CB_TRY(dense_quadratic(P, Ws, nullptr, 8, nullptr, nullptr, m, n, false, P.dsc + 1, st));   // tr(W H W^T)
+  }
   if (out->W_scaled != nullptr)
     CB_CUDA(cudaMemcpyAsync(out->W_scaled, Ws, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
 
@@ -470,12 +547,17 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         CB_TRY(resid_absmax(Ws, lrp, numel, P.amax, st));
         CB_TRY(quant_err(Ws, lrp, P.h_eff, m, n, P.amax, 1e-8f, p->q_bits, P.codes_cur, P.qscale_cur, P.dsc + 2, st));
         have_q = true;
-        num_ready = true;
+        num_ready = !P.dense;   // the fused numerator is the diagonal metric
+        if (P.dense) CB_CUDA(cudaMemsetAsync(P.dsc + 2, 0, sizeof(double), st));
       } else if (which == 1 && p->compute_lr) {
         // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
         CB_TRY(form_y(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
-                      p->aware ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
-        if (P.use_tc) {
+                      (p->aware && !P.dense) ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
+        if (P.dense && p->aware) {
+          // form_y ran with sqrt_h == 1 for the dense case, so P.Y is the plain residual W - Q
+          CB_TRY(lowrank_core_dense(P.Y, P.Hs, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step,
+                                    warm_valid && p->warm_start, P.Lcur, P.Rcur, P.HP, P.lr, st));
+        } else if (P.use_tc) {
           CB_TRY(to_bf16(P.Y, m, n, n, P.tc.Yb, n, P.tc.Ytb, m, nullptr, st));
           CB_TRY(lowrank_core_tc(m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
                                  warm_valid && p->warm_start, P.Lcur, P.Rcur, nullptr, nullptr, P.tc, st));
@@ -490,8 +572,11 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         lrbuf_valid = true;
       }
       if (!num_ready) {
-        CB_TRY(err_accum(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
-                         (have_lr && lrbuf_valid) ? P.LRbuf : nullptr, P.h_eff, m, n, P.dsc + 2, st));
+        const void* qc = have_q ? P.codes_cur : nullptr;
+        const float* lrp2 = (have_lr && lrbuf_valid) ? P.LRbuf : nullptr;
+        const int qb = p->compute_q ? p->q_bits : 8;
+        if (P.dense) CB_TRY(dense_quadratic(P, Ws, qc, qb, P.qscale_cur, lrp2, m, n, false, P.dsc + 2, st));
+        else CB_TRY(err_accum(Ws, qc, qb, P.qscale_cur, lrp2, P.h_eff, m, n, P.dsc + 2, st));
       }
       updated[oi] = true;
       // `updated` is keyed by name in the reference (alg.py:91), so duplicates in update_order share a flag

@@ -46,6 +46,10 @@ int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st);
 int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes, void* dst, cudaStream_t st);
+int form_e(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR, int64_t m, int64_t n,
+           float* E, cudaStream_t st);
+int dot_accum(const float* a, const float* b, int64_t numel, double* out, cudaStream_t st);
+int symmetrize(const float* H, int64_t n, float* Hs, cudaStream_t st);
 
 // gemm_tc.cu -- tcgen05 path: C[M,N] (+)= alpha * A[M,K] * B[N,K]^T, bf16 K-major operands
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);

@@ -290,6 +290,57 @@ err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const
   if (threadIdx.x == 0) atomicAdd(num, acc);
 }
 
+// ---------------------------------------------------------------- dense-Hessian helpers
+// E = Ws - Q - L R written out (the dense metric tr(E H E^T) needs E as a GEMM operand)
+template <int VEC, typename code_t>
+__global__ void __launch_bounds__(256)
+form_e_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
+              float lv, const float* __restrict__ LR, int64_t numel, float* __restrict__ E) {
+  const float s = codes != nullptr ? qscale[0] : 0.f;
+  const ScaleRecip lvr = make_scale_recip(lv);
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> w, p;
+    w.load(Ws + i);
+    if (LR != nullptr) p.load_stream(LR + i);
+    int c[VEC];
+    if (codes != nullptr) load_codes<VEC, code_t>(codes + i, c);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      if (codes != nullptr) w.v[k] -= dequant_val(c[k], s, lvr);
+      if (LR != nullptr) w.v[k] -= p.v[k];
+    }
+    w.store(E + i);
+  }
+}
+
+// out += sum_i a_i * b_i  (b == a gives a squared Frobenius norm)
+__global__ void __launch_bounds__(256)
+dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t numel, double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  float part = 0.f;
+  int cnt = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    part = fmaf(a[i], b[i], part);
+    if (++cnt == 32) { acc += (double)part; part = 0.f; cnt = 0; }
+  }
+  acc += (double)part;
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// Hs = (H + H^T) / 2  (alg.py:54)
+__global__ void __launch_bounds__(256)
+symmetrize_kernel(const float* __restrict__ H, int64_t n, float* __restrict__ Hs) {
+  const int64_t total = n * n, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t i = e / n, j = e - i * n;
+    Hs[e] = (H[e] + H[j * n + i]) / 2.f;
+  }
+}
+
 // ---------------------------------------------------------------- selection / bookkeeping
 __global__ void select_outer_kernel(double* num, const double* den, float* errors, int step, float* scalars,
                                     int* flags, int all_updated) {
@@ -483,6 +534,30 @@ int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes,
   if (elem_bytes == 1) transpose_kernel<int8_t><<<grid, 256, 0, st>>>((const int8_t*)src, rows, cols, (int8_t*)dst);
   else if (elem_bytes == 2) transpose_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)src, rows, cols, (int16_t*)dst);
   else transpose_kernel<float><<<grid, 256, 0, st>>>((const float*)src, rows, cols, (float*)dst);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+int form_e(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR, int64_t m, int64_t n,
+           float* E, cudaStream_t st) {
+  const int64_t numel = m * n;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  const bool v4 = can_vec4(n, {Ws, codes, LR, E});
+#define CB_FE(VEC, T, G) \
+  form_e_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, numel, E)
+  if (bits <= 8) { if (v4) CB_FE(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_FE(1, int8_t, grid_for(numel, 256 * 4, 8)); }
+  else { if (v4) CB_FE(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_FE(1, int16_t, grid_for(numel, 256 * 4, 8)); }
+#undef CB_FE
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int dot_accum(const float* a, const float* b, int64_t numel, double* out, cudaStream_t st) {
+  dot_kernel<<<grid_for(numel, 256 * 8, 4), 256, 0, st>>>(a, b, numel, out);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int symmetrize(const float* H, int64_t n, float* Hs, cudaStream_t st) {
+  symmetrize_kernel<<<grid_for(n * n, 256 * 4, 4), 256, 0, st>>>(H, n, Hs);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

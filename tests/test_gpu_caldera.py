@@ -59,10 +59,6 @@ def _weighted_error_torch(W, h, Q, L, R):
 def test_golden(path):
     z, kw, H = _load(path)
     p = _params(kw)
-    if "H" in z:
-        with pytest.raises(NotImplementedError):
-            caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False, scale_W=bool(z["scale_W"]))
-        pytest.skip("dense (non-diagonal) Hessian: not built yet")
     scale_W = bool(z["scale_W"])
     gs = float(z["global_scale"]) if scale_W else None
     d = caldera(p, torch.from_numpy(z["W"]), H, device=DEV, use_tqdm=False, scale_W=scale_W, global_scale=gs)
@@ -102,10 +98,17 @@ def test_golden(path):
     assert got_best <= ref_best * (1 + tol), (got_best, ref_best)
     assert got_best >= ref_best * (1 - max(10 * tol, 2e-2)), (got_best, ref_best)
     # ---- self consistency: the error reported for the returned iterate is the error of the returned tensors
-    h = None if H is None else torch.diagonal(H).to(DEV)
-    if kw.get("sigma_reg", 0) and p.activation_aware_LR and h is not None and float(h.min()) < kw["sigma_reg"]:
-        h = h + (kw["sigma_reg"] - float(h.min()))
-    consistent = _weighted_error_torch(d.W.to(DEV), h, d.Q, d.L, d.R)
+    if "H" in z:
+        Hd = H.to(DEV).double()
+        Hd = (Hd + Hd.T) / 2
+        Wd64 = d.W.to(DEV).double()
+        E64 = (d.Q + d.L @ d.R).double() - Wd64
+        consistent = float((torch.trace(E64 @ Hd @ E64.T) / torch.trace(Wd64 @ Hd @ Wd64.T)).sqrt())
+    else:
+        h = None if H is None else torch.diagonal(H).to(DEV)
+        if kw.get("sigma_reg", 0) and p.activation_aware_LR and h is not None and float(h.min()) < kw["sigma_reg"]:
+            h = h + (kw["sigma_reg"] - float(h.min()))
+        consistent = _weighted_error_torch(d.W.to(DEV), h, d.Q, d.L, d.R)
     assert d.best_step == int(np.argmin(seq_got[k - 1:])) + k - 1
     np.testing.assert_allclose(consistent, seq_got[d.best_step], rtol=5e-5)
     # ---- codes
@@ -240,3 +243,12 @@ def test_tensor_core_path_agrees_with_simt():
     np.testing.assert_allclose(_weighted_error_torch(a.W.to(DEV), hd, a.Q, a.L, a.R),
                                [e for pair in zip(a.errors["Q"], a.errors["LR"]) for e in pair][a.best_step],
                                rtol=5e-5)
+
+
+def test_dense_hessian_sigma_reg_not_supported():
+    """A dense H with sigma_reg > 0 needs lambda_min(H) (alg.py:59-63); not built: fails loudly."""
+    W = torch.randn(64, 48)
+    X = torch.randn(200, 48)
+    with pytest.raises(NotImplementedError):
+        caldera(_params(dict(rank=4, iters=1, L_bits=16, R_bits=16, sigma_reg=1e-3, update_order=["Q", "LR"])),
+                W, X.T @ X / 200, device=DEV, use_tqdm=False)
