@@ -81,6 +81,24 @@ __device__ __forceinline__ float div_by_scale(float x, const ScaleRecip& r) {
 __device__ __forceinline__ int quant_code(float x, const ScaleRecip& r, float lv) {
   return __float2int_rn(__fmul_rn(div_by_scale(x, r), lv));
 }
+// branch-free core of div_by_scale for callers that tested r.exact once per block
+__device__ __forceinline__ float div_by_scale_exact(float x, const ScaleRecip& r) {
+  const float q0 = __fmul_rn(x, r.y);
+  const float q1 = fmaf(fmaf(-q0, r.s, x), r.y, q0);
+  return fmaf(fmaf(-q1, r.s, x), r.y, q1);
+}
+// four codes sharing one scale: the (rare) IEEE-divide fallback is taken once for all four
+__device__ __forceinline__ void quant_code4(const float4& v, const ScaleRecip& r, float lv, int& c0, int& c1, int& c2, int& c3) {
+  if (r.exact) {
+    c0 = __float2int_rn(__fmul_rn(div_by_scale_exact(v.x, r), lv));
+    c1 = __float2int_rn(__fmul_rn(div_by_scale_exact(v.y, r), lv));
+    c2 = __float2int_rn(__fmul_rn(div_by_scale_exact(v.z, r), lv));
+    c3 = __float2int_rn(__fmul_rn(div_by_scale_exact(v.w, r), lv));
+  } else {
+    c0 = quant_code(v.x, r.s, lv); c1 = quant_code(v.y, r.s, lv);
+    c2 = quant_code(v.z, r.s, lv); c3 = quant_code(v.w, r.s, lv);
+  }
+}
 // quantization.py:105, 295
 __device__ __forceinline__ float dequant_val(int code, float s, float lv) {
   return __fmul_rn(__fdiv_rn((float)code, lv), s);
@@ -88,7 +106,7 @@ __device__ __forceinline__ float dequant_val(int code, float s, float lv) {
 // same value with the reciprocal of the level count hoisted (lv = 2^(b-1) - 1 never has an
 // all-ones significand, so the exact path always applies)
 __device__ __forceinline__ float dequant_val(int code, float s, const ScaleRecip& lvr) {
-  return __fmul_rn(div_by_scale((float)code, lvr), s);
+  return __fmul_rn(div_by_scale_exact((float)code, lvr), s);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -60,8 +60,8 @@ quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, flo
         if (ok[j] && (lane % (LPB > 0 ? LPB : 1)) == 0) scales[idx / (BLOCK > 0 ? BLOCK : 1)] = sr.s;
       }
       const float s = sr.s;
-      const int c0 = quant_code(v[j].x, sr, lv), c1 = quant_code(v[j].y, sr, lv);
-      const int c2 = quant_code(v[j].z, sr, lv), c3 = quant_code(v[j].w, sr, lv);
+      int c0, c1, c2, c3;
+      quant_code4(v[j], sr, lv, c0, c1, c2, c3);
       if (codes != nullptr && ok[j]) {
         if (BITS <= 8) {
           uint32_t w = (uint32_t)(uint8_t)(int8_t)c0 | ((uint32_t)(uint8_t)(int8_t)c1 << 8) |
