@@ -15,7 +15,28 @@ import torch
 from . import _lib
 from .params import CalderaParams, CalderaDecomposition, QuantInfo  # noqa: F401  (re-exported like the reference)
 from .quantization import QuantizerFactory, LowMemoryQuantizer, AbstractQuantizer  # noqa: F401
-from .runner import CalderaLayerRunner
+from .runner import CalderaLayerRunner, workspace_bytes
+
+import threading
+
+# Scratch arenas are reused across calls (one per device and calling thread): a layer needs
+# ~0.5 GiB of workspace at 4096 x 4096 and re-allocating it per call costs more than the H2D copy.
+_WS_CACHE = {}
+
+
+def _cached_workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    key = (dev.index, threading.get_ident())
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        _WS_CACHE[key] = None
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    """Drops the cached scratch arenas (they are otherwise kept for the life of the process)."""
+    _WS_CACHE.clear()
 
 _ORDER_CODE = {"Q": 0, "LR": 1}
 
@@ -149,8 +170,9 @@ def caldera(
                           use_tensor_cores)
 
         f32 = dict(dtype=torch.float32, device=dev)
+        ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
         run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
-                                 want_w_scaled=(W_copy != "none"))
+                                 want_w_scaled=(W_copy != "none"), workspace=ws)
         run.enqueue(Wd, Hd)
         host = run.read_small()                           # the one synchronisation of the layer
         nsteps = run.nsteps
@@ -159,7 +181,8 @@ def caldera(
         Q_packed, L_packed, R_packed = run.Q_packed, run.L_packed, run.R_packed
         Q_scale, L_scale, R_scale = run.Q_scale, run.L_scale, run.R_scale
         W_scaled = run.W_scaled
-        run.ws = None                                     # release the workspace
+        run.ws = None                                     # the arena stays in the per-thread cache
+        del ws
 
     errs = host[:nsteps].tolist()
     scal = host[run.nerr_pad:run.nerr_pad + 8]

@@ -17,91 +17,126 @@ template <int BITS> struct CodeT { using type = int8_t; };
 template <> struct CodeT<16> { using type = int16_t; };
 
 // ---------------------------------------------------------------- fast path
-// One warp handles tiles of 512 consecutive elements: 4 fully coalesced 512-byte loads
-// (lane l owns elements 4l..4l+3 of each 128-element chunk).  LPB = lanes per quantisation
-// block (block/4) for block in {32,64,128}; LPB == 0 means one scale for the whole tensor,
-// already reduced into scales[0] by absmax_fast_kernel.
-template <int BITS, int LPB>
+// One warp handles tiles of 1024 consecutive elements as 4 chunks of 256: every lane issues
+// one 256-bit streaming load per chunk (LDG.E.256, 1 KiB per warp instruction, all four in
+// flight before the first use) and owns 8 consecutive elements of it.  LPB = lanes that share
+// a quantisation block (block / 8) for block in {32, 64, 128, 256}; the block abs-max is a
+// log2(LPB)-step shuffle reduction and never leaves registers.  LPB == 0 means one scale for
+// the whole tensor, already reduced into scales[0] by absmax_fast_kernel.  FULL: numel is a
+// multiple of 1024, so no lane is ever out of range.
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 ld_stream8(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+template <int BITS, int LPB, bool FULL>
 __global__ void __launch_bounds__(256)
-quant_fast_kernel(const float* __restrict__ x, int64_t numel, int64_t block, float eps,
+quant_fast_kernel(const float* __restrict__ x, int64_t numel, float eps,
                   void* __restrict__ codes, uint8_t* __restrict__ packed,
                   float* __restrict__ scales, float* __restrict__ dequant) {
   using code_t = typename CodeT<BITS>::type;
   constexpr int LV = (1 << (BITS - 1)) - 1;
+  constexpr int BLOCK = LPB * 8;            // elements per quantisation block (compile time)
   const float lv = (float)LV;
+  const ScaleRecip lvr = make_scale_recip(lv);
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ntiles = (numel + 511) >> 9;
-  constexpr int BLOCK = LPB * 4;            // elements per quantisation block (compile time)
-  const ScaleRecip lvr = make_scale_recip(lv);
+  const int64_t ntiles = (numel + 1023) >> 10;
   ScaleRecip whole = make_scale_recip(1.f);
   if (LPB == 0) whole = make_scale_recip(fmaxf(scales[0], eps));
 
   for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
-    const int64_t base = tile << 9;
-    float4 v[4];
+    const int64_t base = (tile << 10) + lane * 8;
+    F8 v[4];
     bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int64_t idx = base + j * 128 + lane * 4;
-      ok[j] = idx < numel;
-      v[j] = ok[j] ? ld_stream4(x + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t idx = base + j * 256;
+      ok[j] = FULL || idx < numel;
+      if (ok[j]) v[j] = ld_stream8(x + idx);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j].v[e] = 0.f;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t idx = base + j * 128 + lane * 4;
+      const int64_t idx = base + j * 256;
       ScaleRecip sr = whole;
       if (LPB > 0) {
-        float a = fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+        float a = fabsf(v[j].v[0]);
+#pragma unroll
+        for (int e = 1; e < 8; ++e) a = fmaxf(a, fabsf(v[j].v[e]));
 #pragma unroll
         for (int o = LPB / 2; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
         sr = make_scale_recip(fmaxf(a, eps));
         if (ok[j] && (lane % (LPB > 0 ? LPB : 1)) == 0) scales[idx / (BLOCK > 0 ? BLOCK : 1)] = sr.s;
       }
       const float s = sr.s;
-      int c0, c1, c2, c3;
-      quant_code4(v[j], sr, lv, c0, c1, c2, c3);
+      int c[8];
+      if (sr.exact) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] = __float2int_rn(__fmul_rn(div_by_scale_exact(v[j].v[e], sr), lv));
+      } else {   // uniform over the lanes that share the scale, rare
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] = quant_code(v[j].v[e], s, lv);
+      }
       if (codes != nullptr && ok[j]) {
         if (BITS <= 8) {
-          uint32_t w = (uint32_t)(uint8_t)(int8_t)c0 | ((uint32_t)(uint8_t)(int8_t)c1 << 8) |
-                       ((uint32_t)(uint8_t)(int8_t)c2 << 16) | ((uint32_t)(uint8_t)(int8_t)c3 << 24);
-          *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(codes) + idx) = w;
-        } else {
           uint2 w;
-          w.x = (uint32_t)(uint16_t)(int16_t)c0 | ((uint32_t)(uint16_t)(int16_t)c1 << 16);
-          w.y = (uint32_t)(uint16_t)(int16_t)c2 | ((uint32_t)(uint16_t)(int16_t)c3 << 16);
-          *reinterpret_cast<uint2*>(reinterpret_cast<code_t*>(codes) + idx) = w;
+          w.x = (uint32_t)(uint8_t)(int8_t)c[0] | ((uint32_t)(uint8_t)(int8_t)c[1] << 8) |
+                ((uint32_t)(uint8_t)(int8_t)c[2] << 16) | ((uint32_t)(uint8_t)(int8_t)c[3] << 24);
+          w.y = (uint32_t)(uint8_t)(int8_t)c[4] | ((uint32_t)(uint8_t)(int8_t)c[5] << 8) |
+                ((uint32_t)(uint8_t)(int8_t)c[6] << 16) | ((uint32_t)(uint8_t)(int8_t)c[7] << 24);
+          *reinterpret_cast<uint2*>(reinterpret_cast<int8_t*>(codes) + idx) = w;
+        } else {
+          uint4 w;
+          w.x = (uint32_t)(uint16_t)(int16_t)c[0] | ((uint32_t)(uint16_t)(int16_t)c[1] << 16);
+          w.y = (uint32_t)(uint16_t)(int16_t)c[2] | ((uint32_t)(uint16_t)(int16_t)c[3] << 16);
+          w.z = (uint32_t)(uint16_t)(int16_t)c[4] | ((uint32_t)(uint16_t)(int16_t)c[5] << 16);
+          w.w = (uint32_t)(uint16_t)(int16_t)c[6] | ((uint32_t)(uint16_t)(int16_t)c[7] << 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<code_t*>(codes) + idx) = w;
         }
       }
       if (dequant != nullptr && ok[j]) {
-        st_stream4(dequant + idx, make_float4(dequant_val(c0, s, lvr), dequant_val(c1, s, lvr),
-                                              dequant_val(c2, s, lvr), dequant_val(c3, s, lvr)));
+        st_stream4(dequant + idx, make_float4(dequant_val(c[0], s, lvr), dequant_val(c[1], s, lvr),
+                                              dequant_val(c[2], s, lvr), dequant_val(c[3], s, lvr)));
+        st_stream4(dequant + idx + 4, make_float4(dequant_val(c[4], s, lvr), dequant_val(c[5], s, lvr),
+                                                  dequant_val(c[6], s, lvr), dequant_val(c[7], s, lvr)));
       }
       if (packed != nullptr) {
         if (BITS == 2) {
-          // byte = q0*64 + q1*16 + q2*4 + q3 (quantization.py:217-220), one byte per lane;
-          // four neighbouring lanes are gathered into one 32-bit store.
-          uint32_t b = (uint32_t)(((c0 + LV) << 6) | ((c1 + LV) << 4) | ((c2 + LV) << 2) | (c3 + LV));
-          uint32_t t = b | (__shfl_down_sync(0xffffffffu, b, 1) << 8);
-          uint32_t w = t | (__shfl_down_sync(0xffffffffu, t, 2) << 16);
-          if (ok[j] && (lane & 3) == 0) *reinterpret_cast<uint32_t*>(packed + (idx >> 2)) = w;
+          // byte = q0*64 + q1*16 + q2*4 + q3 (quantization.py:217-220): two bytes per lane, two
+          // neighbouring lanes are gathered into one 32-bit store
+          const uint32_t b0 = (uint32_t)(((c[0] + LV) << 6) | ((c[1] + LV) << 4) | ((c[2] + LV) << 2) | (c[3] + LV));
+          const uint32_t b1 = (uint32_t)(((c[4] + LV) << 6) | ((c[5] + LV) << 4) | ((c[6] + LV) << 2) | (c[7] + LV));
+          const uint32_t h = b0 | (b1 << 8);
+          const uint32_t w = h | (__shfl_down_sync(0xffffffffu, h, 1) << 16);
+          if (ok[j] && (lane & 1) == 0) *reinterpret_cast<uint32_t*>(packed + (idx >> 2)) = w;
         } else if (BITS == 4) {
-          // byte = q0*16 + q1 (quantization.py:152), two bytes per lane
-          uint32_t h = (uint32_t)(((c0 + LV) << 4) | (c1 + LV)) | ((uint32_t)(((c2 + LV) << 4) | (c3 + LV)) << 8);
-          uint32_t w = h | (__shfl_down_sync(0xffffffffu, h, 1) << 16);
-          if (ok[j] && (lane & 1) == 0) *reinterpret_cast<uint32_t*>(packed + (idx >> 1)) = w;
+          // byte = q0*16 + q1 (quantization.py:152): four bytes per lane
+          const uint32_t w = (uint32_t)(((c[0] + LV) << 4) | (c[1] + LV)) | ((uint32_t)(((c[2] + LV) << 4) | (c[3] + LV)) << 8) |
+                             ((uint32_t)(((c[4] + LV) << 4) | (c[5] + LV)) << 16) | ((uint32_t)(((c[6] + LV) << 4) | (c[7] + LV)) << 24);
+          if (ok[j]) *reinterpret_cast<uint32_t*>(packed + (idx >> 1)) = w;
         } else if (BITS == 8) {
-          uint32_t w = (uint32_t)(c0 + LV) | ((uint32_t)(c1 + LV) << 8) | ((uint32_t)(c2 + LV) << 16) |
-                       ((uint32_t)(c3 + LV) << 24);
-          if (ok[j]) *reinterpret_cast<uint32_t*>(packed + idx) = w;
+          uint2 w;
+          w.x = (uint32_t)(c[0] + LV) | ((uint32_t)(c[1] + LV) << 8) | ((uint32_t)(c[2] + LV) << 16) | ((uint32_t)(c[3] + LV) << 24);
+          w.y = (uint32_t)(c[4] + LV) | ((uint32_t)(c[5] + LV) << 8) | ((uint32_t)(c[6] + LV) << 16) | ((uint32_t)(c[7] + LV) << 24);
+          if (ok[j]) *reinterpret_cast<uint2*>(packed + idx) = w;
         } else {
           // big-endian offset uint16
-          uint32_t s0 = (uint32_t)(c0 + LV), s1 = (uint32_t)(c1 + LV), s2 = (uint32_t)(c2 + LV), s3 = (uint32_t)(c3 + LV);
-          uint2 w;
-          w.x = (s0 >> 8) | ((s0 & 255u) << 8) | ((s1 >> 8) << 16) | ((s1 & 255u) << 24);
-          w.y = (s2 >> 8) | ((s2 & 255u) << 8) | ((s3 >> 8) << 16) | ((s3 & 255u) << 24);
-          if (ok[j]) *reinterpret_cast<uint2*>(packed + idx * 2) = w;
+          uint32_t sw[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const uint32_t sy = (uint32_t)(c[e] + LV); sw[e] = (sy >> 8) | ((sy & 255u) << 8); }
+          uint4 w;
+          w.x = sw[0] | (sw[1] << 16); w.y = sw[2] | (sw[3] << 16); w.z = sw[4] | (sw[5] << 16); w.w = sw[6] | (sw[7] << 16);
+          if (ok[j]) *reinterpret_cast<uint4*>(packed + idx * 2) = w;
         }
       }
     }
@@ -313,24 +348,34 @@ static int quantize_bits(const float* x, int64_t rows, int64_t cols, int64_t sr,
   const int64_t numel = rows * cols;
   const bool whole = (block == numel);
   const bool contiguous = (sc == 1 && sr == cols) || (rows == 1 && sc == 1);
-  const bool fast = contiguous && aligned16(x) && (numel % 16 == 0) &&
+  auto aligned32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+  const bool fast = contiguous && aligned32(x) && (numel % 16 == 0) &&
                     (codes == nullptr || aligned16(codes)) && (packed == nullptr || aligned16(packed)) &&
                     (dequant == nullptr || aligned16(dequant)) &&
-                    (whole || block == 32 || block == 64 || block == 128);
+                    (whole || block == 32 || block == 64 || block == 128 || block == 256);
   if (fast) {
-    const int grid = grid_for((numel + 511) / 512, 8, 8);  // 8 warps per CTA, one 512-element tile per warp-iteration
+    const int grid = grid_for((numel + 1023) / 1024, 8, 8);  // 8 warps per CTA, one 1024-element tile per warp-iteration
+    const bool full = (numel % 1024 == 0);
+#define CB_QF(LPB)                                                                                               \
+  do {                                                                                                           \
+    if (full) quant_fast_kernel<BITS, LPB, true><<<grid, 256, 0, st>>>(x, numel, eps, codes, packed, scales, dequant); \
+    else quant_fast_kernel<BITS, LPB, false><<<grid, 256, 0, st>>>(x, numel, eps, codes, packed, scales, dequant);     \
+  } while (0)
     if (whole) {
       CB_CUDA(cudaMemsetAsync(scales, 0, sizeof(float), st));
       absmax_fast_kernel<<<grid_for(numel / 4, 256 * 4, 8), 256, 0, st>>>(x, numel, scales);
       CB_CHECK_LAUNCH();
-      quant_fast_kernel<BITS, 0><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+      CB_QF(0);
     } else if (block == 32) {
-      quant_fast_kernel<BITS, 8><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+      CB_QF(4);
     } else if (block == 64) {
-      quant_fast_kernel<BITS, 16><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+      CB_QF(8);
+    } else if (block == 128) {
+      CB_QF(16);
     } else {
-      quant_fast_kernel<BITS, 32><<<grid, 256, 0, st>>>(x, numel, block, eps, codes, packed, scales, dequant);
+      CB_QF(32);
     }
+#undef CB_QF
     CB_CHECK_LAUNCH();
     return CB_OK;
   }

@@ -13,9 +13,13 @@ import torch
 from . import _lib
 
 
+def workspace_bytes(c_params, m: int, n: int, h_kind: int) -> int:
+    return int(_lib.load().cb_caldera_layer_workspace_bytes(C.byref(c_params), m, n, h_kind)) or 256
+
+
 class CalderaLayerRunner:
     def __init__(self, c_params: "_lib.cb_caldera_params", m: int, n: int, h_kind: int, device: torch.device,
-                 want_packed: bool = True, want_w_scaled: bool = True):
+                 want_packed: bool = True, want_w_scaled: bool = True, workspace: Optional[torch.Tensor] = None):
         self.lib = _lib.load()
         self.p = c_params
         self.m, self.n, self.h_kind, self.device = int(m), int(n), int(h_kind), device
@@ -47,7 +51,10 @@ class CalderaLayerRunner:
                 self.R_packed = torch.empty(self.lib.cb_packed_bytes(r * n, p.r_bits), dtype=torch.uint8, device=device)
             self.W_scaled = torch.empty((m, n), **f32) if (p.scale_w and want_w_scaled) else None
             self.ws_bytes = int(self.lib.cb_caldera_layer_workspace_bytes(C.byref(p), m, n, h_kind)) or 256
-            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+            if workspace is not None and workspace.numel() >= self.ws_bytes and workspace.device == device:
+                self.ws = workspace
+            else:
+                self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.out = _lib.cb_caldera_out()
         for name in ("Q", "L", "R", "Q_idxs", "Q_scale", "Q_packed", "L_idxs", "R_idxs", "L_scale", "R_scale",
                      "L_packed", "R_packed", "W_scaled"):
