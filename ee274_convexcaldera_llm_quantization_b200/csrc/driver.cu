@@ -404,17 +404,22 @@ split3_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int trans
   }
 }
 
-static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
-  if (P.use_tc) {
+static int lr_product_raw(bool use_tc, const float* Lcur, const float* Rcur, int64_t m, int64_t n, int64_t r,
+                          float* LRbuf, bf16* Lb16, bf16* Rtb16, int* watchdog, cudaStream_t st) {
+  if (use_tc) {
     // A' = [Lh | Lh | Ll] (m x 3r),  B' = [Rh^T | Rl^T | Rh^T] (n x 3r)
-    split3_kernel<<<grid_for(m * r, 256 * 4, 4), 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16);
+    split3_kernel<<<grid_for(m * r, 256 * 4, 4), 256, 0, st>>>(Lcur, m, r, 0, 0, Lb16);
     CB_CHECK_LAUNCH();
-    split3_kernel<<<grid_for(r * n, 256 * 4, 4), 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16);
+    split3_kernel<<<grid_for(r * n, 256 * 4, 4), 256, 0, st>>>(Rcur, r, n, 1, 1, Rtb16);
     CB_CHECK_LAUNCH();
-    return gemm_tc(m, n, 3 * r, 1.f, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
-                   P.flags + 4, nullptr, st);
+    return gemm_tc(m, n, 3 * r, 1.f, Lb16, 3 * r, Rtb16, 3 * r, LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
+                   watchdog, nullptr, st);
   }
-  return sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st);
+  return sgemm(m, n, r, 1.f, Lcur, r, 1, Rcur, n, 1, LRbuf, n, 1, false, nullptr, st);
+}
+
+static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
+  return lr_product_raw(P.use_tc, P.Lcur, P.Rcur, m, n, r, P.LRbuf, P.Lb16, P.Rtb16, P.flags + 4, st);
 }
 
 static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
@@ -690,4 +695,116 @@ extern "C" int cb_weighted_error(const float* W, int64_t m, int64_t n, const voi
   CB_TRY(err_accum(W, q_codes, q_codes != nullptr ? q_bits : 8, q_scale, LRbuf, hw, m, n, out_num, st));
   if (out_den != nullptr) CB_TRY(err_accum(W, nullptr, 8, nullptr, nullptr, hw, m, n, out_den, st));
   return CB_OK;
+}
+
+// ---------------------------------------------------------------- Convex-CALDERA prox solver
+// Accelerated proximal gradient on the reduced program of oracle/convex_oracle.py
+// (solve_convex_optimization, RCR/convex_caldera/decomposition/convex_caldera.py:128-241, as
+// documented in README.md:89-93).  One iteration = one fused pass forming both prox arguments,
+// a rank-capped randomized singular-value thresholding of V_L (the same subspace iteration /
+// Rayleigh-Ritz machinery as LR_init, warm-started from the previous iterate), a dense rebuild of
+// L, and a fused radial shrink of R with the smooth part of the objective.
+namespace cb {
+struct ConvexPlan {
+  float *VL, *VR, *Lw;
+  bf16 *Lb16, *Rtb16;
+  int* flags;
+  LowrankBufs lr;
+  LowrankTcBufs tc;
+  bool use_tc;
+};
+static int plan_convex(Arena& a, int64_t m, int64_t n, int64_t r, int64_t q, int use_tensor_cores, ConvexPlan& P) {
+  P.VL = a.take<float>(m * n);
+  P.VR = a.take<float>(m * n);
+  P.Lw = a.take<float>(m * r);
+  P.flags = a.take<int>(8);
+  P.lr = plan_lowrank(a, m, n, q, nullptr, nullptr);
+  P.use_tc = use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, q);
+  if (P.use_tc) {
+    P.tc = plan_lowrank_tc(a, m, n, q, nullptr);
+    P.Lb16 = a.take<bf16>(3 * m * r);
+    P.Rtb16 = a.take<bf16>(3 * n * r);
+  }
+  return a.ok() ? CB_OK : CB_ERR_WORKSPACE;
+}
+}  // namespace cb
+
+extern "C" size_t cb_convex_prox_workspace_bytes(int64_t m, int64_t n, int64_t rank_cap, int64_t q_width,
+                                                 int use_tensor_cores) {
+  if (m <= 0 || n <= 0 || rank_cap < 1 || q_width < rank_cap || q_width > 512 || q_width > m || q_width > n) return 0;
+  Arena a{nullptr, 0, 0};
+  ConvexPlan P{};
+  plan_convex(a, m, n, rank_cap, q_width, use_tensor_cores, P);
+  return a.off + 256;
+}
+
+extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, int64_t n, float mu, float tau_star,
+                                    float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                                    int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                                    int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                                    float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  if (W == nullptr || L == nullptr || Lp == nullptr || R == nullptr || Rp == nullptr || Lf == nullptr ||
+      Rf == nullptr || svals == nullptr || scalars == nullptr || theta_io == nullptr || ws == nullptr)
+    return CB_ERR_ARG;
+  if (m <= 0 || n <= 0 || rank_cap < 1 || q_width < rank_cap || q_width > m || q_width > n || n_iters < 0) return CB_ERR_ARG;
+  if (q_width > 512) return CB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t r = rank_cap, q = q_width;
+  Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+  ConvexPlan P{};
+  CB_TRY(plan_convex(a, m, n, r, q, use_tensor_cores, P));
+  P.lr.status = P.flags;
+  P.tc.status = P.flags;
+  if (!warm) CB_CUDA(cudaMemsetAsync(P.flags, 0, sizeof(int) * 8, st));
+  const bool constrained = mu < 0.f;
+  float *Lc = L, *Lprev = Lp, *Rc = R, *Rprev = Rp;
+  double theta = *theta_io;
+  bool warm_valid = warm != 0;
+  for (int it = 0; it < n_iters; ++it) {
+    const double theta_next = (1.0 + sqrt(1.0 + 4.0 * theta * theta)) / 2.0;
+    const float beta = (float)((theta - 1.0) / theta_next);
+    theta = theta_next;
+    CB_CUDA(cudaMemsetAsync(scalars + 3, 0, sizeof(double) * 2, st));        // smooth term, ||V_R||^2
+    CB_TRY(cvx_point(W, Lc, Lprev, Rc, Rprev, h, m, n, beta, step_t, P.VL, P.VR, scalars + 4, st));
+    // singular-value thresholding of V_L: top-r factors U sqrt(S), sqrt(S) V^T and S^2
+    const float* sig2;
+    if (P.use_tc) {
+      CB_TRY(to_bf16(P.VL, m, n, n, P.tc.Yb, n, P.tc.Ytb, m, nullptr, st));
+      CB_TRY(lowrank_core_tc(m, n, r, q, power_iters, seed + 977ull * (uint64_t)it, 0, nullptr, warm_valid, Lf, Rf,
+                             nullptr, nullptr, P.tc, st));
+      sig2 = P.tc.evals;
+    } else {
+      CB_TRY(lowrank_core(P.VL, m, n, r, q, power_iters, seed + 977ull * (uint64_t)it, 0, nullptr, warm_valid, Lf, Rf,
+                          P.lr, st));
+      sig2 = P.lr.evals;
+    }
+    warm_valid = true;
+    CB_TRY(cvx_shrink(sig2, (int)r, step_t * (constrained ? 0.f : mu), tau_star, constrained ? 1 : 0, scalars + 4,
+                      step_t * lambda_reg, kappa, q0, svals + r, svals, scalars, st));
+    CB_TRY(scale_cols(Lf, m, r, svals + r, 0, P.Lw, st));
+    // the new L overwrites the buffer of the iterate before last, then roles rotate
+    CB_TRY(lr_product_raw(P.use_tc, P.Lw, Rf, m, n, r, Lprev, P.Lb16, P.Rtb16, P.flags + 2, st));
+    CB_TRY(cvx_finish(W, Lprev, P.VR, h, m, n, scalars, Rprev, scalars + 3, st));
+    float* tmp = Lc; Lc = Lprev; Lprev = tmp;
+    tmp = Rc; Rc = Rprev; Rprev = tmp;
+  }
+  if (Lc != L) {
+    // odd number of iterations: swap contents so that (L, R) hold the iterate and (Lp, Rp) the previous one
+    CB_CUDA(cudaMemcpyAsync(P.VL, L, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(L, Lp, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(Lp, P.VL, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(P.VR, R, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(R, Rp, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(Rp, P.VR, sizeof(float) * m * n, cudaMemcpyDeviceToDevice, st));
+  }
+  *theta_io = theta;
+  return CB_OK;
+}
+
+extern "C" int cb_scale_f32(const float* X, int64_t rows, int64_t cols, const float* v, int axis, int mode, float* out,
+                            void* stream) {
+  if (X == nullptr || v == nullptr || out == nullptr || rows <= 0 || cols <= 0 || mode < 0 || mode > 3) return CB_ERR_ARG;
+  return axis == 0 ? cb::scale_rows(X, rows, cols, v, mode, out, (cudaStream_t)stream)
+                   : cb::scale_cols(X, rows, cols, v, mode, out, (cudaStream_t)stream);
 }

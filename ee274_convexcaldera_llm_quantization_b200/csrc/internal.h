@@ -50,6 +50,12 @@ int form_e(const float* Ws, const void* codes, int bits, const float* qscale, co
            float* E, cudaStream_t st);
 int dot_accum(const float* a, const float* b, int64_t numel, double* out, cudaStream_t st);
 int symmetrize(const float* H, int64_t n, float* Hs, cudaStream_t st);
+int cvx_point(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, const float* h,
+              int64_t m, int64_t n, float beta, float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st);
+int cvx_shrink(const float* sigma2, int r, float thresh, float tau_star, int constrained, const double* vr_sumsq,
+               float t_lambda, float kappa, float q0, float* colw, float* s_out, double* sc, cudaStream_t st);
+int cvx_finish(const float* W, const float* Lnew, const float* VR, const float* h, int64_t m, int64_t n, const double* sc,
+               float* Rnew, double* smooth, cudaStream_t st);
 
 // gemm_tc.cu -- tcgen05 path: C[M,N] (+)= alpha * A[M,K] * B[N,K]^T, bf16 K-major operands
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);

@@ -341,6 +341,176 @@ symmetrize_kernel(const float* __restrict__ H, int64_t n, float* __restrict__ Hs
   }
 }
 
+// ---------------------------------------------------------------- Convex-CALDERA prox steps
+// Extrapolation point, gradient of the smooth term and the two prox arguments in one pass
+// (diagonal H):  Y = X + beta (X - Xprev);  G = (W - Y_L - Y_R) (.) h;  V = Y + t G.
+// Also accumulates ||V_R||_F^2 for the radial shrink of the R block.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_point_kernel(const float* __restrict__ W, const float* __restrict__ L, const float* __restrict__ Lp,
+                 const float* __restrict__ R, const float* __restrict__ Rp, const float* __restrict__ h,
+                 int64_t numel, int64_t n, float beta, float t, float* __restrict__ VL, float* __restrict__ VR,
+                 double* __restrict__ vr_sumsq) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
+    FVec<VEC> w, l, lp, r, rp, hv, vl, vr;
+    w.load_stream(W + i); l.load(L + i); lp.load_stream(Lp + i); r.load(R + i); rp.load_stream(Rp + i);
+    if (h != nullptr) hv.load(h + j);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float yl = l.v[k] + beta * (l.v[k] - lp.v[k]);
+      const float yr = r.v[k] + beta * (r.v[k] - rp.v[k]);
+      const float g = (w.v[k] - yl - yr) * (h != nullptr ? hv.v[k] : 1.f);
+      vl.v[k] = fmaf(t, g, yl);
+      vr.v[k] = fmaf(t, g, yr);
+      part = fmaf(vr.v[k], vr.v[k], part);
+    }
+    vl.store(VL + i);
+    vr.store(VR + i);
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(vr_sumsq, acc);
+}
+
+// sc[]: [0] nuclear norm of the new L, [1] alpha, [2] ||R_new||^2; sigma2[] are squared singular
+// values of V_L (descending).  Writes the column weights w_i = shrink(sigma_i) / sqrt(sigma_i) ... see below.
+// The factors handed over are Lf = U sqrt(S), Rf = sqrt(S) V^T, so  U diag(s') V^T = (Lf diag(s'/S)) Rf.
+__global__ void __launch_bounds__(512)
+cvx_shrink_kernel(const float* __restrict__ sigma2, int r, float thresh, float tau_star, int constrained,
+                  const double* __restrict__ vr_sumsq, float t_lambda, float kappa, float q0,
+                  float* __restrict__ colw, float* __restrict__ s_out, double* __restrict__ sc) {
+  __shared__ float s_sig[512];
+  __shared__ float s_theta;
+  const int tid = threadIdx.x;
+  if (tid < r) s_sig[tid] = sqrtf(fmaxf(sigma2[tid], 0.f));
+  __syncthreads();
+  if (tid == 0) {
+    float theta = thresh;
+    if (constrained) {
+      // projection of the (descending, non-negative) singular values onto {sum <= tau_star}
+      double css = 0.0;
+      for (int i = 0; i < r; ++i) css += s_sig[i];
+      theta = 0.f;
+      if (css > (double)tau_star) {
+        double run = 0.0;
+        int kk = 0;
+        for (int i = 0; i < r; ++i) {
+          run += s_sig[i];
+          if ((double)s_sig[i] * (i + 1) > run - (double)tau_star) kk = i;
+        }
+        run = 0.0;
+        for (int i = 0; i <= kk; ++i) run += s_sig[i];
+        theta = (float)((run - (double)tau_star) / (double)(kk + 1));
+      }
+    }
+    s_theta = theta;
+  }
+  __syncthreads();
+  float mine = 0.f;
+  if (tid < r) {
+    const float sg = s_sig[tid];
+    mine = fmaxf(sg - s_theta, 0.f);
+    colw[tid] = sg > 0.f ? mine / sg : 0.f;
+    s_out[tid] = mine;
+  }
+  __shared__ float red[16];
+  float tot = warp_sum(mine);
+  if ((tid & 31) == 0) red[tid >> 5] = tot;
+  __syncthreads();
+  if (tid == 0) {
+    double nuc = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) nuc += red[w];
+    // radial prox of t*lambda*max(q0, ||R||^2 / kappa) at V_R
+    const double v = vr_sumsq[0];
+    double alpha = 1.0;
+    if (v / kappa > q0) {
+      const double a1 = 1.0 / (1.0 + 2.0 * t_lambda / kappa);
+      alpha = (a1 * a1 * v / kappa >= q0) ? a1 : sqrt((double)q0 * kappa / v);
+    }
+    sc[0] = nuc;
+    sc[1] = alpha;
+    sc[2] = alpha * alpha * v;
+  }
+}
+
+// R_new = alpha V_R, and the smooth term 1/2 sum_j h_j (W - L_new - R_new)^2
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_finish_kernel(const float* __restrict__ W, const float* __restrict__ Lnew, const float* __restrict__ VR,
+                  const float* __restrict__ h, int64_t numel, int64_t n, const double* __restrict__ sc,
+                  float* __restrict__ Rnew, double* __restrict__ smooth) {
+  __shared__ double red[32];
+  const float alpha = (float)sc[1];
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    const int64_t j = CB_CHUNK_COL(VEC, n);
+    FVec<VEC> w, l, v, hv;
+    w.load_stream(W + i); l.load(Lnew + i); v.load_stream(VR + i);
+    if (h != nullptr) hv.load(h + j);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      v.v[k] *= alpha;
+      const float e = w.v[k] - l.v[k] - v.v[k];
+      part = fmaf((h != nullptr ? hv.v[k] : 1.f) * e, e, part);
+    }
+    v.store(Rnew + i);
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(smooth, 0.5 * acc);
+}
+
+// quantize_residual (convex_caldera.py:342-373): delta = 2 t / (2^b - 1) (t / 2^15 for b = 16),
+// R_int = clamp(rint(R / delta), +-(2^(b-1) - 1)); out = base + delta * R_int
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_quant_residual_kernel(const float* __restrict__ R, const float* __restrict__ base, int64_t numel, const float* __restrict__ amax,
+                          int bits, float* __restrict__ Rq, float* __restrict__ Wc, float* __restrict__ delta_out) {
+  const float tmax = amax[0];
+  const float delta = bits < 16 ? __fdiv_rn(2.f * tmax, (float)((1 << bits) - 1)) : __fdiv_rn(tmax, 32768.f);
+  const float mx = (float)((1 << (bits - 1)) - 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) delta_out[0] = delta;
+  const ScaleRecip dr = make_scale_recip(delta);
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> r, b, q, wc;
+    r.load_stream(R + i);
+    if (base != nullptr) b.load_stream(base + i);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float c = rintf(div_by_scale(r.v[k], dr));
+      c = fminf(fmaxf(c, -mx), mx);
+      q.v[k] = __fmul_rn(delta, c);
+      wc.v[k] = base != nullptr ? b.v[k] + q.v[k] : q.v[k];
+    }
+    q.store(Rq + i);
+    if (Wc != nullptr) wc.store(Wc + i);
+  }
+}
+
+// out[0] += sum x, out[1] += sum x^2, out[2] += sum (x - y)^2 (y may be null)
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t numel, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const double v = (double)x[i];
+    s1 += v;
+    s2 += v * v;
+    if (y != nullptr) { const double d = v - (double)y[i]; s3 += d * d; }
+  }
+  s1 = block_sum(s1, red); s2 = block_sum(s2, red); s3 = block_sum(s3, red);
+  if (threadIdx.x == 0) { atomicAdd(out, s1); atomicAdd(out + 1, s2); atomicAdd(out + 2, s3); }
+}
+
 // ---------------------------------------------------------------- selection / bookkeeping
 __global__ void select_outer_kernel(double* num, const double* den, float* errors, int step, float* scalars,
                                     int* flags, int all_updated) {
@@ -562,6 +732,34 @@ int symmetrize(const float* H, int64_t n, float* Hs, cudaStream_t st) {
   return CB_OK;
 }
 
+int cvx_point(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, const float* h,
+              int64_t m, int64_t n, float beta, float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {W, L, Lp, R, Rp, h, VL, VR}))
+    cvx_point_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, L, Lp, R, Rp, h, numel, n, beta, t, VL, VR, vr_sumsq);
+  else
+    cvx_point_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, L, Lp, R, Rp, h, numel, n, beta, t, VL, VR, vr_sumsq);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int cvx_shrink(const float* sigma2, int r, float thresh, float tau_star, int constrained, const double* vr_sumsq,
+               float t_lambda, float kappa, float q0, float* colw, float* s_out, double* sc, cudaStream_t st) {
+  if (r > 512) return CB_ERR_UNSUPPORTED;
+  cvx_shrink_kernel<<<1, 512, 0, st>>>(sigma2, r, thresh, tau_star, constrained, vr_sumsq, t_lambda, kappa, q0, colw, s_out, sc);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int cvx_finish(const float* W, const float* Lnew, const float* VR, const float* h, int64_t m, int64_t n, const double* sc,
+               float* Rnew, double* smooth, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {W, Lnew, VR, h, Rnew}))
+    cvx_finish_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Lnew, VR, h, numel, n, sc, Rnew, smooth);
+  else
+    cvx_finish_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Lnew, VR, h, numel, n, sc, Rnew, smooth);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
 }  // namespace cb
 
 extern "C" int cb_hessian_probe(const float* H, int64_t n, float* diag, int* is_diag, void* stream) {
@@ -571,6 +769,29 @@ extern "C" int cb_hessian_probe(const float* H, int64_t n, float* diag, int* is_
   cb::hessian_probe_kernel<<<cb::grid_for(n * n, 256 * 8, 4), 256, 0, st>>>(H, n, diag, is_diag);
   CB_CHECK_LAUNCH();
   cb::probe_finish_kernel<<<1, 1, 0, st>>>(is_diag);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" int cb_sum_stats(const float* x, const float* y, int64_t numel, double* out3, void* stream) {
+  if (x == nullptr || out3 == nullptr || numel < 0) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cb::stats_kernel<<<cb::grid_for(numel, 256 * 8, 4), 256, 0, st>>>(x, y, numel, out3);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" int cb_quantize_residual_f32(const float* R, const float* base, int64_t rows, int64_t cols, int bits,
+                                        float* Rq, float* Wc, float* delta_out, float* scratch, void* stream) {
+  if (R == nullptr || Rq == nullptr || delta_out == nullptr || scratch == nullptr || rows <= 0 || cols <= 0) return CB_ERR_ARG;
+  if (bits < 2 || bits > 16) return CB_ERR_BITS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t numel = rows * cols;
+  CB_TRY(cb::resid_absmax(R, nullptr, numel, scratch, st));
+  if (cb::can_vec4(cols, {R, base, Rq, Wc}))
+    cb::cvx_quant_residual_kernel<4><<<cb::grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(R, base, numel, scratch, bits, Rq, Wc, delta_out);
+  else
+    cb::cvx_quant_residual_kernel<1><<<cb::grid_for(numel, 256 * 4, 8), 256, 0, st>>>(R, base, numel, scratch, bits, Rq, Wc, delta_out);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

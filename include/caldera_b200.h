@@ -21,9 +21,9 @@
  *                           quantize_matrix :245-250, activation_aware_error :286-302)
  *   cb_lowrank_init        LR_init                   RCR/caldera/decomposition/alg.py:201-235
  *   cb_weighted_error      activation_aware_error    RCR/caldera/decomposition/alg.py:286-302
- *   cb_convex_prox_layer   solve_convex_optimization + low_rank_factorization +
- *                          quantize_residual + compute_certificates
- *                          RCR/convex_caldera/decomposition/convex_caldera.py:128-419
+ *   cb_convex_prox_iters   solve_convex_optimization  RCR/convex_caldera/decomposition/convex_caldera.py:128-241
+ *   cb_quantize_residual_f32  quantize_residual        RCR/convex_caldera/decomposition/convex_caldera.py:342-373
+ *   cb_sum_stats           kappa / c / certificates     RCR/convex_caldera/decomposition/convex_caldera.py:120-123, 404-406
  */
 #ifndef CALDERA_B200_H
 #define CALDERA_B200_H
@@ -201,6 +201,43 @@ size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, i
 int cb_caldera_layer(const cb_caldera_params* p, const float* W, int64_t m, int64_t n,
                      const float* h, int h_kind, const cb_caldera_out* out,
                      void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- Convex-CALDERA */
+
+/* out3[0] += sum x, out3[1] += sum x^2, out3[2] += sum (x - y)^2 (y may be NULL); device doubles the
+ * caller zeroes.  kappa = ||W||_F, c = 0.1 var(W) (convex_caldera.py:120-123) and the
+ * certificates (convex_caldera.py:404-406) are built from these. */
+int cb_sum_stats(const float* x, const float* y, int64_t numel, double* out3, void* stream);
+
+/* n_iters accelerated proximal-gradient iterations of the reduced Convex-CALDERA program
+ *   min 1/2 ||(W-L-R) diag(h)^(1/2)||_F^2 + mu ||L||_* + lambda max(q0, ||R||_F^2 / kappa)
+ * (mu < 0 selects the constrained form ||L||_* <= tau_star).  Replaces the CVXPY/SCS solve of
+ * solve_convex_optimization (convex_caldera.py:128-241); see oracle/convex_oracle.py for the
+ * reduction.  State L, Lp, R, Rp (m x n, zero-initialised by the caller for a cold start) is
+ * updated in place; Lf (m x rank_cap) and Rf (rank_cap x n) receive U sqrt(S), sqrt(S) V^T of
+ * the last thresholding argument, svals[0:rank_cap] the thresholded singular values of L and
+ * svals[rank_cap:2*rank_cap] the ratios s'/S.  scalars (device doubles, >= 5): [0] ||L||_*,
+ * [1] radial factor, [2] ||R||_F^2, [3] smooth term, [4] scratch.  *theta_io is the host-side
+ * FISTA momentum state (start at 1.0; reset to 1.0 to restart). */
+int cb_convex_prox_iters(const float* W, const float* h, int64_t m, int64_t n, float mu, float tau_star,
+                         float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                         int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                         int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                         float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                         void* stream);
+size_t cb_convex_prox_workspace_bytes(int64_t m, int64_t n, int64_t rank_cap, int64_t q_width,
+                                      int use_tensor_cores);
+
+/* quantize_residual (convex_caldera.py:342-373): delta = 2 max|R| / (2^bits - 1) (max|R| / 2^15 for
+ * bits == 16), R_int = clamp(rint(R / delta), +-(2^(bits-1) - 1)), Rq = delta * R_int and, when
+ * base/Wc are given, Wc = base + Rq (the reconstruction L* + delta R_int, :484-485).
+ * scratch: one device float. */
+int cb_quantize_residual_f32(const float* R, const float* base, int64_t rows, int64_t cols, int bits,
+                             float* Rq, float* Wc, float* delta_out, float* scratch, void* stream);
+
+/* out = X scaled along rows (axis 0) or columns (axis 1) by v: mode 0 multiply, 1 divide. */
+int cb_scale_f32(const float* X, int64_t rows, int64_t cols, const float* v, int axis, int mode, float* out,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,86 @@
+"""GPU convex_caldera() (cb_convex_prox_iters + post-processing) against the numpy oracle.
+The oracle is the documented program, not a run of the reference (which cannot run: no
+cvxpy, infeasible cone) -- parity for this entry point is "unpinned" (DESIGN.md section 5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import convex_oracle as co
+from src.convex_caldera.decomposition.convex_caldera import ConvexCalderaParams, convex_caldera
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _problem(seed, m, n, decay=1.0):
+    rng = np.random.default_rng(seed)
+    U = np.linalg.qr(rng.standard_normal((m, m)))[0]
+    V = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    k = min(m, n)
+    s = 2.0 * np.arange(1, k + 1) ** -decay
+    W = ((U[:, :k] * s) @ V[:k, :] + 0.01 * rng.standard_normal((m, n))).astype(np.float32)
+    h = (0.5 + rng.random(n)).astype(np.float32)
+    return W, h
+
+
+@pytest.mark.parametrize("m,n,mu,lam,tau,tc", [
+    (96, 128, 0.01, 0.5, None, False), (96, 128, 0.1, 0.01, None, False), (128, 96, None, 0.5, 3.0, False),
+    (320, 256, 0.02, 1.0, None, True), (320, 256, 0.02, 1.0, None, False)])
+def test_matches_oracle(m, n, mu, lam, tau, tc):
+    W, h = _problem(m + n, m, n)
+    kw = dict(mu=mu, lambda_reg=lam, tau_star=tau, B_tot=4.0, solver_tol=1e-7)
+    ref = co.convex_oracle(W, np.diag(h), params=co.ConvexOracleParams(max_iters=1500, **kw))
+    rank_cap = min(m, n)                      # no truncation: same program as the dense-SVD oracle
+    d = convex_caldera(torch.from_numpy(W), torch.from_numpy(h), params=ConvexCalderaParams(**kw), device=DEV,
+                       rank_cap=min(rank_cap, 224), sketch_width=min(rank_cap, 224), power_iters=3, max_iters=1500,
+                       check_every=25, use_tensor_cores=tc)
+    tol = 2e-3 if tc else 5e-4
+    assert abs(d.objective_value - ref["objective_value"]) <= tol * abs(ref["objective_value"]), \
+        (d.objective_value, ref["objective_value"])
+    assert d.b_star[0] == ref["b_star"] and d.b_discrete[0] == ref["b_discrete"]
+    assert abs(d.group_info["kappa"] - ref["kappa"]) < 1e-4 * ref["kappa"]
+    assert abs(d.group_info["c"] - ref["c"]) < 1e-4 * ref["c"]
+    rel_ref = ref["certificates"]["relative_error"]
+    assert abs(d.duality_gap - rel_ref) <= max(5e-3, 0.05 * rel_ref), (d.duality_gap, rel_ref)
+    # structure of the result (convex_caldera.py:494-514)
+    assert d.L_star.shape == d.R_star.shape == d.W_compressed.shape == (m, n)
+    assert torch.allclose(d.W_compressed, d.L_star + d.R_star, atol=1e-6)
+    L, R = d.group_info["L"], d.group_info["R_lr"]
+    assert L.shape == (m, d.effective_rank) and R.shape == (d.effective_rank, n)
+    if ref["nuclear_norm"] > 0:
+        assert abs(float(d.group_info["singular_values"].sum()) - ref["nuclear_norm"]) <= 2e-2 * ref["nuclear_norm"]
+        rel = float((L @ R - d.L_star).norm() / d.L_star.norm().clamp_min(1e-12))
+        assert rel < (2e-2 if tc else 2e-3), rel
+    else:
+        assert d.effective_rank == 0 and float(d.L_star.abs().max()) < 1e-5
+    # the residual lives on the reference's grid: integer multiples of delta, clamped
+    delta = d.group_info["delta"]
+    codes = d.R_star / delta
+    assert float((codes - codes.round()).abs().max()) < 1e-3
+    assert float(codes.abs().max()) <= 2 ** (int(d.b_discrete[0]) - 1) - 1 + 1e-3
+
+
+def test_quantize_residual_matches_reference_arithmetic():
+    from ee274_convexcaldera_llm_quantization_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    R = torch.randn(64, 96, generator=g)
+    for bits in (2, 3, 4, 8, 16):
+        want, delta = co.quantize_residual(R.numpy(), bits)
+        Rd = R.to(DEV)
+        out = torch.empty_like(Rd)
+        dd = torch.empty(2, device=DEV)
+        _lib.check(lib.cb_quantize_residual_f32(_lib.ptr(Rd), None, 64, 96, bits, _lib.ptr(out), None, _lib.ptr(dd[0:1]),
+                                                _lib.ptr(dd[1:2]), _lib.stream_ptr()), "qres")
+        assert abs(float(dd[0]) - delta) <= 1e-7 * delta
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_error_conventions():
+    W = torch.randn(32, 32)
+    with pytest.raises(ValueError):
+        convex_caldera(W, params=ConvexCalderaParams(B_tot=1.0, b_min=2.0), device=DEV)
+    with pytest.raises(NotImplementedError):
+        convex_caldera(W, calibration_data=torch.randn(100, 32), device=DEV)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        convex_caldera(W, device="cpu")
