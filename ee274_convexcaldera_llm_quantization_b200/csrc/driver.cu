@@ -225,7 +225,8 @@ struct LayerPlan {
   float *Lscale_cur, *Rscale_cur, *Lscale_in, *Rscale_in;
   LowrankBufs lr;
   LowrankTcBufs tc;
-  bf16 *Lb16, *Rtb16;   // bf16 copies of L (m x r) and R^T (n x r) for the tensor-core L R product
+  bf16 *Lb16, *Rtb16;   // bf16 hi/lo splits of L (m x 3r) and R^T (n x 3r) for the tensor-core L R product
+  bf16 *Rsb16, *Ltb16;  // LPLR operands: R (.) sqrt(h) (r x n) and L^T (r x m)
   // dense (non-diagonal) Hessian
   float *Hs, *Ebuf, *Tbuf, *HP, *HRt;
   int64_t q;
@@ -264,6 +265,10 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
       L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr);
       L.Lb16 = a.take<bf16>(3 * m * r);
       L.Rtb16 = a.take<bf16>(3 * n * r);
+      if (L.quant_factors) {
+        L.Rsb16 = a.take<bf16>(r * n);
+        L.Ltb16 = a.take<bf16>(r * m);
+      }
     }
     if (L.quant_factors) {
       L.Rw = a.take<float>(r * n);
@@ -464,6 +469,52 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
   return CB_OK;
 }
 
+// Tensor-core variant of the LPLR loop (diagonal / identity Hessian): the three m x n x r
+// contractions per inner iteration run on gemm_tc against the bf16 operands Yb = res (.) sqrt(h)
+// and Ytb = Yb^T that the rank-r step already built:
+//   res diag(h) R^T = Yb (R (.) sqrt(h))^T,        L^T res = (L^T Ytb^T) (.) 1/sqrt(h)
+// The r x r Gram matrices are accumulated in fp32 (split-K atomics) and factorised in fp32.
+static int lplr_refine_tc(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+  const int64_t r = p->rank;
+  const float* res = p->aware ? P.RES : P.Y;
+  int* wd = P.flags + 4;
+  for (int k = 0; k < p->lplr_iters; ++k) {
+    // ---- L update (alg.py:163 / :167)
+    CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st));
+    CB_CUDA(cudaMemsetAsync(P.Gs, 0, sizeof(float) * r * r, st));
+    CB_TRY(gemm_tc(r, r, n, 1.f, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+    CB_CUDA(cudaMemsetAsync(P.Bl, 0, sizeof(float) * m * r, st));
+    CB_TRY(gemm_tc(m, r, n, 1.f, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));
+    // ---- R update (alg.py:175)
+    CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st));
+    CB_CUDA(cudaMemsetAsync(P.Gs, 0, sizeof(float) * r * r, st));
+    CB_TRY(gemm_tc(r, r, m, 1.f, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+    CB_CUDA(cudaMemsetAsync(P.Br, 0, sizeof(float) * r * n, st));
+    CB_TRY(gemm_tc(r, n, m, 1.f, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr,
+                   nullptr, 0, wd, nullptr, st));
+    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));
+    // ---- inner error and best-so-far (alg.py:182-188)
+    CB_TRY(lr_product(P, m, n, r, st));
+    CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
+    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
+    const int* f = P.flags + 1;
+    CB_TRY(copy_if(f, P.Lb, P.Lcur, sizeof(float) * m * r, st));
+    CB_TRY(copy_if(f, P.Rb, P.Rcur, sizeof(float) * r * n, st));
+    CB_TRY(copy_if(f, P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits), st));
+    CB_TRY(copy_if(f, P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits), st));
+    CB_TRY(copy_if(f, P.Lscale_in, P.Lscale_cur, sizeof(float), st));
+    CB_TRY(copy_if(f, P.Rscale_in, P.Rscale_cur, sizeof(float), st));
+  }
+  CB_CUDA(cudaMemcpyAsync(P.Lcur, P.Lb, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(P.Rcur, P.Rb, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  return CB_OK;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -571,7 +622,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
                               warm_valid && p->warm_start, P.Lcur, P.Rcur, P.lr, st));
         }
         warm_valid = true;
-        if (P.quant_factors) CB_TRY(lplr_refine(p, P, m, n, st));
+        if (P.quant_factors) CB_TRY(P.use_tc ? lplr_refine_tc(p, P, m, n, st) : lplr_refine(p, P, m, n, st));
         have_lr = true;
         CB_TRY(lr_product(P, m, n, r, st));
         lrbuf_valid = true;
