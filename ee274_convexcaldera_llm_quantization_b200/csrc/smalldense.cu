@@ -16,9 +16,8 @@ constexpr int QMAX = 512;       // largest supported matrix
 constexpr int TMAXR = QMAX - NB;  // most rows below a diagonal block
 
 struct CholSmem {
-  float D[NB][NB + 1];             // diagonal block / its Cholesky factor
-  float Di[NB][NB + 1];            // inverse of the factor
-  float Praw[TMAXR][NB + 1];       // panel rows before the triangular solve (row-major)
+  float D[NB][NB + 4];             // diagonal block / its Cholesky factor (rows 16-byte aligned)
+  float Praw[TMAXR][NB + 1];       // scratch shared with the triangular-inverse chains
   float Pt[NB][TMAXR + 4];         // solved panel, transposed: Pt[c][row]
   float diag0[QMAX];               // backup of the diagonal for the ridge retry
   float rdiag[NB];                 // reciprocal diagonal of the current 32 x 32 factor
@@ -28,21 +27,22 @@ struct CholSmem {
 
 // In-place Cholesky of the lower triangle of G (row-major, leading dimension q).  The strict
 // upper triangle is never written, so together with diag0 it is a backup of the input.
-__device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Linv, CholSmem& s) {
+// Per 32-wide panel: (1) warp 0 factors the diagonal block in registers (lane = row, all
+// indices static after unrolling, broadcasts by shuffle); (2) every thread owns one row below
+// the block and solves x L_kk^T = a by forward substitution in registers, reading L_kk as
+// 128-bit shared-memory broadcasts; (3) 4 x 4 register tiles apply the rank-32 update to the
+// trailing lower triangle from the transposed panel in shared memory.
+__device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k0 = 0; k0 < q; k0 += NB) {
     const int nb = min(NB, q - k0);
-    // 1. diagonal block -> shared
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int i = e >> 5, j = e & 31;
       float v = 0.f;
       if (i < nb && j <= i) v = G[(size_t)(k0 + i) * q + k0 + j];
       s.D[i][j] = v;
-      s.Di[i][j] = 0.f;
     }
     __syncthreads();
-    // 2. warp 0 factorises it and inverts the factor, entirely in registers: lane i owns
-    //    row i of the block (a[c], fully unrolled so indexing is static) and column i of the inverse
     if (warp == 0) {
       float a[NB];
 #pragma unroll
@@ -68,56 +68,50 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
       }
       if (bad && lane == 0) s.fail = 1;
 #pragma unroll
-      for (int c = 0; c < NB; ++c) s.D[lane][c] = a[c];       // row `lane` of the factor
-      __syncwarp();
-      // inverse X = L^-1, lane = column: x_i = (delta_ic - sum_{k<i} L[i][k] x_k) / L[i][i];
-      // L is read back from shared memory (broadcast) so only x[] stays in registers
-      float x[NB];
-#pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        float acc = (lane == i) ? 1.f : 0.f;
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-          if (k < i) acc = fmaf(-s.D[i][k], x[k], acc);
-        x[i] = (lane <= i) ? acc * s.rdiag[i] : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < NB; ++c) s.Di[c][lane] = x[c];      // column `lane` of the inverse
+      for (int c = 0; c < NB; ++c) s.D[lane][c] = a[c];
     }
     __syncthreads();
-    // write the factor back, publish the inverse block
+    // factor back to global
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int i = e >> 5, j = e & 31;
-      if (i < nb && j <= i) {
-        G[(size_t)(k0 + i) * q + k0 + j] = s.D[i][j];
-        if (Linv != nullptr) Linv[(size_t)(k0 + i) * q + k0 + j] = s.Di[i][j];
-      }
+      if (i < nb && j <= i) G[(size_t)(k0 + i) * q + k0 + j] = s.D[i][j];
     }
     const int T = q - k0 - nb;  // rows below the block
     if (T <= 0) { __syncthreads(); continue; }
-    // 3a. stage the raw panel (coalesced along the row)
-    for (int e = tid; e < T * NB; e += blockDim.x) {
-      const int i = e >> 5, k = e & 31;
-      s.Praw[i][k] = (k < nb) ? G[(size_t)(k0 + nb + i) * q + k0 + k] : 0.f;
-    }
-    __syncthreads();
-    // 3b. P = Praw * Lkk^-T : P[i][c] = sum_{k<=c} Praw[i][k] * Di[c][k]; lanes = consecutive rows
-    for (int e = tid; e < T * nb; e += blockDim.x) {
-      const int c = e / T, i = e - c * T;
-      float acc = 0.f;
-      for (int k = 0; k <= c; ++k) acc += s.Praw[i][k] * s.Di[c][k];
-      s.Pt[c][i] = acc;
-      G[(size_t)(k0 + nb + i) * q + k0 + c] = acc;
+    // panel: one row per thread (T <= 480 < blockDim), x <- x L_kk^-T by forward substitution
+    for (int row = tid; row < T; row += blockDim.x) {
+      float* grow = G + (size_t)(k0 + nb + row) * q + k0;
+      float x[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) x[c] = (c < nb) ? grow[c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        float acc = x[c];
+#pragma unroll
+        for (int k4 = 0; k4 < NB / 4; ++k4) {
+          if (4 * k4 < c) {
+            const float4 d = *reinterpret_cast<const float4*>(&s.D[c][4 * k4]);   // broadcast
+            if (4 * k4 + 0 < c) acc = fmaf(-x[4 * k4 + 0], d.x, acc);
+            if (4 * k4 + 1 < c) acc = fmaf(-x[4 * k4 + 1], d.y, acc);
+            if (4 * k4 + 2 < c) acc = fmaf(-x[4 * k4 + 2], d.z, acc);
+            if (4 * k4 + 3 < c) acc = fmaf(-x[4 * k4 + 3], d.w, acc);
+          }
+        }
+        x[c] = acc * s.rdiag[c];
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        if (c < nb) grow[c] = x[c];
+        s.Pt[c][row] = (c < nb) ? x[c] : 0.f;
+      }
     }
     // zero-pad the panel to a multiple of 4 rows so 128-bit reads below stay in bounds
     for (int e = tid; e < 4 * NB; e += blockDim.x) {
       const int c = e >> 2, i = T + (e & 3);
       if (i < TMAXR + 4) s.Pt[c][i] = 0.f;
     }
-    if (nb < NB)
-      for (int e = tid; e < (NB - nb) * (TMAXR + 4); e += blockDim.x) s.Pt[nb + e / (TMAXR + 4)][e % (TMAXR + 4)] = 0.f;
     __syncthreads();
-    // 4. trailing update on the lower triangle, 4x4 register tiles
+    // trailing update on the lower triangle, 4x4 register tiles
     const int Ti = (T + 3) >> 2;
     const int ntile = Ti * (Ti + 1) / 2;
     for (int t = tid; t < ntile; t += blockDim.x) {
@@ -153,6 +147,37 @@ __device__ void chol_factor(float* __restrict__ G, int q, float* __restrict__ Li
       }
     }
     __syncthreads();
+  }
+}
+
+// Inverses of all 32 x 32 diagonal blocks of the factor at once: warp b takes block b, lane =
+// row while loading / column of the inverse while solving, L[i][k] is broadcast from lane i.
+__device__ void diag_block_inverses(const float* G, int q, float* Linv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nblk = (q + NB - 1) / NB;
+  for (int b = warp; b < nblk; b += nwarps) {
+    const int r0 = b * NB, nb = min(NB, q - r0);
+    float a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      a[c] = (lane < nb && c <= lane) ? G[(size_t)(r0 + lane) * q + r0 + c] : (c == lane ? 1.f : 0.f);
+    float x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      float acc = (lane == i) ? 1.f : 0.f;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        if (k < i) {
+          const float lik = __shfl_sync(0xffffffffu, a[k], i);
+          acc = fmaf(-lik, x[k], acc);
+        }
+      }
+      const float lii = __shfl_sync(0xffffffffu, a[i], i);
+      x[i] = (lane <= i) ? acc / lii : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i < nb && lane <= i && lane < nb) Linv[(size_t)(r0 + i) * q + r0 + lane] = x[i];
   }
 }
 
@@ -266,7 +291,7 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
   int retries = 0;
 
   while (true) {
-    chol_factor(G, q, Linv, s);
+    chol_factor(G, q, s);
     __syncthreads();
     const int failed = s.fail;
     __syncthreads();
@@ -282,7 +307,11 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
     ++retries;
     __syncthreads();
   }
-  if (Linv != nullptr) tri_inverse(G, q, Linv, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
+  if (Linv != nullptr) {
+    diag_block_inverses(G, q, Linv);
+    __syncthreads();
+    tri_inverse(G, q, Linv, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
+  }
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }
 

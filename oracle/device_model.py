@@ -54,7 +54,7 @@ def weighted_err(W, h, Q, L, R, den):
 
 
 def caldera_device_model(params: OracleParams, W, h, scale_W=True, q=None, niter=None, seed=0,
-                         warm_start=True, global_scale=None):
+                         warm_start=True, global_scale=None, niter_warm=None):
     W = np.asarray(W, dtype=F32)
     m, n = W.shape
     r = params.rank
@@ -86,8 +86,9 @@ def caldera_device_model(params: OracleParams, W, h, scale_W=True, q=None, niter
             if which == "LR" and params.compute_low_rank_factors:
                 res = W - cur.Q
                 Y = res * sh[None, :] if aware else res
-                Zo, V, sig, B = subspace_lowrank(Y, r, q, niter, rng, Zprev if warm_start else None)
-                Zprev = Zo
+                ni = niter if (Zprev is None or not warm_start or niter_warm is None) else niter_warm
+                Zo, V, sig, B = subspace_lowrank(Y, r, q, ni, rng, Zprev if warm_start else None)
+                Zprev = Zo       # (the device also rotates it into Ritz vectors; the span is the same)
                 if aware:
                     L = Zo @ V.T
                     R = (V @ B) / sh[None, :]
