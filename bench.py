@@ -182,21 +182,39 @@ def roofline_probes(dev, peaks):
     out["quantize_pack_b2_bs64"] = {"bound": "hbm", "achieved": bytes_q / t / 1e9, "peak": peaks["hbm_gbs"],
                                     "unit": "GB/s", "frac": bytes_q / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                     "seconds": t, "algorithmic_bytes": bytes_q}
-    # (b) sketch contraction Z = Y P (m x n) x (n x q), the dominant kernel of the LR update
-    q = 2 * RANK
-    P = torch.randn(N, q, device=dev)
-    Z = torch.empty(M, q, device=dev)
+    # (b) sketch contraction Zt[q, m] = Pt[q, K=n] * Y[m, K=n]^T on the tcgen05 kernel: the kernel with
+    #     the largest share of GPU time per layer (ncu launch list, profiles/).  bf16 operands in HBM.
+    q = 224
+    ys = [x.bfloat16() for x in xs]
+    Pt = torch.randn(q, N, device=dev).bfloat16()
+    Zt = torch.empty(q, M, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def sketch():
+        y = ys[k[0] % 3]
+        k[0] += 1
+        lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zt), M, 1, _lib.ptr(flag),
+                            _lib.stream_ptr())
+    t = time_kernel(sketch, iters=20)
+    flops = 2.0 * M * N * q
+    out["sketch_gemm_tcgen05"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"],
+                                  "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                                  "seconds": t, "algorithmic_flops": flops,
+                                  "hbm_gbs": (2 * M * N + 2 * q * N + 4 * q * M) / t / 1e9,
+                                  "note": "skinny: arithmetic intensity q/2 = 112 flop/B on bf16 Y, "
+                                          "min(tensor peak, AI x HBM) = 733 TFLOP/s"}
+    assert int(flag.item()) == 0
+    # (c) whole-tensor quantise + pack (the form caldera() itself uses, alg.py:247): two passes
+    def quant_whole():
         x = xs[k[0] % 3]
         k[0] += 1
-        lib.cb_sgemm_strided(M, q, N, 1.0, _lib.ptr(x), N, 1, _lib.ptr(P), q, 1, _lib.ptr(Z), q, 1, 0,
-                             _lib.stream_ptr())
-    t = time_kernel(sketch, iters=10)
-    flops = 2.0 * M * N * q
-    out["sketch_gemm_fp32"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"],
-                               "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
-                               "seconds": t, "algorithmic_flops": flops}
+        lib.cb_quantize_f32(_lib.ptr(x), M, N, N, 1, 2, 0, 1e-8, None, _lib.ptr(packed), _lib.ptr(scales), None,
+                            _lib.stream_ptr())
+    t = time_kernel(quant_whole)
+    bytes_w = 8 * numel + numel // 4
+    out["quantize_pack_b2_whole"] = {"bound": "hbm", "achieved": bytes_w / t / 1e9, "peak": peaks["hbm_gbs"],
+                                     "unit": "GB/s", "frac": bytes_w / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                     "seconds": t, "algorithmic_bytes": bytes_w}
     return out
 
 
@@ -349,14 +367,14 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "l2": "per-step working set ~0.5 GiB > 126 MB L2; 3 layers rotated",
                            "layers_in_flight": nstreams, "single_layer_latency_ms": layer_latency_ms,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
-                           "sketch_width": 2 * RANK, "power_iters": 8, "peaks": peaks["source"]},
+                           "sketch_width": 224, "power_iters": 8, "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "errors_last_layer": [round(e, 6) for e in errs]}
         if world == 1:
             probes = roofline_probes(dev, peaks)
-            dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_fp32")
+            dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_tcgen05")
             line["roofline"] = {k: probes[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             line["roofline"]["kernel"] = dominant
             line["roofline_all"] = probes
@@ -379,7 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--streams", type=int, default=4, help="independent layers kept in flight per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="independent layers kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
