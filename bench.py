@@ -270,6 +270,11 @@ def run_ours(args):
     runners = [CalderaLayerRunner(cp, M, N, _lib.CB_H_DIAG, dev, want_packed=True, want_w_scaled=False)
                for _ in range(nstreams)]
     runner = runners[0]
+    if not args.no_graph:
+        for s_, r_ in zip(streams, runners):
+            with torch.cuda.stream(s_):
+                r_.capture()
+        torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -286,7 +291,10 @@ def run_ours(args):
         for i in range(count):
             W, h = dev_layers[(first + i) % npool]
             with torch.cuda.stream(streams[i % nstreams]):
-                runners[i % nstreams].enqueue(W, h)
+                if args.no_graph:
+                    runners[i % nstreams].enqueue(W, h)
+                else:
+                    runners[i % nstreams].launch(W, h, seed=1000 + rank)
         for s_ in streams:
             ev = torch.cuda.Event()
             ev.record(s_)
@@ -311,7 +319,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record()
-    runner.enqueue(*dev_layers[0])
+    if args.no_graph:
+        runner.enqueue(*dev_layers[0])
+    else:
+        runner.launch(*dev_layers[0], seed=1000 + rank)
     l1.record()
     torch.cuda.synchronize()
     layer_latency_ms = l0.elapsed_time(l1)
@@ -329,7 +340,8 @@ def run_ours(args):
         W, h = host_layers[i % npool]
         torch.cuda.set_device(dev)
         with torch.cuda.stream(e2e_streams[w]):
-            d = caldera(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank)
+            d = caldera(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank,
+                        use_cuda_graph=not args.no_graph)
             out_hosts[w]["Q_packed"].copy_(d.Q_packed, non_blocking=True)
             out_hosts[w]["L"].copy_(d.L, non_blocking=True)
             out_hosts[w]["R"].copy_(d.R, non_blocking=True)
@@ -365,7 +377,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "per-step working set ~0.5 GiB > 126 MB L2; 3 layers rotated",
-                           "layers_in_flight": nstreams, "single_layer_latency_ms": layer_latency_ms,
+                           "layers_in_flight": nstreams, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": 8, "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -397,6 +409,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
     ap.add_argument("--streams", type=int, default=8, help="independent layers kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -36,7 +36,7 @@ class cb_caldera_params(C.Structure):
 class cb_caldera_out(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in (
         "Q", "L", "R", "Q_idxs", "Q_scale", "Q_packed", "L_idxs", "R_idxs", "L_scale", "R_scale",
-        "L_packed", "R_packed", "W_scaled", "errors", "scalars")]
+        "L_packed", "R_packed", "W_scaled", "errors", "seed_dev", "scalars")]
 
 
 _SIGNATURES = {

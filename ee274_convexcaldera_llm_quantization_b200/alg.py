@@ -35,8 +35,34 @@ def _cached_workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
 
 
 def release_workspaces() -> None:
-    """Drops the cached scratch arenas (they are otherwise kept for the life of the process)."""
+    """Drops the cached scratch arenas and captured graphs (otherwise kept for the life of the process)."""
     _WS_CACHE.clear()
+    _GRAPH_CACHE.clear()
+
+
+# Captured CUDA graphs of the whole layer, one per (device, thread, parameters, shape): a call then
+# costs one graph launch instead of ~600 kernel launches from Python.  Results are copied out of the
+# graph's fixed output buffers before they are returned.
+_GRAPH_CACHE = {}
+_GRAPH_CACHE_MAX = 4
+
+
+def _params_signature(p) -> tuple:
+    return tuple(getattr(p, name) if name != "order" else tuple(p.order)
+                 for name, _ in p._fields_ if name != "seed")
+
+
+def _graph_runner(p, m, n, h_kind, dev, want_packed, want_w_scaled):
+    key = (dev.index, threading.get_ident(), _params_signature(p), m, n, h_kind, want_packed, want_w_scaled)
+    run = _GRAPH_CACHE.get(key)
+    if run is None:
+        mine = [k for k in _GRAPH_CACHE if k[0] == key[0] and k[1] == key[1]]
+        while len(mine) >= _GRAPH_CACHE_MAX:
+            _GRAPH_CACHE.pop(mine.pop(0))
+        run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=want_packed, want_w_scaled=want_w_scaled)
+        run.capture()
+        _GRAPH_CACHE[key] = run
+    return run
 
 _ORDER_CODE = {"Q": 0, "LR": 1}
 
@@ -134,6 +160,7 @@ def caldera(
     seed: int = 0,
     return_packed: bool = True,
     use_tensor_cores: bool = True,
+    use_cuda_graph: bool = False,
 ):
     """Runs CALDERA: decomposes W into Q + L R (alg.py:24-112), all arithmetic on `device`.
 
@@ -144,6 +171,7 @@ def caldera(
     global_scale  inject the reference's global_scale instead of recomputing it;
     sketch_width / power_iters / warm_start / seed  knobs of the randomized rank-r step;
     use_tensor_cores  bf16 tcgen05 contractions for aligned shapes (default) or fp32 SIMT everywhere;
+    use_cuda_graph  replay a captured CUDA graph of the layer (cached per shape/parameters/thread);
     return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed.
     `use_tqdm` is accepted and ignored (the loop runs on the device).
     """
@@ -164,25 +192,36 @@ def caldera(
             raise AttributeError("'NoneType' object has no attribute 'A_idxs'")
 
     with torch.cuda.device(dev):
-        Wd = W.to(dev, torch.float32, non_blocking=True).contiguous()
+        # graph mode stages W straight into the captured graph's input buffer (one H2D copy)
+        Wd = None if use_cuda_graph else W.to(dev, torch.float32, non_blocking=True).contiguous()
         h_kind, Hd = _classify_hessian(H, n, dev)
         p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed,
                           use_tensor_cores)
 
         f32 = dict(dtype=torch.float32, device=dev)
-        ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
-        run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
-                                 want_w_scaled=(W_copy != "none"), workspace=ws)
-        run.enqueue(Wd, Hd)
-        host = run.read_small()                           # the one synchronisation of the layer
+        if use_cuda_graph:
+            p.seed = 0
+            run = _graph_runner(p, m, n, h_kind, dev, return_packed, W_copy != "none")
+            run.launch(W, Hd, seed)
+            host = run.read_small()                       # the one synchronisation of the layer
+            clone = lambda t: None if t is None else t.clone()   # noqa: E731  (graph buffers are reused)
+        else:
+            ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
+            run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
+                                     want_w_scaled=(W_copy != "none"), workspace=ws)
+            run.enqueue(Wd, Hd)
+            host = run.read_small()                       # the one synchronisation of the layer
+            clone = lambda t: t                           # noqa: E731
+            run.ws = None                                 # the arena stays in the per-thread cache
+            del ws
         nsteps = run.nsteps
-        Q, L, R = run.Q, run.L, run.R
-        Q_idxs, L_idxs, R_idxs = run.Q_idxs, run.L_idxs, run.R_idxs
-        Q_packed, L_packed, R_packed = run.Q_packed, run.L_packed, run.R_packed
+        Q, L, R = clone(run.Q), clone(run.L), clone(run.R)
+        Q_idxs, L_idxs, R_idxs = clone(run.Q_idxs), clone(run.L_idxs), clone(run.R_idxs)
+        Q_packed, L_packed, R_packed = clone(run.Q_packed), clone(run.L_packed), clone(run.R_packed)
         Q_scale, L_scale, R_scale = run.Q_scale, run.L_scale, run.R_scale
-        W_scaled = run.W_scaled
-        run.ws = None                                     # the arena stays in the per-thread cache
-        del ws
+        W_scaled = clone(run.W_scaled)
+        if use_cuda_graph and not scale_W:
+            Wd = run.W_in.clone()
 
     errs = host[:nsteps].tolist()
     scal = host[run.nerr_pad:run.nerr_pad + 8]

@@ -30,6 +30,7 @@ static inline bool bits_ok(int b) { return b == 2 || b == 4 || b == 8 || b == 16
 struct LowrankBufs {
   float *P, *Po, *Z, *Zo, *G, *Linv, *B, *work, *evals, *V;
   int* status;  // [0] cholesky retries (max), [1] jacobi sweeps
+  const uint64_t* seed_dev = nullptr;   // optional per-layer seed in device memory, added to the host seed
 };
 
 static LowrankBufs plan_lowrank(Arena& a, int64_t m, int64_t n, int64_t q, float* Zo_persistent, int* status) {
@@ -61,7 +62,7 @@ static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t
                         int aware, const float* inv_sqrt_h, bool warm_valid, float* L, float* R,
                         const LowrankBufs& b, cudaStream_t st) {
   if (!warm_valid) {
-    CB_TRY(fill_randn(b.P, n * q, seed, st));
+    CB_TRY(fill_randn(b.P, n * q, seed, b.seed_dev, st));
     CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.P, q, 1, b.Z, q, 1, false, nullptr, st));
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
   }
@@ -107,6 +108,7 @@ struct LowrankTcBufs {
   bf16 *Linvb, *Bb, *Btb, *Vb;    // q x q, q x n, n x q, q x q
   float *G, *Linv, *work, *evals, *V;
   int* status;                    // [0] cholesky retries, [1] jacobi sweeps, [2] gemm watchdog
+  const uint64_t* seed_dev = nullptr;
 };
 
 static bool lowrank_tc_usable(int64_t m, int64_t n, int64_t r, int64_t q) {
@@ -125,7 +127,9 @@ static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, 
   return b;
 }
 
-__global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p, int64_t count, uint64_t seed) {
+__global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p, int64_t count, uint64_t seed,
+                                                         const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed += seed_dev[0];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     p[i] = __float2bfloat16_rn(gaussian_from(seed, (uint64_t)i));
@@ -150,7 +154,7 @@ static int lowrank_core_tc(int64_t m, int64_t n, int64_t r, int64_t q, int niter
                            const LowrankTcBufs& b, cudaStream_t st) {
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
   if (!warm_valid) {
-    randn_bf16_kernel<<<grid_for(q * n, 256 * 4, 4), 256, 0, st>>>(b.Ptb, q * n, seed);
+    randn_bf16_kernel<<<grid_for(q * n, 256 * 4, 4), 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev);
     CB_CHECK_LAUNCH();
     // Zt[q, m] = Pt[q, K=n] * Y[m, K=n]^T
     CB_TRY(gemm_tc(q, m, n, 1.f, b.Ptb, n, b.Yb, n, nullptr, 0, b.Ztb, m, b.Zb, q, nullptr, nullptr, 1, wd, nullptr, st));
@@ -346,7 +350,7 @@ static int lowrank_core_dense(const float* res, const float* Hs, int64_t m, int6
                               int niter, uint64_t seed, bool warm_valid, float* L, float* R, float* HP,
                               const LowrankBufs& b, cudaStream_t st) {
   if (!warm_valid) {
-    CB_TRY(fill_randn(b.P, n * q, seed, st));
+    CB_TRY(fill_randn(b.P, n * q, seed, b.seed_dev, st));
     CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st));
     CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st));
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
@@ -546,7 +550,10 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   CB_TRY(plan_layer(a, p, m, n, scale_w, h_kind, P));
   if (P.quant_factors && (out->L_idxs == nullptr || out->R_idxs == nullptr || out->L_scale == nullptr || out->R_scale == nullptr))
     return CB_ERR_ARG;
-  if (p->compute_lr) { P.lr.status = P.flags + 2; P.tc.status = P.flags + 2; }
+  if (p->compute_lr) {
+    P.lr.status = P.flags + 2; P.tc.status = P.flags + 2;
+    P.lr.seed_dev = out->seed_dev; P.tc.seed_dev = out->seed_dev;
+  }
 
   // ---- initial state: Q = 0, L = 0, R = 0 (alg.py:71-75)
   CB_CUDA(cudaMemsetAsync(P.dsc, 0, sizeof(double) * 4, st));

@@ -42,7 +42,7 @@ int select_outer(double* num, const double* den, float* errors, int step, float*
                  int all_updated, cudaStream_t st);
 int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st);
 int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st);
-int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st);
+int fill_randn(float* p, int64_t count, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
 int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int transpose_codes(const void* src, int64_t rows, int64_t cols, int elem_bytes, void* dst, cudaStream_t st);

@@ -548,7 +548,9 @@ copy_if_kernel(const int* __restrict__ flag, uint8_t* __restrict__ dst, const ui
   }
 }
 
-__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ p, int64_t count, uint64_t seed) {
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ p, int64_t count, uint64_t seed,
+                                                    const uint64_t* __restrict__ seed_dev) {
+  if (seed_dev != nullptr) seed += seed_dev[0];   // per-layer seed kept in device memory (CUDA-graph replays)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     p[i] = gaussian_from(seed, (uint64_t)i);
@@ -684,8 +686,8 @@ int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStrea
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int fill_randn(float* p, int64_t count, uint64_t seed, cudaStream_t st) {
-  randn_kernel<<<grid_for(count, 256 * 4, 4), 256, 0, st>>>(p, count, seed);
+int fill_randn(float* p, int64_t count, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st) {
+  randn_kernel<<<grid_for(count, 256 * 4, 4), 256, 0, st>>>(p, count, seed, seed_dev);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -63,6 +63,12 @@ class CalderaLayerRunner:
         # raw addresses: data_ptr() of an empty slice (update_order == []) is null
         self.out.errors = self.small.data_ptr()
         self.out.scalars = self.small.data_ptr() + 4 * self.nerr_pad
+        # per-layer seed lives in device memory so that a captured graph can be replayed with any seed
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.out.seed_dev = self.seed_dev.data_ptr()
+        self.graph = None
+        self.W_in = None
+        self.h_in = None
 
     def enqueue(self, W: torch.Tensor, h: Optional[torch.Tensor]) -> None:
         """Asynchronous: enqueues the whole layer on the current stream of `device`."""
@@ -71,6 +77,38 @@ class CalderaLayerRunner:
             st = self.lib.cb_caldera_layer(C.byref(self.p), _lib.ptr(W), self.m, self.n, _lib.ptr(h), self.h_kind,
                                            C.byref(self.out), _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr())
         _lib.check(st, "caldera")
+
+    # ---- CUDA-graph replay: one graph launch per layer instead of ~600 kernel launches
+    def capture(self) -> None:
+        """Captures the whole layer into a CUDA graph reading from runner-owned input buffers."""
+        if self.graph is not None:
+            return
+        with torch.cuda.device(self.device):
+            self.W_in = torch.empty((self.m, self.n), dtype=torch.float32, device=self.device)
+            self.h_in = None
+            if self.h_kind == _lib.CB_H_DIAG:
+                self.h_in = torch.ones(self.n, dtype=torch.float32, device=self.device)
+            elif self.h_kind == _lib.CB_H_DENSE:
+                self.h_in = torch.eye(self.n, dtype=torch.float32, device=self.device)
+            self.W_in.normal_(0.0, 0.02)
+            self.enqueue(self.W_in, self.h_in)          # eager warm-up: one-time attribute setup happens outside capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue(self.W_in, self.h_in)
+            self.graph = g
+
+    def launch(self, W: torch.Tensor, h: Optional[torch.Tensor], seed: int = 0) -> None:
+        """Asynchronous on the current stream: stage the inputs (device or pinned host tensors) into the
+        graph's input buffers and replay it."""
+        if self.graph is None:
+            self.capture()
+        with torch.cuda.device(self.device):
+            self.W_in.copy_(W, non_blocking=True)
+            if self.h_in is not None and h is not None:
+                self.h_in.copy_(h, non_blocking=True)
+            self.seed_dev.fill_(int(seed))
+            self.graph.replay()
 
     def read_small(self) -> torch.Tensor:
         """The one host synchronisation of a layer: error trajectory, scalars, scales."""

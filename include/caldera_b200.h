@@ -191,6 +191,8 @@ typedef struct cb_caldera_out {
   uint8_t* R_packed;   /* optional */
   float* W_scaled;     /* optional m x n: W / global_scale (CalderaDecomposition.W) */
   float* errors;       /* iters * n_order floats, in sub-step order                 */
+  const uint64_t* seed_dev; /* optional device uint64 added to params.seed: lets a captured CUDA graph of the
+                          layer be replayed with a different seed per layer                       */
   float* scalars;      /* 8 floats: [0]=global_scale [1]=min_error [2]=best_step
                           [5],[6],[7] hold int32 bit patterns: cholesky ridge retries (max over
                           the layer), jacobi sweeps (last solve), tcgen05 pipeline watchdog */

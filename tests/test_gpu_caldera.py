@@ -252,3 +252,19 @@ def test_dense_hessian_sigma_reg_not_supported():
     with pytest.raises(NotImplementedError):
         caldera(_params(dict(rank=4, iters=1, L_bits=16, R_bits=16, sigma_reg=1e-3, update_order=["Q", "LR"])),
                 W, X.T @ X / 200, device=DEV, use_tqdm=False)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """caldera(use_cuda_graph=True) replays a captured graph of the layer: same numbers as the eager
+    launch sequence, for different inputs and seeds through the same cached graph."""
+    g = torch.Generator().manual_seed(21)
+    kw = dict(Q_bits=2, L_bits=4, R_bits=4, rank=16, iters=2, lplr_iters=2, update_order=["Q", "LR"])
+    for trial in range(3):
+        W = 0.02 * torch.randn(512, 384, generator=g)
+        h = 0.5 + torch.rand(384, generator=g)
+        a = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=False)
+        b = caldera(_params(kw), W.pin_memory(), h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=True)
+        assert a.errors == b.errors
+        assert torch.equal(a.Q_idxs, b.Q_idxs) and torch.equal(a.L, b.L) and torch.equal(a.R_idxs, b.R_idxs)
+        assert torch.equal(a.Q_packed, b.Q_packed) and torch.equal(a.W, b.W)
+        assert a.best_step == b.best_step and a.global_scale == b.global_scale
