@@ -6,6 +6,7 @@ once and every layer is a single asynchronous enqueue on the current stream."""
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional
 
 import torch
@@ -15,6 +16,10 @@ from . import _lib
 
 def workspace_bytes(c_params, m: int, n: int, h_kind: int) -> int:
     return int(_lib.load().cb_caldera_layer_workspace_bytes(C.byref(c_params), m, n, h_kind)) or 256
+
+
+# stream capture is a process-wide affair for torch's allocator and RNG bookkeeping: one at a time
+_CAPTURE_LOCK = threading.Lock()
 
 
 class CalderaLayerRunner:
@@ -83,7 +88,7 @@ class CalderaLayerRunner:
         """Captures the whole layer into a CUDA graph reading from runner-owned input buffers."""
         if self.graph is not None:
             return
-        with torch.cuda.device(self.device):
+        with _CAPTURE_LOCK, torch.cuda.device(self.device):
             self.W_in = torch.empty((self.m, self.n), dtype=torch.float32, device=self.device)
             self.h_in = None
             if self.h_kind == _lib.CB_H_DIAG:
@@ -94,7 +99,7 @@ class CalderaLayerRunner:
             self.enqueue(self.W_in, self.h_in)          # eager warm-up: one-time attribute setup happens outside capture
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.enqueue(self.W_in, self.h_in)
             self.graph = g
 
