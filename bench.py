@@ -355,7 +355,7 @@ def run_ours(args):
         with cf.ThreadPoolExecutor(max_workers=nworkers) as ex:
             return list(ex.map(work, range(nworkers)))
     e2e_steps = max(1, args.steps)
-    run_e2e(0, min(args.warmup, nworkers))
+    run_e2e(0, max(min(args.warmup, nworkers), nworkers))   # every worker warms its stream, workspace and graph
     barrier()
     t0 = time.perf_counter()
     run_e2e(args.warmup, e2e_steps)

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "cb_version": (C.c_int, []),
     "cb_status_string": (C.c_char_p, [C.c_int]),
     "cb_kernel_launch_count": (C.c_int64, []),
+    "cb_note_launches": (None, [C.c_int64]),
     "cb_quantize_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                   C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_dequantize_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64,

@@ -11,6 +11,10 @@ extern "C" int64_t cb_kernel_launch_count(void) {
   return (int64_t)__atomic_load_n(&cb::g_launch_count, __ATOMIC_RELAXED);
 }
 
+extern "C" void cb_note_launches(int64_t n) {
+  if (n > 0) cb::note_launch((int)n);
+}
+
 extern "C" const char* cb_status_string(int status) {
   switch (status) {
     case CB_OK: return "ok";

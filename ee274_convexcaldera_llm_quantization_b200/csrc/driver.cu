@@ -614,14 +614,21 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         if (P.dense) CB_CUDA(cudaMemsetAsync(P.dsc + 2, 0, sizeof(double), st));
       } else if (which == 1 && p->compute_lr) {
         // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
-        CB_TRY(form_y(Ws, have_q ? P.codes_cur : nullptr, p->compute_q ? p->q_bits : 8, P.qscale_cur,
-                      (p->aware && !P.dense) ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
+        const void* qcodes = have_q ? P.codes_cur : nullptr;
+        const int qbits = p->compute_q ? p->q_bits : 8;
+        if (P.use_tc) {
+          // one fused pass: residual -> both bf16 operand orientations (+ fp32 residual for the LPLR loop;
+          // when not activation aware that residual is Y itself)
+          CB_TRY(form_y_bf16(Ws, qcodes, qbits, P.qscale_cur, p->aware ? P.sqrt_h : nullptr, m, n, P.tc.Yb, P.tc.Ytb,
+                             P.quant_factors ? (p->aware ? P.RES : P.Y) : nullptr, st));
+        } else {
+          CB_TRY(form_y(Ws, qcodes, qbits, P.qscale_cur, (p->aware && !P.dense) ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
+        }
         if (P.dense && p->aware) {
           // form_y ran with sqrt_h == 1 for the dense case, so P.Y is the plain residual W - Q
           CB_TRY(lowrank_core_dense(P.Y, P.Hs, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step,
                                     warm_valid && p->warm_start, P.Lcur, P.Rcur, P.HP, P.lr, st));
         } else if (P.use_tc) {
-          CB_TRY(to_bf16(P.Y, m, n, n, P.tc.Yb, n, P.tc.Ytb, m, nullptr, st));
           CB_TRY(lowrank_core_tc(m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
                                  warm_valid && p->warm_start, P.Lcur, P.Rcur, nullptr, nullptr, P.tc, st));
         } else {

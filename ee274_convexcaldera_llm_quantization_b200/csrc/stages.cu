@@ -290,6 +290,58 @@ err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const
   if (threadIdx.x == 0) atomicAdd(num, acc);
 }
 
+// ---------------------------------------------------------------- fused residual -> bf16 operands
+// One pass for the tensor-core rank-r step: res = Ws - dequant(codes), Y = res (.) sqrt(h) written as
+// the two K-major bf16 operands Yb (m x n) and Ytb (n x m, transposed through a shared-memory tile),
+// plus the fp32 residual when the LPLR loop needs it.  Replaces form_y + two conversion passes.
+template <typename code_t>
+__global__ void __launch_bounds__(256)
+form_y_bf16_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
+                   float lv, const float* __restrict__ sqrt_h, int m, int n, __nv_bfloat16* __restrict__ Yb,
+                   __nv_bfloat16* __restrict__ Ytb, float* __restrict__ RES) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][68];   // [col][row]
+  const float s = codes != nullptr ? qscale[0] : 0.f;
+  const ScaleRecip lvr = make_scale_recip(lv);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int col = blockIdx.x * 64 + 4 * tx;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rl = ty + 16 * k, row = blockIdx.y * 64 + rl;
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < m && col < n) {
+      const int64_t i = (int64_t)row * n + col;
+      FVec<4> w, sh;
+      w.load_stream(Ws + i);
+      if (sqrt_h != nullptr) sh.load(sqrt_h + col);
+      int c[4];
+      if (codes != nullptr) load_codes<4, code_t>(codes + i, c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (codes != nullptr) w.v[j] -= dequant_val(c[j], s, lvr);
+        y[j] = sqrt_h != nullptr ? w.v[j] * sh.v[j] : w.v[j];
+      }
+      if (RES != nullptr) w.store(RES + i);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(Yb + i) = pk;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[4 * tx + j][rl] = __float2bfloat16_rn(y[j]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int cl = ty + 16 * k;                 // column of the tile = row of Ytb
+    const int gc = blockIdx.x * 64 + cl, gr = blockIdx.y * 64 + 4 * tx;
+    if (gc < n && gr < m) {
+      const uint2 pk = *reinterpret_cast<const uint2*>(&tile[cl][4 * tx]);
+      *reinterpret_cast<uint2*>(Ytb + (int64_t)gc * m + gr) = pk;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- dense-Hessian helpers
 // E = Ws - Q - L R written out (the dense metric tr(E H E^T) needs E as a GEMM operand)
 template <int VEC, typename code_t>
@@ -758,6 +810,20 @@ int cvx_finish(const float* W, const float* Lnew, const float* VR, const float* 
     cvx_finish_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Lnew, VR, h, numel, n, sc, Rnew, smooth);
   else
     cvx_finish_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Lnew, VR, h, numel, n, sc, Rnew, smooth);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+// requires m % 4 == 0, n % 4 == 0 (the tensor-core path asks for multiples of 8) and 16-byte aligned bases
+int form_y_bf16(const float* Ws, const void* codes, int bits, const float* qscale, const float* sqrt_h, int64_t m,
+                int64_t n, __nv_bfloat16* Yb, __nv_bfloat16* Ytb, float* RES, cudaStream_t st) {
+  if (m % 4 != 0 || n % 4 != 0 || !aligned16(Ws) || !aligned16(Yb) || !aligned16(Ytb)) return CB_ERR_ARG;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64));
+  if (bits <= 8)
+    form_y_bf16_kernel<int8_t><<<grid, 256, 0, st>>>(Ws, reinterpret_cast<const int8_t*>(codes), qscale, lv, sqrt_h, (int)m, (int)n, Yb, Ytb, RES);
+  else
+    form_y_bf16_kernel<int16_t><<<grid, 256, 0, st>>>(Ws, reinterpret_cast<const int16_t*>(codes), qscale, lv, sqrt_h, (int)m, (int)n, Yb, Ytb, RES);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

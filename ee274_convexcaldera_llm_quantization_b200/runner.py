@@ -99,8 +99,10 @@ class CalderaLayerRunner:
             self.enqueue(self.W_in, self.h_in)          # eager warm-up: one-time attribute setup happens outside capture
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = self.lib.cb_kernel_launch_count()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.enqueue(self.W_in, self.h_in)
+            self.graph_kernels = int(self.lib.cb_kernel_launch_count() - n0)   # kernel nodes in the graph
             self.graph = g
 
     def launch(self, W: torch.Tensor, h: Optional[torch.Tensor], seed: int = 0) -> None:
@@ -114,6 +116,7 @@ class CalderaLayerRunner:
                 self.h_in.copy_(h, non_blocking=True)
             self.seed_dev.fill_(int(seed))
             self.graph.replay()
+            self.lib.cb_note_launches(self.graph_kernels)
 
     def read_small(self) -> torch.Tensor:
         """The one host synchronisation of a layer: error trajectory, scalars, scales."""

@@ -52,6 +52,9 @@ int cb_version(void);
 const char* cb_status_string(int status);
 /* Number of kernels this library has launched in this process (all streams). */
 int64_t cb_kernel_launch_count(void);
+/* Adds n to that counter: a caller replaying a captured CUDA graph of library kernels reports the
+ * kernels the replay launched (the library cannot see graph replays). */
+void cb_note_launches(int64_t n);
 
 /* ------------------------------------------------------------------------- quantiser */
 
