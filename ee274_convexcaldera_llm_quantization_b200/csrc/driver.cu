@@ -42,7 +42,7 @@ static LowrankBufs plan_lowrank(Arena& a, int64_t m, int64_t n, int64_t q, float
   b.G = a.take<float>(q * q);
   b.Linv = a.take<float>(q * q);
   b.B = a.take<float>(q * n);
-  b.work = a.take<float>(q * q);
+  b.work = a.take<float>(q * q + q + 8);
   b.evals = a.take<float>(q);
   b.V = a.take<float>(q * q);
   b.status = status;
@@ -121,7 +121,7 @@ static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, 
   b.Ptb = a.take<bf16>(q * n); b.Pb = a.take<bf16>(n * q); b.Potb = a.take<bf16>(q * n);
   b.Ztb = a.take<bf16>(q * m); b.Zb = a.take<bf16>(m * q); b.Zotb = a.take<bf16>(q * m); b.Zob = a.take<bf16>(m * q);
   b.Linvb = a.take<bf16>(q * q); b.Bb = a.take<bf16>(q * n); b.Btb = a.take<bf16>(n * q); b.Vb = a.take<bf16>(q * q);
-  b.G = a.take<float>(q * q); b.Linv = a.take<float>(q * q); b.work = a.take<float>(q * q);
+  b.G = a.take<float>(q * q); b.Linv = a.take<float>(q * q); b.work = a.take<float>(q * q + q + 8);
   b.evals = a.take<float>(q); b.V = a.take<float>(q * q);
   b.status = status;
   return b;

@@ -6,8 +6,11 @@
 //     replaces the truncated SVD of LR_init (alg.py:214-217).
 // Both are single-CTA, latency-bound kernels: the matrices are at most 1 MiB and stay in
 // L1/L2; panels are staged in shared memory.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace cb {
 
@@ -536,6 +539,128 @@ jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ eval
   if (tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
 }
 
+// Thread-block-cluster variant: 8 CTAs (one cluster, 8 SMs) share every round of the
+// round-robin tournament.  The q x q working matrix lives in global memory and stays in L2
+// (all accesses bypass L1: ld/st.global.cg), a group of LPP lanes owns one column pair per
+// round and keeps both columns in registers between the dot products and the rotation, and
+// rounds are separated by a hardware cluster barrier (release/acquire at cluster scope).
+// LPP = 8 lanes per pair for q <= 256 (256 threads per CTA), 16 for q <= 512 (512 threads).
+constexpr int JC_CTAS = 8;
+
+template <int LPP, int NV4>
+__global__ void __cluster_dims__(JC_CTAS, 1, 1) __launch_bounds__(32 * LPP, 1)
+jacobi_cluster_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, float* __restrict__ evecs,
+                      float* work, int* sweeps_out, int* rot_counters, float* lam_buf, int max_sweeps, float tol) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ int s_rot;
+  const int cta = (int)cluster.block_rank();
+  const int nthreads = 32 * LPP;
+  const int tid = threadIdx.x;
+  const int g = tid / LPP, gl = tid % LPP;
+  const int groups_per_cta = nthreads / LPP;           // 32
+  const int NG = groups_per_cta * JC_CTAS;             // 256 pairs per pass
+  const int ggroup = cta * groups_per_cta + g;
+  // work[v][i] = Lc[i][v] (i >= v), 0 above the diagonal
+  for (int e = cta * nthreads + tid; e < q * q; e += nthreads * JC_CTAS) {
+    const int i = e / q, v = e - i * q;
+    __stcg(work + (size_t)v * q + i, (i >= v) ? Lc[e] : 0.f);
+  }
+  if (tid == 0) s_rot = 0;
+  cluster.sync();
+  const int qe = q + (q & 1);
+  const int npairs = qe >> 1;
+  const int q4 = q >> 2;                               // q % 4 == 0
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    for (int t = 0; t < qe - 1; ++t) {
+      for (int pbase = 0; pbase < npairs; pbase += NG) {
+        const int pi = pbase + ggroup;
+        int a = 0, b = 0;
+        if (pi == 0) { a = qe - 1; b = t; }
+        else if (pi < npairs) { a = (t + pi) % (qe - 1); b = (t - pi + (qe - 1)) % (qe - 1); }
+        const bool live = (pi < npairs && a < q && b < q);
+        float4* xa = reinterpret_cast<float4*>(work + (size_t)(live ? a : 0) * q);
+        float4* xb = reinterpret_cast<float4*>(work + (size_t)(live ? b : 0) * q);
+        float4 x[NV4], y[NV4];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          const int i4 = gl + LPP * k;
+          if (i4 < q4 && live) { x[k] = __ldcg(xa + i4); y[k] = __ldcg(xb + i4); }
+          else { x[k] = make_float4(0.f, 0.f, 0.f, 0.f); y[k] = x[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          al = fmaf(x[k].x, x[k].x, al); al = fmaf(x[k].y, x[k].y, al); al = fmaf(x[k].z, x[k].z, al); al = fmaf(x[k].w, x[k].w, al);
+          be = fmaf(y[k].x, y[k].x, be); be = fmaf(y[k].y, y[k].y, be); be = fmaf(y[k].z, y[k].z, be); be = fmaf(y[k].w, y[k].w, be);
+          ga = fmaf(x[k].x, y[k].x, ga); ga = fmaf(x[k].y, y[k].y, ga); ga = fmaf(x[k].z, y[k].z, ga); ga = fmaf(x[k].w, y[k].w, ga);
+        }
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        if (live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
+          const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
+          const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cd = 1.0 / sqrt(1.0 + tt * tt);
+          const float c = (float)cd, sn = (float)(cd * tt);
+#pragma unroll
+          for (int k = 0; k < NV4; ++k) {
+            const int i4 = gl + LPP * k;
+            if (i4 < q4) {
+              __stcg(xa + i4, make_float4(c * x[k].x - sn * y[k].x, c * x[k].y - sn * y[k].y, c * x[k].z - sn * y[k].z, c * x[k].w - sn * y[k].w));
+              __stcg(xb + i4, make_float4(sn * x[k].x + c * y[k].x, sn * x[k].y + c * y[k].y, sn * x[k].z + c * y[k].z, sn * x[k].w + c * y[k].w));
+            }
+          }
+          if (gl == 0) atomicAdd(&s_rot, 1);
+        }
+      }
+      cluster.sync();
+      // the other parity's counter was last read right after the previous sweep's final barrier;
+      // every CTA is past that read once it has arrived at this round's barrier
+      if (t == 0 && cta == 0 && tid == 0) __stcg(rot_counters + ((sweep + 1) & 1), 0);
+    }
+    if (tid == 0) {
+      if (s_rot > 0) atomicAdd(rot_counters + (sweep & 1), s_rot);
+      s_rot = 0;
+    }
+    cluster.sync();
+    const int rot = __ldcg(rot_counters + (sweep & 1));
+    if (rot == 0) { ++sweep; break; }
+  }
+  // eigenvalues = squared column norms
+  for (int v = ggroup; v < q; v += NG) {
+    const float4* xv = reinterpret_cast<const float4*>(work + (size_t)v * q);
+    float acc = 0.f;
+    for (int i4 = gl; i4 < q4; i4 += LPP) { const float4 z = __ldcg(xv + i4); acc = fmaf(z.x, z.x, acc); acc = fmaf(z.y, z.y, acc); acc = fmaf(z.z, z.z, acc); acc = fmaf(z.w, z.w, acc); }
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (gl == 0) __stcg(lam_buf + v, acc);
+  }
+  cluster.sync();
+  // rank (descending, ties by index) and normalised, sorted output; one group per vector
+  for (int vbase = 0; vbase < q; vbase += NG) {
+    const int v = vbase + ggroup;
+    const bool live = v < q;
+    const float lv = live ? __ldcg(lam_buf + v) : 0.f;
+    int rk = 0;
+    if (live)
+      for (int u = gl; u < q; u += LPP) { const float lu = __ldcg(lam_buf + u); rk += (lu > lv) || (lu == lv && u < v); }
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    if (live) {
+      const float inv = lv > 0.f ? __fdiv_rn(1.f, __fsqrt_rn(lv)) : 0.f;
+      const float4* xv = reinterpret_cast<const float4*>(work + (size_t)v * q);
+      float4* ov = reinterpret_cast<float4*>(evecs + (size_t)rk * q);
+      for (int i4 = gl; i4 < q4; i4 += LPP) { float4 z = __ldcg(xv + i4); z.x *= inv; z.y *= inv; z.z *= inv; z.w *= inv; ov[i4] = z; }
+      if (gl == 0) evals[rk] = lv;
+    }
+  }
+  if (cta == 0 && tid == 0 && sweeps_out != nullptr) *sweeps_out = sweep;
+}
+
 // A column pair is rotated while |<x,y>| > tol * |x| |y|.  The captured energy of the
 // Rayleigh-Ritz step is second order in the residual coupling, so 3e-5 leaves it exact to fp32.
 constexpr float kJacobiTol = 3e-5f;
@@ -544,6 +669,16 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
                           cudaStream_t st) {
   if (Lc == nullptr || evals == nullptr || evecs == nullptr || work == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
+  if (q % 4 == 0 && q >= 64 && aligned16(work) && aligned16(evecs)) {
+    // cluster kernel: `work` holds q*q floats of column storage followed by q floats of norms and 2 counters
+    float* lam_buf = work + (size_t)q * q;
+    int* counters = reinterpret_cast<int*>(lam_buf + q);
+    CB_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
+    if (q <= 256) jacobi_cluster_kernel<8, 8><<<JC_CTAS, 256, 0, st>>>(Lc, q, evals, evecs, work, sweeps, counters, lam_buf, 30, kJacobiTol);
+    else jacobi_cluster_kernel<16, 8><<<JC_CTAS, 512, 0, st>>>(Lc, q, evals, evecs, work, sweeps, counters, lam_buf, 30, kJacobiTol);
+    CB_CHECK_LAUNCH();
+    return CB_OK;
+  }
   if (q <= JS_QMAX && q % 4 == 0) {
     const size_t smem = ((size_t)q * (q + 4) + 2 * (size_t)q) * sizeof(float);
     static bool attr_set = false;

@@ -128,7 +128,7 @@ size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t 
 int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream);
 /* Eigen-decomposition of the SPD matrix G = Lc Lc^T from its Cholesky factor by one-sided
  * Jacobi on Lc's columns.  evals[q] descending, evecs row k = k-th eigenvector.
- * work: q*q floats. */
+ * work: q*q + q + 8 floats of scratch (column storage, norms, sweep counters). */
 int cb_jacobi_eigh_from_chol_f32(const float* Lc, int64_t q, float* evals, float* evecs,
                                  float* work, int* sweeps, void* stream);
 /* C = alpha * op(A) op(B) (+ C) with arbitrary element strides: A(i,k) = A[i*a_rs + k*a_cs],

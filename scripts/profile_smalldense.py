@@ -18,7 +18,7 @@ Linv = torch.empty(q, q, device=dev)
 status = torch.zeros(2, dtype=torch.int32, device=dev)
 evals = torch.empty(q, device=dev)
 evecs = torch.empty(q, q, device=dev)
-work = torch.empty(q, q, device=dev)
+work = torch.empty(q * q + q + 8, device=dev)
 for rep in range(3):
     G = G0.clone()
     torch.cuda.synchronize()

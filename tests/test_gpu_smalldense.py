@@ -89,7 +89,7 @@ def test_jacobi_eigh(q):
     Lc = Lc + torch.triu(torch.full((q, q), 123.0, device=DEV), 1)   # upper triangle must be ignored
     evals = torch.empty(q, device=DEV)
     evecs = torch.empty(q, q, device=DEV)
-    work = torch.empty(q, q, device=DEV)
+    work = torch.empty(q * q + q + 8, device=DEV)
     sweeps = torch.zeros(1, dtype=torch.int32, device=DEV)
     _lib.check(lib.cb_jacobi_eigh_from_chol_f32(_lib.ptr(Lc), q, _lib.ptr(evals), _lib.ptr(evecs), _lib.ptr(work),
                                                 _lib.ptr(sweeps), _lib.stream_ptr()), "jacobi")
