@@ -156,30 +156,49 @@ def gather_blobs(blobs: List[torch.Tensor], dst: Optional[int] = 0, group=None) 
 # ----------------------------------------------------------------------------- driver
 def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor, Optional[torch.Tensor]]]]],
                      shapes: Sequence[Tuple[int, int]], params, rank: int, world_size: int,
-                     device: Optional[torch.device] = None, pack: bool = True, **caldera_kwargs):
+                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 8,
+                     **caldera_kwargs):
     """Decomposes this rank's shard of `layers`.
 
     layers[i] = (name, loader) where loader() returns (W, H) -- generated or loaded directly
-    on the owning GPU, so no weight ever crosses ranks.  Returns (indices, results) with
-    results[j] the blob (pack=True) or the CalderaDecomposition of layer indices[j].  The
-    per-layer seed is derived from the layer index only, so the sharded run equals the
-    single-GPU run layer for layer."""
+    on the owning GPU (or in pinned host memory), so no weight ever crosses ranks.  Returns
+    (indices, results) with results[j] the blob (pack=True) or the CalderaDecomposition of
+    layer indices[j].  The per-layer seed is derived from the layer index only, so the sharded
+    run equals the single-GPU run layer for layer.
+
+    `streams` layers are kept in flight per GPU (one worker thread + CUDA stream each, largest
+    layers first): the latency-bound factorisation kernels of one layer overlap with the
+    bandwidth- and tensor-bound kernels of the others."""
+    import concurrent.futures as cf
     from .alg import caldera
     quantised = params.compute_low_rank_factors and (params.L_bits < 16 or params.R_bits < 16)
     costs = [layer_cost(m, n, params.rank, params.iters, params.lplr_iters, quantised) for (m, n) in shapes]
     mine = lpt_assign(costs, world_size)[rank]
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    results = []
-    for i in mine:
-        name, loader = layers[i]
-        W, H = loader()
-        kw = dict(caldera_kwargs)
-        kw.setdefault("seed", 1000 + i)
-        kw.setdefault("W_copy", "none")
-        dec = caldera(params, W, H, device=dev, use_tqdm=False, **kw)
-        if pack:
-            results.append(pack_decomposition(name, dec, params.Q_bits, params.L_bits, params.R_bits,
-                                              tuple(W.shape)))
-        else:
-            results.append(dec)
+    nworkers = max(1, min(int(streams), len(mine)))
+    order = sorted(range(len(mine)), key=lambda j: (-costs[mine[j]], j))     # big layers first
+    results = [None] * len(mine)
+    cuda_streams = [torch.cuda.Stream(device=dev) for _ in range(nworkers)]
+
+    def work(w):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(cuda_streams[w]):
+            for j in order[w::nworkers]:
+                i = mine[j]
+                name, loader = layers[i]
+                W, H = loader()
+                kw = dict(caldera_kwargs)
+                kw.setdefault("seed", 1000 + i)
+                kw.setdefault("W_copy", "none")
+                kw.setdefault("use_cuda_graph", True)
+                dec = caldera(params, W, H, device=dev, use_tqdm=False, **kw)
+                results[j] = pack_decomposition(name, dec, params.Q_bits, params.L_bits, params.R_bits,
+                                                tuple(W.shape)) if pack else dec
+            cuda_streams[w].synchronize()
+
+    if nworkers == 1:
+        work(0)
+    else:
+        with cf.ThreadPoolExecutor(max_workers=nworkers) as ex:
+            list(ex.map(work, range(nworkers)))
     return mine, results
