@@ -40,11 +40,13 @@ def release_workspaces() -> None:
     _GRAPH_CACHE.clear()
 
 
-# Captured CUDA graphs of the whole layer, one per (device, thread, parameters, shape): a call then
-# costs one graph launch instead of ~600 kernel launches from Python.  Results are copied out of the
-# graph's fixed output buffers before they are returned.
+# Captured CUDA graphs of the whole layer.  Runners (graph + fixed input/output buffers + workspace)
+# are pooled per (device, parameters, shape): a call borrows an idle one -- or captures a new one --
+# and hands it back when its results have been copied out, so concurrent callers (threads/streams)
+# each replay their own graph and a warm pool is reused by whoever comes next.
 _GRAPH_CACHE = {}
-_GRAPH_CACHE_MAX = 4
+_GRAPH_LOCK = threading.Lock()
+_GRAPH_POOL_MAX = 16
 
 
 def _params_signature(p) -> tuple:
@@ -52,17 +54,23 @@ def _params_signature(p) -> tuple:
                  for name, _ in p._fields_ if name != "seed")
 
 
-def _graph_runner(p, m, n, h_kind, dev, want_packed, want_w_scaled):
-    key = (dev.index, threading.get_ident(), _params_signature(p), m, n, h_kind, want_packed, want_w_scaled)
-    run = _GRAPH_CACHE.get(key)
-    if run is None:
-        mine = [k for k in _GRAPH_CACHE if k[0] == key[0] and k[1] == key[1]]
-        while len(mine) >= _GRAPH_CACHE_MAX:
-            _GRAPH_CACHE.pop(mine.pop(0))
-        run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=want_packed, want_w_scaled=want_w_scaled)
-        run.capture()
-        _GRAPH_CACHE[key] = run
-    return run
+def _acquire_graph_runner(p, m, n, h_kind, dev, want_packed, want_w_scaled):
+    key = (dev.index, _params_signature(p), m, n, h_kind, want_packed, want_w_scaled)
+    with _GRAPH_LOCK:
+        pool = _GRAPH_CACHE.setdefault(key, [])
+        if pool:
+            return key, pool.pop()
+    run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=want_packed, want_w_scaled=want_w_scaled)
+    run.capture()
+    return key, run
+
+
+def _release_graph_runner(key, run) -> None:
+    with _GRAPH_LOCK:
+        pool = _GRAPH_CACHE.setdefault(key, [])
+        if len(pool) < _GRAPH_POOL_MAX:
+            pool.append(run)
+
 
 _ORDER_CODE = {"Q": 0, "LR": 1}
 
@@ -201,7 +209,7 @@ def caldera(
         f32 = dict(dtype=torch.float32, device=dev)
         if use_cuda_graph:
             p.seed = 0
-            run = _graph_runner(p, m, n, h_kind, dev, return_packed, W_copy != "none")
+            graph_key, run = _acquire_graph_runner(p, m, n, h_kind, dev, return_packed, W_copy != "none")
             run.launch(W, Hd, seed)
             host = run.read_small()                       # the one synchronisation of the layer
             clone = lambda t: None if t is None else t.clone()   # noqa: E731  (graph buffers are reused)
@@ -220,8 +228,11 @@ def caldera(
         Q_packed, L_packed, R_packed = clone(run.Q_packed), clone(run.L_packed), clone(run.R_packed)
         Q_scale, L_scale, R_scale = run.Q_scale, run.L_scale, run.R_scale
         W_scaled = clone(run.W_scaled)
-        if use_cuda_graph and not scale_W:
-            Wd = run.W_in.clone()
+        if use_cuda_graph:
+            if not scale_W:
+                Wd = run.W_in.clone()
+            torch.cuda.current_stream().synchronize()     # copies out of the graph's buffers are done
+            _release_graph_runner(graph_key, run)
 
     errs = host[:nsteps].tolist()
     scal = host[run.nerr_pad:run.nerr_pad + 8]

@@ -15,6 +15,7 @@
 //   * every mbarrier wait is bounded: a broken pipeline sets *error_flag and drains instead
 //     of hanging the GPU.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
 
@@ -339,9 +340,17 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
   const int64_t mt = (M + TC_BM - 1) / TC_BM;
+  // CB_GEMM_MIN_CTAS (default 120): how many CTAs a grid must reach before a fatter N tile is
+  // preferred.  Fatter tiles move fewer bytes per flop (less SM-time, better throughput when several
+  // layers are in flight); thinner tiles fill the machine for one layer (lower latency).
+  static int min_ctas = -1;
+  if (min_ctas < 0) {
+    const char* e = getenv("CB_GEMM_MIN_CTAS");
+    min_ctas = (e != nullptr && atoi(e) > 0) ? atoi(e) : 120;
+  }
   int bn = 64;
-  if (N >= 192 && mt * ((N + 255) / 256) >= 120) bn = 256;
-  else if (N >= 96 && mt * ((N + 127) / 128) >= 120) bn = 128;
+  if (N >= 192 && mt * ((N + 255) / 256) >= min_ctas) bn = 256;
+  else if (N >= 96 && mt * ((N + 127) / 128) >= min_ctas) bn = 128;
   else if (N >= 192 && splitk == 1 && mt * ((N + 63) / 64) < 32) bn = 256;   // tiny grids: fewer, fatter CTAs
   const int64_t tiles = mt * ((N + bn - 1) / bn);
   int splits = splitk;

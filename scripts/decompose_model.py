@@ -63,9 +63,10 @@ for i in mine:
 layers = [(names[i], (lambda i=i: store[i])) for i in range(len(names))]
 
 # warm-up: one small-rank pass per distinct shape builds workspaces, graphs and attributes
+# (`streams` concurrent copies, so that every worker finds a captured graph in the pool)
 for shp in sorted(set(shapes[i] for i in mine)):
     i = next(k for k in mine if shapes[k] == shp)
-    sch.decompose_layers([layers[i]], [shapes[i]], params, 0, 1, device=dev, streams=1)
+    sch.decompose_layers([layers[i]] * a.streams, [shapes[i]] * a.streams, params, 0, 1, device=dev, streams=a.streams)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
