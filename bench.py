@@ -248,6 +248,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = load_peaks()
+    if args.gemm_ctas > 0:
+        lib.cb_set_gemm_target_ctas(args.gemm_ctas)
 
     fac = QuantizerFactory(method="uniform", block_size=64)
     qp = CalderaParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=ITERS, lplr_iters=5,
@@ -410,6 +412,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
+    ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")
     ap.add_argument("--streams", type=int, default=8, help="independent layers kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

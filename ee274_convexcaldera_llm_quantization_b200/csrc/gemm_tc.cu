@@ -323,6 +323,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcA
   return CB_OK;
 }
 
+int g_target_ctas = -1;
+
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
   return M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && lda % 8 == 0 &&
          ldb % 8 == 0 && lda >= K && ldb >= K && aligned16(A) && aligned16(B);
@@ -340,14 +342,17 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
   const int64_t mt = (M + TC_BM - 1) / TC_BM;
-  // CB_GEMM_MIN_CTAS (default 120): how many CTAs a grid must reach before a fatter N tile is
-  // preferred.  Fatter tiles move fewer bytes per flop (less SM-time, better throughput when several
-  // layers are in flight); thinner tiles fill the machine for one layer (lower latency).
-  static int min_ctas = -1;
-  if (min_ctas < 0) {
+  // g_target_ctas: how many CTAs a grid should reach before a fatter N tile / fewer K splits are
+  // preferred.  Every gemm_tc CTA owns an SM (192 KiB of shared memory), so grids from different
+  // streams only overlap when they are small: ~32-CTA grids let four layers' contractions run side by
+  // side and move fewer bytes per flop (throughput mode, several layers in flight); ~120-CTA grids
+  // fill the machine for one layer (latency mode, the default).  Set by cb_set_gemm_target_ctas or
+  // the CB_GEMM_MIN_CTAS environment variable.
+  if (g_target_ctas < 0) {
     const char* e = getenv("CB_GEMM_MIN_CTAS");
-    min_ctas = (e != nullptr && atoi(e) > 0) ? atoi(e) : 120;
+    g_target_ctas = (e != nullptr && atoi(e) > 0) ? atoi(e) : 120;
   }
+  const int min_ctas = g_target_ctas;
   int bn = 64;
   if (N >= 192 && mt * ((N + 255) / 256) >= min_ctas) bn = 256;
   else if (N >= 96 && mt * ((N + 127) / 128) >= min_ctas) bn = 128;
@@ -356,7 +361,8 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   int splits = splitk;
   if (splits <= 0) {
     splits = 1;
-    if (tiles < kNumSMs) splits = (int)((kNumSMs + tiles - 1) / tiles);
+    const int fill = min_ctas >= 120 ? kNumSMs : min_ctas;
+    if (tiles < fill) splits = (int)((fill + tiles - 1) / tiles);
     const int max_splits = total_kb / 4 > 0 ? total_kb / 4 : 1;  // at least 4 K blocks per slice
     if (splits > max_splits) splits = max_splits;
   }
@@ -446,3 +452,5 @@ extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64
   return cb::to_bf16(X, rows, cols, ldx, reinterpret_cast<__nv_bfloat16*>(Y_bf16), ldy,
                      reinterpret_cast<__nv_bfloat16*>(Yt_bf16), ldyt, colscale, (cudaStream_t)stream);
 }
+
+extern "C" void cb_set_gemm_target_ctas(int n) { cb::g_target_ctas = n > 0 ? n : 120; }

@@ -147,6 +147,10 @@ int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha,
 int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
                     const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int* error_flag,
                     void* stream);
+/* Grid-size policy of the tcgen05 contractions: ~120 (default) fills the machine for a single layer
+ * (lowest latency); ~32 keeps grids small so that the contractions of several layers in flight on
+ * different streams overlap (highest throughput).  Process-wide. */
+void cb_set_gemm_target_ctas(int n);
 /* fp32 (rows x cols, ldx) -> bf16 copy Y (ldy) and/or transposed copy Yt (cols x rows, ldyt),
  * optionally scaling column c by colscale[c] first. */
 int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
