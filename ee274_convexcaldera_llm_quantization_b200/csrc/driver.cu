@@ -31,7 +31,9 @@ struct LowrankBufs {
   float *P, *Po, *Z, *Zo, *G, *Linv, *B, *work, *evals, *V;
   int* status;  // [0] cholesky retries (max), [1] jacobi sweeps
   const uint64_t* seed_dev = nullptr;   // optional per-layer seed in device memory, added to the host seed
+  SplitWs sw;   // split-K scratch shared by every contraction of the layer (they all run on one stream)
 };
+
 
 static LowrankBufs plan_lowrank(Arena& a, int64_t m, int64_t n, int64_t q, float* Zo_persistent, int* status) {
   LowrankBufs b;
@@ -45,15 +47,16 @@ static LowrankBufs plan_lowrank(Arena& a, int64_t m, int64_t n, int64_t q, float
   b.work = a.take<float>(q * q + q + 8);
   b.evals = a.take<float>(q);
   b.V = a.take<float>(q * q);
+  b.sw.buf = a.take<float>(kSplitWsBytes / sizeof(float)); b.sw.bytes = kSplitWsBytes;
   b.status = status;
   return b;
 }
 
 // X (N x q) -> Xo (N x q) with orthonormal columns: CholeskyQR, G = X^T X = Lc Lc^T, Xo = X Lc^-T
 static int orthonormalize(const float* X, int64_t N, int64_t q, float* Xo, const LowrankBufs& b, cudaStream_t st) {
-  CB_TRY(sgemm(q, q, N, 1.f, X, 1, q, X, q, 1, b.G, q, 1, false, nullptr, st));
+  CB_TRY(sgemm(q, q, N, 1.f, X, 1, q, X, q, 1, b.G, q, 1, false, nullptr, st, &b.sw));
   CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st));
-  CB_TRY(sgemm(N, q, q, 1.f, X, q, 1, b.Linv, 1, q, Xo, q, 1, false, nullptr, st));
+  CB_TRY(sgemm(N, q, q, 1.f, X, q, 1, b.Linv, 1, q, Xo, q, 1, false, nullptr, st, &b.sw));
   return CB_OK;
 }
 
@@ -63,26 +66,26 @@ static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t
                         const LowrankBufs& b, cudaStream_t st) {
   if (!warm_valid) {
     CB_TRY(fill_randn(b.P, n * q, seed, b.seed_dev, st));
-    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.P, q, 1, b.Z, q, 1, false, nullptr, st));
+    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.P, q, 1, b.Z, q, 1, false, nullptr, st, &b.sw));
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
   }
   for (int it = 0; it < niter; ++it) {
-    CB_TRY(sgemm(n, q, m, 1.f, Y, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));  // P = Y^T Zo
+    CB_TRY(sgemm(n, q, m, 1.f, Y, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st, &b.sw));  // P = Y^T Zo
     CB_TRY(orthonormalize(b.P, n, q, b.Po, b, st));
-    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.Po, q, 1, b.Z, q, 1, false, nullptr, st));  // Z = Y Po
+    CB_TRY(sgemm(m, q, n, 1.f, Y, n, 1, b.Po, q, 1, b.Z, q, 1, false, nullptr, st, &b.sw));  // Z = Y Po
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
   }
   // second pass (CholeskyQR2) so the Rayleigh-Ritz basis is orthonormal to fp32 accuracy
   CB_TRY(orthonormalize(b.Zo, m, q, b.Z, b, st));
   CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
   // B = Zo^T Y (q x n); G = B B^T; eigen-decomposition through the Cholesky factor
-  CB_TRY(sgemm(q, n, m, 1.f, b.Zo, 1, q, Y, n, 1, b.B, n, 1, false, nullptr, st));
-  CB_TRY(sgemm(q, q, n, 1.f, b.B, n, 1, b.B, 1, n, b.G, q, 1, false, nullptr, st));
+  CB_TRY(sgemm(q, n, m, 1.f, b.Zo, 1, q, Y, n, 1, b.B, n, 1, false, nullptr, st, &b.sw));
+  CB_TRY(sgemm(q, q, n, 1.f, b.B, n, 1, b.B, 1, n, b.G, q, 1, false, nullptr, st, &b.sw));
   CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
   CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
   // L = Zo V_r^T, R = V_r B (column-scaled by 1/sqrt(h) when aware: S V^T H^-1/2, alg.py:220-225)
-  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st));
-  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.B, n, 1, R, n, 1, false, aware ? inv_sqrt_h : nullptr, st));
+  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st, &b.sw));
+  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.B, n, 1, R, n, 1, false, aware ? inv_sqrt_h : nullptr, st, &b.sw));
   if (!aware) {
     // L = U sqrt(S), R = sqrt(S) V^T (alg.py:233-234); evals are squared singular values
     CB_TRY(scale_cols(L, m, r, b.evals, 2, L, st));
@@ -90,7 +93,7 @@ static int lowrank_core(const float* Y, int64_t m, int64_t n, int64_t r, int64_t
   }
   // leave the basis rotated into its Ritz vectors (sorted): the next warm-started solve then
   // sees a nearly diagonal projected matrix and the Jacobi step converges in 2-3 sweeps
-  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st));
+  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st, &b.sw));
   CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
@@ -109,13 +112,14 @@ struct LowrankTcBufs {
   float *G, *Linv, *work, *evals, *V;
   int* status;                    // [0] cholesky retries, [1] jacobi sweeps, [2] gemm watchdog
   const uint64_t* seed_dev = nullptr;
+  SplitWs sw;                     // the layer's split-K scratch (same one as LowrankBufs::sw)
 };
 
 static bool lowrank_tc_usable(int64_t m, int64_t n, int64_t r, int64_t q) {
   return m % 8 == 0 && n % 8 == 0 && q % 8 == 0 && r % 8 == 0 && m >= 256 && n >= 256 && q >= 16;
 }
 
-static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, int* status) {
+static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, int* status, const SplitWs& sw) {
   LowrankTcBufs b;
   b.Yb = a.take<bf16>(m * n); b.Ytb = a.take<bf16>(n * m);
   b.Ptb = a.take<bf16>(q * n); b.Pb = a.take<bf16>(n * q); b.Potb = a.take<bf16>(q * n);
@@ -123,6 +127,7 @@ static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, 
   b.Linvb = a.take<bf16>(q * q); b.Bb = a.take<bf16>(q * n); b.Btb = a.take<bf16>(n * q); b.Vb = a.take<bf16>(q * q);
   b.G = a.take<float>(q * q); b.Linv = a.take<float>(q * q); b.work = a.take<float>(q * q + q + 8);
   b.evals = a.take<float>(q); b.V = a.take<float>(q * q);
+  b.sw = sw;
   b.status = status;
   return b;
 }
@@ -140,10 +145,8 @@ __global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p, i
 static int orthonormalize_tc(const bf16* Xt, const bf16* X, int64_t N, int64_t q, bf16* Xot, bf16* Xo,
                              const LowrankTcBufs& b, cudaStream_t st) {
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
-  CB_CUDA(cudaMemsetAsync(b.G, 0, sizeof(float) * q * q, st));
-  CB_TRY(gemm_tc(q, q, N, 1.f, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
-  CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st));
-  CB_TRY(to_bf16(b.Linv, q, q, q, b.Linvb, q, nullptr, 0, nullptr, st));
+  CB_TRY(gemm_tc(q, q, N, 1.f, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &b.sw));
+  CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st, b.Linvb));
   // Xot[q, N] = Linv[q, K=q] * X[N, K=q]^T
   CB_TRY(gemm_tc(q, N, q, 1.f, b.Linvb, q, X, q, nullptr, 0, Xot, N, Xo, q, nullptr, nullptr, 1, wd, nullptr, st));
   return CB_OK;
@@ -173,8 +176,7 @@ static int lowrank_core_tc(int64_t m, int64_t n, int64_t r, int64_t q, int niter
   CB_TRY(orthonormalize_tc(b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
   // B[q, n] = Zot[q, K=m] * Yt[n, K=m]^T  (bf16 in both orientations); G = B B^T in fp32
   CB_TRY(gemm_tc(q, n, m, 1.f, b.Zotb, m, b.Ytb, m, nullptr, 0, b.Bb, n, b.Btb, q, nullptr, nullptr, 1, wd, nullptr, st));
-  CB_CUDA(cudaMemsetAsync(b.G, 0, sizeof(float) * q * q, st));
-  CB_TRY(gemm_tc(q, q, n, 1.f, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+  CB_TRY(gemm_tc(q, q, n, 1.f, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &b.sw));
   CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
   CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
   CB_TRY(to_bf16(b.V, q, q, q, b.Vb, q, nullptr, 0, nullptr, st));
@@ -266,7 +268,7 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
     L.lr = plan_lowrank(a, m, n, L.q, L.Zwarm, nullptr);
     L.use_tc = p->use_tensor_cores != 0 && !L.dense && lowrank_tc_usable(m, n, r, L.q);
     if (L.use_tc) {
-      L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr);
+      L.tc = plan_lowrank_tc(a, m, n, L.q, nullptr, L.lr.sw);
       L.Lb16 = a.take<bf16>(3 * m * r);
       L.Rtb16 = a.take<bf16>(3 * n * r);
       if (L.quant_factors) {
@@ -351,27 +353,27 @@ static int lowrank_core_dense(const float* res, const float* Hs, int64_t m, int6
                               const LowrankBufs& b, cudaStream_t st) {
   if (!warm_valid) {
     CB_TRY(fill_randn(b.P, n * q, seed, b.seed_dev, st));
-    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st));
-    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st));
+    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st, &b.sw));
+    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st, &b.sw));
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
   }
   for (int it = 0; it < niter; ++it) {
-    CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));   // P = res^T Zo
+    CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st, &b.sw));   // P = res^T Zo
     CB_TRY(orthonormalize(b.P, n, q, b.Po, b, st));
-    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.Po, q, 1, HP, q, 1, false, nullptr, st));     // HP = H Po
-    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st));     // Z = res HP
+    CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.Po, q, 1, HP, q, 1, false, nullptr, st, &b.sw));     // HP = H Po
+    CB_TRY(sgemm(m, q, n, 1.f, res, n, 1, HP, q, 1, b.Z, q, 1, false, nullptr, st, &b.sw));     // Z = res HP
     CB_TRY(orthonormalize(b.Z, m, q, b.Zo, b, st));
   }
   CB_TRY(orthonormalize(b.Zo, m, q, b.Z, b, st));
   CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
-  CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st));     // P = res^T Zo
-  CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st));
-  CB_TRY(sgemm(q, q, n, 1.f, b.P, 1, q, HP, q, 1, b.G, q, 1, false, nullptr, st));       // G = P^T H P
+  CB_TRY(sgemm(n, q, m, 1.f, res, 1, n, b.Zo, q, 1, b.P, q, 1, false, nullptr, st, &b.sw));     // P = res^T Zo
+  CB_TRY(sgemm(n, q, n, 1.f, Hs, n, 1, b.P, q, 1, HP, q, 1, false, nullptr, st, &b.sw));
+  CB_TRY(sgemm(q, q, n, 1.f, b.P, 1, q, HP, q, 1, b.G, q, 1, false, nullptr, st, &b.sw));       // G = P^T H P
   CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st));
   CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st));
-  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st));       // L = Zo V_r^T
-  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.P, 1, q, R, n, 1, false, nullptr, st));        // R = V_r P^T
-  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st));     // Ritz rotation (warm start)
+  CB_TRY(sgemm(m, r, q, 1.f, b.Zo, q, 1, b.V, 1, q, L, r, 1, false, nullptr, st, &b.sw));       // L = Zo V_r^T
+  CB_TRY(sgemm(r, n, q, 1.f, b.V, q, 1, b.P, 1, q, R, n, 1, false, nullptr, st, &b.sw));        // R = V_r P^T
+  CB_TRY(sgemm(m, q, q, 1.f, b.Zo, q, 1, b.V, 1, q, b.Z, q, 1, false, nullptr, st, &b.sw));     // Ritz rotation (warm start)
   CB_CUDA(cudaMemcpyAsync(b.Zo, b.Z, sizeof(float) * m * q, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
@@ -384,7 +386,7 @@ static int dense_quadratic(const LayerPlan& P, const float* A, const void* codes
     CB_TRY(form_e(A, codes, bits, qscale, LR, m, n, P.Ebuf, st));
     E = P.Ebuf;
   }
-  CB_TRY(sgemm(m, n, n, 1.f, E, n, 1, P.Hs, n, 1, P.Tbuf, n, 1, false, nullptr, st));
+  CB_TRY(sgemm(m, n, n, 1.f, E, n, 1, P.Hs, n, 1, P.Tbuf, n, 1, false, nullptr, st, &P.lr.sw));
   return dot_accum(P.Tbuf, squared ? P.Tbuf : E, m * n, out, st);
 }
 
@@ -437,26 +439,26 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
   for (int k = 0; k < p->lplr_iters; ++k) {
     // ---- L update: weighted normal equations (alg.py:163 / :167)
     if (P.dense && p->aware) {
-      CB_TRY(sgemm(n, r, n, 1.f, P.Hs, n, 1, P.Rcur, 1, n, P.HRt, r, 1, false, nullptr, st));   // H R^T
-      CB_TRY(sgemm(r, r, n, 1.f, P.Rcur, n, 1, P.HRt, r, 1, P.Gs, r, 1, false, nullptr, st));   // R H R^T
-      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, P.HRt, r, 1, P.Bl, r, 1, false, nullptr, st));      // res H R^T
+      CB_TRY(sgemm(n, r, n, 1.f, P.Hs, n, 1, P.Rcur, 1, n, P.HRt, r, 1, false, nullptr, st, &P.lr.sw));   // H R^T
+      CB_TRY(sgemm(r, r, n, 1.f, P.Rcur, n, 1, P.HRt, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));   // R H R^T
+      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, P.HRt, r, 1, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));      // res H R^T
     } else {
       const float* Rw = P.Rcur;
       if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
-      CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st));     // R diag(h) R^T
-      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st));        // res diag(h) R^T
+      CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));     // R diag(h) R^T
+      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));        // res diag(h) R^T
     }
     CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st));
+    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
     CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));  // alg.py:171-172
     // ---- R update (alg.py:175)
-    CB_TRY(sgemm(r, r, m, 1.f, P.Lcur, 1, r, P.Lcur, r, 1, P.Gs, r, 1, false, nullptr, st));  // L^T L
-    CB_TRY(sgemm(r, n, m, 1.f, P.Lcur, 1, r, res, n, 1, P.Br, n, 1, false, nullptr, st));     // L^T res
+    CB_TRY(sgemm(r, r, m, 1.f, P.Lcur, 1, r, P.Lcur, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));  // L^T L
+    CB_TRY(sgemm(r, n, m, 1.f, P.Lcur, 1, r, res, n, 1, P.Br, n, 1, false, nullptr, st, &P.lr.sw));     // L^T res
     CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st));
+    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
     CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));  // alg.py:179-180
     // ---- inner error ||(res - L R) H_sqrt||_F and best-so-far (alg.py:182-188)
-    CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st));
+    CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st, &P.lr.sw));
     if (P.dense) CB_TRY(dense_quadratic(P, res, nullptr, 8, nullptr, P.LRbuf, m, n, !p->aware, P.dsc + 3, st));
     else CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
     CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
@@ -485,22 +487,18 @@ static int lplr_refine_tc(const cb_caldera_params* p, const LayerPlan& P, int64_
   for (int k = 0; k < p->lplr_iters; ++k) {
     // ---- L update (alg.py:163 / :167)
     CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st));
-    CB_CUDA(cudaMemsetAsync(P.Gs, 0, sizeof(float) * r * r, st));
-    CB_TRY(gemm_tc(r, r, n, 1.f, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
-    CB_CUDA(cudaMemsetAsync(P.Bl, 0, sizeof(float) * m * r, st));
-    CB_TRY(gemm_tc(m, r, n, 1.f, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
+    CB_TRY(gemm_tc(r, r, n, 1.f, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
+    CB_TRY(gemm_tc(m, r, n, 1.f, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
     CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st));
+    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
     CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));
     // ---- R update (alg.py:175)
     CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st));
-    CB_CUDA(cudaMemsetAsync(P.Gs, 0, sizeof(float) * r * r, st));
-    CB_TRY(gemm_tc(r, r, m, 1.f, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st));
-    CB_CUDA(cudaMemsetAsync(P.Br, 0, sizeof(float) * r * n, st));
+    CB_TRY(gemm_tc(r, r, m, 1.f, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
     CB_TRY(gemm_tc(r, n, m, 1.f, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr,
-                   nullptr, 0, wd, nullptr, st));
+                   nullptr, 0, wd, nullptr, st, &P.tc.sw));
     CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st));
+    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
     CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));
     // ---- inner error and best-so-far (alg.py:182-188)
     CB_TRY(lr_product(P, m, n, r, st));
@@ -786,7 +784,7 @@ static int plan_convex(Arena& a, int64_t m, int64_t n, int64_t r, int64_t q, int
   P.lr = plan_lowrank(a, m, n, q, nullptr, nullptr);
   P.use_tc = use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, q);
   if (P.use_tc) {
-    P.tc = plan_lowrank_tc(a, m, n, q, nullptr);
+    P.tc = plan_lowrank_tc(a, m, n, q, nullptr, P.lr.sw);
     P.Lb16 = a.take<bf16>(3 * m * r);
     P.Rtb16 = a.take<bf16>(3 * n * r);
   }

@@ -58,6 +58,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// the same box delivered to the same shared-memory offset (and signalled on the same barrier offset)
+// of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -79,6 +99,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane base + t), register j = column j
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -115,7 +139,11 @@ struct GemmTcArgs {
   __nv_bfloat16* Ct; int64_t ldct;   // bf16 out, transposed (N x M), may be null (ignored when atomic)
   const float* colscale;             // per output column, may be null
   const float* rowscale;             // per output row, may be null
-  int atomic;                        // 1: split-K partial sums via red.global.add
+  int a_tiled, b_tiled;              // operand stored as contiguous 64 x 64 tiles (see make_tmap_bf16_tiled)
+  int loads_only;                    // measurement aid: run the TMA pipeline but issue no MMA (output undefined)
+  long long* timing;                 // measurement aid: 8 clock64 stamps of CTA (0,0,0), or null
+  int splits;                        // > 1: split-K, raw partial tiles go to `ws` for splitk_reduce_kernel
+  float* ws;                         // [tile][split][BN/32][128][32] fp32 partial tiles
   int* error_flag;
 };
 
@@ -130,10 +158,63 @@ struct TcSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
+// One thread's 32 consecutive output columns of one row: scaling, then the fp32 / bf16 /
+// transposed-bf16 stores the caller asked for.
+__device__ __forceinline__ void store_chunk(const GemmTcArgs& args, int row, int col0, float rs, float (&v)[32]) {
+  if (row >= args.M || col0 >= args.N) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = v[j] * args.alpha * rs;
+    if (args.colscale != nullptr && col0 + j < args.N) x *= args.colscale[col0 + j];
+    v[j] = x;
+  }
+  const bool full = (col0 + 32 <= args.N);
+  if (args.C != nullptr) {
+    float* p = args.C + (int64_t)row * args.ldc + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < args.N) p[j] = v[j];
+    }
+  }
+  if (args.Cb != nullptr) {
+    __nv_bfloat16* p = args.Cb + (int64_t)row * args.ldcb + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 w;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
+        w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(p + j) = w;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < args.N) p[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+  if (args.Ct != nullptr) {
+    // transposed: lanes hold consecutive rows -> coalesced 64-byte runs per column
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < args.N) args.Ct[(int64_t)(col0 + j) * args.ldct + row] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+// CL > 1: the CL CTAs of a cluster own neighbouring N tiles of the same M tile and K range, so they all
+// consume the same A tile.  Each loads 1/CL of it and multicasts the slice into every CTA's stage
+// buffer: A crosses the L2 -> SM fabric once per cluster instead of once per CTA.  A stage may be
+// refilled only after all CL consumers have drained it, so "empty" barriers count CL arrivals and the
+// MMA warp's commit is multicast to every CTA of the cluster.
+template <int BN, int STAGES, int CL>
+__device__ __forceinline__ void
+gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& args) {
   using S = TcSmem<BN, STAGES>;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t cta_rank = CL > 1 ? cluster_cta_rank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + STAGES * S::A_BYTES;
@@ -146,6 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  long long* stamps = (args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? args.timing : nullptr;
+  if (stamps != nullptr && threadIdx.x == 0) stamps[0] = clock64();               // kernel entry
   const int total_kb = (args.K + TC_BK - 1) / TC_BK;
   const int kb0 = blockIdx.z * args.kb_per_split;
   const int nkb = min(total_kb, kb0 + args.kb_per_split) - kb0;
@@ -154,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
       mbar_init(tmem_full_bar, 1);
       fence_barrier_init();
     }
@@ -162,20 +245,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(tmem_slot, BN);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peers' barriers exist before anything remote lands on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   bool ok = true;
 
   if (warp == 0) {
     if (lane == 0) {
+      if (stamps != nullptr) stamps[1] = clock64();                                // prologue done
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
+        if (stamps != nullptr && i == nkb - 1) stamps[2] = clock64();              // last load about to be issued
         mbar_expect_tx(full_bar(s), (uint32_t)(S::A_BYTES + S::B_BYTES));
-        tma_load_2d(a_base + s * S::A_BYTES, &tmA, full_bar(s), (kb0 + i) * TC_BK, m_blk * TC_BM);
-        tma_load_2d(b_base + s * S::B_BYTES, &tmB, full_bar(s), (kb0 + i) * TC_BK, n_blk * BN);
+        if constexpr (CL > 1)
+          tma_load_2d_mc(a_base + s * S::A_BYTES + cta_rank * (S::A_BYTES / CL), &tmA, full_bar(s), (kb0 + i) * TC_BK,
+                         m_blk * TC_BM + (int)cta_rank * (TC_BM / CL), kMask);
+        else if (args.a_tiled) tma_load_4d(a_base + s * S::A_BYTES, &tmA, full_bar(s), 0, 0, kb0 + i, m_blk * (TC_BM / 64));
+        else tma_load_2d(a_base + s * S::A_BYTES, &tmA, full_bar(s), (kb0 + i) * TC_BK, m_blk * TC_BM);
+        if (args.b_tiled) tma_load_4d(b_base + s * S::B_BYTES, &tmB, full_bar(s), 0, 0, kb0 + i, n_blk * (BN / 64));
+        else tma_load_2d(b_base + s * S::B_BYTES, &tmB, full_bar(s), (kb0 + i) * TC_BK, n_blk * BN);
       }
     }
   } else if (warp == 1) {
@@ -185,15 +276,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         if (!mbar_wait(full_bar(s), ph)) { ok = false; break; }
+        if (stamps != nullptr && i == 0) stamps[3] = clock64();                    // first stage landed
+        if (stamps != nullptr && i == nkb - 1) stamps[4] = clock64();              // last stage landed
         tc_fence_after();
         const uint64_t adesc = make_smem_desc_sw128(a_base + s * S::A_BYTES);
         const uint64_t bdesc = make_smem_desc_sw128(b_base + s * S::B_BYTES);
+        if (args.loads_only) {
+          if (i == 0) umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar(s)) : "memory");
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr>>4) field
           umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
+        // stage reusable once these MMAs have read it (in every CTA that shares the A slices)
+        if constexpr (CL > 1) umma_commit_mc(empty_bar(s), kMask);
+        else umma_commit(empty_bar(s));
       }
       umma_commit(tmem_full_bar);   // accumulator complete
     }
@@ -201,80 +301,158 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
     const int qd = warp & 3;
     if (!mbar_wait(tmem_full_bar, 0)) ok = false;
+    if (stamps != nullptr && threadIdx.x == 64) stamps[5] = clock64();             // accumulator complete
     ok = __all_sync(0xffffffffu, ok);
     tc_fence_after();
-    const int row = m_blk * TC_BM + qd * 32 + lane;
+    const int trow = qd * 32 + lane;               // row inside the tile
+    const int row = m_blk * TC_BM + trow;
     const float rs = (args.rowscale != nullptr && row < args.M) ? args.rowscale[row] : 1.f;
-    if (ok) {
+    if (args.splits <= 1) {
+      if (ok) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
-        const int col0 = n_blk * BN + c0;
-        if (row < args.M && col0 < args.N) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) * args.alpha * rs;
-            if (args.colscale != nullptr && col0 + j < args.N) x *= args.colscale[col0 + j];
-            v[j] = x;
-          }
-          const bool full = (col0 + 32 <= args.N);
-          if (args.atomic) {
-            float* p = args.C + (int64_t)row * args.ldc + col0;
-            if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          store_chunk(args, row, n_blk * BN + c0, rs, v);
+        }
+      }
+    } else {
+      // Split-K without atomics, so that results do not depend on arrival order: every slice
+      // parks its raw partial tile in the workspace ([tile][slice][BN/32][128][32] floats) and
+      // splitk_reduce_kernel, launched right behind on the same stream, adds the slices up in
+      // slice order and writes the outputs.
+      const int tile = m_blk * gridDim.x + n_blk;
+      if (ok) {
+        float* mine = args.ws + ((size_t)tile * args.splits + blockIdx.z) * (BN * TC_BM) + (size_t)trow * 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
+          float4* dst = reinterpret_cast<float4*>(mine + (size_t)(c0 / 32) * (TC_BM * 32));
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < args.N) atomicAdd(p + j, v[j]);
-            }
-          } else {
-            if (args.C != nullptr) {
-              float* p = args.C + (int64_t)row * args.ldc + col0;
-              if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < args.N) p[j] = v[j];
-              }
-            }
-            if (args.Cb != nullptr) {
-              __nv_bfloat16* p = args.Cb + (int64_t)row * args.ldcb + col0;
-              if (full && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 w;
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                  w.x = *reinterpret_cast<uint32_t*>(&t0); w.y = *reinterpret_cast<uint32_t*>(&t1);
-                  w.z = *reinterpret_cast<uint32_t*>(&t2); w.w = *reinterpret_cast<uint32_t*>(&t3);
-                  *reinterpret_cast<uint4*>(p + j) = w;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < args.N) p[j] = __float2bfloat16_rn(v[j]);
-              }
-            }
-            if (args.Ct != nullptr) {
-              // transposed: lanes hold consecutive rows -> coalesced 64-byte runs per column
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < args.N) args.Ct[(int64_t)(col0 + j) * args.ldct + row] = __float2bfloat16_rn(v[j]);
-            }
-          }
+          for (int j = 0; j < 8; ++j)
+            __stcg(dst + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
         }
       }
     }
   }
   if (!ok && args.error_flag != nullptr) atomicExch(args.error_flag, 1);
+  if (stamps != nullptr && threadIdx.x == 64) stamps[6] = clock64();               // epilogue stores issued
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still write or signal here
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+  if (stamps != nullptr && threadIdx.x == 0) stamps[7] = clock64();               // exit
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
+  gemm_tc_body<BN, STAGES, 1>(tmA, tmB, args);
+}
+
+template <int BN, int STAGES, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
+  gemm_tc_body<BN, STAGES, CL>(tmA, tmB, args);
+}
+
+// Measurement aid (bench / scripts only): back-to-back tcgen05.mma on one resident shared-memory
+// stage, no TMA and no per-stage barriers, to read off what the tensor pipe itself sustains for a
+// 128 x N x 16 instruction with both operands in shared memory.  out[0] = cycles for `n_mma` MMAs.
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mma_rate_probe_kernel(int n_mma, int distinct_k, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + 4 * TC_BM * TC_BK * 2;
+  const uint32_t bar = b_base + 4 * BN * TC_BK * 2;
+  const uint32_t tmem_slot = bar + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operands: zeros are as good as anything for timing
+  for (uint32_t i = threadIdx.x; i < (uint32_t)(4 * (TC_BM + BN) * TC_BK * 2 / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)))[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) {
+    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; ++i) {
+      const int st = (i / 4) % 4, k = i % 4;          // walk 4 stages x 4 K steps like the real main loop
+      const int sk = distinct_k ? k : 0, ss = distinct_k ? st : 0;
+      const uint64_t adesc = make_smem_desc_sw128(a_base + ss * (TC_BM * TC_BK * 2)) + (uint64_t)(2 * sk);
+      const uint64_t bdesc = make_smem_desc_sw128(b_base + ss * (BN * TC_BK * 2)) + (uint64_t)(2 * sk);
+      umma_bf16(tmem_base, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    if (blockIdx.x == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+// Second half of a split-K contraction: one thread per 4 output columns sums the slices of its
+// partial tile in slice order, then scales and stores like the unsplit epilogue.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const GemmTcArgs args, int bn, int tiles_n, int64_t total4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  // idx enumerates float4 slots in workspace order: [tile][chunk][row in tile][8]
+  const int j4 = (int)(idx & 7);
+  const int trow = (int)((idx >> 3) & (TC_BM - 1));
+  const int64_t rest = idx >> 10;                       // tile * (bn/32) + chunk
+  const int chunks = bn / 32;
+  const int chunk = (int)(rest % chunks);
+  const int tile = (int)(rest / chunks);
+  const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+  const size_t tile_elems = (size_t)bn * TC_BM;
+  const float* src = args.ws + (size_t)tile * args.splits * tile_elems + (size_t)chunk * (TC_BM * 32) +
+                     (size_t)trow * 32 + (size_t)j4 * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+  for (int z = 0; z < args.splits; ++z) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * tile_elems));
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  const int row = m_blk * TC_BM + trow;
+  const int col = n_blk * bn + chunk * 32 + j4 * 4;
+  if (row >= args.M || col >= args.N) return;
+  const float rs = args.alpha * (args.rowscale != nullptr ? args.rowscale[row] : 1.f);
+  float v[4] = {acc.x * rs, acc.y * rs, acc.z * rs, acc.w * rs};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (args.colscale != nullptr && col + j < args.N) v[j] *= args.colscale[col + j];
+  if (args.C != nullptr) {
+    float* p = args.C + (int64_t)row * args.ldc + col;
+    if (col + 4 <= args.N && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else
+      for (int j = 0; j < 4; ++j)
+        if (col + j < args.N) p[j] = v[j];
+  }
+  for (int j = 0; j < 4; ++j) {
+    if (col + j >= args.N) break;
+    if (args.Cb != nullptr) args.Cb[(int64_t)row * args.ldcb + col + j] = __float2bfloat16_rn(v[j]);
+    if (args.Ct != nullptr) args.Ct[(int64_t)(col + j) * args.ldct + row] = __float2bfloat16_rn(v[j]);
   }
 }
 
@@ -309,6 +487,24 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64
   return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
 }
 
+// The same matrix stored as contiguous 64 (rows) x 64 (K) tiles, K blocks of one row block adjacent:
+// element (r, k) lives at ((r/64) * (K/64) + k/64) * 4096 + (r%64) * 64 + k%64.  A CTA that walks K
+// for its rows then streams one contiguous region of HBM instead of 128-byte pieces 2*ld bytes apart.
+// rows and K must be multiples of 64.  The box lands in shared memory exactly like the 2-D one.
+static int make_tmap_bf16_tiled(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return CB_ERR_UNSUPPORTED;
+  if (rows % 64 != 0 || K % 64 != 0 || box_rows % 64 != 0) return CB_ERR_ARG;
+  cuuint64_t gdim[4] = {64, 64, (cuuint64_t)(K / 64), (cuuint64_t)(rows / 64)};
+  cuuint64_t gstride[3] = {128, 8192, (cuuint64_t)(K / 64) * 8192};
+  cuuint32_t box[4] = {64, 64, 1, (cuuint32_t)(box_rows / 64)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& args, int splits, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
@@ -323,21 +519,40 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcA
   return CB_OK;
 }
 
+template <int BN, int STAGES, int CL>
+static int launch_tc_mc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& args, int splits, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr = true;
+  }
+  dim3 grid((unsigned)((args.N + BN - 1) / BN), (unsigned)((args.M + TC_BM - 1) / TC_BM), (unsigned)splits);
+  gemm_tc_mc_kernel<BN, STAGES, CL><<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, args);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
 int g_target_ctas = -1;
+long long* g_timing = nullptr;   // measurement aid, see cb_set_gemm_timing
+int g_cluster = -1;   // CTAs sharing one multicast A tile (1 = off); CB_GEMM_CLUSTER overrides
 
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
   return M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && lda % 8 == 0 &&
          ldb % 8 == 0 && lda >= K && ldb >= K && aligned16(A) && aligned16(B);
 }
 
-// splitk <= 0: choose automatically so the grid fills the machine.  With split-K the fp32
-// output C must be zero-initialised by the caller (partials are atomically added) unless
-// `accumulate` semantics are wanted.
+// splitk <= 0: choose automatically so the grid fills the machine.  Split-K needs the scratch in
+// `sw` (see SplitWs) and runs as two launches (partial tiles, then splitk_reduce_kernel); outputs are
+// overwritten, never accumulated into, and the sum over K slices is taken in slice order, so a given
+// (shape, grid policy) always produces the same bits.
 int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A, int64_t lda,
             const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, __nv_bfloat16* Cb, int64_t ldcb,
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
-            int* error_flag, int* splits_used, cudaStream_t st) {
+            int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw, int tiled_operands) {
   if (!gemm_tc_supported(M, N, K, A, lda, B, ldb)) return CB_ERR_UNSUPPORTED;
+  const bool a_tiled = (tiled_operands & 1) != 0, b_tiled = (tiled_operands & 2) != 0;
+  if ((a_tiled && (M % 64 != 0 || K % 64 != 0)) || (b_tiled && (N % 64 != 0 || K % 64 != 0))) return CB_ERR_ARG;
   // largest N tile that still yields >= ~0.8 waves of CTAs; otherwise the smallest tile
   // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
@@ -367,21 +582,53 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
     if (splits > max_splits) splits = max_splits;
   }
   if (splits > total_kb) splits = total_kb;
+  if (splits > 1) {
+    // bounded by the scratch the caller provided
+    const size_t per_split = (size_t)tiles * TC_BM * bn * sizeof(float);
+    const int fit = (sw != nullptr && sw->buf != nullptr) ? (int)(sw->bytes / per_split) : 1;
+    if (splits > fit) splits = fit;
+  }
   if (splits < 1) splits = 1;
   int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;
-  if (splits > 1 && C == nullptr) return CB_ERR_ARG;
   if (splits_used != nullptr) *splits_used = splits;
   CUtensorMap ta, tb;
-  CB_TRY(make_tmap_bf16(&ta, A, M, K, lda, TC_BM));
-  CB_TRY(make_tmap_bf16(&tb, B, N, K, ldb, bn));
+  // multicast of the A tile across neighbouring N tiles (smallest N tile only: that is where A traffic dominates)
+  const bool loads_only = (tiled_operands & 4) != 0;
+  if (g_cluster < 0) {
+    const char* e = getenv("CB_GEMM_CLUSTER");
+    g_cluster = (e != nullptr) ? atoi(e) : 4;
+  }
+  int cl = 1;
+  const int64_t tiles_n = (N + bn - 1) / bn;
+  if (bn == 64 && !a_tiled && !loads_only && tiles_n >= 8) {
+    if (g_cluster >= 8 && tiles_n % 8 == 0) cl = 8;
+    else if (g_cluster >= 4 && tiles_n % 4 == 0) cl = 4;
+    else if (g_cluster >= 2 && tiles_n % 2 == 0) cl = 2;
+  }
+  if (a_tiled) CB_TRY(make_tmap_bf16_tiled(&ta, A, M, K, TC_BM));
+  else CB_TRY(make_tmap_bf16(&ta, A, M, K, lda, TC_BM / cl));
+  if (b_tiled) CB_TRY(make_tmap_bf16_tiled(&tb, B, N, K, bn));
+  else CB_TRY(make_tmap_bf16(&tb, B, N, K, ldb, bn));
   GemmTcArgs args;
   args.M = (int)M; args.N = (int)N; args.K = (int)K; args.kb_per_split = kb_per; args.alpha = alpha;
   args.C = C; args.ldc = ldc; args.Cb = Cb; args.ldcb = ldcb; args.Ct = Ct; args.ldct = ldct;
-  args.colscale = colscale; args.rowscale = rowscale; args.atomic = splits > 1 ? 1 : 0; args.error_flag = error_flag;
-  if (bn == 256) return launch_tc<256, 4>(ta, tb, args, splits, st);
-  if (bn == 128) return launch_tc<128, 6>(ta, tb, args, splits, st);
-  return launch_tc<64, 8>(ta, tb, args, splits, st);
+  args.colscale = colscale; args.rowscale = rowscale; args.error_flag = error_flag;
+  args.splits = splits; args.ws = splits > 1 ? sw->buf : nullptr;
+  args.a_tiled = a_tiled ? 1 : 0; args.b_tiled = b_tiled ? 1 : 0; args.loads_only = loads_only ? 1 : 0;
+  args.timing = g_timing;
+  if (bn == 256) CB_TRY((launch_tc<256, 4>(ta, tb, args, splits, st)));
+  else if (bn == 128) CB_TRY((launch_tc<128, 6>(ta, tb, args, splits, st)));
+  else if (cl == 8) CB_TRY((launch_tc_mc<64, 8, 8>(ta, tb, args, splits, st)));
+  else if (cl == 4) CB_TRY((launch_tc_mc<64, 8, 4>(ta, tb, args, splits, st)));
+  else if (cl == 2) CB_TRY((launch_tc_mc<64, 8, 2>(ta, tb, args, splits, st)));
+  else CB_TRY((launch_tc<64, 8>(ta, tb, args, splits, st)));
+  if (splits > 1) {
+    const int64_t total4 = tiles * TC_BM * (bn / 4);
+    splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(args, bn, (int)((N + bn - 1) / bn), total4);
+    CB_CHECK_LAUNCH();
+  }
+  return CB_OK;
 }
 
 // fp32 -> bf16 (optionally transposed and/or scaled) conversions around the tensor-core path
@@ -433,17 +680,23 @@ int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat
 }  // namespace cb
 
 // C ABI: exported so the tensor-core path can be validated in isolation against a reference GEMM
+extern "C" size_t cb_gemm_bf16_tn_workspace_bytes(void) { return cb::kSplitWsBytes; }
+
 extern "C" int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
-                               const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int* error_flag,
-                               void* stream) {
+                               const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int operand_layout,
+                               int* error_flag, void* workspace, size_t workspace_bytes, void* stream) {
   if (A_bf16 == nullptr || B_bf16 == nullptr || C == nullptr) return CB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   int splits = 0;
-  // split-K accumulates atomically: clear the output first (row by row when ldc > N)
-  if (splitk != 1) CB_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+  cb::SplitWs sw;
+  if (workspace != nullptr && workspace_bytes > 0) {
+    sw.buf = reinterpret_cast<float*>(workspace); sw.bytes = workspace_bytes;
+  } else if (splitk > 1) {
+    return CB_ERR_WORKSPACE;
+  }
   return cb::gemm_tc(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A_bf16), lda,
                      reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, C, ldc, nullptr, 0, nullptr, 0, nullptr,
-                     nullptr, splitk, error_flag, &splits, st);
+                     nullptr, splitk, error_flag, &splits, st, &sw, operand_layout);
 }
 
 extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
@@ -453,4 +706,26 @@ extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64
                      reinterpret_cast<__nv_bfloat16*>(Yt_bf16), ldyt, colscale, (cudaStream_t)stream);
 }
 
+// Measurement aid: cycles for n_mma back-to-back 128 x bn x 16 bf16 MMAs on every SM of a `grid`-CTA launch
+// (out: 2 device int64: [0] issue + drain, [1] issue only).
+extern "C" int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream) {
+  if (out_cycles == nullptr || n_mma < 1 || grid < 1) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 4 * (cb::TC_BM + bn) * cb::TC_BK * 2 + 64 + 1024;
+#define CB_PROBE(BN)                                                                                              \
+  do {                                                                                                            \
+    CB_CUDA(cudaFuncSetAttribute(cb::mma_rate_probe_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    cb::mma_rate_probe_kernel<BN><<<grid, cb::TC_THREADS, smem, st>>>(n_mma, distinct_k, (long long*)out_cycles);  \
+  } while (0)
+  if (bn == 64) CB_PROBE(64);
+  else if (bn == 128) CB_PROBE(128);
+  else if (bn == 256) CB_PROBE(256);
+  else return CB_ERR_ARG;
+#undef CB_PROBE
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" void cb_set_gemm_timing(void* stamps_dev) { cb::g_timing = reinterpret_cast<long long*>(stamps_dev); }
 extern "C" void cb_set_gemm_target_ctas(int n) { cb::g_target_ctas = n > 0 ? n : 120; }
+extern "C" void cb_set_gemm_cluster(int n) { cb::g_cluster = n >= 1 ? n : 4; }

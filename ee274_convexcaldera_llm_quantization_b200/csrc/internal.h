@@ -6,13 +6,24 @@
 
 namespace cb {
 
+// Scratch for split-K: the partial tiles of every K slice, summed in slice order by a reduce launch
+// that follows the contraction on the same stream (no floating-point atomics).  Without it, or when
+// it is too small, the contraction runs unsplit.
+struct SplitWs {
+  float* buf = nullptr;
+  size_t bytes = 0;
+};
+constexpr size_t kSplitWsBytes = 12u << 20;
+
+
 // sgemm.cu -- C(i,j) = alpha * sum_k A(i,k) B(k,j) [* colscale[j]] (+ C), arbitrary strides
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
           const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
-          bool accumulate, const float* colscale, cudaStream_t st);
+          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw = nullptr);
 
 // smalldense.cu
-int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st);
+int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st,
+                     __nv_bfloat16* Linv_bf16 = nullptr);
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
                           cudaStream_t st);
 
@@ -64,7 +75,8 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t l
 int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A, int64_t lda,
             const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, __nv_bfloat16* Cb, int64_t ldcb,
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
-            int* error_flag, int* splits_used, cudaStream_t st);
+            int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw = nullptr,
+            int tiled_operands = 0 /* bit 0: A, bit 1: B stored as contiguous 64 x 64 tiles */);
 int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
             __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st);
 

@@ -3,8 +3,10 @@
 // This is the path for contractions whose shapes the tcgen05 tile kernels (gemm_tc.cu) do
 // not cover -- ragged or tiny dimensions, the r x r / q x q products of the least-squares
 // and orthonormalisation steps -- and the in-library reference those kernels are checked
-// against.  Shared-memory tiled, register micro-tiles, split-K through fp32 atomics when
-// the output alone cannot fill 148 SMs.
+// against.  Shared-memory tiled, register micro-tiles; split-K when the output alone cannot
+// fill 148 SMs and the caller provides scratch: every K slice parks its register tile in the
+// scratch and the last CTA of a tile to arrive sums the slices in slice order (no floating-
+// point atomics, so equal inputs give equal bits).
 #include "common.cuh"
 #include "internal.h"
 
@@ -16,7 +18,8 @@ sgemm_kernel(int M, int N, int K, float alpha,
              const float* __restrict__ A, int64_t a_rs, int64_t a_cs,
              const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
              float* __restrict__ C, int64_t c_rs, int64_t c_cs,
-             const float* __restrict__ colscale, int klen, int mode /*0 store, 1 accumulate, 2 atomic*/) {
+             const float* __restrict__ colscale, int klen, int mode /*0 store, 1 accumulate*/,
+             float* __restrict__ split_ws) {
   constexpr int TM = 16 * MT, TN = 16 * MT, TK = 16;
   constexpr int H = MT / 4;
   __shared__ __align__(16) float As[TK][TM + 4];
@@ -67,6 +70,19 @@ sgemm_kernel(int M, int N, int K, float alpha,
     __syncthreads();
   }
 
+  if (gridDim.z > 1) {
+    // split-K: park the raw register tile ([tile][slice][thread][MT*MT]); sgemm_splitk_reduce_kernel
+    // follows on the same stream
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    float4* mine = reinterpret_cast<float4*>(split_ws + ((size_t)tile * gridDim.z + blockIdx.z) * (256 * MT * MT) +
+                                             (size_t)tid * (MT * MT));
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < MT; j += 4) __stcg(mine + (i * MT + j) / 4, make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]));
+    return;
+  }
+
 #pragma unroll
   for (int i = 0; i < MT; ++i) {
     const int gm = bm + (i / 4) * 64 + ty * 4 + (i & 3);
@@ -78,10 +94,47 @@ sgemm_kernel(int M, int N, int K, float alpha,
       float v = alpha * acc[i][j];
       if (colscale != nullptr) v *= colscale[gn];
       float* p = C + (int64_t)gm * c_rs + (int64_t)gn * c_cs;
-      if (mode == 2) atomicAdd(p, v);
-      else if (mode == 1) *p += v;
+      if (mode == 1) *p += v;
       else *p = v;
     }
+  }
+}
+
+// Sums the K slices of a split sgemm in slice order; one thread per 4 consecutive output columns.
+template <int MT>
+__global__ void __launch_bounds__(256)
+sgemm_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int tiles_n, int M, int N, float alpha,
+                           float* __restrict__ C, int64_t c_rs, int64_t c_cs, const float* __restrict__ colscale,
+                           int mode, int64_t total4) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  constexpr int QUADS = MT * MT / 4, T = 16 * MT;
+  const int quad = (int)(idx % QUADS);
+  const int tid = (int)((idx / QUADS) & 255);
+  const int tile = (int)(idx / (QUADS * 256));
+  const size_t tile_elems = (size_t)256 * MT * MT;
+  const float* src = ws + (size_t)tile * splits * tile_elems + (size_t)tid * (MT * MT) + (size_t)quad * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+  for (int z = 0; z < splits; ++z) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * tile_elems));
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  const int i = (quad * 4) / MT, j = (quad * 4) % MT;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int gm = (tile / tiles_n) * T + (i / 4) * 64 + ty * 4 + (i & 3);
+  const int gn0 = (tile % tiles_n) * T + (j / 4) * 64 + tx * 4;
+  if (gm >= M) return;
+  const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int gn = gn0 + c;
+    if (gn >= N) break;
+    float x = alpha * v[c];
+    if (colscale != nullptr) x *= colscale[gn];
+    float* p = C + (int64_t)gm * c_rs + (int64_t)gn * c_cs;
+    if (mode == 1) *p += x;
+    else *p = x;
   }
 }
 
@@ -95,7 +148,7 @@ __global__ void fill_strided_kernel(float* C, int M, int N, int64_t c_rs, int64_
 
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
           const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
-          bool accumulate, const float* colscale, cudaStream_t st) {
+          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw) {
   if (M < 0 || N < 0 || K < 0 || (M > 0 && N > 0 && (C == nullptr)) ||
       (K > 0 && M > 0 && N > 0 && (A == nullptr || B == nullptr)))
     return CB_ERR_ARG;
@@ -112,28 +165,25 @@ int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t 
   const int T = big ? 128 : 64;
   const int64_t tiles = ((M + T - 1) / T) * ((N + T - 1) / T);
   int splitk = 1;
-  if (tiles < 2 * kNumSMs && K >= 512) {
+  if (tiles < 2 * kNumSMs && K >= 512 && sw != nullptr && sw->buf != nullptr) {
     splitk = (int)((2 * kNumSMs + tiles - 1) / tiles);
     const int maxsplit = (int)(K / 128);
     if (splitk > maxsplit) splitk = maxsplit;
+    const int fit = (int)(sw->bytes / ((size_t)tiles * T * T * sizeof(float)));   // scratch the caller provided
+    if (splitk > fit) splitk = fit;
     if (splitk < 1) splitk = 1;
   }
   int klen = (int)((K + splitk - 1) / splitk);
   klen = ((klen + 15) / 16) * 16;
   splitk = (int)((K + klen - 1) / klen);
-  int mode = accumulate ? 1 : 0;
-  if (splitk > 1) {
-    if (!accumulate) {
-      fill_strided_kernel<<<grid_for(M * N, 256, 4), 256, 0, st>>>(C, (int)M, (int)N, c_rs, c_cs, 0.f);
-      CB_CHECK_LAUNCH();
-    }
-    mode = 2;
-  }
+  const int mode = accumulate ? 1 : 0;
+  float* split_ws = splitk > 1 ? sw->buf : nullptr;
   dim3 grid((unsigned)((N + T - 1) / T), (unsigned)((M + T - 1) / T), (unsigned)splitk);
   const bool akc = (a_cs == 1), bnc = (b_cs == 1);
 #define CB_SGEMM_LAUNCH(MT, AK, BN)                                                                     \
   sgemm_kernel<MT, AK, BN><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, a_rs, a_cs, B, b_rs, \
-                                                 b_cs, C, c_rs, c_cs, colscale, klen, mode)
+                                                 b_cs, C, c_rs, c_cs, colscale, klen, mode, \
+                                                 split_ws)
   if (big) {
     if (akc && bnc) CB_SGEMM_LAUNCH(8, true, true);
     else if (akc) CB_SGEMM_LAUNCH(8, true, false);
@@ -147,6 +197,18 @@ int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t 
   }
 #undef CB_SGEMM_LAUNCH
   CB_CHECK_LAUNCH();
+  if (splitk > 1) {
+    const int64_t total4 = tiles * 256 * (big ? 16 : 4);
+    const unsigned blocks = (unsigned)((total4 + 255) / 256);
+    const int tiles_n = (int)((N + T - 1) / T);
+    if (big)
+      sgemm_splitk_reduce_kernel<8><<<blocks, 256, 0, st>>>(split_ws, splitk, tiles_n, (int)M, (int)N, alpha, C, c_rs, c_cs,
+                                                           colscale, mode, total4);
+    else
+      sgemm_splitk_reduce_kernel<4><<<blocks, 256, 0, st>>>(split_ws, splitk, tiles_n, (int)M, (int)N, alpha, C, c_rs, c_cs,
+                                                           colscale, mode, total4);
+    CB_CHECK_LAUNCH();
+  }
   return CB_OK;
 }
 
@@ -156,5 +218,5 @@ extern "C" int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha, co
                                 int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C,
                                 int64_t c_rs, int64_t c_cs, int accumulate, void* stream) {
   return cb::sgemm(M, N, K, alpha, A, a_rs, a_cs, B, b_rs, b_cs, C, c_rs, c_cs, accumulate != 0, nullptr,
-                   (cudaStream_t)stream);
+                   (cudaStream_t)stream, nullptr);
 }

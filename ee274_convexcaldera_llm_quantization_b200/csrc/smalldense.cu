@@ -277,7 +277,8 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tile
 constexpr int CHOL_THREADS = 512;   // 128 registers/thread: the 32x32 diagonal factor lives in registers
 
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __restrict__ status) {
+chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfloat16* __restrict__ Linv_bf16,
+                int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -314,11 +315,15 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, int* __r
     diag_block_inverses(G, q, Linv);
     __syncthreads();
     tri_inverse(G, q, Linv, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
+    // the tensor-core contractions consume Linv as a bf16 operand: emit it here rather than
+    // in a separate conversion launch (tri_inverse ends with a CTA barrier)
+    if (Linv_bf16 != nullptr)
+      for (int e = tid; e < q * q; e += blockDim.x) Linv_bf16[e] = __float2bfloat16_rn(Linv[e]);
   }
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }
 
-int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st) {
+int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st, __nv_bfloat16* Linv_bf16) {
   if (G == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
   static bool attr_set = false;
@@ -326,7 +331,7 @@ int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st)
     CB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
     attr_set = true;
   }
-  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, status);
+  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -142,15 +142,33 @@ int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha,
 /* C (M x N fp32, ldc) = alpha * A (M x K) * B (N x K)^T with bf16 operands, both K-major
  * (lda, ldb in elements, multiples of 8), fp32 accumulation in tensor memory: the
  * tcgen05 / TMEM / TMA contraction kernel (csrc/gemm_tc.cu).  splitk <= 0 picks the K split
- * that fills the machine.  *error_flag (device int, may be NULL) is set if the in-kernel
- * pipeline watchdog fired.  Exported for validation against cb_sgemm_strided. */
+ * that fills the machine.  Split-K is atomics-free (partial tiles meet in `workspace`, device
+ * memory of cb_gemm_bf16_tn_workspace_bytes() bytes, and are summed in slice order), so equal
+ * inputs give equal bits; with workspace == NULL the contraction runs unsplit (splitk > 1 is then
+ * CB_ERR_WORKSPACE).  *error_flag (device int, may be NULL) is set if the in-kernel pipeline
+ * watchdog fired.  operand_layout bit 0 / bit 1: A / B is stored as contiguous 64 x 64 tiles (element
+ * (r, k) at ((r/64) * (K/64) + k/64) * 4096 + (r%64) * 64 + k%64; rows and K multiples of 64; lda/ldb
+ * ignored), the HBM-friendly layout the layer driver keeps its m x n operands in.  Exported for
+ * validation against cb_sgemm_strided. */
+size_t cb_gemm_bf16_tn_workspace_bytes(void);
 int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
-                    const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int* error_flag,
-                    void* stream);
+                    const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int operand_layout,
+                    int* error_flag, void* workspace, size_t workspace_bytes, void* stream);
 /* Grid-size policy of the tcgen05 contractions: ~120 (default) fills the machine for a single layer
  * (lowest latency); ~32 keeps grids small so that the contractions of several layers in flight on
  * different streams overlap (highest throughput).  Process-wide. */
 void cb_set_gemm_target_ctas(int n);
+/* How many neighbouring CTAs (a thread-block cluster; 1, 2, 4 or 8) share one TMA-multicast copy of
+ * the A tile in the narrow-tile contraction.  Results do not depend on it.  Process-wide. */
+void cb_set_gemm_cluster(int n);
+/* Measurement aid for bench.py / scripts: cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16,
+ * bf16, both operands resident in shared memory, no TMA, no per-stage barriers) take on an SM, on a
+ * grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */
+/* Measurement aid: when non-NULL, CTA (0,0,0) of every tcgen05 contraction writes 8 clock64 stamps
+ * (entry, prologue done, last load issued, first stage landed, last stage landed, accumulator
+ * complete, epilogue stores issued, exit) to this device buffer.  Process-wide; NULL turns it off. */
+void cb_set_gemm_timing(void* stamps_dev);
+int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream);
 /* fp32 (rows x cols, ldx) -> bf16 copy Y (ldy) and/or transposed copy Yt (cols x rows, ldyt),
  * optionally scaling column c by colscale[c] first. */
 int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,

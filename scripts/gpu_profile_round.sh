@@ -19,7 +19,7 @@ $T 400 ncu --profile-from-start off --set full --clock-control none --import-sou
     -o gpurun_out/prof_layer python scripts/profile_layer.py > gpurun_out/prof_ncu2.log 2>&1
 $T 300 ncu --set full --clock-control none --import-source on -k regex:quant_fast_kernel -s 8 -c 1 \
     -o gpurun_out/prof_quant python scripts/profile_quant.py 2 64 > gpurun_out/prof_ncu3.log 2>&1
-$T 300 ncu --set full --clock-control none --import-source on -k regex:"chol_inv_kernel|jacobi_smem_kernel" -s 4 -c 2 \
+$T 300 ncu --set full --clock-control none --import-source on -k regex:"chol_inv_kernel|jacobi_cluster_kernel|jacobi_smem_kernel" -s 4 -c 2 \
     -o gpurun_out/prof_small python scripts/profile_smalldense.py 224 > gpurun_out/prof_ncu4.log 2>&1
 cat gpurun_out/prof_layer_plain.log gpurun_out/prof_layer_lr4_plain.log gpurun_out/prof_quant_plain.log
 tail -2 gpurun_out/prof_small_plain.log

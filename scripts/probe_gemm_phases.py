@@ -1,0 +1,30 @@
+"""Phase breakdown (clock64 stamps of CTA 0) of the sketch contraction for tile widths / cluster sizes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ee274_convexcaldera_llm_quantization_b200 import _lib
+lib = _lib.load()
+dev = "cuda"
+M = N = 4096
+q = 224
+Y = torch.randn(M, N, device=dev).bfloat16()
+Pt = torch.randn(q, N, device=dev).bfloat16()
+Zt = torch.empty(q, M, device=dev)
+flag = torch.zeros(1, dtype=torch.int32, device=dev)
+ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+stamps = torch.zeros(8, dtype=torch.int64, device=dev)
+lib.cb_set_gemm_timing(_lib.ptr(stamps))
+names = ["prologue", "->last load issued", "first stage landed (from entry)", "last stage landed (from entry)",
+         "accumulator complete (from entry)", "epilogue done (from entry)", "exit (from entry)"]
+for ctas, cl, split, layout, tag in ((120, 1, 1, 0, "bn64"), (120, 4, 1, 0, "bn64 cl4"), (120, 1, 1, 4, "bn64 loads-only"),
+                                     (32, 1, 1, 0, "bn256"), (32, 1, 4, 0, "bn256 split4"), (64, 1, 2, 0, "bn128 split2")):
+    lib.cb_set_gemm_target_ctas(ctas); lib.cb_set_gemm_cluster(cl)
+    for _ in range(3):
+        lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(Y), N, _lib.ptr(Zt), M, split, layout,
+                            _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    t = stamps.tolist()
+    e = t[0]
+    print(f"{tag}: prologue {t[1]-e}, last-load-issued {t[2]-e}, first-landed {t[3]-e}, last-landed {t[4]-e}, "
+          f"acc-complete {t[5]-e}, epilogue-done {t[6]-e}, exit {t[7]-e} clk")
+lib.cb_set_gemm_timing(None)

@@ -268,3 +268,28 @@ def test_cuda_graph_replay_matches_eager():
         assert torch.equal(a.Q_idxs, b.Q_idxs) and torch.equal(a.L, b.L) and torch.equal(a.R_idxs, b.R_idxs)
         assert torch.equal(a.Q_packed, b.Q_packed) and torch.equal(a.W, b.W)
         assert a.best_step == b.best_step and a.global_scale == b.global_scale
+
+
+@pytest.mark.parametrize("tc", [True, False], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("lbits", [16, 4])
+def test_repeated_runs_are_bitwise_identical(tc, lbits):
+    """a layer's result depends only on (W, H, params, seed) -- not on which GPU, stream or
+    neighbour it ran beside.  Split-K contractions sum their slices in a fixed order (no floating-point
+    atomics), so repeated runs agree bit for bit even while another stream perturbs CTA scheduling."""
+    g = torch.Generator().manual_seed(31)
+    m, n, r = 2048, 1536, 64
+    W = 0.02 * torch.randn(m, n, generator=g)
+    h = 0.5 + torch.rand(n, generator=g)
+    kw = dict(Q_bits=2, L_bits=lbits, R_bits=lbits, rank=r, iters=2, lplr_iters=2, update_order=["Q", "LR"])
+    first = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=9, use_tensor_cores=tc)
+    noise_stream = torch.cuda.Stream()
+    X = torch.randn(4096, 4096, device=DEV)
+    for trial in range(3):
+        with torch.cuda.stream(noise_stream):
+            for _ in range(8 * (trial + 1)):
+                X = torch.tanh(X @ X) * 0.01
+        again = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=9, use_tensor_cores=tc)
+        assert again.errors == first.errors
+        assert torch.equal(again.Q_idxs, first.Q_idxs) and torch.equal(again.L, first.L) and torch.equal(again.R, first.R)
+        assert again.best_step == first.best_step
+    torch.cuda.synchronize()
