@@ -5,7 +5,7 @@
 
 Metric (BASELINE.json): decomposed matrices / s at 4096 x 4096, rank 128, 2-bit Q
 (config[1]: L/R 16-bit, activation aware, 5 outer iterations, update_order Q,LR).
-One step = one full caldera() decomposition of one synthetic layer.
+One step = one batch of `--streams` independent layers (one full caldera() decomposition each).
 
   value     matrices/s with inputs resident in HBM (cb_caldera_layer enqueued back to back,
             CUDA-event timed, max over ranks)
@@ -26,6 +26,11 @@ import subprocess
 import sys
 import threading
 import time
+
+# Independent layers run on their own CUDA streams.  The driver multiplexes streams onto 8 hardware
+# work queues by default, which falsely serialises layers once more than 8 are in flight; 32 is the
+# maximum.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -190,19 +195,55 @@ def roofline_probes(dev, peaks):
     Zt = torch.empty(q, M, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def sketch():
+    Zts = [torch.empty(q, M, device=dev) for _ in range(4)]
+    flops = 2.0 * M * N * q
+
+    def sketch(j=0):
         y = ys[k[0] % 3]
         k[0] += 1
-        lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zt), M, 1, 0, _lib.ptr(flag),
+        lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zts[j]), M, 1, 0, _lib.ptr(flag),
                             None, 0, _lib.stream_ptr())
-    t = time_kernel(sketch, iters=20)
-    flops = 2.0 * M * N * q
-    out["sketch_gemm_tcgen05"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"],
-                                  "unit": "TFLOP/s", "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None,
-                                  "seconds": t, "algorithmic_flops": flops,
-                                  "hbm_gbs": (2 * M * N + 2 * q * N + 4 * q * M) / t / 1e9,
-                                  "note": "skinny: arithmetic intensity q/2 = 112 flop/B on bf16 Y, "
-                                          "min(tensor peak, AI x HBM) = 733 TFLOP/s"}
+
+    def entry(t, note, **extra):
+        e = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+             "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None, "seconds": t,
+             "algorithmic_flops": flops, "hbm_gbs": (2 * M * N + 2 * q * N + 4 * q * M) / t / 1e9, "note": note}
+        e.update(extra)
+        return e
+    skinny = "skinny: arithmetic intensity q/2 = 112 flop/B on bf16 Y, min(tensor peak, AI x HBM) = 733 TFLOP/s"
+    # as it runs in the timed region (throughput mode): 32-CTA grids of 128 x 256 tiles, four of them
+    # side by side on different streams; seconds = elapsed / launches
+    lib.cb_set_gemm_target_ctas(32)
+    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    for j, s_ in enumerate(side):
+        with torch.cuda.stream(s_):
+            for _ in range(3):
+                sketch(j)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rounds = 20
+    e0.record()
+    for s_ in side:
+        s_.wait_event(e0)
+    for _ in range(rounds):
+        for j, s_ in enumerate(side):
+            with torch.cuda.stream(s_):
+                sketch(j)
+    for s_ in side:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        torch.cuda.current_stream().wait_event(ev)
+    e1.record()
+    torch.cuda.synchronize()
+    t4 = e0.elapsed_time(e1) * 1e-3 / (rounds * 4)
+    out["sketch_gemm_tcgen05"] = entry(t4, skinny + "; 32-CTA grid, 4 launches in flight (as in the timed region)",
+                                       grid_ctas=32, in_flight=4)
+    out["sketch_gemm_tcgen05_32cta_alone"] = entry(time_kernel(sketch, iters=20), skinny + "; 32-CTA grid alone "
+                                                   "(occupies 32 of 148 SMs)", grid_ctas=32, in_flight=1)
+    lib.cb_set_gemm_target_ctas(120)
+    out["sketch_gemm_tcgen05_128cta_alone"] = entry(time_kernel(sketch, iters=20), skinny + "; latency-mode grid "
+                                                    "(128 x 64 tiles, 128 CTAs) alone", grid_ctas=128, in_flight=1)
+    _lib.set_execution_mode(_lib.execution_mode())     # restore the grid policy of the current mode
     assert int(flag.item()) == 0
     # (c) whole-tensor quantise + pack (the form caldera() itself uses, alg.py:247): two passes
     def quant_whole():
@@ -248,6 +289,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     peaks = load_peaks()
+    # many independent layers in flight: the library's throughput mode (small contraction grids that
+    # overlap across streams, single-CTA eigensolver); "latency" is the single-layer optimum
+    _lib.set_execution_mode(args.mode)
     if args.gemm_ctas > 0:
         lib.cb_set_gemm_target_ctas(args.gemm_ctas)
 
@@ -333,7 +377,7 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API, host buffers in, packed result out
     import concurrent.futures as cf
-    nworkers = nstreams
+    nworkers = max(1, min(nstreams, args.e2e_workers))
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
                  for _ in range(nworkers)]
@@ -381,7 +425,8 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "per-step working set ~0.5 GiB > 126 MB L2; 3 layers rotated",
-                           "layers_per_step": batch, "layers_in_flight": nstreams, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
+                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": nworkers,
+                           "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": 8, "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -414,8 +459,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
+    ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
+                    help="library execution mode (cb_set_execution_mode)")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")
-    ap.add_argument("--streams", type=int, default=8, help="independent layers kept in flight per GPU")
+    ap.add_argument("--streams", type=int, default=32, help="independent layers kept in flight per GPU")
+    ap.add_argument("--e2e-workers", type=int, default=16, help="host threads driving the public API in the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,7 +71,8 @@ _SIGNATURES = {
                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
     "cb_set_gemm_target_ctas": (None, [C.c_int]),
-    "cb_set_gemm_cluster": (None, [C.c_int]),
+    "cb_set_execution_mode": (C.c_int, [C.c_int]),
+    "cb_set_gemm_kblocks": (None, [C.c_int]),
     "cb_set_gemm_timing": (None, [C.c_void_p]),
     "cb_probe_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_convert_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
@@ -110,6 +111,25 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_MODES = {"latency": 0, "throughput": 1}
+_mode = "latency"
+
+
+def set_execution_mode(mode: str) -> None:
+    """"latency" (default): a single layer finishes as early as possible.  "throughput": many layers are
+    in flight on different streams (include/caldera_b200.h, cb_set_execution_mode).  Process-wide;
+    captured CUDA graphs are keyed by the mode they were captured in."""
+    global _mode
+    if mode not in _MODES:
+        raise ValueError(f"execution mode must be one of {sorted(_MODES)}, got {mode!r}")
+    check(load().cb_set_execution_mode(_MODES[mode]), "set_execution_mode")
+    _mode = mode
+
+
+def execution_mode() -> str:
+    return _mode
 
 
 def exported_symbols():

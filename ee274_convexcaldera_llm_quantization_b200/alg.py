@@ -46,7 +46,7 @@ def release_workspaces() -> None:
 # each replay their own graph and a warm pool is reused by whoever comes next.
 _GRAPH_CACHE = {}
 _GRAPH_LOCK = threading.Lock()
-_GRAPH_POOL_MAX = 16
+_GRAPH_POOL_MAX = 32
 
 
 def _params_signature(p) -> tuple:
@@ -55,7 +55,7 @@ def _params_signature(p) -> tuple:
 
 
 def _acquire_graph_runner(p, m, n, h_kind, dev, want_packed, want_w_scaled):
-    key = (dev.index, _params_signature(p), m, n, h_kind, want_packed, want_w_scaled)
+    key = (dev.index, _params_signature(p), m, n, h_kind, want_packed, want_w_scaled, _lib.execution_mode())
     with _GRAPH_LOCK:
         pool = _GRAPH_CACHE.setdefault(key, [])
         if pool:

@@ -1,5 +1,6 @@
 // Shared device/host helpers for libcaldera_b200 (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -7,6 +8,16 @@
 #include "../../include/caldera_b200.h"
 
 namespace cb {
+
+// Measurement aid (never set in production): CB_DEBUG_SKIP is a bit mask of kernel classes whose
+// launches are dropped so that their share of a multi-stream run can be read off the change in
+// throughput (results are then garbage).  1: Cholesky, 2: Jacobi, 4: tcgen05 contractions.
+inline int debug_skip() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CB_DEBUG_SKIP"); v = e != nullptr ? atoi(e) : 0; }
+  return v;
+}
+
 
 // ---------------------------------------------------------------- launch bookkeeping
 extern long long g_launch_count;  // defined in api.cu

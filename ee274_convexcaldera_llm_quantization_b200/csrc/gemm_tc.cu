@@ -58,25 +58,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+// 3-D box (64 K elements x rows x k-blocks): several 64-wide K blocks with one instruction
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-// the same box delivered to the same shared-memory offset (and signalled on the same barrier offset)
-// of every CTA of the cluster named in `mask`
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_cta_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -99,10 +85,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t gets row (lane base + t), register j = column j
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -139,7 +121,6 @@ struct GemmTcArgs {
   __nv_bfloat16* Ct; int64_t ldct;   // bf16 out, transposed (N x M), may be null (ignored when atomic)
   const float* colscale;             // per output column, may be null
   const float* rowscale;             // per output row, may be null
-  int a_tiled, b_tiled;              // operand stored as contiguous 64 x 64 tiles (see make_tmap_bf16_tiled)
   int loads_only;                    // measurement aid: run the TMA pipeline but issue no MMA (output undefined)
   long long* timing;                 // measurement aid: 8 clock64 stamps of CTA (0,0,0), or null
   int splits;                        // > 1: split-K, raw partial tiles go to `ws` for splitk_reduce_kernel
@@ -150,10 +131,15 @@ struct GemmTcArgs {
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_THREADS = 192;
 
-template <int BN, int STAGES>
+// One pipeline stage holds KB consecutive 64-wide K blocks of the A and B tiles, each block in the
+// canonical 128-byte-swizzled K-major layout (rows 128 bytes apart), fetched by one TMA instruction
+// per operand: issuing a tensor copy costs ~230 cycles of the producer thread whatever its size
+// (measured, scripts/probe_gemm_phases.py), so narrow tiles are only fed fast enough with KB = 2.
+template <int BN, int STAGES, int KB>
 struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int A_BLK = TC_BM * TC_BK * 2, B_BLK = BN * TC_BK * 2;
+  static constexpr int A_BYTES = KB * A_BLK;
+  static constexpr int B_BYTES = KB * B_BLK;
   static constexpr int BAR_OFF = STAGES * (A_BYTES + B_BYTES);
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
@@ -204,17 +190,10 @@ __device__ __forceinline__ void store_chunk(const GemmTcArgs& args, int row, int
   }
 }
 
-// CL > 1: the CL CTAs of a cluster own neighbouring N tiles of the same M tile and K range, so they all
-// consume the same A tile.  Each loads 1/CL of it and multicasts the slice into every CTA's stage
-// buffer: A crosses the L2 -> SM fabric once per cluster instead of once per CTA.  A stage may be
-// refilled only after all CL consumers have drained it, so "empty" barriers count CL arrivals and the
-// MMA warp's commit is multicast to every CTA of the cluster.
-template <int BN, int STAGES, int CL>
-__device__ __forceinline__ void
-gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& args) {
-  using S = TcSmem<BN, STAGES>;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
-  const uint32_t cta_rank = CL > 1 ? cluster_cta_rank() : 0u;
+template <int BN, int STAGES, int KB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
+  using S = TcSmem<BN, STAGES, KB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + STAGES * S::A_BYTES;
@@ -233,11 +212,12 @@ gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a
   const int kb0 = blockIdx.z * args.kb_per_split;
   const int nkb = min(total_kb, kb0 + args.kb_per_split) - kb0;
   if (nkb <= 0) return;  // uniform per CTA
+  const int nst = (nkb + KB - 1) / KB;   // pipeline iterations; the last may hold fewer than KB valid blocks
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       mbar_init(tmem_full_bar, 1);
       fence_barrier_init();
     }
@@ -245,8 +225,7 @@ gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a
     tmem_alloc(tmem_slot, BN);
   }
   tc_fence_before();
-  if constexpr (CL > 1) cluster_sync_all();   // peers' barriers exist before anything remote lands on them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   bool ok = true;
@@ -254,46 +233,53 @@ gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a
   if (warp == 0) {
     if (lane == 0) {
       if (stamps != nullptr) stamps[1] = clock64();                                // prologue done
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < nst; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         if (!mbar_wait(empty_bar(s), ph ^ 1u)) { ok = false; break; }
-        if (stamps != nullptr && i == nkb - 1) stamps[2] = clock64();              // last load about to be issued
+        if (stamps != nullptr && i == nst - 1) stamps[2] = clock64();              // last load about to be issued
         mbar_expect_tx(full_bar(s), (uint32_t)(S::A_BYTES + S::B_BYTES));
-        if constexpr (CL > 1)
-          tma_load_2d_mc(a_base + s * S::A_BYTES + cta_rank * (S::A_BYTES / CL), &tmA, full_bar(s), (kb0 + i) * TC_BK,
-                         m_blk * TC_BM + (int)cta_rank * (TC_BM / CL), kMask);
-        else if (args.a_tiled) tma_load_4d(a_base + s * S::A_BYTES, &tmA, full_bar(s), 0, 0, kb0 + i, m_blk * (TC_BM / 64));
-        else tma_load_2d(a_base + s * S::A_BYTES, &tmA, full_bar(s), (kb0 + i) * TC_BK, m_blk * TC_BM);
-        if (args.b_tiled) tma_load_4d(b_base + s * S::B_BYTES, &tmB, full_bar(s), 0, 0, kb0 + i, n_blk * (BN / 64));
-        else tma_load_2d(b_base + s * S::B_BYTES, &tmB, full_bar(s), (kb0 + i) * TC_BK, n_blk * BN);
+        const int kb = kb0 + i * KB;
+        if constexpr (KB == 1) {
+          tma_load_2d(a_base + s * S::A_BYTES, &tmA, full_bar(s), kb * TC_BK, m_blk * TC_BM);
+          tma_load_2d(b_base + s * S::B_BYTES, &tmB, full_bar(s), kb * TC_BK, n_blk * BN);
+        } else {
+          // blocks past the end of K are zero-filled; blocks past this CTA's K slice are loaded but not used
+          tma_load_3d(a_base + s * S::A_BYTES, &tmA, full_bar(s), 0, m_blk * TC_BM, kb);
+          tma_load_3d(b_base + s * S::B_BYTES, &tmB, full_bar(s), 0, n_blk * BN, kb);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < nst; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
         if (!mbar_wait(full_bar(s), ph)) { ok = false; break; }
         if (stamps != nullptr && i == 0) stamps[3] = clock64();                    // first stage landed
-        if (stamps != nullptr && i == nkb - 1) stamps[4] = clock64();              // last stage landed
+        if (stamps != nullptr && i == nst - 1) stamps[4] = clock64();              // last stage landed
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(a_base + s * S::A_BYTES);
-        const uint64_t bdesc = make_smem_desc_sw128(b_base + s * S::B_BYTES);
         if (args.loads_only) {
-          if (i == 0) umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+          if (i == 0) umma_bf16(tmem_base, make_smem_desc_sw128(a_base), make_smem_desc_sw128(b_base), idesc, 0u);
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_bar(s)) : "memory");
           continue;
         }
+        const int valid = min(KB, nkb - i * KB);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        for (int b = 0; b < KB; ++b) {
+          if (b < valid) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + s * S::A_BYTES + b * S::A_BLK);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + s * S::B_BYTES + b * S::B_BLK);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+              umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (i > 0 || b > 0 || k > 0) ? 1u : 0u);
+            }
+          }
         }
-        // stage reusable once these MMAs have read it (in every CTA that shares the A slices)
-        if constexpr (CL > 1) umma_commit_mc(empty_bar(s), kMask);
-        else umma_commit(empty_bar(s));
+        umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
       }
       umma_commit(tmem_full_bar);   // accumulator complete
     }
@@ -343,25 +329,12 @@ gemm_tc_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a
   if (!ok && args.error_flag != nullptr) atomicExch(args.error_flag, 1);
   if (stamps != nullptr && threadIdx.x == 64) stamps[6] = clock64();               // epilogue stores issued
   tc_fence_before();
-  if constexpr (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still write or signal here
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
   if (stamps != nullptr && threadIdx.x == 0) stamps[7] = clock64();               // exit
-}
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
-  gemm_tc_body<BN, STAGES, 1>(tmA, tmB, args);
-}
-
-template <int BN, int STAGES, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
-gemm_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcArgs args) {
-  gemm_tc_body<BN, STAGES, CL>(tmA, tmB, args);
 }
 
 // Measurement aid (bench / scripts only): back-to-back tcgen05.mma on one resident shared-memory
@@ -487,55 +460,42 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, int64_t rows, int64
   return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
 }
 
-// The same matrix stored as contiguous 64 (rows) x 64 (K) tiles, K blocks of one row block adjacent:
-// element (r, k) lives at ((r/64) * (K/64) + k/64) * 4096 + (r%64) * 64 + k%64.  A CTA that walks K
-// for its rows then streams one contiguous region of HBM instead of 128-byte pieces 2*ld bytes apart.
-// rows and K must be multiples of 64.  The box lands in shared memory exactly like the 2-D one.
-static int make_tmap_bf16_tiled(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+// The same matrix seen as (64 K elements) x rows x (K / 64 blocks), so that one box fetches `kblocks`
+// consecutive 64-wide K blocks of `box_rows` rows; they land one after the other in shared memory,
+// each in the same swizzled layout as a 2-D box.  K must be a multiple of 64 (a ragged last block
+// would run into the next row instead of being zero-filled); blocks at or past K / 64 are zero-filled.
+static int make_tmap_bf16_kblocks(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                                  int kblocks) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return CB_ERR_UNSUPPORTED;
-  if (rows % 64 != 0 || K % 64 != 0 || box_rows % 64 != 0) return CB_ERR_ARG;
-  cuuint64_t gdim[4] = {64, 64, (cuuint64_t)(K / 64), (cuuint64_t)(rows / 64)};
-  cuuint64_t gstride[3] = {128, 8192, (cuuint64_t)(K / 64) * 8192};
-  cuuint32_t box[4] = {64, 64, 1, (cuuint32_t)(box_rows / 64)};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  if (K % TC_BK != 0) return CB_ERR_ARG;
+  cuuint64_t gdim[3] = {(cuuint64_t)TC_BK, (cuuint64_t)rows, (cuuint64_t)(K / TC_BK)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)TC_BK * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, (cuuint32_t)kblocks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KB>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& args, int splits, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, KB>;
   static bool attr = false;
   if (!attr) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr = true;
   }
   dim3 grid((unsigned)((args.N + BN - 1) / BN), (unsigned)((args.M + TC_BM - 1) / TC_BM), (unsigned)splits);
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, args);
-  CB_CHECK_LAUNCH();
-  return CB_OK;
-}
-
-template <int BN, int STAGES, int CL>
-static int launch_tc_mc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& args, int splits, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
-  static bool attr = false;
-  if (!attr) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_mc_kernel<BN, STAGES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr = true;
-  }
-  dim3 grid((unsigned)((args.N + BN - 1) / BN), (unsigned)((args.M + TC_BM - 1) / TC_BM), (unsigned)splits);
-  gemm_tc_mc_kernel<BN, STAGES, CL><<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, args);
+  gemm_tc_kernel<BN, STAGES, KB><<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, args);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
 
 int g_target_ctas = -1;
 long long* g_timing = nullptr;   // measurement aid, see cb_set_gemm_timing
-int g_cluster = -1;   // CTAs sharing one multicast A tile (1 = off); CB_GEMM_CLUSTER overrides
+int g_kblocks = -1;              // K blocks per TMA instruction for the narrow tiles (CB_GEMM_KBLOCKS: 1 or 2)
 
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
   return M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && lda % 8 == 0 &&
@@ -549,10 +509,9 @@ bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t l
 int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A, int64_t lda,
             const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, __nv_bfloat16* Cb, int64_t ldcb,
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
-            int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw, int tiled_operands) {
+            int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw, int probe_flags) {
   if (!gemm_tc_supported(M, N, K, A, lda, B, ldb)) return CB_ERR_UNSUPPORTED;
-  const bool a_tiled = (tiled_operands & 1) != 0, b_tiled = (tiled_operands & 2) != 0;
-  if ((a_tiled && (M % 64 != 0 || K % 64 != 0)) || (b_tiled && (N % 64 != 0 || K % 64 != 0))) return CB_ERR_ARG;
+  if (debug_skip() & 4) return CB_OK;
   // largest N tile that still yields >= ~0.8 waves of CTAs; otherwise the smallest tile
   // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
@@ -592,37 +551,38 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   int kb_per = (total_kb + splits - 1) / splits;
   splits = (total_kb + kb_per - 1) / kb_per;
   if (splits_used != nullptr) *splits_used = splits;
+  const bool loads_only = (probe_flags & 1) != 0;
+  if (g_kblocks < 0) {
+    const char* e = getenv("CB_GEMM_KBLOCKS");
+    g_kblocks = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+  }
+  // two K blocks per TMA instruction where the tile is narrow enough for the stage to stay <= 64 KiB
+  const int kbs = (bn <= 128 && K % TC_BK == 0 && g_kblocks >= 2) ? 2 : 1;
+  if (kbs > 1 && kb_per % kbs != 0 && splits > 1) {
+    kb_per = (kb_per + kbs - 1) / kbs * kbs;              // K slices start on a stage boundary
+    splits = (total_kb + kb_per - 1) / kb_per;
+    if (splits_used != nullptr) *splits_used = splits;
+  }
   CUtensorMap ta, tb;
-  // multicast of the A tile across neighbouring N tiles (smallest N tile only: that is where A traffic dominates)
-  const bool loads_only = (tiled_operands & 4) != 0;
-  if (g_cluster < 0) {
-    const char* e = getenv("CB_GEMM_CLUSTER");
-    g_cluster = (e != nullptr) ? atoi(e) : 4;
+  if (kbs > 1) {
+    CB_TRY(make_tmap_bf16_kblocks(&ta, A, M, K, lda, TC_BM, kbs));
+    CB_TRY(make_tmap_bf16_kblocks(&tb, B, N, K, ldb, bn, kbs));
+  } else {
+    CB_TRY(make_tmap_bf16(&ta, A, M, K, lda, TC_BM));
+    CB_TRY(make_tmap_bf16(&tb, B, N, K, ldb, bn));
   }
-  int cl = 1;
-  const int64_t tiles_n = (N + bn - 1) / bn;
-  if (bn == 64 && !a_tiled && !loads_only && tiles_n >= 8) {
-    if (g_cluster >= 8 && tiles_n % 8 == 0) cl = 8;
-    else if (g_cluster >= 4 && tiles_n % 4 == 0) cl = 4;
-    else if (g_cluster >= 2 && tiles_n % 2 == 0) cl = 2;
-  }
-  if (a_tiled) CB_TRY(make_tmap_bf16_tiled(&ta, A, M, K, TC_BM));
-  else CB_TRY(make_tmap_bf16(&ta, A, M, K, lda, TC_BM / cl));
-  if (b_tiled) CB_TRY(make_tmap_bf16_tiled(&tb, B, N, K, bn));
-  else CB_TRY(make_tmap_bf16(&tb, B, N, K, ldb, bn));
   GemmTcArgs args;
   args.M = (int)M; args.N = (int)N; args.K = (int)K; args.kb_per_split = kb_per; args.alpha = alpha;
   args.C = C; args.ldc = ldc; args.Cb = Cb; args.ldcb = ldcb; args.Ct = Ct; args.ldct = ldct;
   args.colscale = colscale; args.rowscale = rowscale; args.error_flag = error_flag;
   args.splits = splits; args.ws = splits > 1 ? sw->buf : nullptr;
-  args.a_tiled = a_tiled ? 1 : 0; args.b_tiled = b_tiled ? 1 : 0; args.loads_only = loads_only ? 1 : 0;
+  args.loads_only = loads_only ? 1 : 0;
   args.timing = g_timing;
-  if (bn == 256) CB_TRY((launch_tc<256, 4>(ta, tb, args, splits, st)));
-  else if (bn == 128) CB_TRY((launch_tc<128, 6>(ta, tb, args, splits, st)));
-  else if (cl == 8) CB_TRY((launch_tc_mc<64, 8, 8>(ta, tb, args, splits, st)));
-  else if (cl == 4) CB_TRY((launch_tc_mc<64, 8, 4>(ta, tb, args, splits, st)));
-  else if (cl == 2) CB_TRY((launch_tc_mc<64, 8, 2>(ta, tb, args, splits, st)));
-  else CB_TRY((launch_tc<64, 8>(ta, tb, args, splits, st)));
+  if (bn == 256) CB_TRY((launch_tc<256, 4, 1>(ta, tb, args, splits, st)));
+  else if (bn == 128 && kbs == 2) CB_TRY((launch_tc<128, 3, 2>(ta, tb, args, splits, st)));
+  else if (bn == 128) CB_TRY((launch_tc<128, 6, 1>(ta, tb, args, splits, st)));
+  else if (kbs == 2) CB_TRY((launch_tc<64, 4, 2>(ta, tb, args, splits, st)));
+  else CB_TRY((launch_tc<64, 8, 1>(ta, tb, args, splits, st)));
   if (splits > 1) {
     const int64_t total4 = tiles * TC_BM * (bn / 4);
     splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(args, bn, (int)((N + bn - 1) / bn), total4);
@@ -683,7 +643,7 @@ int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat
 extern "C" size_t cb_gemm_bf16_tn_workspace_bytes(void) { return cb::kSplitWsBytes; }
 
 extern "C" int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
-                               const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int operand_layout,
+                               const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int probe_flags,
                                int* error_flag, void* workspace, size_t workspace_bytes, void* stream) {
   if (A_bf16 == nullptr || B_bf16 == nullptr || C == nullptr) return CB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -696,7 +656,7 @@ extern "C" int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, con
   }
   return cb::gemm_tc(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A_bf16), lda,
                      reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, C, ldc, nullptr, 0, nullptr, 0, nullptr,
-                     nullptr, splitk, error_flag, &splits, st, &sw, operand_layout);
+                     nullptr, splitk, error_flag, &splits, st, &sw, probe_flags);
 }
 
 extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
@@ -728,4 +688,11 @@ extern "C" int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, vo
 
 extern "C" void cb_set_gemm_timing(void* stamps_dev) { cb::g_timing = reinterpret_cast<long long*>(stamps_dev); }
 extern "C" void cb_set_gemm_target_ctas(int n) { cb::g_target_ctas = n > 0 ? n : 120; }
-extern "C" void cb_set_gemm_cluster(int n) { cb::g_cluster = n >= 1 ? n : 4; }
+
+extern "C" int cb_set_execution_mode(int mode) {
+  if (mode == 0) { cb::g_target_ctas = 120; cb::g_jacobi_single = 0; }        // CB_MODE_LATENCY
+  else if (mode == 1) { cb::g_target_ctas = 32; cb::g_jacobi_single = 1; }    // CB_MODE_THROUGHPUT
+  else return CB_ERR_ARG;
+  return CB_OK;
+}
+extern "C" void cb_set_gemm_kblocks(int n) { cb::g_kblocks = n == 1 ? 1 : 2; }

@@ -16,6 +16,11 @@ struct SplitWs {
 constexpr size_t kSplitWsBytes = 12u << 20;
 
 
+// execution-mode knobs (cb_set_execution_mode): grid-size target of the tcgen05 contractions and the
+// eigensolver variant; -1 = not yet initialised (environment, then defaults)
+extern int g_target_ctas;
+extern int g_jacobi_single;
+
 // sgemm.cu -- C(i,j) = alpha * sum_k A(i,k) B(k,j) [* colscale[j]] (+ C), arbitrary strides
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
           const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
@@ -76,7 +81,7 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
             const __nv_bfloat16* B, int64_t ldb, float* C, int64_t ldc, __nv_bfloat16* Cb, int64_t ldcb,
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
             int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw = nullptr,
-            int tiled_operands = 0 /* bit 0: A, bit 1: B stored as contiguous 64 x 64 tiles */);
+            int probe_flags = 0 /* bit 0: loads only (measurement aid) */);
 int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
             __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st);
 

@@ -326,6 +326,7 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfl
 int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st, __nv_bfloat16* Linv_bf16) {
   if (G == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
+  if (debug_skip() & 1) return CB_OK;
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
@@ -672,11 +673,22 @@ jacobi_cluster_kernel(const float* __restrict__ Lc, int q, float* __restrict__ e
 // Rayleigh-Ritz step is second order in the residual coupling, so 3e-5 leaves it exact to fp32.
 constexpr float kJacobiTol = 3e-5f;
 
+int g_jacobi_single = -1;
+
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
                           cudaStream_t st) {
   if (Lc == nullptr || evals == nullptr || evecs == nullptr || work == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
-  if (q % 4 == 0 && q >= 64 && aligned16(work) && aligned16(evecs)) {
+  if (debug_skip() & 2) return CB_OK;
+  // The 8-CTA cluster kernel has the lower latency (one layer in flight); the single-CTA kernel spends
+  // ~3x less SM time (many layers in flight).  cb_set_execution_mode / CB_JACOBI_SINGLE=1 select the
+  // latter where it applies.
+  if (g_jacobi_single < 0) {
+    const char* e = getenv("CB_JACOBI_SINGLE");
+    g_jacobi_single = (e != nullptr && atoi(e) == 1) ? 1 : 0;
+  }
+  const bool prefer_single = g_jacobi_single == 1 && q <= JS_QMAX;
+  if (!prefer_single && q % 4 == 0 && q >= 64 && aligned16(work) && aligned16(evecs)) {
     // cluster kernel: `work` holds q*q floats of column storage followed by q floats of norms and 2 counters
     float* lam_buf = work + (size_t)q * q;
     int* counters = reinterpret_cast<int*>(lam_buf + q);

@@ -20,6 +20,19 @@ def workspace_bytes(c_params, m: int, n: int, h_kind: int) -> int:
 
 # stream capture is a process-wide affair for torch's allocator and RNG bookkeeping: one at a time
 _CAPTURE_LOCK = threading.Lock()
+# Captures run on a dedicated high-priority stream per device.  torch hands out ordinary streams from a
+# pool of 32 per device and priority, round robin, so the default capture stream of torch.cuda.graph can
+# be the very stream another worker thread is using (and synchronising) -- which invalidates the capture.
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _CAPTURE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device, priority=-1)
+        _CAPTURE_STREAMS[key] = st
+    return st
 
 
 class CalderaLayerRunner:
@@ -100,7 +113,7 @@ class CalderaLayerRunner:
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = self.lib.cb_kernel_launch_count()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            with torch.cuda.graph(g, stream=_capture_stream(self.device), capture_error_mode="thread_local"):
                 self.enqueue(self.W_in, self.h_in)
             self.graph_kernels = int(self.lib.cb_kernel_launch_count() - n0)   # kernel nodes in the graph
             self.graph = g

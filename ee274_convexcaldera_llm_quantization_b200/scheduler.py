@@ -154,9 +154,22 @@ def gather_blobs(blobs: List[torch.Tensor], dst: Optional[int] = 0, group=None) 
 
 
 # ----------------------------------------------------------------------------- driver
+_WORKER_STREAMS = {}
+
+
+def _worker_streams(dev: torch.device, count: int):
+    """The job's streams, created once per device: torch recycles a pool of 32 streams per device round
+    robin, so making fresh ones on every call would sooner or later alias two workers (or a worker and
+    the graph-capture stream) onto one CUDA stream."""
+    pool = _WORKER_STREAMS.setdefault(dev.index, [])
+    while len(pool) < count:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:count]
+
+
 def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor, Optional[torch.Tensor]]]]],
                      shapes: Sequence[Tuple[int, int]], params, rank: int, world_size: int,
-                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 8,
+                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 16,
                      **caldera_kwargs):
     """Decomposes this rank's shard of `layers`.
 
@@ -168,9 +181,23 @@ def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor
 
     `streams` layers are kept in flight per GPU (one worker thread + CUDA stream each, largest
     layers first): the latency-bound factorisation kernels of one layer overlap with the
-    bandwidth- and tensor-bound kernels of the others."""
+    bandwidth- and tensor-bound kernels of the others.  The job always runs in the library's
+    "throughput" execution mode (small contraction grids, single-CTA eigensolver), whatever `streams`
+    and the world size are, so that a sharded run equals the single-GPU run bit for bit; the previous
+    mode is restored on return."""
     import concurrent.futures as cf
+    from . import _lib
     from .alg import caldera
+    previous_mode = _lib.execution_mode()
+    _lib.set_execution_mode("throughput")
+    try:
+        return _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, caldera, cf,
+                                 caldera_kwargs)
+    finally:
+        _lib.set_execution_mode(previous_mode)
+
+
+def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, caldera, cf, caldera_kwargs):
     quantised = params.compute_low_rank_factors and (params.L_bits < 16 or params.R_bits < 16)
     costs = [layer_cost(m, n, params.rank, params.iters, params.lplr_iters, quantised) for (m, n) in shapes]
     mine = lpt_assign(costs, world_size)[rank]
@@ -178,9 +205,19 @@ def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor
     nworkers = max(1, min(int(streams), len(mine)))
     order = sorted(range(len(mine)), key=lambda j: (-costs[mine[j]], j))     # big layers first
     results = [None] * len(mine)
-    cuda_streams = [torch.cuda.Stream(device=dev) for _ in range(nworkers)]
+    cuda_streams = _worker_streams(dev, nworkers)
 
     def work(w):
+        try:
+            _work(w)
+        except BaseException:
+            # ThreadPoolExecutor.map re-raises in worker order, not in time order: show every failure as it happens
+            import sys
+            import traceback
+            sys.stderr.write(f"[decompose_layers] worker {w} failed:\n{traceback.format_exc()}\n")
+            raise
+
+    def _work(w):
         torch.cuda.set_device(dev)
         with torch.cuda.stream(cuda_streams[w]):
             for j in order[w::nworkers]:

@@ -146,21 +146,30 @@ int cb_sgemm_strided(int64_t M, int64_t N, int64_t K, float alpha,
  * memory of cb_gemm_bf16_tn_workspace_bytes() bytes, and are summed in slice order), so equal
  * inputs give equal bits; with workspace == NULL the contraction runs unsplit (splitk > 1 is then
  * CB_ERR_WORKSPACE).  *error_flag (device int, may be NULL) is set if the in-kernel pipeline
- * watchdog fired.  operand_layout bit 0 / bit 1: A / B is stored as contiguous 64 x 64 tiles (element
- * (r, k) at ((r/64) * (K/64) + k/64) * 4096 + (r%64) * 64 + k%64; rows and K multiples of 64; lda/ldb
- * ignored), the HBM-friendly layout the layer driver keeps its m x n operands in.  Exported for
- * validation against cb_sgemm_strided. */
+ * watchdog fired.  probe_flags: 0; 1 = measurement aid, run the TMA pipeline without issuing MMAs
+ * (C undefined).  Exported for validation against cb_sgemm_strided. */
 size_t cb_gemm_bf16_tn_workspace_bytes(void);
 int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
-                    const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int operand_layout,
+                    const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int probe_flags,
                     int* error_flag, void* workspace, size_t workspace_bytes, void* stream);
+/* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
+ * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
+ * rounding level between modes (different K-split counts and eigensolver sweep order).
+ *   CB_MODE_LATENCY (default): one layer at a time should finish as early as possible -- contractions
+ *     spread over ~all SMs, the 8-CTA cluster eigensolver.
+ *   CB_MODE_THROUGHPUT: many independent layers are in flight on different streams (the model-level
+ *     job) -- contractions use ~32-CTA grids with the widest tiles (3x less SM time and fabric traffic
+ *     per flop, and four of them fit side by side), the single-CTA eigensolver (3x less SM time). */
+#define CB_MODE_LATENCY 0
+#define CB_MODE_THROUGHPUT 1
+int cb_set_execution_mode(int mode);
 /* Grid-size policy of the tcgen05 contractions: ~120 (default) fills the machine for a single layer
  * (lowest latency); ~32 keeps grids small so that the contractions of several layers in flight on
  * different streams overlap (highest throughput).  Process-wide. */
 void cb_set_gemm_target_ctas(int n);
-/* How many neighbouring CTAs (a thread-block cluster; 1, 2, 4 or 8) share one TMA-multicast copy of
- * the A tile in the narrow-tile contraction.  Results do not depend on it.  Process-wide. */
-void cb_set_gemm_cluster(int n);
+/* 64-wide K blocks fetched per TMA instruction in the narrow-tile contractions (1 or 2, default 2).
+ * Results do not depend on it.  Process-wide. */
+void cb_set_gemm_kblocks(int n);
 /* Measurement aid for bench.py / scripts: cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16,
  * bf16, both operands resident in shared memory, no TMA, no per-stage barriers) take on an SM, on a
  * grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */

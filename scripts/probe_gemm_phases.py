@@ -16,9 +16,10 @@ stamps = torch.zeros(8, dtype=torch.int64, device=dev)
 lib.cb_set_gemm_timing(_lib.ptr(stamps))
 names = ["prologue", "->last load issued", "first stage landed (from entry)", "last stage landed (from entry)",
          "accumulator complete (from entry)", "epilogue done (from entry)", "exit (from entry)"]
-for ctas, cl, split, layout, tag in ((120, 1, 1, 0, "bn64"), (120, 4, 1, 0, "bn64 cl4"), (120, 1, 1, 4, "bn64 loads-only"),
-                                     (32, 1, 1, 0, "bn256"), (32, 1, 4, 0, "bn256 split4"), (64, 1, 2, 0, "bn128 split2")):
-    lib.cb_set_gemm_target_ctas(ctas); lib.cb_set_gemm_cluster(cl)
+for ctas, kbs, split, layout, tag in ((120, 1, 1, 0, "bn64 kb1"), (120, 2, 1, 0, "bn64 kb2"), (120, 2, 1, 1, "bn64 kb2 loads-only"),
+                                      (64, 1, 1, 0, "bn128 kb1"), (64, 2, 1, 0, "bn128 kb2"), (64, 2, 2, 0, "bn128 kb2 split2"),
+                                      (32, 1, 1, 0, "bn256"), (32, 1, 4, 0, "bn256 split4")):
+    lib.cb_set_gemm_target_ctas(ctas); lib.cb_set_gemm_kblocks(kbs)
     for _ in range(3):
         lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(Y), N, _lib.ptr(Zt), M, split, layout,
                             _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())

@@ -33,10 +33,10 @@ def run(splitk, iters=30, layout=0):
 
 
 for ctas, name in ((120, "bn64"), (64, "bn128"), (32, "bn256")):
-    lib.cb_set_gemm_target_ctas(ctas)
-    print(name, " ".join(f"split{s}: {run(s):.1f} us" for s in (1, 2, 4, 8)))
+  for kbs in (1, 2):
+    lib.cb_set_gemm_target_ctas(ctas); lib.cb_set_gemm_kblocks(kbs)
+    print(name, f"kb{kbs}", " ".join(f"split{s}: {run(s):.1f} us" for s in (1, 2, 4, 8)))
 for ctas, name in ((120, "bn64"), (64, "bn128"), (32, "bn256")):
     lib.cb_set_gemm_target_ctas(ctas)
-    lib.cb_set_gemm_cluster(1)
-    print(name, "loads only:", " ".join(f"split{s}: {run(s, layout=4):.1f} us" for s in (1, 2, 4)))
+    print(name, "loads only:", " ".join(f"split{s}: {run(s, layout=1):.1f} us" for s in (1, 2, 4)))
 print("flag", int(flag.item()))

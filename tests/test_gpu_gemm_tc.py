@@ -64,36 +64,19 @@ def test_gemm_tc_split_without_workspace_is_an_error():
     assert st == -4   # CB_ERR_WORKSPACE
 
 
-def _tiled(X):
-    """(rows, K) -> contiguous 64 x 64 tiles, K blocks of one row block adjacent."""
-    r, k = X.shape
-    return X.view(r // 64, 64, k // 64, 64).permute(0, 2, 1, 3).contiguous()
-
-
-@pytest.mark.parametrize("M,N,K,layout", [(256, 4096, 4096, 2), (4096, 128, 4096, 1), (1024, 704, 1536, 3),
-                                           (192, 11008, 4096, 2), (4096, 256, 11008, 1)])
-def test_gemm_tc_tiled_operands(M, N, K, layout):
-    """Operands kept as contiguous 64 x 64 tiles (the driver's HBM layout for the m x n residual):
-    bit-identical to the same contraction on row-major operands."""
+@pytest.mark.parametrize("M,N,K,splitk", [(256, 4096, 4096, 1), (224, 224, 4096, 0), (4096, 128, 4096, 0), (128, 512, 192, 1),
+                                           (256, 1024, 4096 + 64, 3)])
+def test_gemm_tc_kblocks_per_copy_do_not_change_results(M, N, K, splitk):
+    """One or two 64-wide K blocks per TMA instruction (3-D tensor map): same bits."""
     lib = _lib.load()
-    g = torch.Generator(device=DEV).manual_seed(M + N + K)
-    A = torch.randn(M, K, generator=g, device=DEV).bfloat16()
-    B = torch.randn(N, K, generator=g, device=DEV).bfloat16()
-    ws = torch.empty(lib.cb_gemm_bf16_tn_workspace_bytes(), dtype=torch.uint8, device=DEV)
-    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
-    out = []
-    for lay in (0, layout):
-        Aop = _tiled(A) if lay & 1 else A
-        Bop = _tiled(B) if lay & 2 else B
-        C = torch.full((M, N), float("nan"), device=DEV)
-        _lib.check(lib.cb_gemm_bf16_tn(M, N, K, 1.0, _lib.ptr(Aop), K, _lib.ptr(Bop), K, _lib.ptr(C), N, 0, lay,
-                                       _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "gemm")
-        out.append(C)
-    torch.cuda.synchronize()
-    assert int(flag.item()) == 0
-    assert torch.equal(out[0], out[1])
-    ref = A.double() @ B.double().T
-    assert float((out[1].double() - ref).abs().max() / ref.abs().max()) < 2e-5
+    try:
+        lib.cb_set_gemm_kblocks(1)
+        _, C1 = _run(M, N, K, splitk, return_C=True)
+        lib.cb_set_gemm_kblocks(2)
+        _, C2 = _run(M, N, K, splitk, return_C=True)
+    finally:
+        lib.cb_set_gemm_kblocks(2)
+    assert torch.equal(C1, C2)
 
 
 def test_gemm_tc_alpha_and_ld():
