@@ -195,19 +195,21 @@ def roofline_probes(dev, peaks):
     Zt = torch.empty(q, M, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    Zts = [torch.empty(q, M, device=dev) for _ in range(4)]
+    # outputs as in the layer: bf16 row-major (q x m) and transposed (m x q), no fp32 copy
+    Zts = [torch.empty(q, M, device=dev, dtype=torch.bfloat16) for _ in range(4)]
+    Zs = [torch.empty(M, q, device=dev, dtype=torch.bfloat16) for _ in range(4)]
     flops = 2.0 * M * N * q
 
     def sketch(j=0):
         y = ys[k[0] % 3]
         k[0] += 1
-        lib.cb_gemm_bf16_tn(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zts[j]), M, 1, 0, _lib.ptr(flag),
-                            None, 0, _lib.stream_ptr())
+        lib.cb_gemm_bf16_tn_bf16out(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zts[j]), M, _lib.ptr(Zs[j]), q,
+                                    None, None, _lib.ptr(flag), _lib.stream_ptr())
 
     def entry(t, note, **extra):
         e = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
              "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None, "seconds": t,
-             "algorithmic_flops": flops, "hbm_gbs": (2 * M * N + 2 * q * N + 4 * q * M) / t / 1e9, "note": note}
+             "algorithmic_flops": flops, "hbm_gbs": (2 * M * N + 2 * q * N + 2 * 2 * q * M) / t / 1e9, "note": note}
         e.update(extra)
         return e
     skinny = "skinny: arithmetic intensity q/2 = 112 flop/B on bf16 Y, min(tensor peak, AI x HBM) = 733 TFLOP/s"
@@ -220,19 +222,23 @@ def roofline_probes(dev, peaks):
             for _ in range(3):
                 sketch(j)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rounds = 20
-    e0.record()
-    for s_ in side:
-        s_.wait_event(e0)
-    for _ in range(rounds):
+    # fork-join graph: 4 streams x `rounds` launches, so that the host's launch rate is not what is timed
+    cap = torch.cuda.Stream(device=dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
         for j, s_ in enumerate(side):
+            s_.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s_):
-                sketch(j)
-    for s_ in side:
-        ev = torch.cuda.Event()
-        ev.record(s_)
-        torch.cuda.current_stream().wait_event(ev)
+                for _ in range(rounds):
+                    sketch(j)
+        for s_ in side:
+            torch.cuda.current_stream().wait_stream(s_)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     t4 = e0.elapsed_time(e1) * 1e-3 / (rounds * 4)
@@ -377,7 +383,8 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API, host buffers in, packed result out
     import concurrent.futures as cf
-    nworkers = max(1, min(nstreams, args.e2e_workers))
+    auto_workers = min(16, max(4, 2 * host_threads() // max(world, 1)))
+    nworkers = max(1, min(nstreams, args.e2e_workers if args.e2e_workers > 0 else auto_workers))
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
                  for _ in range(nworkers)]
@@ -428,7 +435,7 @@ def run_ours(args):
                            "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": nworkers,
                            "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
-                           "sketch_width": 224, "power_iters": 8, "peaks": peaks["source"]},
+                           "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -436,6 +443,12 @@ def run_ours(args):
         if world == 1:
             probes = roofline_probes(dev, peaks)
             dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_tcgen05")
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")      # ncu --set full, DRAM bytes per launch
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    for name, rec in json.load(f).items():
+                        if name in probes:
+                            probes[name]["traffic"] = rec["traffic"]
             line["roofline"] = {k: probes[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             line["roofline"]["kernel"] = dominant
             line["roofline_all"] = probes
@@ -463,7 +476,8 @@ def main():
                     help="library execution mode (cb_set_execution_mode)")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")
     ap.add_argument("--streams", type=int, default=32, help="independent layers kept in flight per GPU")
-    ap.add_argument("--e2e-workers", type=int, default=16, help="host threads driving the public API in the e2e leg")
+    ap.add_argument("--e2e-workers", type=int, default=0,
+                    help="host threads driving the public API in the e2e leg (0 = min(16, 2 x host cores / ranks), at least 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

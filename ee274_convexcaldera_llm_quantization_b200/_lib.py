@@ -28,7 +28,7 @@ class cb_caldera_params(C.Structure):
         ("aware", C.c_int32), ("n_order", C.c_int32), ("order", C.c_int32 * 8),
         ("rand_svd", C.c_int32), ("sigma_reg", C.c_float), ("scale_w", C.c_int32),
         ("global_scale_in", C.c_float), ("q_block", C.c_int64),
-        ("sketch_width", C.c_int32), ("power_iters", C.c_int32), ("warm_start", C.c_int32),
+        ("sketch_width", C.c_int32), ("power_iters", C.c_int32), ("power_iters_warm", C.c_int32), ("warm_start", C.c_int32),
         ("use_tensor_cores", C.c_int32), ("seed", C.c_uint64),
     ]
 
@@ -70,6 +70,10 @@ _SIGNATURES = {
     "cb_gemm_bf16_tn": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
+    "cb_gemm_bf16_tn_bf16out": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
     "cb_set_gemm_target_ctas": (None, [C.c_int]),
     "cb_set_execution_mode": (C.c_int, [C.c_int]),
     "cb_set_gemm_kblocks": (None, [C.c_int]),

@@ -112,7 +112,7 @@ def _classify_hessian(H: Optional[torch.Tensor], n: int, dev: torch.device):
 
 def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Optional[float] = None,
                   sketch_width: int = 0, power_iters: int = -1, warm_start: bool = True,
-                  seed: int = 0, use_tensor_cores: bool = True) -> _lib.cb_caldera_params:
+                  seed: int = 0, use_tensor_cores: bool = True, power_iters_warm: int = -1) -> _lib.cb_caldera_params:
     order = list(quant_params.update_order)
     for name in order:
         if name not in _ORDER_CODE:
@@ -137,6 +137,7 @@ def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Opti
     p.q_block = 0          # quantize_matrix forces one block per tensor (alg.py:247)
     p.sketch_width = int(sketch_width)
     p.power_iters = int(power_iters)
+    p.power_iters_warm = int(power_iters_warm)
     p.warm_start = int(bool(warm_start))
     p.use_tensor_cores = int(bool(use_tensor_cores))
     p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -164,6 +165,7 @@ def caldera(
     global_scale: Optional[float] = None,
     sketch_width: int = 0,
     power_iters: int = -1,
+    power_iters_warm: int = -1,
     warm_start: bool = True,
     seed: int = 0,
     return_packed: bool = True,
@@ -177,7 +179,9 @@ def caldera(
     W_copy   where CalderaDecomposition.W lives: "cpu" (reference behaviour, alg.py:81),
              "device" or "none";
     global_scale  inject the reference's global_scale instead of recomputing it;
-    sketch_width / power_iters / warm_start / seed  knobs of the randomized rank-r step;
+    sketch_width / power_iters / power_iters_warm / warm_start / seed  knobs of the randomized rank-r step
+             (power iterations of the first, random-start step -- default 12 -- and of the steps warm-started
+             from the previous outer iteration's basis -- default 3; rand_svd=True: 2 and 2);
     use_tensor_cores  bf16 tcgen05 contractions for aligned shapes (default) or fp32 SIMT everywhere;
     use_cuda_graph  replay a captured CUDA graph of the layer (cached per shape/parameters/thread);
     return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed.
@@ -204,7 +208,7 @@ def caldera(
         Wd = None if use_cuda_graph else W.to(dev, torch.float32, non_blocking=True).contiguous()
         h_kind, Hd = _classify_hessian(H, n, dev)
         p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed,
-                          use_tensor_cores)
+                          use_tensor_cores, power_iters_warm)
 
         f32 = dict(dtype=torch.float32, device=dev)
         if use_cuda_graph:

@@ -589,8 +589,14 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   if (out->W_scaled != nullptr)
     CB_CUDA(cudaMemcpyAsync(out->W_scaled, Ws, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
 
-  const int niter = p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 8);
-  bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false;
+  // Power iterations of the randomized rank-r step.  The first (cold, random start) step is the
+  // inaccurate one: its excess over the exact SVD's residual halves every two iterations (5.9e-4 of
+  // the error at 8, 1.7e-4 at 12), while a step warm-started from the previous outer iteration's
+  // basis is already below 1e-4 after 3 (oracle/device_model.py study in DESIGN.md section 2).
+  const int niter_cold = p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 12);
+  const int niter_warm = p->power_iters_warm >= 0 ? p->power_iters_warm
+                                                  : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
+  bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
   bool updated[8] = {false, false, false, false, false, false, false, false};
   int step = 0;
   for (int it = 0; it < p->iters; ++it) {
@@ -622,6 +628,10 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         } else {
           CB_TRY(form_y(Ws, qcodes, qbits, P.qscale_cur, (p->aware && !P.dense) ? P.sqrt_h : nullptr, m, n, P.Y, P.RES, st));
         }
+        // warm only if the basis being reused was fitted to a residual of the same kind: the step after an
+        // LR-first step (Q still zero then) faces a completely different matrix and gets the cold count
+        const int niter = (warm_valid && p->warm_start && basis_saw_q) ? niter_warm : niter_cold;
+        basis_saw_q = have_q || !p->compute_q;
         if (P.dense && p->aware) {
           // form_y ran with sqrt_h == 1 for the dense case, so P.Y is the plain residual W - Q
           CB_TRY(lowrank_core_dense(P.Y, P.Hs, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step,

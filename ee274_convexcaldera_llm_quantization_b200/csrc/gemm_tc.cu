@@ -121,6 +121,7 @@ struct GemmTcArgs {
   __nv_bfloat16* Ct; int64_t ldct;   // bf16 out, transposed (N x M), may be null (ignored when atomic)
   const float* colscale;             // per output column, may be null
   const float* rowscale;             // per output row, may be null
+  int staged;                        // bf16-only outputs whose alignment allows the shared-memory staged epilogue
   int loads_only;                    // measurement aid: run the TMA pipeline but issue no MMA (output undefined)
   long long* timing;                 // measurement aid: 8 clock64 stamps of CTA (0,0,0), or null
   int splits;                        // > 1: split-K, raw partial tiles go to `ws` for splitk_reduce_kernel
@@ -293,7 +294,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int trow = qd * 32 + lane;               // row inside the tile
     const int row = m_blk * TC_BM + trow;
     const float rs = (args.rowscale != nullptr && row < args.M) ? args.rowscale[row] : 1.f;
-    if (args.splits <= 1) {
+    if (args.splits <= 1 && args.staged) {
+      // bf16-only outputs (the sketch / apply contractions): a thread owns a row of the accumulator, so
+      // direct stores are 16-byte pieces 2*ld bytes apart (row-major) or 64-byte runs (transposed).  Stage
+      // the tile through the now idle pipeline buffers in both orientations and write whole rows instead.
+      constexpr int RM_STRIDE = BN * 2 + 16;        // bytes per staged row (row-major tile), padded against bank conflicts
+      constexpr int T_STRIDE = TC_BM * 2 + 16;      // bytes per staged column (transposed tile)
+      uint8_t* stage_rm = smem_raw + (base - smem_u32(smem_raw));
+      uint8_t* stage_t = stage_rm + TC_BM * RM_STRIDE;
+      if (ok) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
+          const int col0 = n_blk * BN + c0;
+          __align__(16) __nv_bfloat16 b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) * args.alpha * rs;
+            if (args.colscale != nullptr && col0 + j < args.N) x *= args.colscale[col0 + j];
+            b[j] = __float2bfloat16_rn(x);
+          }
+          if (args.Cb != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(stage_rm + trow * RM_STRIDE + c0 * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = *reinterpret_cast<const uint4*>(&b[8 * j]);
+          }
+          if (args.Ct != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              *reinterpret_cast<__nv_bfloat16*>(stage_t + (c0 + j) * T_STRIDE + trow * 2) = b[j];
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps
+      if (ok) {
+        const int et = threadIdx.x - 64;                 // 0 .. 127
+        if (args.Cb != nullptr) {
+          constexpr int UPR = BN / 8;                    // 16-byte units per row
+          for (int u = et; u < TC_BM * UPR; u += 128) {
+            const int r_ = u / UPR, cu = u - r_ * UPR;
+            const int grow = m_blk * TC_BM + r_, gcol = n_blk * BN + cu * 8;
+            if (grow < args.M && gcol < args.N)
+              *reinterpret_cast<uint4*>(args.Cb + (int64_t)grow * args.ldcb + gcol) =
+                  *reinterpret_cast<const uint4*>(stage_rm + r_ * RM_STRIDE + cu * 16);
+          }
+        }
+        if (args.Ct != nullptr) {
+          constexpr int UPC = TC_BM / 4;                 // 8-byte units (4 rows) per column
+          for (int u = et; u < BN * UPC; u += 128) {
+            const int c_ = u / UPC, ru = u - c_ * UPC;
+            const int gcol = n_blk * BN + c_, grow = m_blk * TC_BM + ru * 4;
+            if (gcol < args.N && grow < args.M)
+              *reinterpret_cast<uint2*>(args.Ct + (int64_t)gcol * args.ldct + grow) =
+                  *reinterpret_cast<const uint2*>(stage_t + c_ * T_STRIDE + ru * 8);
+          }
+        }
+      }
+    } else if (args.splits <= 1) {
       if (ok) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -495,6 +553,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcA
 
 int g_target_ctas = -1;
 long long* g_timing = nullptr;   // measurement aid, see cb_set_gemm_timing
+int g_staged_epilogue = 1;       // CB_GEMM_STAGED=0 falls back to direct stores (measurement aid)
 int g_kblocks = -1;              // K blocks per TMA instruction for the narrow tiles (CB_GEMM_KBLOCKS: 1 or 2)
 
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
@@ -552,6 +611,10 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   splits = (total_kb + kb_per - 1) / kb_per;
   if (splits_used != nullptr) *splits_used = splits;
   const bool loads_only = (probe_flags & 1) != 0;
+  {
+    static bool read_env = false;
+    if (!read_env) { const char* e = getenv("CB_GEMM_STAGED"); if (e != nullptr && atoi(e) == 0) g_staged_epilogue = 0; read_env = true; }
+  }
   if (g_kblocks < 0) {
     const char* e = getenv("CB_GEMM_KBLOCKS");
     g_kblocks = (e != nullptr && atoi(e) == 1) ? 1 : 2;
@@ -577,6 +640,10 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   args.colscale = colscale; args.rowscale = rowscale; args.error_flag = error_flag;
   args.splits = splits; args.ws = splits > 1 ? sw->buf : nullptr;
   args.loads_only = loads_only ? 1 : 0;
+  // staged epilogue: bf16 outputs only, whole 8-column / 4-row units inside the matrix, vector-aligned
+  args.staged = (g_staged_epilogue != 0 && splits == 1 && C == nullptr && (Cb != nullptr || Ct != nullptr) &&
+                 (Cb == nullptr || (N % 8 == 0 && ldcb % 8 == 0 && aligned16(Cb))) &&
+                 (Ct == nullptr || (M % 4 == 0 && ldct % 4 == 0 && (reinterpret_cast<uintptr_t>(Ct) & 7u) == 0))) ? 1 : 0;
   args.timing = g_timing;
   if (bn == 256) CB_TRY((launch_tc<256, 4, 1>(ta, tb, args, splits, st)));
   else if (bn == 128 && kbs == 2) CB_TRY((launch_tc<128, 3, 2>(ta, tb, args, splits, st)));
@@ -658,6 +725,21 @@ extern "C" int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, con
                      reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, C, ldc, nullptr, 0, nullptr, 0, nullptr,
                      nullptr, splitk, error_flag, &splits, st, &sw, probe_flags);
 }
+
+// Same contraction with the bf16 epilogues the layer driver uses: Cb (M x N, row-major) and/or Ct (N x M,
+// transposed), optional per-column / per-row scaling.  Exported so that the staged epilogue can be tested.
+extern "C" int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
+                                       const void* B_bf16, int64_t ldb, void* Cb_bf16, int64_t ldcb, void* Ct_bf16,
+                                       int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
+                                       void* stream) {
+  if (A_bf16 == nullptr || B_bf16 == nullptr || (Cb_bf16 == nullptr && Ct_bf16 == nullptr)) return CB_ERR_ARG;
+  return cb::gemm_tc(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A_bf16), lda,
+                     reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, nullptr, 0,
+                     reinterpret_cast<__nv_bfloat16*>(Cb_bf16), ldcb, reinterpret_cast<__nv_bfloat16*>(Ct_bf16), ldct,
+                     colscale, rowscale, 1, error_flag, nullptr, (cudaStream_t)stream, nullptr, 0);
+}
+
+extern "C" void cb_set_gemm_staged_epilogue(int on) { cb::g_staged_epilogue = on != 0 ? 1 : 0; }
 
 extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
                                void* Yt_bf16, int64_t ldyt, const float* colscale, void* stream) {

@@ -155,7 +155,9 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
 
 // Inverses of all 32 x 32 diagonal blocks of the factor at once: warp b takes block b, lane =
 // row while loading / column of the inverse while solving, L[i][k] is broadcast from lane i.
-__device__ void diag_block_inverses(const float* G, int q, float* Linv) {
+// Every routine that writes an element of Linv also writes its bf16 copy when `Lb` is given (the
+// tensor-core contractions consume the inverse as a bf16 operand), so no separate conversion pass runs.
+__device__ void diag_block_inverses(const float* G, int q, float* Linv, __nv_bfloat16* Lb) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nblk = (q + NB - 1) / NB;
   for (int b = warp; b < nblk; b += nwarps) {
@@ -180,7 +182,11 @@ __device__ void diag_block_inverses(const float* G, int q, float* Linv) {
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i)
-      if (i < nb && lane <= i && lane < nb) Linv[(size_t)(r0 + i) * q + r0 + lane] = x[i];
+      if (i < nb && lane <= i && lane < nb) {
+        const size_t e = (size_t)(r0 + i) * q + r0 + lane;
+        Linv[e] = x[i];
+        if (Lb != nullptr) Lb[e] = __float2bfloat16_rn(x[i]);
+      }
   }
 }
 
@@ -198,13 +204,16 @@ __device__ __forceinline__ void chain_sync(int chain) {
   asm volatile("bar.sync %0, 128;" ::"r"(chain + 1) : "memory");
 }
 
-__device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tiles) {
+__device__ void tri_inverse(const float* G, int q, float* Linv, __nv_bfloat16* Lb, ChainTiles* tiles) {
   const int tid = threadIdx.x;
   const int nblk = (q + NB - 1) / NB;
   // strict upper triangle and not-yet-computed blocks start at zero
   for (int e = tid; e < q * q; e += blockDim.x) {
     const int i = e / q, j = e - i * q;
-    if ((i / NB) != (j / NB) || j > i) Linv[e] = 0.f;
+    if ((i / NB) != (j / NB) || j > i) {
+      Linv[e] = 0.f;
+      if (Lb != nullptr) Lb[e] = __float2bfloat16_rn(0.f);
+    }
   }
   __syncthreads();
   const int chain = tid >> 7, ct = tid & 127;
@@ -264,7 +273,10 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, ChainTiles* tile
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const int gc = j * NB + oc0 + c;
-              if (gc < q) Linv[(size_t)gr * q + gc] = -out[c];
+              if (gc < q) {
+                Linv[(size_t)gr * q + gc] = -out[c];
+                if (Lb != nullptr) Lb[(size_t)gr * q + gc] = __float2bfloat16_rn(-out[c]);
+              }
             }
           }
         }
@@ -312,13 +324,9 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfl
     __syncthreads();
   }
   if (Linv != nullptr) {
-    diag_block_inverses(G, q, Linv);
+    diag_block_inverses(G, q, Linv, Linv_bf16);
     __syncthreads();
-    tri_inverse(G, q, Linv, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
-    // the tensor-core contractions consume Linv as a bf16 operand: emit it here rather than
-    // in a separate conversion launch (tri_inverse ends with a CTA barrier)
-    if (Linv_bf16 != nullptr)
-      for (int e = tid; e < q * q; e += blockDim.x) Linv_bf16[e] = __float2bfloat16_rn(Linv[e]);
+    tri_inverse(G, q, Linv, Linv_bf16, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
   }
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }

@@ -25,13 +25,16 @@ _MAGIC = b"CALDB200"
 
 # ----------------------------------------------------------------------------- partitioning
 def layer_cost(m: int, n: int, rank: int, iters: int, lplr_iters: int = 0, quantised_factors: bool = False,
-               sketch_width: Optional[int] = None, power_iters: int = 8) -> float:
-    """Flop model of one layer: sketch passes dominate."""
+               sketch_width: Optional[int] = None, power_iters: int = 12, power_iters_warm: int = 3) -> float:
+    """Flop model of one layer: sketch passes dominate.  The first rank-r step starts
+    cold (`power_iters`), the later ones from the previous basis (`power_iters_warm`)."""
     q = sketch_width if sketch_width else max(2 * rank, rank + 32)
-    per_iter = 2.0 * m * n * q * (2 + 2 * power_iters) + 4.0 * m * n * rank
+    it = max(iters, 1)
+    sketch = 2.0 * m * n * q * ((2 + 2 * power_iters) + (it - 1) * (2 + 2 * power_iters_warm))
+    rest = 4.0 * m * n * rank
     if quantised_factors:
-        per_iter += 6.0 * m * n * rank * lplr_iters
-    return per_iter * max(iters, 1)
+        rest += 6.0 * m * n * rank * lplr_iters
+    return sketch + rest * it
 
 
 def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:

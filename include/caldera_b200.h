@@ -152,6 +152,16 @@ size_t cb_gemm_bf16_tn_workspace_bytes(void);
 int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
                     const void* B_bf16, int64_t ldb, float* C, int64_t ldc, int splitk, int probe_flags,
                     int* error_flag, void* workspace, size_t workspace_bytes, void* stream);
+/* The same contraction with the bf16 epilogues the layer driver uses: Cb (M x N row-major bf16, ldcb) and/or
+ * Ct (N x M bf16, the transpose, ldct), either may be NULL; optional per-column / per-row fp32 scaling
+ * (NULL = none).  When the outputs are vector-aligned (N % 8 == 0, ldcb % 8 == 0; M % 4 == 0, ldct % 4 == 0)
+ * the tile is staged through shared memory and written as whole rows; cb_set_gemm_staged_epilogue(0)
+ * forces the direct-store epilogue (same results).  Exported for validation. */
+int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
+                            const void* B_bf16, int64_t ldb, void* Cb_bf16, int64_t ldcb, void* Ct_bf16,
+                            int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
+                            void* stream);
+void cb_set_gemm_staged_epilogue(int on);
 /* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
  * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
  * rounding level between modes (different K-split counts and eigensolver sweep order).
@@ -202,7 +212,9 @@ typedef struct cb_caldera_params {
   int64_t q_block;          /* 0 = whole-tensor scale (reference semantics, alg.py:247);
                                >0 = per-block scales (opt-in extension)   */
   int32_t sketch_width;     /* 0 = default (2*rank)                       */
-  int32_t power_iters;      /* <0 = default (2 if rand_svd else 8)        */
+  int32_t power_iters;      /* of a cold (random-start) rank-r step; <0 = default (2 if rand_svd else 12) */
+  int32_t power_iters_warm; /* of a step warm-started from the previous outer iteration's basis;
+                               <0 = default (power_iters if that is given, else 2 if rand_svd else 3) */
   int32_t warm_start;       /* reuse the previous outer iteration's basis */
   int32_t use_tensor_cores; /* 1: bf16 tcgen05 contractions where the shape allows (dims % 8 == 0,
                                m, n >= 256); 0: fp32 SIMT contractions everywhere        */

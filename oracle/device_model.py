@@ -73,7 +73,9 @@ def caldera_device_model(params: OracleParams, W, h, scale_W=True, q=None, niter
     if q is None:
         q = min(max(2 * r, r + 32), min(m, n)) if not params.rand_svd else min(2 * r, min(m, n))
     if niter is None:
-        niter = 2 if params.rand_svd else 8
+        niter = 2 if params.rand_svd else 12       # cold (random start) step, as csrc/driver.cu
+        if niter_warm is None:
+            niter_warm = 2 if params.rand_svd else 3   # steps warm-started from the previous basis
     rng = np.random.default_rng(seed)
 
     cur = OracleDecomposition(Q=np.zeros((m, n), F32), L=np.zeros((m, r), F32), R=np.zeros((r, n), F32), W=W)
@@ -81,12 +83,14 @@ def caldera_device_model(params: OracleParams, W, h, scale_W=True, q=None, niter
     errors = {k: [] for k in params.update_order}
     updated = {k: False for k in params.update_order}
     min_error, step, Zprev = float("inf"), 0, None
+    basis_saw_q = False      # the device reuses a basis with the warm count only if it was fitted to W - Q with Q != 0
     for _ in range(params.iters):
         for which in params.update_order:
             if which == "LR" and params.compute_low_rank_factors:
                 res = W - cur.Q
                 Y = res * sh[None, :] if aware else res
-                ni = niter if (Zprev is None or not warm_start or niter_warm is None) else niter_warm
+                ni = niter if (Zprev is None or not warm_start or niter_warm is None or not basis_saw_q) else niter_warm
+                basis_saw_q = bool(np.any(cur.Q)) or not params.compute_quantized_component
                 Zo, V, sig, B = subspace_lowrank(Y, r, q, ni, rng, Zprev if warm_start else None)
                 Zprev = Zo       # (the device also rotates it into Ritz vectors; the span is the same)
                 if aware:

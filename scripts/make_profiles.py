@@ -66,9 +66,55 @@ def raw(rep, title, out_name):
             f.write(f"| `{name}` | " + " | ".join(vals) + " |\n")
 
 
-launches("prof_layer_launches.csv", "Launch list: one 4096x4096 layer, rank 128, Q 2-bit, L/R 16-bit (BASELINE config 2)")
-launches("prof_layer_lr4_launches.csv", "Launch list: one 4096x4096 layer, rank 128, Q 2-bit, L/R 4-bit (LPLR loop)")
+launches("prof_layer_launches.csv", "Launch list: one 4096x4096 layer, rank 128, Q 2-bit, L/R 16-bit (BASELINE config 2), "
+         "throughput execution mode (the mode bench.py runs in)")
+launches("prof_layer_lr4_launches.csv", "Launch list: one 4096x4096 layer, rank 128, Q 2-bit, L/R 4-bit (LPLR loop), throughput mode")
+launches("prof_layer_latency_launches.csv", "Launch list: the same layer in latency execution mode (128-CTA grids, cluster eigensolver)")
 raw("prof_layer.ncu-rep", "Full captures inside the layer (tcgen05 GEMM, fused element-wise stages)", "layer_kernels")
 raw("prof_quant.ncu-rep", "Full capture: quantise + pack, 4096x4096 fp32 -> 2-bit, block 64", "quant_kernel")
 raw("prof_small.ncu-rep", "Full captures: Cholesky+inverse and Jacobi Rayleigh-Ritz, q = 224", "smalldense_kernels")
+
+
+def traffic():
+    """profiles/traffic.json: DRAM bytes per launch (read + write) of the kernels bench.py reports a roofline
+    for, from the --set full captures.  bench.py copies them into `roofline.traffic`."""
+    import json
+    out = {}
+
+    def rows_of(rep):
+        src = os.path.join(G, rep)
+        if not os.path.exists(src):
+            return None, []
+        txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        return rows[0], rows[2:]
+
+    def to_bytes(v, unit):
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        return float(v.replace(",", "")) * mult
+
+    for rep, pick, key in (("prof_layer.ncu-rep", "gemm_tc_kernel", "sketch_gemm_tcgen05"),
+                           ("prof_quant.ncu-rep", "quant_fast_kernel", "quantize_pack_b2_bs64")):
+        src = os.path.join(G, rep)
+        if not os.path.exists(src):
+            continue
+        txt = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(txt)))
+        hdr, units = rows[0], rows[1]
+        ki, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        cand = [r for r in rows[2:] if pick in r[ki]]
+        if not cand:
+            continue
+        r = max(cand, key=lambda r: float(r[ti].replace(",", "")))      # the sketch contraction is the longest gemm_tc launch
+        out[key] = {"kernel": r[ki].split("(")[0].replace("void ", ""),
+                    "dram_bytes_read": to_bytes(r[ri], units[ri]), "dram_bytes_write": to_bytes(r[wi], units[wi]),
+                    "time_us_under_ncu": float(r[ti].replace(",", "")) * ({"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[ti], 1)),
+                    "source": f"profiles/{tag}: {rep}, ncu --set full --clock-control none"}
+        out[key]["traffic"] = out[key]["dram_bytes_read"] + out[key]["dram_bytes_write"]
+    with open(os.path.join(OUT, "traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+traffic()
 print(os.listdir(OUT))

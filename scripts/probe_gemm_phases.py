@@ -28,4 +28,19 @@ for ctas, kbs, split, layout, tag in ((120, 1, 1, 0, "bn64 kb1"), (120, 2, 1, 0,
     e = t[0]
     print(f"{tag}: prologue {t[1]-e}, last-load-issued {t[2]-e}, first-landed {t[3]-e}, last-landed {t[4]-e}, "
           f"acc-complete {t[5]-e}, epilogue-done {t[6]-e}, exit {t[7]-e} clk")
+# the same contraction with the layer's bf16 epilogues (row-major + transposed), staged vs direct stores
+Zb = torch.empty(q, M, device=dev, dtype=torch.bfloat16)
+Zbt = torch.empty(M, q, device=dev, dtype=torch.bfloat16)
+for ctas, staged, tag in ((120, 1, "bn64 kb2 bf16-out staged"), (120, 0, "bn64 kb2 bf16-out direct"),
+                          (32, 1, "bn256 bf16-out staged"), (32, 0, "bn256 bf16-out direct")):
+    lib.cb_set_gemm_target_ctas(ctas); lib.cb_set_gemm_kblocks(2); lib.cb_set_gemm_staged_epilogue(staged)
+    for _ in range(3):
+        lib.cb_gemm_bf16_tn_bf16out(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(Y), N, _lib.ptr(Zb), M, _lib.ptr(Zbt), q,
+                                    None, None, _lib.ptr(flag), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    t = stamps.tolist()
+    e = t[0]
+    print(f"{tag}: prologue {t[1]-e}, first-landed {t[3]-e}, last-landed {t[4]-e}, acc-complete {t[5]-e}, "
+          f"epilogue-done {t[6]-e}, exit {t[7]-e} clk")
+lib.cb_set_gemm_staged_epilogue(1)
 lib.cb_set_gemm_timing(None)

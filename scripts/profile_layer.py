@@ -27,10 +27,13 @@ ap.add_argument("--lbits", type=int, default=16)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--no-tc", action="store_true")
+ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
+                help="library execution mode; bench.py runs in throughput mode")
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
+_lib.set_execution_mode(a.mode)
 qp = CalderaParams(Q_bits=2, L_bits=a.lbits, R_bits=a.lbits, rank=a.rank, iters=a.iters, lplr_iters=5,
                    update_order=["Q", "LR"])
 cp = make_c_params(qp, True, seed=1000, use_tensor_cores=not a.no_tc)
@@ -49,6 +52,6 @@ torch.cuda.profiler.stop()
 small = run.read_small()
 errs = small[:run.nsteps].tolist()
 stats = small[run.nerr_pad + 5:run.nerr_pad + 8].view(torch.int32).tolist()
-print(f"layer {a.m}x{a.n} r={a.rank} lbits={a.lbits}: {dt * 1e3:.2f} ms, "
+print(f"layer {a.m}x{a.n} r={a.rank} lbits={a.lbits} mode={a.mode}: {dt * 1e3:.2f} ms, "
       f"{_lib.load().cb_kernel_launch_count() - n0} launches, chol_retries={stats[0]} jacobi_sweeps={stats[1]} tc_watchdog={stats[2]}, "
       f"errors {[round(e, 5) for e in errs]}")

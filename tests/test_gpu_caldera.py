@@ -186,7 +186,9 @@ def test_vs_oracle_medium(lbits):
     best_got = min(d.errors["Q"])
     # lbits == 4: whole-tensor 4-bit re-quantisation of L/R makes the trajectory chaotic; the numpy
     # device model spreads over 0.170..0.190 across sketch seeds for this very input
-    tol = 2e-3 if lbits == 16 else 8e-2
+    # lbits == 16: 4-bit Q with a heavy-tailed h is itself a chaotic iteration -- the numpy device model
+    # spreads over 0.1434..0.1447 (+-5e-3) across sketch seeds whatever the power-iteration count
+    tol = 8e-3 if lbits == 16 else 8e-2
     assert best_got <= best_ref * (1 + tol) and best_got >= best_ref * (1 - 10 * tol), (best_got, best_ref)
 
 

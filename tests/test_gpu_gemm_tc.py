@@ -79,6 +79,51 @@ def test_gemm_tc_kblocks_per_copy_do_not_change_results(M, N, K, splitk):
     assert torch.equal(C1, C2)
 
 
+@pytest.mark.parametrize("M,N,K,ctas", [(224, 4096, 4096, 120), (224, 4096, 4096, 32), (4096, 224, 224, 120),
+                                         (224, 1024, 256, 64), (100, 72, 200, 120), (256, 520, 128, 32)])
+@pytest.mark.parametrize("outs", ["both", "rowmajor", "transposed"])
+def test_gemm_tc_bf16_epilogues(M, N, K, ctas, outs):
+    """bf16 row-major / transposed outputs with scaling: shared-memory staged epilogue == direct stores ==
+    torch, for every tile width (grid policy) and for shapes that cannot be staged (ragged N / M)."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.zeros(M, Kp, device=DEV, dtype=torch.bfloat16)
+    B = torch.zeros(N, Kp, device=DEV, dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    B[:, :K] = torch.randn(N, K, generator=g, device=DEV).bfloat16()
+    cs = torch.rand(N, generator=g, device=DEV) + 0.5
+    rs = torch.rand(M, generator=g, device=DEV) + 0.5
+    ldcb, ldct = (N + 7) // 8 * 8, (M + 7) // 8 * 8
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    res = []
+    try:
+        lib.cb_set_gemm_target_ctas(ctas)
+        for staged in (1, 0):
+            lib.cb_set_gemm_staged_epilogue(staged)
+            Cb = torch.full((M, ldcb), 7.0, device=DEV, dtype=torch.bfloat16)
+            Ct = torch.full((N, ldct), 7.0, device=DEV, dtype=torch.bfloat16)
+            _lib.check(lib.cb_gemm_bf16_tn_bf16out(M, N, K, 0.5, _lib.ptr(A), Kp, _lib.ptr(B), Kp,
+                                                   _lib.ptr(Cb) if outs != "transposed" else None, ldcb,
+                                                   _lib.ptr(Ct) if outs != "rowmajor" else None, ldct,
+                                                   _lib.ptr(cs), _lib.ptr(rs), _lib.ptr(flag), _lib.stream_ptr()), "gemm")
+            res.append((Cb, Ct))
+    finally:
+        lib.cb_set_gemm_staged_epilogue(1)
+        lib.cb_set_gemm_target_ctas(120)
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0
+    ref = (0.5 * (A[:, :K].double() @ B[:, :K].double().T) * rs[:, None].double() * cs[None, :].double())
+    for Cb, Ct in res:
+        if outs != "transposed":
+            assert float((Cb[:, :N].double() - ref).abs().max() / ref.abs().max()) < 6e-3       # bf16 rounding
+            assert bool((Cb[:, N:] == 7.0).all())                                              # padding untouched
+        if outs != "rowmajor":
+            assert float((Ct[:, :M].double() - ref.T).abs().max() / ref.abs().max()) < 6e-3
+            assert bool((Ct[:, M:] == 7.0).all())
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_gemm_tc_alpha_and_ld():
     assert _run(256, 192, 320, 1, lda=384, ldb=512, alpha=-0.5) < 2e-5
 
