@@ -17,7 +17,9 @@ from .params import CalderaParams, CalderaDecomposition, QuantInfo  # noqa: F401
 from .quantization import QuantizerFactory, LowMemoryQuantizer, AbstractQuantizer  # noqa: F401
 from .runner import CalderaLayerRunner, workspace_bytes
 
+import os
 import threading
+import time
 
 # Scratch arenas are reused across calls (one per device and calling thread): a layer needs
 # ~0.5 GiB of workspace at 4096 x 4096 and re-allocating it per call costs more than the H2D copy.
@@ -73,6 +75,14 @@ def _release_graph_runner(key, run) -> None:
 
 
 _ORDER_CODE = {"Q": 0, "LR": 1}
+
+# optional host-side phase timers of the graph path (CB_CALDERA_TIMES=1): seconds summed over calls/threads
+_PHASE_TIMES = {"acquire": 0.0, "launch": 0.0, "wait": 0.0, "copy_out": 0.0, "calls": 0}
+_PHASE_ON = bool(os.environ.get("CB_CALDERA_TIMES"))
+
+
+def phase_times() -> dict:
+    return dict(_PHASE_TIMES)
 
 
 def _resolve_device(device, W: torch.Tensor) -> torch.device:
@@ -171,6 +181,7 @@ def caldera(
     return_packed: bool = True,
     use_tensor_cores: bool = True,
     use_cuda_graph: bool = False,
+    return_dense: bool = True,
 ):
     """Runs CALDERA: decomposes W into Q + L R (alg.py:24-112), all arithmetic on `device`.
 
@@ -184,7 +195,9 @@ def caldera(
              from the previous outer iteration's basis -- default 3; rand_svd=True: 2 and 2);
     use_tensor_cores  bf16 tcgen05 contractions for aligned shapes (default) or fp32 SIMT everywhere;
     use_cuda_graph  replay a captured CUDA graph of the layer (cached per shape/parameters/thread);
-    return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed.
+    return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed;
+    return_dense  False: leave Q, Q_idxs (and L_idxs / R_idxs) unset -- for callers that only consume the packed
+             codes, scales and factors (the model-level job), which saves the m x n fp32 + int8 copies per layer.
     `use_tqdm` is accepted and ignored (the loop runs on the device).
     """
     if len(W.shape) != 2:
@@ -213,9 +226,13 @@ def caldera(
         f32 = dict(dtype=torch.float32, device=dev)
         if use_cuda_graph:
             p.seed = 0
+            t0 = time.perf_counter()
             graph_key, run = _acquire_graph_runner(p, m, n, h_kind, dev, return_packed, W_copy != "none")
+            t1 = time.perf_counter()
             run.launch(W, Hd, seed)
+            t2 = time.perf_counter()
             host = run.read_small()                       # the one synchronisation of the layer
+            t3 = time.perf_counter()
             clone = lambda t: None if t is None else t.clone()   # noqa: E731  (graph buffers are reused)
         else:
             ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
@@ -227,16 +244,24 @@ def caldera(
             run.ws = None                                 # the arena stays in the per-thread cache
             del ws
         nsteps = run.nsteps
-        Q, L, R = clone(run.Q), clone(run.L), clone(run.R)
-        Q_idxs, L_idxs, R_idxs = clone(run.Q_idxs), clone(run.L_idxs), clone(run.R_idxs)
+        dense = clone if return_dense else (lambda t: None)       # noqa: E731
+        Q, L, R = dense(run.Q), clone(run.L), clone(run.R)
+        Q_idxs, L_idxs, R_idxs = dense(run.Q_idxs), dense(run.L_idxs), dense(run.R_idxs)
         Q_packed, L_packed, R_packed = clone(run.Q_packed), clone(run.L_packed), clone(run.R_packed)
-        Q_scale, L_scale, R_scale = run.Q_scale, run.L_scale, run.R_scale
+        # (cloned here, before the runner goes back to the pool where another thread may replay it)
+        Q_scale, L_scale, R_scale = clone(run.Q_scale), clone(run.L_scale), clone(run.R_scale)
         W_scaled = clone(run.W_scaled)
         if use_cuda_graph:
             if not scale_W:
                 Wd = run.W_in.clone()
             torch.cuda.current_stream().synchronize()     # copies out of the graph's buffers are done
             _release_graph_runner(graph_key, run)
+            if _PHASE_ON:
+                t4 = time.perf_counter()
+                with _GRAPH_LOCK:
+                    for key_, dt_ in (("acquire", t1 - t0), ("launch", t2 - t1), ("wait", t3 - t2), ("copy_out", t4 - t3)):
+                        _PHASE_TIMES[key_] += dt_
+                    _PHASE_TIMES["calls"] += 1
 
     errs = host[:nsteps].tolist()
     scal = host[run.nerr_pad:run.nerr_pad + 8]
@@ -255,11 +280,14 @@ def caldera(
     dec.SV = torch.ones(m, **f32)
     if taken and p.compute_q:
         dec.Q_idxs = Q_idxs
-        dec.Q_scale = Q_scale.clone().reshape(1, 1)
+        dec.Q_scale = Q_scale.reshape(1, 1) if use_cuda_graph else Q_scale.clone().reshape(1, 1)
         dec.Q_packed = Q_packed
     if taken and quant_factors:
         dec.L_idxs, dec.R_idxs = L_idxs, R_idxs
-        dec.L_scale, dec.R_scale = L_scale.clone().reshape(1, 1), R_scale.clone().reshape(1, 1)
+        if use_cuda_graph:
+            dec.L_scale, dec.R_scale = L_scale.reshape(1, 1), R_scale.reshape(1, 1)
+        else:
+            dec.L_scale, dec.R_scale = L_scale.clone().reshape(1, 1), R_scale.clone().reshape(1, 1)
         dec.L_packed, dec.R_packed = L_packed, R_packed
     Wkeep = W_scaled if scale_W else Wd
     if W_copy == "cpu":

@@ -15,6 +15,8 @@ the blobs live on the GPU, gloo in the CPU tests).
 from __future__ import annotations
 
 import json
+import os
+import time
 import struct
 from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -56,10 +58,12 @@ def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:
 _FIELDS = ("Q_packed", "Q_scale", "L", "R", "L_packed", "R_packed", "L_scale", "R_scale")
 
 
-def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, shape: Tuple[int, int]) -> torch.Tensor:
+def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, shape: Tuple[int, int],
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Serialises what a consumer of the decomposition needs: packed Q codes + scale, and the
     factors (packed codes + scales when quantised, fp16 otherwise; fp32 if `l_bits` >= 32).
-    Layout: magic | u64 header length | JSON header | 16-byte aligned payload sections."""
+    Layout: magic | u64 header length | JSON header | 16-byte aligned payload sections.
+    `out` (uint8, device): write the blob into its head and return that view when it fits."""
     tensors: Dict[str, torch.Tensor] = {}
     for f in _FIELDS:
         t = getattr(dec, f, None)
@@ -90,6 +94,9 @@ def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, sh
     hpad = (-(len(_MAGIC) + 8 + len(header))) % 16
     head = _MAGIC + struct.pack("<Q", len(header) + hpad) + header + b" " * hpad
     head_t = torch.frombuffer(bytearray(head), dtype=torch.uint8).to(device)
+    total = head_t.numel() + offset
+    if out is not None and out.numel() >= total and out.device == head_t.device:
+        return torch.cat([head_t] + parts, out=out[:total])
     return torch.cat([head_t] + parts) if parts else head_t
 
 
@@ -191,12 +198,19 @@ def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor
     import concurrent.futures as cf
     from . import _lib
     from .alg import caldera
+    import sys
     previous_mode = _lib.execution_mode()
+    previous_switch = sys.getswitchinterval()
     _lib.set_execution_mode("throughput")
+    # worker threads alternate between short bursts of Python (a few torch calls) and long GIL-free waits on
+    # their stream; with the default 5 ms switch interval a thread that wakes up can sit behind another one's
+    # burst for milliseconds while its GPU stream idles
+    sys.setswitchinterval(float(os.environ.get("CB_SWITCH_INTERVAL", "0.0002")))
     try:
         return _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, caldera, cf,
                                  caldera_kwargs)
     finally:
+        sys.setswitchinterval(previous_switch)
         _lib.set_execution_mode(previous_mode)
 
 
@@ -209,6 +223,24 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
     order = sorted(range(len(mine)), key=lambda j: (-costs[mine[j]], j))     # big layers first
     results = [None] * len(mine)
     cuda_streams = _worker_streams(dev, nworkers)
+    slots = [None] * len(mine)
+    if pack and mine:
+        # The blobs are the only allocations that outlive a layer.  torch's caching allocator keeps free
+        # blocks per stream, so blobs allocated by the workers on their own streams would each be a fresh
+        # cudaMalloc (taking the driver's allocation lock while other threads launch graphs: measured 2.5-5 s
+        # instead of 1.3 s for the 224-layer job).  One arena, sliced per layer, instead.
+        def blob_bytes(m, n):
+            q = m * n * max(params.Q_bits, 1) // 8 if params.compute_quantized_component else 0
+            quantised_lr = params.L_bits < 16 or params.R_bits < 16
+            lr = (m + n) * params.rank * (1 if quantised_lr else 2) if params.compute_low_rank_factors else 0
+            return (q + lr + (1 << 15) + 255) // 256 * 256
+        sizes = [blob_bytes(*shapes[i]) for i in mine]
+        arena = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+        off = 0
+        for j, sz in enumerate(sizes):
+            slots[j] = arena[off:off + sz]
+            off += sz
+    host_time = [[0.0, 0.0] for _ in range(nworkers)]       # seconds inside caldera() / pack per worker
 
     def work(w):
         try:
@@ -231,9 +263,15 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
                 kw.setdefault("seed", 1000 + i)
                 kw.setdefault("W_copy", "none")
                 kw.setdefault("use_cuda_graph", True)
+                if pack and not os.environ.get("CB_RETURN_DENSE"):
+                    kw.setdefault("return_dense", False)       # the blob holds packed codes and factors only
+                t0 = time.perf_counter()
                 dec = caldera(params, W, H, device=dev, use_tqdm=False, **kw)
+                t1 = time.perf_counter()
                 results[j] = pack_decomposition(name, dec, params.Q_bits, params.L_bits, params.R_bits,
-                                                tuple(W.shape)) if pack else dec
+                                                tuple(W.shape), out=slots[j]) if pack else dec
+                host_time[w][0] += t1 - t0
+                host_time[w][1] += time.perf_counter() - t1
             cuda_streams[w].synchronize()
 
     if nworkers == 1:
@@ -241,4 +279,8 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
     else:
         with cf.ThreadPoolExecutor(max_workers=nworkers) as ex:
             list(ex.map(work, range(nworkers)))
+    if os.environ.get("CB_SCHEDULER_TIMES"):
+        import sys
+        sys.stderr.write(f"[decompose_layers] rank {rank}: per-worker seconds in caldera() "
+                         f"{[round(t[0], 3) for t in host_time]}, in pack {[round(t[1], 3) for t in host_time]}\n")
     return mine, results

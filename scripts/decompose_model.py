@@ -90,5 +90,8 @@ if rank == 0:
                       "decompose_wall_s": float(tt[0]), "gather_wall_s": float(tt[1]), "gathered_bytes": int(nbytes),
                       "layers_per_s": nlayers / float(tt[0]), "first_layer": first["name"],
                       "first_layer_best_error": min(first["errors"]["LR"])}))
+if os.environ.get("CB_CALDERA_TIMES"):
+    from ee274_convexcaldera_llm_quantization_b200.alg import phase_times
+    print(f"rank {rank} host phases of caldera() summed over worker threads: {phase_times()}", file=sys.stderr)
 if world > 1:
     dist.destroy_process_group()
