@@ -597,6 +597,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   const int niter_warm = p->power_iters_warm >= 0 ? p->power_iters_warm
                                                   : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
   bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
+  bool amax_valid = false;   // P.amax already holds max |Ws - LRbuf| (computed by the pass that evaluated the error)
   bool updated[8] = {false, false, false, false, false, false, false, false};
   int step = 0;
   for (int it = 0; it < p->iters; ++it) {
@@ -611,7 +612,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
           lrbuf_valid = true;
           lrp = P.LRbuf;
         }
-        CB_TRY(resid_absmax(Ws, lrp, numel, P.amax, st));
+        if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(Ws, lrp, numel, P.amax, st));
         CB_TRY(quant_err(Ws, lrp, P.h_eff, m, n, P.amax, 1e-8f, p->q_bits, P.codes_cur, P.qscale_cur, P.dsc + 2, st));
         have_q = true;
         num_ready = !P.dense;   // the fused numerator is the diagonal metric
@@ -648,13 +649,19 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         have_lr = true;
         CB_TRY(lr_product(P, m, n, r, st));
         lrbuf_valid = true;
+        amax_valid = false;
       }
       if (!num_ready) {
         const void* qc = have_q ? P.codes_cur : nullptr;
         const float* lrp2 = (have_lr && lrbuf_valid) ? P.LRbuf : nullptr;
         const int qb = p->compute_q ? p->q_bits : 8;
         if (P.dense) CB_TRY(dense_quadratic(P, Ws, qc, qb, P.qscale_cur, lrp2, m, n, false, P.dsc + 2, st));
-        else CB_TRY(err_accum(Ws, qc, qb, P.qscale_cur, lrp2, P.h_eff, m, n, P.dsc + 2, st));
+        else {
+          // right after an LR update this pass also delivers the abs-max the next Q update needs
+          const bool want_amax = which == 1 && lrp2 != nullptr && p->compute_q;
+          CB_TRY(err_accum(Ws, qc, qb, P.qscale_cur, lrp2, P.h_eff, m, n, P.dsc + 2, st, want_amax ? P.amax : nullptr));
+          if (want_amax) amax_valid = true;
+        }
       }
       updated[oi] = true;
       // `updated` is keyed by name in the reference (alg.py:91), so duplicates in update_order share a flag
@@ -666,21 +673,22 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
       }
       CB_TRY(select_outer(P.dsc + 2, P.dsc + 1, out->errors, step, P.scalars, P.flags, all_updated ? 1 : 0, st));
       // ---- best_decomp = deepcopy(curr_decomp) (alg.py:107), device side
-      const int* f = P.flags;
+      CopySegments best;
       if (have_q) {
-        CB_TRY(copy_if(f, out->Q_idxs, P.codes_cur, (size_t)numel * code_bytes(p->q_bits), st));
-        CB_TRY(copy_if(f, out->Q_scale, P.qscale_cur, sizeof(float), st));
+        best.add(out->Q_idxs, P.codes_cur, (size_t)numel * code_bytes(p->q_bits));
+        best.add(out->Q_scale, P.qscale_cur, sizeof(float));
       }
       if (have_lr) {
-        CB_TRY(copy_if(f, out->L, P.Lcur, sizeof(float) * m * r, st));
-        CB_TRY(copy_if(f, out->R, P.Rcur, sizeof(float) * r * n, st));
+        best.add(out->L, P.Lcur, sizeof(float) * m * r);
+        best.add(out->R, P.Rcur, sizeof(float) * r * n);
         if (P.quant_factors) {
-          CB_TRY(copy_if(f, P.Lcodes_out, P.Lcodes_in, (size_t)m * r * code_bytes(p->l_bits), st));
-          CB_TRY(copy_if(f, out->R_idxs, P.Rcodes_in, (size_t)r * n * code_bytes(p->r_bits), st));
-          CB_TRY(copy_if(f, out->L_scale, P.Lscale_in, sizeof(float), st));
-          CB_TRY(copy_if(f, out->R_scale, P.Rscale_in, sizeof(float), st));
+          best.add(P.Lcodes_out, P.Lcodes_in, (size_t)m * r * code_bytes(p->l_bits));
+          best.add(out->R_idxs, P.Rcodes_in, (size_t)r * n * code_bytes(p->r_bits));
+          best.add(out->L_scale, P.Lscale_in, sizeof(float));
+          best.add(out->R_scale, P.Rscale_in, sizeof(float));
         }
       }
+      CB_TRY(copy_if_multi(P.flags, best, st));
       // the Q update invalidates nothing; the LR update refreshed LRbuf above
     }
   }

@@ -53,11 +53,23 @@ int quant_err(const float* Ws, const float* LR, const float* h, int64_t m, int64
 int form_y(const float* Ws, const void* codes, int bits, const float* qscale, const float* sqrt_h,
            int64_t m, int64_t n, float* Y, float* RES, cudaStream_t st);
 int err_accum(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR,
-              const float* w, int64_t m, int64_t n, double* num, cudaStream_t st);
+              const float* w, int64_t m, int64_t n, double* num, cudaStream_t st, float* amax_next = nullptr);
 int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags,
                  int all_updated, cudaStream_t st);
 int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st);
 int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st);
+// up to 8 (dst, src, bytes) segments copied by one launch when *flag != 0
+struct CopySegments {
+  void* dst[8];
+  const void* src[8];
+  size_t bytes[8];
+  int count = 0;
+  void add(void* d, const void* s_, size_t b) {
+    if (b == 0 || count >= 8) return;
+    dst[count] = d; src[count] = s_; bytes[count] = b; ++count;
+  }
+};
+int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st);
 int fill_randn(float* p, int64_t count, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
 int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);

@@ -262,11 +262,13 @@ template <int VEC, typename code_t>
 __global__ void __launch_bounds__(256)
 err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
            float lv, const float* __restrict__ LR, const float* __restrict__ wcol, int64_t numel, int64_t n,
-           double* __restrict__ num) {
+           double* __restrict__ num, float* __restrict__ amax_next) {
   __shared__ double red[32];
+  __shared__ float redf[32];
   const float s = codes != nullptr ? qscale[0] : 0.f;
   const ScaleRecip lvr = make_scale_recip(lv);
   double acc = 0.0;
+  float amx = 0.f;   // max |Ws - LR|: the abs-max the next Q update would otherwise need a pass of its own for
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
     const int64_t j = CB_CHUNK_COL(VEC, n);
@@ -283,11 +285,16 @@ err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const
       if (codes != nullptr) e -= dequant_val(c[k], s, lvr);
       if (LR != nullptr) e -= p.v[k];
       part = fmaf((wcol != nullptr ? hv.v[k] : 1.f) * e, e, part);
+      if (amax_next != nullptr) amx = fmaxf(amx, fabsf(LR != nullptr ? w.v[k] - p.v[k] : w.v[k]));
     }
     acc += (double)part;
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(num, acc);
+  if (amax_next != nullptr) {
+    amx = block_max(amx, redf);
+    if (threadIdx.x == 0) atomic_max_nonneg(amax_next, amx);
+  }
 }
 
 // ---------------------------------------------------------------- fused residual -> bf16 operands
@@ -600,6 +607,26 @@ copy_if_kernel(const int* __restrict__ flag, uint8_t* __restrict__ dst, const ui
   }
 }
 
+// best_decomp = deepcopy(curr_decomp) for all its parts in one launch: blockIdx.y selects the segment
+__global__ void __launch_bounds__(256) copy_if_multi_kernel(const int* __restrict__ flag, const CopySegments segs) {
+  if (flag != nullptr && flag[0] == 0) return;
+  const int k = blockIdx.y;
+  const size_t bytes = segs.bytes[k];
+  uint8_t* __restrict__ dst = reinterpret_cast<uint8_t*>(segs.dst[k]);
+  const uint8_t* __restrict__ src = reinterpret_cast<const uint8_t*>(segs.src[k]);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+    const size_t n16 = bytes >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = t0; i < n16; i += stride) d4[i] = s4[i];
+    for (size_t i = (n16 << 4) + t0; i < bytes; i += stride) dst[i] = src[i];
+  } else {
+    for (size_t i = t0; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+
 __global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ p, int64_t count, uint64_t seed,
                                                     const uint64_t* __restrict__ seed_dev) {
   if (seed_dev != nullptr) seed += seed_dev[0];   // per-layer seed kept in device memory (CUDA-graph replays)
@@ -708,12 +735,13 @@ int form_y(const float* Ws, const void* codes, int bits, const float* qscale, co
   return CB_OK;
 }
 int err_accum(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR, const float* w,
-              int64_t m, int64_t n, double* num, cudaStream_t st) {
+              int64_t m, int64_t n, double* num, cudaStream_t st, float* amax_next) {
   const int64_t numel = m * n;
+  if (amax_next != nullptr) CB_CUDA(cudaMemsetAsync(amax_next, 0, sizeof(float), st));
   const float lv = (float)((1 << (bits - 1)) - 1);
   const bool v4 = can_vec4(n, {Ws, codes, LR, w});
 #define CB_ER(VEC, T, G) \
-  err_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num)
+  err_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num, amax_next)
   if (bits <= 8) { if (v4) CB_ER(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int8_t, grid_for(numel, 256 * 4, 8)); }
   else { if (v4) CB_ER(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int16_t, grid_for(numel, 256 * 4, 8)); }
 #undef CB_ER
@@ -735,6 +763,16 @@ int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStrea
   const int vec_ok = aligned16(dst) && aligned16(src);
   copy_if_kernel<<<grid_for((int64_t)(bytes / 16 + 1), 256 * 4, 4), 256, 0, st>>>(
       flag, reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(src), bytes, vec_ok);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st) {
+  if (segs.count <= 0) return CB_OK;
+  size_t biggest = 0;
+  for (int k = 0; k < segs.count; ++k) biggest = segs.bytes[k] > biggest ? segs.bytes[k] : biggest;
+  if (biggest == 0) return CB_OK;
+  dim3 grid((unsigned)grid_for((int64_t)(biggest / 16 + 1), 256 * 4, 4), (unsigned)segs.count);
+  copy_if_multi_kernel<<<grid, 256, 0, st>>>(flag, segs);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
