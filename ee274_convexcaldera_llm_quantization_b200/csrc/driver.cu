@@ -597,6 +597,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   const int niter_warm = p->power_iters_warm >= 0 ? p->power_iters_warm
                                                   : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
   bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
+  bool y_valid = false;      // P.tc.Yb / Ytb (and RES) already hold the operands of the current Q
   bool amax_valid = false;   // P.amax already holds max |Ws - LRbuf| (computed by the pass that evaluated the error)
   bool updated[8] = {false, false, false, false, false, false, false, false};
   int step = 0;
@@ -613,7 +614,15 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
           lrp = P.LRbuf;
         }
         if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(Ws, lrp, numel, P.amax, st));
-        CB_TRY(quant_err(Ws, lrp, P.h_eff, m, n, P.amax, 1e-8f, p->q_bits, P.codes_cur, P.qscale_cur, P.dsc + 2, st));
+        if (P.use_tc && p->compute_lr && m % 4 == 0 && n % 4 == 0) {
+          // the rank-r step that follows contracts over Y = (Ws - Q) (.) sqrt(h): build its bf16 operands here
+          CB_TRY(quant_form_y_bf16(Ws, lrp, P.h_eff, p->aware ? P.sqrt_h : nullptr, m, n, P.amax, 1e-8f, p->q_bits,
+                                   P.codes_cur, P.qscale_cur, P.dsc + 2, P.tc.Yb, P.tc.Ytb,
+                                   P.quant_factors ? (p->aware ? P.RES : P.Y) : nullptr, st));
+          y_valid = true;
+        } else {
+          CB_TRY(quant_err(Ws, lrp, P.h_eff, m, n, P.amax, 1e-8f, p->q_bits, P.codes_cur, P.qscale_cur, P.dsc + 2, st));
+        }
         have_q = true;
         num_ready = !P.dense;   // the fused numerator is the diagonal metric
         if (P.dense) CB_CUDA(cudaMemsetAsync(P.dsc + 2, 0, sizeof(double), st));
@@ -621,7 +630,11 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
         // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
         const void* qcodes = have_q ? P.codes_cur : nullptr;
         const int qbits = p->compute_q ? p->q_bits : 8;
-        if (P.use_tc) {
+        if (P.use_tc && y_valid) {
+          // the Q update that produced the current codes already wrote Yb / Ytb (and the fp32 residual);
+          // good for one LR update (a second one in a row rebuilds them below)
+          y_valid = false;
+        } else if (P.use_tc) {
           // one fused pass: residual -> both bf16 operand orientations (+ fp32 residual for the LPLR loop;
           // when not activation aware that residual is Y itself)
           CB_TRY(form_y_bf16(Ws, qcodes, qbits, P.qscale_cur, p->aware ? P.sqrt_h : nullptr, m, n, P.tc.Yb, P.tc.Ytb,

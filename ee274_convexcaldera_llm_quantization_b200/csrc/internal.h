@@ -80,6 +80,10 @@ int dot_accum(const float* a, const float* b, int64_t numel, double* out, cudaSt
 int symmetrize(const float* H, int64_t n, float* Hs, cudaStream_t st);
 int form_y_bf16(const float* Ws, const void* codes, int bits, const float* qscale, const float* sqrt_h, int64_t m,
                 int64_t n, __nv_bfloat16* Yb, __nv_bfloat16* Ytb, float* RES, cudaStream_t st);
+// quant_err + form_y_bf16 in one pass (see stages.cu)
+int quant_form_y_bf16(const float* Ws, const float* LR, const float* h_err, const float* sqrt_h, int64_t m, int64_t n,
+                      const float* amax, float eps, int bits, void* codes, float* qscale, double* num,
+                      __nv_bfloat16* Yb, __nv_bfloat16* Ytb, float* RES, cudaStream_t st);
 int cvx_point(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, const float* h,
               int64_t m, int64_t n, float beta, float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st);
 int cvx_shrink(const float* sigma2, int r, float thresh, float tau_star, int constrained, const double* vr_sumsq,

@@ -349,6 +349,74 @@ form_y_bf16_kernel(const float* __restrict__ Ws, const code_t* __restrict__ code
   }
 }
 
+// Q update and operand builder in one pass (tensor-core path): quantise res = Ws - LR with the scale the
+// abs-max pass delivered, store the codes, accumulate the weighted error of the new iterate, and write
+// Y = (Ws - Q) (.) sqrt(h) as both bf16 operands (+ the fp32 residual for the LPLR loop).  Same element
+// arithmetic as quant_err_kernel followed by form_y_bf16_kernel, one read of Ws instead of two and no
+// read-back of the codes.
+template <typename code_t>
+__global__ void __launch_bounds__(256)
+quant_form_y_bf16_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, const float* __restrict__ h_err,
+                         const float* __restrict__ sqrt_h, int m, int n, const float* __restrict__ amax, float eps,
+                         float lv, code_t* __restrict__ codes, float* __restrict__ qscale, double* __restrict__ num,
+                         __nv_bfloat16* __restrict__ Yb, __nv_bfloat16* __restrict__ Ytb, float* __restrict__ RES) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][68];   // [col][row]
+  __shared__ double red[32];
+  const float s = fmaxf(amax[0], eps);
+  const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) qscale[0] = s;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int col = blockIdx.x * 64 + 4 * tx;
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rl = ty + 16 * k, row = blockIdx.y * 64 + rl;
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < m && col < n) {
+      const int64_t i = (int64_t)row * n + col;
+      FVec<4> w, p, he, sh;
+      w.load_stream(Ws + i);
+      if (LR != nullptr) p.load_stream(LR + i);
+      if (h_err != nullptr) he.load(h_err + col);
+      if (sqrt_h != nullptr) sh.load(sqrt_h + col);
+      int c[4];
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float res = LR != nullptr ? w.v[j] - p.v[j] : w.v[j];
+        c[j] = quant_code(res, sr, lv);
+        const float dq = dequant_val(c[j], s, lvr);
+        const float e = res - dq;
+        part = fmaf((h_err != nullptr ? he.v[j] : 1.f) * e, e, part);
+        w.v[j] -= dq;                                      // Ws - Q
+        y[j] = sqrt_h != nullptr ? w.v[j] * sh.v[j] : w.v[j];
+      }
+      acc += (double)part;
+      store_codes<4, code_t>(codes + i, c);
+      if (RES != nullptr) w.store(RES + i);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(Yb + i) = pk;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[4 * tx + j][rl] = __float2bfloat16_rn(y[j]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int cl = ty + 16 * k;                 // column of the tile = row of Ytb
+    const int gc = blockIdx.x * 64 + cl, gr = blockIdx.y * 64 + 4 * tx;
+    if (gc < n && gr < m) {
+      const uint2 pk = *reinterpret_cast<const uint2*>(&tile[cl][4 * tx]);
+      *reinterpret_cast<uint2*>(Ytb + (int64_t)gc * m + gr) = pk;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(num, acc);
+}
+
 // ---------------------------------------------------------------- dense-Hessian helpers
 // E = Ws - Q - L R written out (the dense metric tr(E H E^T) needs E as a GEMM operand)
 template <int VEC, typename code_t>
@@ -862,6 +930,23 @@ int form_y_bf16(const float* Ws, const void* codes, int bits, const float* qscal
     form_y_bf16_kernel<int8_t><<<grid, 256, 0, st>>>(Ws, reinterpret_cast<const int8_t*>(codes), qscale, lv, sqrt_h, (int)m, (int)n, Yb, Ytb, RES);
   else
     form_y_bf16_kernel<int16_t><<<grid, 256, 0, st>>>(Ws, reinterpret_cast<const int16_t*>(codes), qscale, lv, sqrt_h, (int)m, (int)n, Yb, Ytb, RES);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+int quant_form_y_bf16(const float* Ws, const float* LR, const float* h_err, const float* sqrt_h, int64_t m, int64_t n,
+                      const float* amax, float eps, int bits, void* codes, float* qscale, double* num,
+                      __nv_bfloat16* Yb, __nv_bfloat16* Ytb, float* RES, cudaStream_t st) {
+  if (m % 4 != 0 || n % 4 != 0 || !aligned16(Ws) || !aligned16(Yb) || !aligned16(Ytb) || (LR != nullptr && !aligned16(LR)))
+    return CB_ERR_ARG;
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  dim3 grid((unsigned)((n + 63) / 64), (unsigned)((m + 63) / 64));
+  if (bits <= 8)
+    quant_form_y_bf16_kernel<int8_t><<<grid, 256, 0, st>>>(Ws, LR, h_err, sqrt_h, (int)m, (int)n, amax, eps, lv,
+                                                           reinterpret_cast<int8_t*>(codes), qscale, num, Yb, Ytb, RES);
+  else
+    quant_form_y_bf16_kernel<int16_t><<<grid, 256, 0, st>>>(Ws, LR, h_err, sqrt_h, (int)m, (int)n, amax, eps, lv,
+                                                            reinterpret_cast<int16_t*>(codes), qscale, num, Yb, Ytb, RES);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
