@@ -15,6 +15,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
+from ee274_convexcaldera_llm_quantization_b200 import _lib
 from oracle import caldera_oracle as orc
 from src.caldera.utils.dataclasses import CalderaParams
 from src.caldera.utils.quantization import QuantizerFactory, unpack_codes
@@ -295,3 +296,30 @@ def test_repeated_runs_are_bitwise_identical(tc, lbits):
         assert torch.equal(again.Q_idxs, first.Q_idxs) and torch.equal(again.L, first.L) and torch.equal(again.R, first.R)
         assert again.best_step == first.best_step
     torch.cuda.synchronize()
+
+
+def test_fullsize_golden_headline_config():
+    """BASELINE config 2 at full size (4096 x 4096, rank 128, Q 2-bit, 5 iterations) against the UNMODIFIED
+    reference run on CPU (tests/golden/make_golden_fullsize.py): iterate-0 error from the bit-identical
+    quantiser input, global_scale, and the best error within the 1e-3 relative bar of the north star."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_c2.json")) as f:
+        z = json.load(f)
+    g = torch.Generator().manual_seed(1000)
+    W = 0.02 * torch.randn(4096, 4096, generator=g, dtype=torch.float32)
+    h = 0.5 + torch.rand(4096, generator=g, dtype=torch.float32)
+    kw = dict(Q_bits=2, L_bits=16, R_bits=16, rank=128, iters=5, update_order=["Q", "LR"])
+    for mode in ("latency", "throughput"):
+        try:
+            _lib.set_execution_mode(mode)
+            d = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, W_copy="none")
+        finally:
+            _lib.set_execution_mode("latency")
+        np.testing.assert_allclose(d.global_scale, z["global_scale"], rtol=2e-7)
+        np.testing.assert_allclose(d.errors["Q"][0], z["errors"]["Q"][0], rtol=2e-6)     # no rank-r step involved yet
+        np.testing.assert_allclose(d.errors["LR"][0], z["errors"]["LR"][0], rtol=1e-3)   # first rank-r step vs exact SVD
+        flat = [e for pair in zip(d.errors["Q"], d.errors["LR"]) for e in pair]
+        best = min(flat[1:])
+        assert abs(best - z["best_error"]) <= 1e-3 * z["best_error"], (mode, best, z["best_error"])
+        assert flat[d.best_step] == best
