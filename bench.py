@@ -396,7 +396,7 @@ def run_ours(args):
         torch.cuda.set_device(dev)
         with torch.cuda.stream(e2e_streams[w]):
             d = caldera(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank,
-                        use_cuda_graph=not args.no_graph)
+                        use_cuda_graph=not args.no_graph, return_dense=not args.e2e_packed_only)
             out_hosts[w]["Q_packed"].copy_(d.Q_packed, non_blocking=True)
             out_hosts[w]["L"].copy_(d.L, non_blocking=True)
             out_hosts[w]["R"].copy_(d.R, non_blocking=True)
@@ -432,7 +432,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "per-step working set ~0.5 GiB > 126 MB L2; 3 layers rotated",
-                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": nworkers,
+                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": nworkers, "e2e_result": "packed Q codes + scale, L, R" if args.e2e_packed_only else "dense + packed",
                            "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
@@ -472,6 +472,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
+    ap.add_argument("--e2e-dense", dest="e2e_packed_only", action="store_false",
+                    help="e2e leg: also materialise the dense fp32 Q / int8 codes copies in the returned decomposition "
+                         "(default: packed codes + factors only, which is what is copied back to the host)")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="library execution mode (cb_set_execution_mode)")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")

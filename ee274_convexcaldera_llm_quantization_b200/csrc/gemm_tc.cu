@@ -130,7 +130,13 @@ struct GemmTcArgs {
 };
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 192;
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue.  A warp may only read the
+// TMEM lanes of its quadrant (warp % 4), so the eight epilogue warps are two groups of four: group 0 drains
+// the lower half of the accumulator's columns, group 1 the upper half (one warp per scheduler is latency
+// bound at ~900 cycles per 32-column chunk; two halve the drain time of the 128 x 256 tile).
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 
 // One pipeline stage holds KB consecutive 64-wide K blocks of the A and B tiles, each block in the
 // canonical 128-byte-swizzled K-major layout (rows 128 bytes apart), fetched by one TMA instruction
@@ -287,6 +293,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
     const int qd = warp & 3;
+    const int egrp = (warp - 2) >> 2;                                   // 0 or 1
+    constexpr int EPI_COLS = BN / (TC_EPI_WARPS / 4);                   // columns drained by each group
+    const int c_begin = egrp * EPI_COLS, c_end = c_begin + EPI_COLS;
     if (!mbar_wait(tmem_full_bar, 0)) ok = false;
     if (stamps != nullptr && threadIdx.x == 64) stamps[5] = clock64();             // accumulator complete
     ok = __all_sync(0xffffffffu, ok);
@@ -304,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint8_t* stage_t = stage_rm + TC_BM * RM_STRIDE;
       if (ok) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
           const int col0 = n_blk * BN + c0;
@@ -327,12 +336,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps
+      if (stamps != nullptr && threadIdx.x == 64) stamps[8] = clock64();           // staged: tile in shared memory
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");     // the epilogue warps
+      if (stamps != nullptr && threadIdx.x == 64) stamps[9] = clock64();           // staged: barrier passed
       if (ok) {
-        const int et = threadIdx.x - 64;                 // 0 .. 127
+        const int et = threadIdx.x - 64;                 // 0 .. TC_EPI_THREADS - 1
         if (args.Cb != nullptr) {
           constexpr int UPR = BN / 8;                    // 16-byte units per row
-          for (int u = et; u < TC_BM * UPR; u += 128) {
+#pragma unroll 4
+          for (int u = et; u < TC_BM * UPR; u += TC_EPI_THREADS) {
             const int r_ = u / UPR, cu = u - r_ * UPR;
             const int grow = m_blk * TC_BM + r_, gcol = n_blk * BN + cu * 8;
             if (grow < args.M && gcol < args.N)
@@ -342,7 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (args.Ct != nullptr) {
           constexpr int UPC = TC_BM / 4;                 // 8-byte units (4 rows) per column
-          for (int u = et; u < BN * UPC; u += 128) {
+#pragma unroll 4
+          for (int u = et; u < BN * UPC; u += TC_EPI_THREADS) {
             const int c_ = u / UPC, ru = u - c_ * UPC;
             const int gcol = n_blk * BN + c_, grow = m_blk * TC_BM + ru * 4;
             if (gcol < args.N && grow < args.M)
@@ -354,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (args.splits <= 1) {
       if (ok) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
           float v[32];
@@ -372,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ok) {
         float* mine = args.ws + ((size_t)tile * args.splits + blockIdx.z) * (BN * TC_BM) + (size_t)trow * 32;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r);
           float4* dst = reinterpret_cast<float4*>(mine + (size_t)(c0 / 32) * (TC_BM * 32));

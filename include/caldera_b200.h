@@ -183,9 +183,10 @@ void cb_set_gemm_kblocks(int n);
 /* Measurement aid for bench.py / scripts: cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16,
  * bf16, both operands resident in shared memory, no TMA, no per-stage barriers) take on an SM, on a
  * grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */
-/* Measurement aid: when non-NULL, CTA (0,0,0) of every tcgen05 contraction writes 8 clock64 stamps
- * (entry, prologue done, last load issued, first stage landed, last stage landed, accumulator
- * complete, epilogue stores issued, exit) to this device buffer.  Process-wide; NULL turns it off. */
+/* Measurement aid: when non-NULL, CTA (0,0,0) of every tcgen05 contraction writes clock64 stamps to this
+ * device buffer of 12 int64 ([0..7]: entry, prologue done, last load issued, first stage landed, last
+ * stage landed, accumulator complete, epilogue stores issued, exit; [8..9]: staged epilogue -- tile in
+ * shared memory, barrier passed).  Process-wide; NULL turns it off. */
 void cb_set_gemm_timing(void* stamps_dev);
 int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream);
 /* fp32 (rows x cols, ldx) -> bf16 copy Y (ldy) and/or transposed copy Yt (cols x rows, ldyt),

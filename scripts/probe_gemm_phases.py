@@ -12,7 +12,7 @@ Pt = torch.randn(q, N, device=dev).bfloat16()
 Zt = torch.empty(q, M, device=dev)
 flag = torch.zeros(1, dtype=torch.int32, device=dev)
 ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
-stamps = torch.zeros(8, dtype=torch.int64, device=dev)
+stamps = torch.zeros(12, dtype=torch.int64, device=dev)
 lib.cb_set_gemm_timing(_lib.ptr(stamps))
 names = ["prologue", "->last load issued", "first stage landed (from entry)", "last stage landed (from entry)",
          "accumulator complete (from entry)", "epilogue done (from entry)", "exit (from entry)"]
@@ -41,6 +41,6 @@ for ctas, staged, tag in ((120, 1, "bn64 kb2 bf16-out staged"), (120, 0, "bn64 k
     t = stamps.tolist()
     e = t[0]
     print(f"{tag}: prologue {t[1]-e}, first-landed {t[3]-e}, last-landed {t[4]-e}, acc-complete {t[5]-e}, "
-          f"epilogue-done {t[6]-e}, exit {t[7]-e} clk")
+          f"staged-in-smem {t[8]-e}, barrier {t[9]-e}, epilogue-done {t[6]-e}, exit {t[7]-e} clk")
 lib.cb_set_gemm_staged_epilogue(1)
 lib.cb_set_gemm_timing(None)
