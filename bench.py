@@ -383,7 +383,7 @@ def run_ours(args):
 
     # ---- end-to-end timing through the public API, host buffers in, packed result out
     import concurrent.futures as cf
-    auto_workers = min(16, max(4, 2 * host_threads() // max(world, 1)))
+    auto_workers = min(24, max(4, 3 * host_threads() // (2 * max(world, 1))))
     nworkers = max(1, min(nstreams, args.e2e_workers if args.e2e_workers > 0 else auto_workers))
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
@@ -480,7 +480,7 @@ def main():
     ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")
     ap.add_argument("--streams", type=int, default=32, help="independent layers kept in flight per GPU")
     ap.add_argument("--e2e-workers", type=int, default=0,
-                    help="host threads driving the public API in the e2e leg (0 = min(16, 2 x host cores / ranks), at least 4)")
+                    help="host threads driving the public API in the e2e leg (0 = min(24, 1.5 x host cores / ranks), at least 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
