@@ -408,6 +408,221 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (stamps != nullptr && threadIdx.x == 0) stamps[7] = clock64();               // exit
 }
 
+// ---------------------------------------------------------------- packed-code consumer
+// y[T, m] = gs * ( (s / lv) * x[T, n] * C[m, n]^T  +  t[T, r] * L[m, r]^T )      
+// C are the b-bit codes of Q read straight from their packed form (never materialised in HBM), t = x R^T
+// comes from a preceding contraction.  Same pipeline as gemm_tc_kernel, except that the B tile of a code
+// K block is produced by the worker warps: thread = tile row, 64 codes expanded through a shared-memory
+// lookup table into the bf16 integers -lv .. lv (exact) and written in the 128-byte-swizzled K-major layout
+// the MMA descriptor expects; the whole-tensor scale is applied once in the epilogue.  The rank-r part runs
+// as extra K blocks (A = t, B = L, both by TMA) into a second TMEM accumulator.
+struct PackedLinearArgs {
+  int T, m, n, r;
+  int nkb_codes, nkb_lr;
+  const uint8_t* packed;      // m x n codes, BITS each, MSB-first
+  const float* q_scale;       // device scalar
+  float gs, lv;
+  float* y; int64_t ldy;
+  int* error_flag;
+};
+
+constexpr int PL_BN = 128, PL_STAGES = 6, PL_WORKERS = 128;
+constexpr int PL_THREADS = 64 + PL_WORKERS;
+struct PlSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = PL_BN * TC_BK * 2;
+  static constexpr int BAR_OFF = PL_STAGES * (A_BYTES + B_BYTES);
+  static constexpr int LUT_OFF = BAR_OFF + (2 * PL_STAGES + 1) * 8 + 16;
+  static constexpr int TOTAL = LUT_OFF + 2048 + 1024;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(PL_THREADS, 1)
+packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT,
+                     const __grid_constant__ CUtensorMap tmL, const PackedLinearArgs args) {
+  using S = PlSmem;
+  constexpr int PER = 8 / BITS;                 // codes per packed byte
+  constexpr int ROW_BYTES = TC_BK * BITS / 8;   // packed bytes of one tile row per K block (16 / 32 / 64)
+  constexpr int LVI = (1 << (BITS - 1)) - 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_base = base, b_base = base + PL_STAGES * S::A_BYTES;
+  const uint32_t bar_base = base + S::BAR_OFF;
+  auto full_bar = [&](int s_) { return bar_base + 8u * s_; };
+  auto empty_bar = [&](int s_) { return bar_base + 8u * (PL_STAGES + s_); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * PL_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * PL_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(base_ptr + S::BAR_OFF + 8 * (2 * PL_STAGES + 1));
+  uint16_t* lut = reinterpret_cast<uint16_t*>(base_ptr + S::LUT_OFF);   // [256][PER] bf16 bit patterns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y;      // tile of m (output columns), tile of T (rows)
+  const int nkb = args.nkb_codes + args.nkb_lr;
+
+  // byte -> PER bf16 integers (code = symbol - lv)
+  for (int e = threadIdx.x; e < 256 * PER; e += blockDim.x) {
+    const int byte = e / PER, j = e % PER;
+    const int sym = (byte >> (8 - BITS * (j + 1))) & ((1 << BITS) - 1);
+    lut[e] = __bfloat16_as_ushort(__int2bfloat16_rn(sym - LVI));
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmL); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s_ = 0; s_ < PL_STAGES; ++s_) { mbar_init(full_bar(s_), 1 + PL_WORKERS / 32); mbar_init(empty_bar(s_), 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * PL_BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  bool ok = true;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s_ = i % PL_STAGES;
+        const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
+        if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
+        if (i < args.nkb_codes) {
+          mbar_expect_tx(full_bar(s_), (uint32_t)S::A_BYTES);
+          tma_load_2d(a_base + s_ * S::A_BYTES, &tmX, full_bar(s_), i * TC_BK, m_blk * TC_BM);
+        } else {
+          const int kb = i - args.nkb_codes;
+          mbar_expect_tx(full_bar(s_), (uint32_t)(S::A_BYTES + S::B_BYTES));
+          tma_load_2d(a_base + s_ * S::A_BYTES, &tmT, full_bar(s_), kb * TC_BK, m_blk * TC_BM);
+          tma_load_2d(b_base + s_ * S::B_BYTES, &tmL, full_bar(s_), kb * TC_BK, n_blk * PL_BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, PL_BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s_ = i % PL_STAGES;
+        const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
+        if (!mbar_wait(full_bar(s_), ph)) { ok = false; break; }
+        tc_fence_after();
+        const bool lr = i >= args.nkb_codes;
+        const uint32_t acc = tmem_base + (lr ? (uint32_t)PL_BN : 0u);
+        const bool first = lr ? (i == args.nkb_codes) : (i == 0);
+        const uint64_t adesc = make_smem_desc_sw128(a_base + s_ * S::A_BYTES);
+        const uint64_t bdesc = make_smem_desc_sw128(b_base + s_ * S::B_BYTES);
+#pragma unroll
+        for (int k2 = 0; k2 < TC_BK / 16; ++k2)
+          umma_bf16(acc, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc, (!first || k2 > 0) ? 1u : 0u);
+        umma_commit(empty_bar(s_));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- worker warps: expand the packed codes of this CTA's 128 rows of C, K block by K block
+    const int t = threadIdx.x - 64;                       // tile row 0 .. 127
+    const int64_t crow = (int64_t)n_blk * PL_BN + t;      // row of C (= output column of y)
+    const bool row_ok = crow < args.m;
+    const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8);
+    uint4 cur[ROW_BYTES / 16], nxt[ROW_BYTES / 16];
+#pragma unroll
+    for (int w = 0; w < ROW_BYTES / 16; ++w) {
+      cur[w] = make_uint4(0, 0, 0, 0);
+      if (row_ok && args.nkb_codes > 0) cur[w] = __ldg(reinterpret_cast<const uint4*>(src) + w);
+    }
+    for (int i = 0; i < nkb; ++i) {
+      const int s_ = i % PL_STAGES;
+      const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
+      if (i + 1 < args.nkb_codes) {
+#pragma unroll
+        for (int w = 0; w < ROW_BYTES / 16; ++w) {
+          nxt[w] = make_uint4(0, 0, 0, 0);
+          if (row_ok) nxt[w] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(i + 1) * ROW_BYTES) + w);
+        }
+      }
+      if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
+      if (i < args.nkb_codes) {
+        uint8_t* dst = base_ptr + (b_base - base) + s_ * S::B_BYTES + t * 128;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(cur);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {                      // chunk c = 8 consecutive K elements = BITS packed bytes
+          uint32_t out[4];
+          if (BITS == 2) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int byte_idx = 2 * c + b;
+              const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
+              const uint2 e = *reinterpret_cast<const uint2*>(lut + byte * 4);
+              out[2 * b] = e.x; out[2 * b + 1] = e.y;
+            }
+          } else if (BITS == 4) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int byte_idx = 4 * c + b;
+              const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
+              out[b] = *reinterpret_cast<const uint32_t*>(lut + byte * 2);
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int byte_idx = 8 * c + 2 * b;
+              const uint32_t b0 = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
+              const uint32_t b1 = (words[(byte_idx + 1) >> 2] >> (8 * ((byte_idx + 1) & 3))) & 255u;
+              out[b] = (uint32_t)lut[b0] | ((uint32_t)lut[b1] << 16);
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + ((c ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+        fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+#pragma unroll
+        for (int w = 0; w < ROW_BYTES / 16; ++w) cur[w] = nxt[w];
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(s_)) : "memory");
+    }
+    // ---- epilogue
+    const int qd = warp & 3;
+    if (!mbar_wait(tmem_full_bar, 0)) ok = false;
+    ok = __all_sync(0xffffffffu, ok);
+    tc_fence_after();
+    const int row = m_blk * TC_BM + qd * 32 + lane;
+    const float sc = args.q_scale[0] / args.lv;
+    if (ok) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < PL_BN; c0 += 32) {
+        uint32_t a1[32], a2[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, a1);
+        if (args.nkb_lr > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(PL_BN + c0), a2);
+        const int col0 = n_blk * PL_BN + c0;
+        if (row < args.T && col0 < args.m) {
+          float* p = args.y + (int64_t)row * args.ldy + col0;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = sc * __uint_as_float(a1[j]);
+            if (args.nkb_lr > 0) x += __uint_as_float(a2[j]);
+            v[j] = args.gs * x;
+          }
+          if (col0 + 32 <= args.m && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < args.m) p[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  if (!ok && args.error_flag != nullptr) atomicExch(args.error_flag, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * PL_BN);
+  }
+}
+
 // Measurement aid (bench / scripts only): back-to-back tcgen05.mma on one resident shared-memory
 // stage, no TMA and no per-stage barriers, to read off what the tensor pipe itself sustains for a
 // 128 x N x 16 instruction with both operands in shared memory.  out[0] = cycles for `n_mma` MMAs.
@@ -737,6 +952,87 @@ extern "C" int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, con
   return cb::gemm_tc(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A_bf16), lda,
                      reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, C, ldc, nullptr, 0, nullptr, 0, nullptr,
                      nullptr, splitk, error_flag, &splits, st, &sw, probe_flags);
+}
+
+// ---- packed-code consumer: y = x (Q + L R)^T * global_scale from the packed decomposition
+namespace cb {
+struct PackedLinearPlan {
+  __nv_bfloat16 *xb, *Rb, *Lb, *tb;
+  SplitWs sw;
+  size_t bytes;
+};
+static PackedLinearPlan plan_packed_linear(uint8_t* base, int64_t T, int64_t m, int64_t n, int64_t r) {
+  PackedLinearPlan P{};
+  size_t off = 0;
+  auto take = [&](size_t b) { void* p = base != nullptr ? base + off : nullptr; off += (b + 255) / 256 * 256; return p; };
+  P.xb = reinterpret_cast<__nv_bfloat16*>(take(sizeof(__nv_bfloat16) * T * n));
+  if (r > 0) {
+    P.Rb = reinterpret_cast<__nv_bfloat16*>(take(sizeof(__nv_bfloat16) * r * n));
+    P.Lb = reinterpret_cast<__nv_bfloat16*>(take(sizeof(__nv_bfloat16) * m * r));
+    P.tb = reinterpret_cast<__nv_bfloat16*>(take(sizeof(__nv_bfloat16) * T * r));
+    P.sw.buf = reinterpret_cast<float*>(take(kSplitWsBytes));
+    P.sw.bytes = kSplitWsBytes;
+  }
+  P.bytes = off;
+  return P;
+}
+}  // namespace cb
+
+extern "C" size_t cb_packed_linear_workspace_bytes(int64_t T, int64_t m, int64_t n, int64_t r) {
+  if (T <= 0 || m <= 0 || n <= 0 || r < 0) return 0;
+  return cb::plan_packed_linear(nullptr, T, m, n, r).bytes + 256;
+}
+
+extern "C" int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const uint8_t* q_packed, int q_bits,
+                                    const float* q_scale, const float* L, const float* R, int64_t m, int64_t r,
+                                    float global_scale, float* y, int* error_flag, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  using namespace cb;
+  if (x == nullptr || q_packed == nullptr || q_scale == nullptr || y == nullptr || ws == nullptr) return CB_ERR_ARG;
+  if (T <= 0 || m <= 0 || n <= 0 || r < 0 || (r > 0 && (L == nullptr || R == nullptr))) return CB_ERR_ARG;
+  if (q_bits != 2 && q_bits != 4 && q_bits != 8) return CB_ERR_BITS;
+  if (n % 64 != 0 || r % 8 != 0 || !aligned16(q_packed) || T >= (1ll << 31) || m >= (1ll << 31)) return CB_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  PackedLinearPlan P = plan_packed_linear(base, T, m, n, r);
+  if ((size_t)(base - reinterpret_cast<uint8_t*>(ws)) + P.bytes > ws_bytes) return CB_ERR_WORKSPACE;
+  CB_TRY(to_bf16(x, T, n, n, P.xb, n, nullptr, 0, nullptr, st));
+  if (r > 0) {
+    CB_TRY(to_bf16(R, r, n, n, P.Rb, n, nullptr, 0, nullptr, st));
+    CB_TRY(to_bf16(L, m, r, r, P.Lb, r, nullptr, 0, nullptr, st));
+    // t[T, r] = x R^T (bf16 out, consumed as the A operand of the rank-r K blocks)
+    CB_TRY(gemm_tc(T, r, n, 1.f, P.xb, n, P.Rb, n, nullptr, 0, P.tb, r, nullptr, 0, nullptr, nullptr, 0, error_flag,
+                   nullptr, st, &P.sw));
+  }
+  CUtensorMap tx, tt, tl;
+  CB_TRY(make_tmap_bf16(&tx, P.xb, T, n, n, TC_BM));
+  if (r > 0) {
+    CB_TRY(make_tmap_bf16(&tt, P.tb, T, r, r, TC_BM));
+    CB_TRY(make_tmap_bf16(&tl, P.Lb, m, r, r, PL_BN));
+  } else {
+    tt = tx; tl = tx;
+  }
+  PackedLinearArgs a;
+  a.T = (int)T; a.m = (int)m; a.n = (int)n; a.r = (int)r;
+  a.nkb_codes = (int)(n / TC_BK); a.nkb_lr = (int)((r + TC_BK - 1) / TC_BK);
+  a.packed = q_packed; a.q_scale = q_scale; a.gs = global_scale; a.lv = (float)((1 << (q_bits - 1)) - 1);
+  a.y = y; a.ldy = m; a.error_flag = error_flag;
+  dim3 grid((unsigned)((m + PL_BN - 1) / PL_BN), (unsigned)((T + TC_BM - 1) / TC_BM));
+#define CB_PL(BITS)                                                                                                  \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      CB_CUDA(cudaFuncSetAttribute(packed_linear_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PlSmem::TOTAL)); \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    packed_linear_kernel<BITS><<<grid, PL_THREADS, PlSmem::TOTAL, st>>>(tx, tt, tl, a);                              \
+  } while (0)
+  if (q_bits == 2) CB_PL(2);
+  else if (q_bits == 4) CB_PL(4);
+  else CB_PL(8);
+#undef CB_PL
+  CB_CHECK_LAUNCH();
+  return CB_OK;
 }
 
 // Same contraction with the bf16 epilogues the layer driver uses: Cb (M x N, row-major) and/or Ct (N x M,

@@ -162,6 +162,18 @@ int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const 
                             int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
                             void* stream);
 void cb_set_gemm_staged_epilogue(int on);
+/* ---- consumer of the packed decomposition (the reference reconstructs a dense matrix,
+ * main.py:197 / README.md:182 `W_hat = Q + L @ R`, and multiplies with that) ----
+ * y[T, m] = global_scale * x[T, n] * (Q + L R)^T with Q = (codes / levels) * q_scale read from its packed
+ * form (q_bits in {2, 4, 8}, MSB-first as written by cb_quantize_f32 / cb_caldera_layer; one scale per
+ * tensor, device pointer), L (m x r) and R (r x n) fp32 row-major (r may be 0).  One tcgen05 kernel expands
+ * the codes tile by tile in shared memory (the dense Q never exists in HBM) and runs the rank-r part as extra
+ * K blocks into a second TMEM accumulator; operands are rounded to bf16 (codes are exact), accumulation is
+ * fp32.  Requires n % 64 == 0 and r % 8 == 0.  x, y row-major fp32. */
+size_t cb_packed_linear_workspace_bytes(int64_t T, int64_t m, int64_t n, int64_t r);
+int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const uint8_t* q_packed, int q_bits,
+                         const float* q_scale, const float* L, const float* R, int64_t m, int64_t r,
+                         float global_scale, float* y, int* error_flag, void* ws, size_t ws_bytes, void* stream);
 /* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
  * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
  * rounding level between modes (different K-split counts and eigensolver sweep order).
