@@ -479,7 +479,7 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
 // contractions per inner iteration run on gemm_tc against the bf16 operands Yb = res (.) sqrt(h)
 // and Ytb = Yb^T that the rank-r step already built:
 //   res diag(h) R^T = Yb (R (.) sqrt(h))^T,        L^T res = (L^T Ytb^T) (.) 1/sqrt(h)
-// The r x r Gram matrices are accumulated in fp32 (split-K atomics) and factorised in fp32.
+// The r x r Gram matrices are accumulated in fp32 (split-K slices summed in slice order) and factorised in fp32.
 static int lplr_refine_tc(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
   const int64_t r = p->rank;
   const float* res = p->aware ? P.RES : P.Y;

@@ -1,19 +1,25 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] (+)= alpha * A[M,K] * B[N,K]^T
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = alpha * A[M,K] * B[N,K]^T
 //
 // bf16 operands, both K-major (row-major with K contiguous), fp32 accumulation in tensor
 // memory.  This is the contraction engine of the rank-r step (sketch, Gram and projection
 // products of the randomized subspace iteration) and of the LPLR normal equations.
 //
-//   * one CTA per 128 x BN output tile (BN = 64/128/256) and K-split, 192 threads:
-//       warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 64-wide K blocks)
+//   * one CTA per 128 x BN output tile (BN = 64/128/256) and K slice, 320 threads:
+//       warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 64-wide K blocks, one or two
+//                   K blocks per instruction through a 2-D / 3-D tensor map)
 //       warp 1      TMEM allocator + MMA issuer (one thread issues tcgen05.mma, K = 16 per
 //                   instruction; tcgen05.commit releases the smem stage / signals the epilogue)
-//       warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (lane = row), optional
-//                   column/row scaling, fp32 / bf16 / transposed-bf16 stores or split-K atomics
+//       warps 2-9   epilogue: tcgen05.ld of the fp32 accumulator (lane = row; two groups of four warps,
+//                   half of the columns each), optional column/row scaling, then fp32 stores, bf16 /
+//                   transposed-bf16 outputs staged through shared memory and written as whole rows, or
+//                   the raw partial tile of a K slice (summed in slice order by splitk_reduce_kernel:
+//                   no floating-point atomics anywhere)
 //   * STAGES-deep mbarrier ring between TMA and MMA; out-of-bounds rows/K are zero-filled by
 //     TMA, so any M, N, K works as long as the leading dimensions are multiples of 8 elements.
 //   * every mbarrier wait is bounded: a broken pipeline sets *error_flag and drains instead
 //     of hanging the GPU.
+//   * packed_linear_kernel (below) is the same pipeline with the B tile expanded from bit-packed codes
+//     by the worker warps: the consumer of the packed decomposition.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -116,9 +122,9 @@ struct GemmTcArgs {
   int M, N, K;
   int kb_per_split;       // 64-wide K blocks per grid.z slice
   float alpha;
-  float* C; int64_t ldc;             // fp32 out (store or atomic add), may be null
-  __nv_bfloat16* Cb; int64_t ldcb;   // bf16 out, row-major, may be null (ignored when atomic)
-  __nv_bfloat16* Ct; int64_t ldct;   // bf16 out, transposed (N x M), may be null (ignored when atomic)
+  float* C; int64_t ldc;             // fp32 out, may be null
+  __nv_bfloat16* Cb; int64_t ldcb;   // bf16 out, row-major, may be null
+  __nv_bfloat16* Ct; int64_t ldct;   // bf16 out, transposed (N x M), may be null
   const float* colscale;             // per output column, may be null
   const float* rowscale;             // per output row, may be null
   int staged;                        // bf16-only outputs whose alignment allows the shared-memory staged epilogue
@@ -426,7 +432,7 @@ struct PackedLinearArgs {
   int* error_flag;
 };
 
-constexpr int PL_BN = 128, PL_STAGES = 6, PL_WORKERS = 128;
+constexpr int PL_BN = 128, PL_STAGES = 6, PL_WORKERS = 256;   // two worker threads per tile row
 constexpr int PL_THREADS = 64 + PL_WORKERS;
 struct PlSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = PL_BN * TC_BK * 2;
@@ -519,25 +525,28 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ---- worker warps: expand the packed codes of this CTA's 128 rows of C, K block by K block
-    const int t = threadIdx.x - 64;                       // tile row 0 .. 127
+    // ---- worker warps: expand the packed codes of this CTA's 128 rows of C, K block by K block;
+    //      two threads per row, each expanding half of the row's 64 codes (4 chunks of 8)
+    const int wt = threadIdx.x - 64;                      // 0 .. 255
+    const int t = wt >> 1, half = wt & 1;                 // tile row, which half of the K block
+    constexpr int HB = ROW_BYTES / 2;                     // packed bytes per thread and K block (8 / 16 / 32)
     const int64_t crow = (int64_t)n_blk * PL_BN + t;      // row of C (= output column of y)
     const bool row_ok = crow < args.m;
-    const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8);
-    uint4 cur[ROW_BYTES / 16], nxt[ROW_BYTES / 16];
+    const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8) + half * HB;
+    uint2 cur[HB / 8], nxt[HB / 8];
 #pragma unroll
-    for (int w = 0; w < ROW_BYTES / 16; ++w) {
-      cur[w] = make_uint4(0, 0, 0, 0);
-      if (row_ok && args.nkb_codes > 0) cur[w] = __ldg(reinterpret_cast<const uint4*>(src) + w);
+    for (int w = 0; w < HB / 8; ++w) {
+      cur[w] = make_uint2(0, 0);
+      if (row_ok && args.nkb_codes > 0) cur[w] = __ldg(reinterpret_cast<const uint2*>(src) + w);
     }
     for (int i = 0; i < nkb; ++i) {
       const int s_ = i % PL_STAGES;
       const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
       if (i + 1 < args.nkb_codes) {
 #pragma unroll
-        for (int w = 0; w < ROW_BYTES / 16; ++w) {
-          nxt[w] = make_uint4(0, 0, 0, 0);
-          if (row_ok) nxt[w] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)(i + 1) * ROW_BYTES) + w);
+        for (int w = 0; w < HB / 8; ++w) {
+          nxt[w] = make_uint2(0, 0);
+          if (row_ok) nxt[w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)(i + 1) * ROW_BYTES) + w);
         }
       }
       if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
@@ -545,12 +554,12 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         uint8_t* dst = base_ptr + (b_base - base) + s_ * S::B_BYTES + t * 128;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(cur);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {                      // chunk c = 8 consecutive K elements = BITS packed bytes
+        for (int cc = 0; cc < 4; ++cc) {                   // local chunk: 8 consecutive K elements = BITS packed bytes
           uint32_t out[4];
           if (BITS == 2) {
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-              const int byte_idx = 2 * c + b;
+              const int byte_idx = 2 * cc + b;
               const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
               const uint2 e = *reinterpret_cast<const uint2*>(lut + byte * 4);
               out[2 * b] = e.x; out[2 * b + 1] = e.y;
@@ -558,24 +567,25 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           } else if (BITS == 4) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              const int byte_idx = 4 * c + b;
+              const int byte_idx = 4 * cc + b;
               const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
               out[b] = *reinterpret_cast<const uint32_t*>(lut + byte * 2);
             }
           } else {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              const int byte_idx = 8 * c + 2 * b;
+              const int byte_idx = 8 * cc + 2 * b;
               const uint32_t b0 = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
               const uint32_t b1 = (words[(byte_idx + 1) >> 2] >> (8 * ((byte_idx + 1) & 3))) & 255u;
               out[b] = (uint32_t)lut[b0] | ((uint32_t)lut[b1] << 16);
             }
           }
+          const int c = 4 * half + cc;                     // chunk position inside the 128-byte row
           *reinterpret_cast<uint4*>(dst + ((c ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
         }
         fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
 #pragma unroll
-        for (int w = 0; w < ROW_BYTES / 16; ++w) cur[w] = nxt[w];
+        for (int w = 0; w < HB / 8; ++w) cur[w] = nxt[w];
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(s_)) : "memory");
@@ -587,9 +597,10 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     const int row = m_blk * TC_BM + qd * 32 + lane;
     const float sc = args.q_scale[0] / args.lv;
+    const int egrp = (warp - 2) >> 2;                     // two groups of four warps, half of the columns each
     if (ok) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < PL_BN; c0 += 32) {
+      for (int c0 = egrp * (PL_BN / 2); c0 < (egrp + 1) * (PL_BN / 2); c0 += 32) {
         uint32_t a1[32], a2[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, a1);
         if (args.nkb_lr > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(PL_BN + c0), a2);
