@@ -726,6 +726,68 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   return CB_OK;
 }
 
+// ---------------------------------------------------------------- Hessian accumulation
+// H += X^T X for a batch X (T x n) of calibration activations -- the step main.py:307-311 runs on the CPU in
+// fp64, one sample at a time -- and/or its diagonal sum_t X[t, j]^2.  The product runs on the tcgen05
+// kernel with split-bf16 operands ([hi | hi | lo] x [hi | lo | hi], K = 3T: ~16 mantissa bits per factor).
+__global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) y[i] += x[i];
+}
+__global__ void __launch_bounds__(256)
+colsumsq_kernel(const float* __restrict__ X, int64_t T, int64_t n, int64_t ldx, float* __restrict__ hdiag) {
+  // one thread per column, rows split over blockIdx.y; fp32 partial sums added with one atomic per thread
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t rows_per = (T + gridDim.y - 1) / gridDim.y;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per, t1 = t0 + rows_per < T ? t0 + rows_per : T;
+  float acc = 0.f;
+  for (int64_t t = t0; t < t1; ++t) { const float v = X[t * ldx + j]; acc = fmaf(v, v, acc); }
+  if (t1 > t0) atomicAdd(hdiag + j, acc);
+}
+
+extern "C" size_t cb_hessian_accumulate_workspace_bytes(int64_t T, int64_t n) {
+  if (T <= 0 || n <= 0) return 0;
+  const int64_t T8 = T / 8 * 8;
+  return (size_t)2 * n * 3 * T8 * sizeof(bf16) + (size_t)n * n * sizeof(float) + kSplitWsBytes + 4 * 256;
+}
+
+extern "C" int cb_hessian_accumulate_f32(const float* X, int64_t T, int64_t n, float* H, float* hdiag, int* error_flag,
+                                         void* ws, size_t ws_bytes, void* stream) {
+  if (X == nullptr || T <= 0 || n <= 0 || (H == nullptr && hdiag == nullptr)) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hdiag != nullptr) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)(T >= 1024 ? 32 : (T >= 64 ? 8 : 1)));
+    colsumsq_kernel<<<grid, 256, 0, st>>>(X, T, n, n, hdiag);
+    CB_CHECK_LAUNCH();
+  }
+  if (H == nullptr) return CB_OK;
+  const int64_t T8 = T / 8 * 8;
+  if (n % 8 == 0 && T8 > 0 && aligned16(X)) {
+    if (ws == nullptr || ws_bytes < cb_hessian_accumulate_workspace_bytes(T, n)) return CB_ERR_WORKSPACE;
+    Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+    bf16* A3 = a.take<bf16>(n * 3 * T8);
+    bf16* B3 = a.take<bf16>(n * 3 * T8);
+    float* tmp = a.take<float>(n * n);
+    SplitWs sw;
+    sw.buf = a.take<float>(kSplitWsBytes / sizeof(float)); sw.bytes = kSplitWsBytes;
+    if (!a.ok()) return CB_ERR_WORKSPACE;
+    split3_kernel<<<grid_for(T8 * n, 256 * 4, 4), 256, 0, st>>>(X, T8, n, 1, 0, A3);   // rows = features: [hi | hi | lo]
+    CB_CHECK_LAUNCH();
+    split3_kernel<<<grid_for(T8 * n, 256 * 4, 4), 256, 0, st>>>(X, T8, n, 1, 1, B3);   //                  [hi | lo | hi]
+    CB_CHECK_LAUNCH();
+    CB_TRY(gemm_tc(n, n, 3 * T8, 1.f, A3, 3 * T8, B3, 3 * T8, tmp, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 0,
+                   error_flag, nullptr, st, &sw));
+    axpy_kernel<<<grid_for(n * n, 256 * 4, 4), 256, 0, st>>>(tmp, H, n * n);
+    CB_CHECK_LAUNCH();
+    if (T8 < T)   // the last T % 8 rows: fp32 SIMT, accumulated in place
+      CB_TRY(sgemm(n, n, T - T8, 1.f, X + T8 * n, 1, n, X + T8 * n, n, 1, H, n, 1, true, nullptr, st));
+    return CB_OK;
+  }
+  // ragged shapes: fp32 SIMT contraction, accumulated in place
+  return sgemm(n, n, T, 1.f, X, 1, n, X, n, 1, H, n, 1, true, nullptr, st);
+}
+
 // ---------------------------------------------------------------- stand-alone stages (C ABI)
 extern "C" size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t q_width, int h_kind) {
   if (m <= 0 || n <= 0 || r <= 0 || q_width < r || q_width > 512) return 0;

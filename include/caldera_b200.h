@@ -174,6 +174,15 @@ size_t cb_packed_linear_workspace_bytes(int64_t T, int64_t m, int64_t n, int64_t
 int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const uint8_t* q_packed, int q_bits,
                          const float* q_scale, const float* L, const float* R, int64_t m, int64_t r,
                          float global_scale, float* y, int* error_flag, void* ws, size_t ws_bytes, void* stream);
+/* ---- Hessian accumulation (the reference does `a_aT = activations @ activations.T` in fp64
+ * on the CPU for every calibration sample, main.py:307-311, and convex_caldera.py:108) ----
+ * H (n x n fp32, row-major) += X^T X and/or hdiag (n fp32) += sum_t X[t, j]^2 for a batch X (T x n fp32,
+ * row-major) of activations; either output may be NULL.  The product runs on the tcgen05 kernel with
+ * split-bf16 operands (relative error ~1e-5 of an fp64 product).  The caller zeroes H / hdiag before the
+ * first batch and divides by the sample count at the end. */
+size_t cb_hessian_accumulate_workspace_bytes(int64_t T, int64_t n);
+int cb_hessian_accumulate_f32(const float* X, int64_t T, int64_t n, float* H, float* hdiag, int* error_flag,
+                              void* ws, size_t ws_bytes, void* stream);
 /* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
  * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
  * rounding level between modes (different K-split counts and eigensolver sweep order).

@@ -323,3 +323,23 @@ def test_fullsize_golden_headline_config():
         best = min(flat[1:])
         assert abs(best - z["best_error"]) <= 1e-3 * z["best_error"], (mode, best, z["best_error"])
         assert flat[d.best_step] == best
+
+
+def test_fullsize_golden_config3_quantised_factors():
+    """SURVEY configuration 3 at full size (11008 x 4096, rank 256, Q 2-bit, L/R 4-bit, 5 LPLR iterations) against
+    the UNMODIFIED reference on CPU (tests/golden/make_golden_c3.py)."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_c3.json")) as f:
+        z = json.load(f)
+    g = torch.Generator().manual_seed(1004)
+    W = 0.02 * torch.randn(11008, 4096, generator=g, dtype=torch.float32)
+    h = 0.5 + torch.rand(4096, generator=g, dtype=torch.float32)
+    kw = dict(Q_bits=2, L_bits=4, R_bits=4, rank=256, iters=2, lplr_iters=5, update_order=["Q", "LR"])
+    d = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, W_copy="none")
+    np.testing.assert_allclose(d.global_scale, z["global_scale"], rtol=2e-7)
+    np.testing.assert_allclose(d.errors["Q"][0], z["errors"]["Q"][0], rtol=2e-6)
+    flat = [e for pair in zip(d.errors["Q"], d.errors["LR"]) for e in pair]
+    best = min(flat[1:])
+    # 4-bit whole-tensor re-quantisation of L and R: the reference's own LPLR trajectory is reproducible to ~3e-3
+    # only (DESIGN.md section 5); at this size the randomness averages out
+    assert abs(best - z["best_error"]) <= 3e-3 * z["best_error"], (best, z["best_error"])
+    assert d.L_idxs.shape == (1, 11008 * 256) and d.R_idxs.shape == (1, 256 * 4096)
