@@ -74,6 +74,9 @@ _SIGNATURES = {
                                           C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
+    "cb_hadamard_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "cb_hadamard_transform_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "cb_hessian_accumulate_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "cb_hessian_accumulate_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -85,6 +88,7 @@ _SIGNATURES = {
     "cb_set_execution_mode": (C.c_int, [C.c_int]),
     "cb_set_gemm_kblocks": (None, [C.c_int]),
     "cb_set_gemm_timing": (None, [C.c_void_p]),
+    "cb_set_chol_timing": (None, [C.c_void_p]),
     "cb_probe_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_convert_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

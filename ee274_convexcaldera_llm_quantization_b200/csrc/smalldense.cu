@@ -35,10 +35,12 @@ struct CholSmem {
 // the block and solves x L_kk^T = a by forward substitution in registers, reading L_kk as
 // 128-bit shared-memory broadcasts; (3) 4 x 4 register tiles apply the rank-32 update to the
 // trailing lower triangle from the transposed panel in shared memory.
-__device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
+__device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s, long long* stamps = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int k0 = 0; k0 < q; k0 += NB) {
     const int nb = min(NB, q - k0);
+    long long* ps = (stamps != nullptr && tid == 0 && k0 / NB < 3) ? stamps + 4 + 5 * (k0 / NB) : nullptr;
+    if (ps) ps[0] = clock64();
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int i = e >> 5, j = e & 31;
       float v = 0.f;
@@ -46,6 +48,7 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
       s.D[i][j] = v;
     }
     __syncthreads();
+    if (ps) ps[1] = clock64();   // diagonal block in shared memory
     if (warp == 0) {
       float a[NB];
 #pragma unroll
@@ -74,6 +77,7 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
       for (int c = 0; c < NB; ++c) s.D[lane][c] = a[c];
     }
     __syncthreads();
+    if (ps) ps[2] = clock64();   // diagonal block factored
     // factor back to global
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int i = e >> 5, j = e & 31;
@@ -114,6 +118,7 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
       if (i < TMAXR + 4) s.Pt[c][i] = 0.f;
     }
     __syncthreads();
+    if (ps) ps[3] = clock64();   // panel solved
     // trailing update on the lower triangle, 4x4 register tiles
     const int Ti = (T + 3) >> 2;
     const int ntile = Ti * (Ti + 1) / 2;
@@ -137,6 +142,18 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
       }
+      // read-modify-write of the 4 x 4 tile: all loads first (the compiler must keep a load behind an earlier
+      // store to G, which would serialise sixteen L2 round trips)
+      float g[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = ti * 4 + a;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = tj * 4 + b;
+          g[a][b] = (i < T && j <= i) ? G[(size_t)(k0 + nb + i) * q + k0 + nb + j] : 0.f;
+        }
+      }
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int i = ti * 4 + a;
@@ -145,11 +162,12 @@ __device__ void chol_factor(float* __restrict__ G, int q, CholSmem& s) {
         for (int b = 0; b < 4; ++b) {
           const int j = tj * 4 + b;
           if (j > i) continue;
-          G[(size_t)(k0 + nb + i) * q + k0 + nb + j] -= acc[a][b];
+          G[(size_t)(k0 + nb + i) * q + k0 + nb + j] = g[a][b] - acc[a][b];
         }
       }
     }
     __syncthreads();
+    if (ps) ps[4] = clock64();   // trailing update done
   }
 }
 
@@ -288,9 +306,11 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, __nv_bfloat16* L
 
 constexpr int CHOL_THREADS = 512;   // 128 registers/thread: the 32x32 diagonal factor lives in registers
 
+long long* g_chol_timing = nullptr;   // measurement aid (cb_set_chol_timing): 4 clock64 stamps
+
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfloat16* __restrict__ Linv_bf16,
-                int* __restrict__ status) {
+                int* __restrict__ status, long long* __restrict__ stamps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -305,9 +325,10 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfl
   }
   __syncthreads();
   int retries = 0;
+  if (stamps != nullptr && tid == 0) stamps[0] = clock64();
 
   while (true) {
-    chol_factor(G, q, s);
+    chol_factor(G, q, s, stamps);
     __syncthreads();
     const int failed = s.fail;
     __syncthreads();
@@ -323,10 +344,13 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfl
     ++retries;
     __syncthreads();
   }
+  if (stamps != nullptr && tid == 0) stamps[1] = clock64();      // factor done
   if (Linv != nullptr) {
     diag_block_inverses(G, q, Linv, Linv_bf16);
     __syncthreads();
+    if (stamps != nullptr && tid == 0) stamps[2] = clock64();    // diagonal block inverses done
     tri_inverse(G, q, Linv, Linv_bf16, reinterpret_cast<ChainTiles*>(&s.Praw[0][0]));
+    if (stamps != nullptr && tid == 0) stamps[3] = clock64();    // inverse done
   }
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }
@@ -340,7 +364,7 @@ int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st,
     CB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
     attr_set = true;
   }
-  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status);
+  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status, g_chol_timing);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -724,6 +748,8 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
 }
 
 }  // namespace cb
+
+extern "C" void cb_set_chol_timing(void* stamps_dev) { cb::g_chol_timing = reinterpret_cast<long long*>(stamps_dev); }
 
 extern "C" int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream) {
   return cb::cholesky_inverse(G, (int)q, Linv, status, (cudaStream_t)stream);

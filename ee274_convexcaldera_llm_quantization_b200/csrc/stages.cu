@@ -951,7 +951,71 @@ int quant_form_y_bf16(const float* Ws, const float* LR, const float* h_err, cons
   return CB_OK;
 }
 
+// ---------------------------------------------------------------- Hadamard pre-rotation
+// Normalised Walsh-Hadamard transform (Sylvester ordering, like scipy.linalg.hadamard / sqrt(P)) of every
+// row of a matrix: one CTA per row, the row lives in shared memory for the log2(P) butterfly stages.  Rows
+// are read from `src` (src_rows x src_cols, zero beyond) so the zero padding of main.py:84-90 is implicit.
+__global__ void __launch_bounds__(256)
+fwht_rows_kernel(const float* __restrict__ src, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                 float* __restrict__ dst, int64_t P, float norm) {
+  extern __shared__ float row[];
+  const int64_t r = blockIdx.x;
+  if (r >= src_rows) {            // a zero row transforms to a zero row
+    for (int64_t j = threadIdx.x; j < P; j += blockDim.x) dst[r * P + j] = 0.f;
+    return;
+  }
+  for (int64_t j = threadIdx.x; j < P; j += blockDim.x) row[j] = j < src_cols ? src[r * src_ld + j] : 0.f;
+  __syncthreads();
+  for (int64_t len = 1; len < P; len <<= 1) {
+    for (int64_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+      const int64_t i = ((t / len) * len << 1) + (t % len), j = i + len;
+      const float a = row[i], b = row[j];
+      row[i] = a + b;
+      row[j] = a - b;
+    }
+    __syncthreads();
+  }
+  for (int64_t j = threadIdx.x; j < P; j += blockDim.x) dst[r * P + j] = row[j] * norm;
+}
+
+static int fwht_rows(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, float* dst, int64_t nrows,
+                     int64_t P, cudaStream_t st) {
+  const size_t smem = (size_t)P * sizeof(float);
+  static size_t attr_bytes = 0;
+  if (smem > 48 * 1024 && smem > attr_bytes) {
+    CB_CUDA(cudaFuncSetAttribute(fwht_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  fwht_rows_kernel<<<(unsigned)nrows, 256, smem, st>>>(src, src_rows, src_cols, src_ld, dst, P, 1.f / sqrtf((float)P));
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
 }  // namespace cb
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" size_t cb_hadamard_workspace_bytes(int64_t prows, int64_t pcols) {
+  if (prows <= 0 || pcols <= 0) return 0;
+  return (size_t)prows * pcols * sizeof(float) + 256;
+}
+
+extern "C" int cb_hadamard_transform_f32(const float* W, int64_t rows, int64_t cols, float* out, int64_t prows,
+                                         int64_t pcols, void* ws, size_t ws_bytes, void* stream) {
+  using namespace cb;
+  if (W == nullptr || out == nullptr || ws == nullptr || rows <= 0 || cols <= 0) return CB_ERR_ARG;
+  if (!is_pow2(prows) || !is_pow2(pcols) || prows < rows || pcols < cols) return CB_ERR_ARG;
+  if (prows > 32768 || pcols > 32768) return CB_ERR_UNSUPPORTED;      // one row must fit in shared memory
+  if (ws_bytes < cb_hadamard_workspace_bytes(prows, pcols)) return CB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tmp = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  // out = pad(W) H2 (rows of length pcols), then H1 applied to the columns through two transposes
+  CB_TRY(fwht_rows(W, rows, cols, cols, out, prows, pcols, st));
+  CB_TRY(transpose_codes(out, prows, pcols, 4, tmp, st));                       // tmp: pcols x prows
+  CB_TRY(fwht_rows(tmp, pcols, prows, prows, tmp, pcols, prows, st));           // in place, row by row
+  CB_TRY(transpose_codes(tmp, pcols, prows, 4, out, st));
+  return CB_OK;
+}
 
 extern "C" int cb_hessian_probe(const float* H, int64_t n, float* diag, int* is_diag, void* stream) {
   if (H == nullptr || diag == nullptr || is_diag == nullptr || n <= 0) return CB_ERR_ARG;

@@ -126,6 +126,10 @@ size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t 
  * retried on G + ridge*mean(diag)*I with ridge = 1e-6, 1e-4, 1e-2 and *status gets the
  * number of retries (device int, may be NULL). */
 int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream);
+/* Measurement aid: when non-NULL the Cholesky kernel writes 4 clock64 stamps (start, factor done, diagonal
+ * block inverses done, inverse done; then 5 per panel for the first 3 panels: start, block loaded, block
+ * factored, panel solved, trailing update done) to this device buffer of 24 int64.  Process-wide; NULL = off. */
+void cb_set_chol_timing(void* stamps_dev);
 /* Eigen-decomposition of the SPD matrix G = Lc Lc^T from its Cholesky factor by one-sided
  * Jacobi on Lc's columns.  evals[q] descending, evecs row k = k-th eigenvector.
  * work: q*q + q + 8 floats of scratch (column storage, norms, sweep counters). */
@@ -182,6 +186,15 @@ int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const uint8_t* q_
  * first batch and divides by the sample count at the end. */
 size_t cb_hessian_accumulate_workspace_bytes(int64_t T, int64_t n);
 int cb_hessian_accumulate_f32(const float* X, int64_t T, int64_t n, float* H, float* hdiag, int* error_flag,
+                              void* ws, size_t ws_bytes, void* stream);
+/* ---- Hadamard pre-rotation (main.py:79-133 builds dense normalised Hadamard matrices with
+ * scipy and multiplies on the CPU in fp64) ----
+ * out (prows x pcols fp32) = H1 * pad(W) * H2 with H_k the normalised Sylvester-Hadamard matrix of order
+ * prows / pcols (powers of two >= rows / cols, <= 32768) and pad() the zero padding of main.py:84-90, as a
+ * fast Walsh-Hadamard transform.  The transform is its own inverse (main.py:124-129): apply it to the padded
+ * matrix again and keep the leading rows x cols block. */
+size_t cb_hadamard_workspace_bytes(int64_t prows, int64_t pcols);
+int cb_hadamard_transform_f32(const float* W, int64_t rows, int64_t cols, float* out, int64_t prows, int64_t pcols,
                               void* ws, size_t ws_bytes, void* stream);
 /* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
  * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
