@@ -74,6 +74,10 @@ _SIGNATURES = {
                                           C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
+    "cb_quantize_nf_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "cb_dequantize_nf_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
     "cb_hadamard_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "cb_hadamard_transform_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -483,6 +483,98 @@ extern "C" int cb_pack_codes(const void* codes, int64_t numel, int bits, uint8_t
   return CB_OK;
 }
 
+// ---------------------------------------------------------------- NormalFloat codebooks (nf4 / nf2)
+// quantization.py:56-90: per block s = max(absmax, eps); index = #{thresholds t : x / s > t} with the
+// thresholds midway between neighbouring levels; dequantised value = levels[index] * s.
+namespace cb {
+struct NfTable { float v[16]; int count; };
+
+__global__ void __launch_bounds__(256)
+nf_absmax_kernel(const float* __restrict__ x, int64_t numel, int64_t block, int chunks_per_block,
+                 float* __restrict__ scales) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x / chunks_per_block;
+  const int c = blockIdx.x % chunks_per_block;
+  const int64_t per = (block + chunks_per_block - 1) / chunks_per_block;
+  const int64_t lo = b * block + c * per, hi = min(b * block + block, lo + per);
+  float a = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) a = fmaxf(a, fabsf(x[i]));
+  a = block_max(a, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(scales + b, a);
+}
+__global__ void __launch_bounds__(256)
+nf_code_kernel(const float* __restrict__ x, int64_t numel, int64_t block, float eps, const NfTable thr,
+               float* __restrict__ scales, uint8_t* __restrict__ idx, int finalize_scales) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const int64_t b = i / block;
+    const float s = fmaxf(scales[b], eps);
+    const float w = __fdiv_rn(x[i], s);
+    int k = 0;
+#pragma unroll
+    for (int t = 0; t < 15; ++t) k += (t < thr.count && w > thr.v[t]) ? 1 : 0;
+    idx[i] = (uint8_t)k;
+  }
+  (void)finalize_scales;
+}
+__global__ void __launch_bounds__(256) nf_clamp_scales_kernel(float* __restrict__ scales, int64_t nblk, float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nblk) scales[i] = fmaxf(scales[i], eps);
+}
+__global__ void __launch_bounds__(256)
+nf_dequant_kernel(const uint8_t* __restrict__ idx, const float* __restrict__ scales, int64_t numel, int64_t block,
+                  const NfTable levels, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const int k = min((int)idx[i], levels.count - 1);
+    out[i] = levels.v[k] * scales[i / block];
+  }
+}
+}  // namespace cb
+
+extern "C" int cb_quantize_nf_f32(const float* x, int64_t numel, int64_t block, const float* thresholds_host,
+                                  int n_thresholds, float eps, uint8_t* idx, float* scales, void* stream) {
+  using namespace cb;
+  if (x == nullptr || idx == nullptr || scales == nullptr || thresholds_host == nullptr) return CB_ERR_ARG;
+  if (numel <= 0 || block <= 0 || numel % block != 0) return CB_ERR_BLOCK;
+  if (n_thresholds < 1 || n_thresholds > 15) return CB_ERR_BITS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nblk = numel / block;
+  NfTable thr;
+  thr.count = n_thresholds;
+  for (int t = 0; t < 16; ++t) thr.v[t] = t < n_thresholds ? thresholds_host[t] : 0.f;
+  CB_CUDA(cudaMemsetAsync(scales, 0, sizeof(float) * nblk, st));
+  // enough CTAs per quantisation block to fill the machine when there are few (large) blocks
+  int chunks = 1;
+  if (nblk < 4 * kNumSMs) {
+    const int64_t want = (4 * kNumSMs + nblk - 1) / nblk, most = (block + 1023) / 1024;
+    chunks = (int)(want < most ? want : most);
+  }
+  if (chunks < 1) chunks = 1;
+  if (nblk * chunks > (int64_t)INT32_MAX) return CB_ERR_ARG;
+  nf_absmax_kernel<<<(unsigned)(nblk * chunks), 256, 0, st>>>(x, numel, block, chunks, scales);
+  CB_CHECK_LAUNCH();
+  nf_code_kernel<<<grid_for(numel, 256, 8), 256, 0, st>>>(x, numel, block, eps, thr, scales, idx, 0);
+  CB_CHECK_LAUNCH();
+  nf_clamp_scales_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, st>>>(scales, nblk, eps);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+extern "C" int cb_dequantize_nf_f32(const uint8_t* idx, const float* scales, int64_t numel, int64_t block,
+                                    const float* levels_host, int n_levels, float* out, void* stream) {
+  using namespace cb;
+  if (idx == nullptr || scales == nullptr || levels_host == nullptr || out == nullptr) return CB_ERR_ARG;
+  if (numel <= 0 || block <= 0 || numel % block != 0) return CB_ERR_BLOCK;
+  if (n_levels < 2 || n_levels > 16) return CB_ERR_BITS;
+  NfTable lv;
+  lv.count = n_levels;
+  for (int t = 0; t < 16; ++t) lv.v[t] = t < n_levels ? levels_host[t] : 0.f;
+  nf_dequant_kernel<<<grid_for(numel, 256, 8), 256, 0, (cudaStream_t)stream>>>(idx, scales, numel, block, lv, out);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
 extern "C" int cb_unpack_codes(const uint8_t* packed, int64_t numel, int bits, void* codes, void* stream) {
   if (!bits_ok(bits)) return CB_ERR_BITS;
   if (codes == nullptr || packed == nullptr || numel < 0) return CB_ERR_ARG;

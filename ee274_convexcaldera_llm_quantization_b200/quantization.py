@@ -2,11 +2,14 @@
 
 Same names, constructor arguments, return conventions and exceptions as the reference's
 `LowMemoryQuantizer` / `QuantizerFactory` (quantization.py:18-37, 244-319).  The uniform
-method runs in the sm_100a kernels of csrc/quant.cu; the codebook methods (nf4/nf2/bbint*)
-are outside the hot path and raise NotImplementedError at call time.
+method runs in the sm_100a kernels of csrc/quant.cu; the NormalFloat codebooks (nf4 / nf2,
+quantization.py:39-94) are available through the same class; the bitsandbytes-style methods
+(bbint4 / bbint2: outlier side tables and CSV logging, quantization.py:107-243) are outside the hot
+path and raise NotImplementedError at call time.
 """
 from __future__ import annotations
 
+import ctypes as C
 from abc import ABC, abstractmethod
 from typing import List
 
@@ -16,6 +19,10 @@ from . import _lib
 
 _BITWIDTHS = [2, 4, 8, 16]
 _QUANTIZER_METHODS = ["uniform", "nf4", "nf2", "bbint4", "bbint2"]
+# quantization.py:44-50 and :57-60
+_NF4_LEVELS = [-1.334, -1.0, -0.784, -0.617, -0.476, -0.347, -0.226, -0.112, 0.0, 0.112, 0.226, 0.347, 0.476, 0.617,
+               0.784, 1.0]
+_NF2_LEVELS = [-0.8165, -0.3333, 0.3333, 0.8165]
 
 
 class AbstractQuantizer(ABC):
@@ -45,12 +52,49 @@ class LowMemoryQuantizer(AbstractQuantizer):
         if self.method == "bbint4" and self.num_bits != 4:
             raise ValueError("bbint4 quantization supports only 4 bits.")
 
+        if self.method in ("nf4", "nf2"):
+            # quantization.py:39-66: codebook and the thresholds midway between neighbouring levels (fp32)
+            levels = _NF4_LEVELS if self.method == "nf4" else _NF2_LEVELS
+            self.levels = torch.tensor(levels, dtype=torch.float32)
+            self.thresholds = (self.levels[:-1] + self.levels[1:]) / 2
+
     # -- helpers -----------------------------------------------------------------
     def _check_method(self, what):
-        if self.method != "uniform":
+        if self.method not in ("uniform", "nf4", "nf2"):
             raise NotImplementedError(
                 f"{what} method '{self.method}' not implemented in the B200 path "
-                "(only method='uniform' is on the CALDERA hot path).")
+                "(uniform is on the CALDERA hot path; nf4 / nf2 are available through this class).")
+
+    def _quantize_nf(self, weight: torch.Tensor, epsilon: float):
+        """quantization.py:270-279 with _quantize_nf (:68-88): uint8 level indices, fp32 block scales."""
+        lib = _lib.load()
+        w = (weight if weight.dtype == torch.float32 else weight.float()).contiguous()    # the reference flattens
+        total = w.numel()
+        nblk = total // self.block_size
+        idx = torch.empty((nblk, self.block_size), dtype=torch.uint8, device=w.device)
+        scales = torch.empty((nblk, 1), dtype=torch.float32, device=w.device)
+        thr = (C.c_float * len(self.thresholds))(*[float(t) for t in self.thresholds])
+        with torch.cuda.device(w.device):
+            st = lib.cb_quantize_nf_f32(_lib.ptr(w), total, self.block_size, thr, len(self.thresholds), float(epsilon),
+                                        _lib.ptr(idx), _lib.ptr(scales), _lib.stream_ptr())
+        _lib.check(st, "quantize_block")
+        return idx, scales, weight.shape
+
+    def _dequantize_nf(self, weight_quant: torch.Tensor, weight_params, weight_shape):
+        """quantization.py:296-298 with _dequantize_nf (:90-94)."""
+        lib = _lib.load()
+        numel = 1
+        for s_ in weight_shape:
+            numel *= int(s_)
+        q = weight_quant.contiguous()
+        scales = weight_params.contiguous().float()
+        out = torch.empty(numel, dtype=torch.float32, device=q.device)
+        lv = (C.c_float * len(self.levels))(*[float(t) for t in self.levels])
+        with torch.cuda.device(q.device):
+            st = lib.cb_dequantize_nf_f32(_lib.ptr(q), _lib.ptr(scales), numel, numel // scales.numel(), lv,
+                                          len(self.levels), _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(st, "dequantize_block")
+        return out.reshape(tuple(weight_shape))
 
     def quantize_block(self, weight: torch.Tensor, epsilon: float = 1e-8, return_packed: bool = False):
         """quantization.py:244-288.  With return_packed=True a fourth value, the packed
@@ -64,6 +108,10 @@ class LowMemoryQuantizer(AbstractQuantizer):
                 f"is not divisible by block size {self.block_size}")
         self._check_method("Quantization")
         _lib.require_cuda(weight, "weight")
+        if self.method in ("nf4", "nf2"):
+            if return_packed:
+                raise NotImplementedError("return_packed is available for method='uniform' only")
+            return self._quantize_nf(weight, epsilon)
         lib = _lib.load()
         w = weight if weight.dtype == torch.float32 else weight.float()
         nblk = total // self.block_size
@@ -87,6 +135,8 @@ class LowMemoryQuantizer(AbstractQuantizer):
         uint8 stream produced with return_packed=True."""
         self._check_method("Dequantization")
         _lib.require_cuda(weight_quant, "weight_quant")
+        if self.method in ("nf4", "nf2"):
+            return self._dequantize_nf(weight_quant, weight_params, weight_shape)
         lib = _lib.load()
         numel = 1
         for s in weight_shape:

@@ -80,6 +80,15 @@ int cb_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t stride_r
 int cb_dequantize_f32(const void* codes, const uint8_t* packed, const float* scales,
                       int64_t numel, int bits, int64_t block, float* out, void* stream);
 
+/* NormalFloat codebooks, LowMemoryQuantizer(method="nf4" / "nf2") (RCR/caldera/utils/quantization.py:32-90,
+ * 270-279, 296-298): per block of `block` consecutive elements s = max(absmax, eps); idx = number of
+ * thresholds (host array, midpoints of neighbouring levels) that x / s exceeds; dequant = levels[idx] * s.
+ * x contiguous (the reference flattens), idx uint8, scales fp32 (numel / block). */
+int cb_quantize_nf_f32(const float* x, int64_t numel, int64_t block, const float* thresholds_host, int n_thresholds,
+                       float eps, uint8_t* idx, float* scales, void* stream);
+int cb_dequantize_nf_f32(const uint8_t* idx, const float* scales, int64_t numel, int64_t block,
+                         const float* levels_host, int n_levels, float* out, void* stream);
+
 size_t cb_packed_bytes(int64_t numel, int bits);
 int cb_pack_codes(const void* codes, int64_t numel, int bits, uint8_t* packed, void* stream);
 int cb_unpack_codes(const uint8_t* packed, int64_t numel, int bits, void* codes, void* stream);

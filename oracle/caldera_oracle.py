@@ -64,6 +64,33 @@ def quantize_uniform(x: np.ndarray, bits: int, block_size: Optional[int] = None,
     return codes, scales, tuple(x.shape)
 
 
+NF_LEVELS = {   # quantization.py:44-50 (nf4), :57-60 (nf2)
+    "nf4": np.array([-1.334, -1.0, -0.784, -0.617, -0.476, -0.347, -0.226, -0.112, 0.0, 0.112, 0.226, 0.347, 0.476,
+                     0.617, 0.784, 1.0], dtype=F32),
+    "nf2": np.array([-0.8165, -0.3333, 0.3333, 0.8165], dtype=F32),
+}
+
+
+def quantize_nf(x: np.ndarray, method: str, block_size: int, eps: float = 1e-8):
+    """NormalFloat codebook quantiser (quantization.py:270-279 with _quantize_nf :68-88): per block
+    s = max(absmax, eps); index = number of thresholds (midpoints of neighbouring levels, fp32) that x / s
+    exceeds.  Returns (indices uint8 [nblk, bs], scales fp32 [nblk, 1], shape)."""
+    levels = NF_LEVELS[method]
+    thr = ((levels[:-1] + levels[1:]) / F32(2)).astype(F32)
+    blocks = np.ascontiguousarray(x, dtype=F32).reshape(-1, int(block_size))
+    scales = np.maximum(np.abs(blocks).max(axis=1, keepdims=True), F32(eps)).astype(F32)
+    scaled = (blocks / scales).astype(F32)
+    idx = np.zeros(blocks.shape, dtype=np.uint8)
+    for t in thr:
+        idx += (scaled > t).astype(np.uint8)
+    return idx, scales, tuple(x.shape)
+
+
+def dequantize_nf(idx: np.ndarray, scales: np.ndarray, shape, method: str) -> np.ndarray:
+    """quantization.py:296-298 with _dequantize_nf (:90-94)."""
+    return (NF_LEVELS[method][idx.astype(np.int64)] * scales).astype(F32).reshape(shape)
+
+
 def dequantize_uniform(codes: np.ndarray, scales: np.ndarray, shape, bits: int) -> np.ndarray:
     """x_hat = (float(code) / levels) * scale, reshaped (quantization.py:105, 295, 306)."""
     vals = (codes.astype(F32) / F32(uniform_levels(bits))) * scales.astype(F32)
