@@ -263,7 +263,7 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
                 kw.setdefault("seed", 1000 + i)
                 kw.setdefault("W_copy", "none")
                 kw.setdefault("use_cuda_graph", True)
-                if pack and not os.environ.get("CB_RETURN_DENSE"):
+                if pack:
                     kw.setdefault("return_dense", False)       # the blob holds packed codes and factors only
                 t0 = time.perf_counter()
                 dec = caldera(params, W, H, device=dev, use_tqdm=False, **kw)
