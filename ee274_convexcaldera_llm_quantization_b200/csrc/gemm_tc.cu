@@ -533,21 +533,32 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int64_t crow = (int64_t)n_blk * PL_BN + t;      // row of C (= output column of y)
     const bool row_ok = crow < args.m;
     const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8) + half * HB;
-    uint2 cur[HB / 8], nxt[HB / 8];
+    // the packed codes of the next PF K blocks are kept in registers: one L2 round trip (~800 cycles) is
+    // several K blocks long, so a prefetch distance of one would leave the expansion waiting on memory
+    constexpr int PF = BITS == 2 ? 6 : (BITS == 4 ? 4 : 2);
+    uint2 buf[PF][HB / 8];
 #pragma unroll
-    for (int w = 0; w < HB / 8; ++w) {
-      cur[w] = make_uint2(0, 0);
-      if (row_ok && args.nkb_codes > 0) cur[w] = __ldg(reinterpret_cast<const uint2*>(src) + w);
-    }
+    for (int j = 0; j < PF; ++j)
+#pragma unroll
+      for (int w = 0; w < HB / 8; ++w) {
+        buf[j][w] = make_uint2(0, 0);
+        if (row_ok && j < args.nkb_codes) buf[j][w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)j * ROW_BYTES) + w);
+      }
     for (int i = 0; i < nkb; ++i) {
       const int s_ = i % PL_STAGES;
       const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
-      if (i + 1 < args.nkb_codes) {
+      uint2 cur[HB / 8];
 #pragma unroll
-        for (int w = 0; w < HB / 8; ++w) {
-          nxt[w] = make_uint2(0, 0);
-          if (row_ok) nxt[w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)(i + 1) * ROW_BYTES) + w);
-        }
+      for (int w = 0; w < HB / 8; ++w) cur[w] = buf[0][w];
+#pragma unroll
+      for (int j = 0; j + 1 < PF; ++j)
+#pragma unroll
+        for (int w = 0; w < HB / 8; ++w) buf[j][w] = buf[j + 1][w];
+#pragma unroll
+      for (int w = 0; w < HB / 8; ++w) {
+        buf[PF - 1][w] = make_uint2(0, 0);
+        if (row_ok && i + PF < args.nkb_codes)
+          buf[PF - 1][w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)(i + PF) * ROW_BYTES) + w);
       }
       if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
       if (i < args.nkb_codes) {
@@ -584,8 +595,6 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           *reinterpret_cast<uint4*>(dst + ((c ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
         }
         fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
-#pragma unroll
-        for (int w = 0; w < HB / 8; ++w) cur[w] = nxt[w];
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(s_)) : "memory");
