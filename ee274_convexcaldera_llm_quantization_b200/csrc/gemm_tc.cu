@@ -430,12 +430,17 @@ struct PackedLinearArgs {
   float gs, lv;
   float* y; int64_t ldy;
   int* error_flag;
+  long long* timing;          // measurement aid (cb_set_gemm_timing): 8 clock64 stamps of CTA (0,0), or null
 };
 
-constexpr int PL_BN = 128, PL_STAGES = 6, PL_WORKERS = 256;   // two worker threads per tile row
+constexpr int PL_BN = 128, PL_STAGES = 3, PL_KB = 2, PL_WORKERS = 256;
 constexpr int PL_THREADS = 64 + PL_WORKERS;
+// One stage = PL_KB (2) consecutive 64-wide K blocks of the A and B tiles: the expansion warps pay one
+// proxy fence + barrier round trip per 128 codes instead of per 64 (that round trip, not the expansion
+// itself, bounded the first version at ~1000 cycles per K block).
 struct PlSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2, B_BYTES = PL_BN * TC_BK * 2;
+  static constexpr int A_BLK = TC_BM * TC_BK * 2, B_BLK = PL_BN * TC_BK * 2;
+  static constexpr int A_BYTES = PL_KB * A_BLK, B_BYTES = PL_KB * B_BLK;
   static constexpr int BAR_OFF = PL_STAGES * (A_BYTES + B_BYTES);
   static constexpr int LUT_OFF = BAR_OFF + (2 * PL_STAGES + 1) * 8 + 16;
   static constexpr int TOTAL = LUT_OFF + 2048 + 1024;
@@ -446,7 +451,6 @@ __global__ void __launch_bounds__(PL_THREADS, 1)
 packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmT,
                      const __grid_constant__ CUtensorMap tmL, const PackedLinearArgs args) {
   using S = PlSmem;
-  constexpr int PER = 8 / BITS;                 // codes per packed byte
   constexpr int ROW_BYTES = TC_BK * BITS / 8;   // packed bytes of one tile row per K block (16 / 32 / 64)
   constexpr int LVI = (1 << (BITS - 1)) - 1;
   extern __shared__ uint8_t smem_raw[];
@@ -459,17 +463,29 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * PL_STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (2 * PL_STAGES + 1);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(base_ptr + S::BAR_OFF + 8 * (2 * PL_STAGES + 1));
-  uint16_t* lut = reinterpret_cast<uint16_t*>(base_ptr + S::LUT_OFF);   // [256][PER] bf16 bit patterns
+  uint32_t* lut = reinterpret_cast<uint32_t*>(base_ptr + S::LUT_OFF);   // [16][32]: value x lane
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;      // tile of m (output columns), tile of T (rows)
-  const int nkb = args.nkb_codes + args.nkb_lr;
+  const int ns_codes = (args.nkb_codes + PL_KB - 1) / PL_KB, ns_lr = (args.nkb_lr + PL_KB - 1) / PL_KB;
+  const int ns = ns_codes + ns_lr;                       // pipeline iterations (stages of PL_KB K blocks)
+  long long* stamps = (args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0) ? args.timing : nullptr;
+  if (stamps != nullptr && threadIdx.x == 0) stamps[0] = clock64();              // entry
 
-  // byte -> PER bf16 integers (code = symbol - lv)
-  for (int e = threadIdx.x; e < 256 * PER; e += blockDim.x) {
-    const int byte = e / PER, j = e % PER;
-    const int sym = (byte >> (8 - BITS * (j + 1))) & ((1 << BITS) - 1);
-    lut[e] = __bfloat16_as_ushort(__int2bfloat16_rn(sym - LVI));
+  // Expansion table, one private copy per lane so that a lookup never conflicts (entry (v, lane) lives in bank
+  // `lane`): a byte-indexed table with random indices cost ~5-way bank conflicts and made the kernel
+  // shared-memory bound.  2-bit: nibble -> two codes as a bf16 pair; 4-bit: nibble -> one code.
+  for (int e = threadIdx.x; e < 16 * 32; e += blockDim.x) {
+    const int v = e >> 5;
+    uint32_t entry;
+    if (BITS == 2) {
+      const uint32_t lo = __bfloat16_as_ushort(__int2bfloat16_rn(((v >> 2) & 3) - LVI));   // first code: high bits
+      const uint32_t hi = __bfloat16_as_ushort(__int2bfloat16_rn((v & 3) - LVI));
+      entry = lo | (hi << 16);
+    } else {
+      entry = __bfloat16_as_ushort(__int2bfloat16_rn(v - LVI));
+    }
+    lut[e] = entry;
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmL); }
   if (warp == 1) {
@@ -489,109 +505,118 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      if (stamps != nullptr) stamps[1] = clock64();                                // prologue done
+      for (int i = 0; i < ns; ++i) {
         const int s_ = i % PL_STAGES;
         const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
         if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
-        if (i < args.nkb_codes) {
+        if (i < ns_codes) {
+          // both K blocks of x with one 3-D copy (a block past n / 64 is zero-filled)
           mbar_expect_tx(full_bar(s_), (uint32_t)S::A_BYTES);
-          tma_load_2d(a_base + s_ * S::A_BYTES, &tmX, full_bar(s_), i * TC_BK, m_blk * TC_BM);
+          tma_load_3d(a_base + s_ * S::A_BYTES, &tmX, full_bar(s_), 0, m_blk * TC_BM, i * PL_KB);
         } else {
-          const int kb = i - args.nkb_codes;
-          mbar_expect_tx(full_bar(s_), (uint32_t)(S::A_BYTES + S::B_BYTES));
-          tma_load_2d(a_base + s_ * S::A_BYTES, &tmT, full_bar(s_), kb * TC_BK, m_blk * TC_BM);
-          tma_load_2d(b_base + s_ * S::B_BYTES, &tmL, full_bar(s_), kb * TC_BK, n_blk * PL_BN);
+          const int kb0 = (i - ns_codes) * PL_KB;
+          const int valid = min(PL_KB, args.nkb_lr - kb0);
+          mbar_expect_tx(full_bar(s_), (uint32_t)(valid * (S::A_BLK + S::B_BLK)));
+          for (int b2 = 0; b2 < valid; ++b2) {
+            tma_load_2d(a_base + s_ * S::A_BYTES + b2 * S::A_BLK, &tmT, full_bar(s_), (kb0 + b2) * TC_BK, m_blk * TC_BM);
+            tma_load_2d(b_base + s_ * S::B_BYTES + b2 * S::B_BLK, &tmL, full_bar(s_), (kb0 + b2) * TC_BK, n_blk * PL_BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, PL_BN);
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < ns; ++i) {
         const int s_ = i % PL_STAGES;
         const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
         if (!mbar_wait(full_bar(s_), ph)) { ok = false; break; }
+        if (stamps != nullptr && i == 0) stamps[3] = clock64();                    // first stage complete
+        if (stamps != nullptr && i == ns - 1) stamps[4] = clock64();               // last stage complete
         tc_fence_after();
-        const bool lr = i >= args.nkb_codes;
+        const bool lr = i >= ns_codes;
         const uint32_t acc = tmem_base + (lr ? (uint32_t)PL_BN : 0u);
-        const bool first = lr ? (i == args.nkb_codes) : (i == 0);
-        const uint64_t adesc = make_smem_desc_sw128(a_base + s_ * S::A_BYTES);
-        const uint64_t bdesc = make_smem_desc_sw128(b_base + s_ * S::B_BYTES);
+        const int valid = lr ? min(PL_KB, args.nkb_lr - (i - ns_codes) * PL_KB) : min(PL_KB, args.nkb_codes - i * PL_KB);
+        const bool first_stage = lr ? (i == ns_codes) : (i == 0);
 #pragma unroll
-        for (int k2 = 0; k2 < TC_BK / 16; ++k2)
-          umma_bf16(acc, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc, (!first || k2 > 0) ? 1u : 0u);
+        for (int b2 = 0; b2 < PL_KB; ++b2) {
+          if (b2 < valid) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + s_ * S::A_BYTES + b2 * S::A_BLK);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + s_ * S::B_BYTES + b2 * S::B_BLK);
+#pragma unroll
+            for (int k2 = 0; k2 < TC_BK / 16; ++k2)
+              umma_bf16(acc, adesc + (uint64_t)(2 * k2), bdesc + (uint64_t)(2 * k2), idesc,
+                        (!first_stage || b2 > 0 || k2 > 0) ? 1u : 0u);
+          }
+        }
         umma_commit(empty_bar(s_));
       }
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ---- worker warps: expand the packed codes of this CTA's 128 rows of C, K block by K block;
-    //      two threads per row, each expanding half of the row's 64 codes (4 chunks of 8)
+    // ---- worker warps: expand the packed codes of this CTA's 128 rows of C, stage by stage; two threads
+    //      per row, thread `sub` expanding K block 2 * stage + sub (64 codes = ROW_BYTES contiguous bytes)
     const int wt = threadIdx.x - 64;                      // 0 .. 255
-    const int t = wt >> 1, half = wt & 1;                 // tile row, which half of the K block
-    constexpr int HB = ROW_BYTES / 2;                     // packed bytes per thread and K block (8 / 16 / 32)
+    const int t = wt >> 1, sub = wt & 1;                  // tile row, K block inside the stage
     const int64_t crow = (int64_t)n_blk * PL_BN + t;      // row of C (= output column of y)
     const bool row_ok = crow < args.m;
-    const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8) + half * HB;
-    // the packed codes of the next PF K blocks are kept in registers: one L2 round trip (~800 cycles) is
-    // several K blocks long, so a prefetch distance of one would leave the expansion waiting on memory
-    constexpr int PF = BITS == 2 ? 6 : (BITS == 4 ? 4 : 2);
-    uint2 buf[PF][HB / 8];
+    const uint8_t* src = args.packed + (row_ok ? crow : 0) * ((int64_t)args.n * BITS / 8);
+    constexpr int NW = ROW_BYTES / 16;                    // 128-bit words per thread and stage (1 / 2 / 4)
+    // the packed codes of the next PF stages stay in registers: one L2 round trip is several stages long
+    constexpr int PF = BITS == 2 ? 4 : (BITS == 4 ? 3 : 2);
+    uint4 buf[PF][NW];
+    auto fetch = [&](int stage, uint4 (&dst)[NW]) {
+      const int kb = stage * PL_KB + sub;
 #pragma unroll
-    for (int j = 0; j < PF; ++j)
-#pragma unroll
-      for (int w = 0; w < HB / 8; ++w) {
-        buf[j][w] = make_uint2(0, 0);
-        if (row_ok && j < args.nkb_codes) buf[j][w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)j * ROW_BYTES) + w);
+      for (int w = 0; w < NW; ++w) {
+        dst[w] = make_uint4(0, 0, 0, 0);
+        if (row_ok && kb < args.nkb_codes) dst[w] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)kb * ROW_BYTES) + w);
       }
-    for (int i = 0; i < nkb; ++i) {
+    };
+#pragma unroll
+    for (int j = 0; j < PF; ++j) fetch(j, buf[j]);
+    for (int i = 0; i < ns; ++i) {
       const int s_ = i % PL_STAGES;
       const uint32_t ph = (uint32_t)(i / PL_STAGES) & 1u;
-      uint2 cur[HB / 8];
+      uint4 cur[NW];
 #pragma unroll
-      for (int w = 0; w < HB / 8; ++w) cur[w] = buf[0][w];
+      for (int w = 0; w < NW; ++w) cur[w] = buf[0][w];
 #pragma unroll
       for (int j = 0; j + 1 < PF; ++j)
 #pragma unroll
-        for (int w = 0; w < HB / 8; ++w) buf[j][w] = buf[j + 1][w];
-#pragma unroll
-      for (int w = 0; w < HB / 8; ++w) {
-        buf[PF - 1][w] = make_uint2(0, 0);
-        if (row_ok && i + PF < args.nkb_codes)
-          buf[PF - 1][w] = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)(i + PF) * ROW_BYTES) + w);
-      }
+        for (int w = 0; w < NW; ++w) buf[j][w] = buf[j + 1][w];
+      fetch(i + PF, buf[PF - 1]);
       if (!mbar_wait(empty_bar(s_), ph ^ 1u)) { ok = false; break; }
-      if (i < args.nkb_codes) {
-        uint8_t* dst = base_ptr + (b_base - base) + s_ * S::B_BYTES + t * 128;
+      if (i < ns_codes && i * PL_KB + sub < args.nkb_codes) {
+        uint8_t* dst = base_ptr + (b_base - base) + s_ * S::B_BYTES + sub * S::B_BLK + t * 128;
         const uint32_t* words = reinterpret_cast<const uint32_t*>(cur);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {                   // local chunk: 8 consecutive K elements = BITS packed bytes
+        for (int c = 0; c < 8; ++c) {                      // chunk: 8 consecutive K elements = BITS packed bytes
           uint32_t out[4];
           if (BITS == 2) {
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const int byte_idx = 2 * cc + b;
-              const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
-              const uint2 e = *reinterpret_cast<const uint2*>(lut + byte * 4);
-              out[2 * b] = e.x; out[2 * b + 1] = e.y;
-            }
+            // 2 packed bytes = 4 nibbles = 4 output words (two codes each)
+            const uint32_t hw = (words[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;     // bytes 2c (low), 2c + 1 (high)
+            out[0] = lut[((hw >> 4) & 15u) * 32 + lane];
+            out[1] = lut[(hw & 15u) * 32 + lane];
+            out[2] = lut[((hw >> 12) & 15u) * 32 + lane];
+            out[3] = lut[((hw >> 8) & 15u) * 32 + lane];
           } else if (BITS == 4) {
+            const uint32_t w4 = words[c];                                          // bytes 4c .. 4c + 3
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int byte_idx = 4 * cc + b;
-              const uint32_t byte = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
-              out[b] = *reinterpret_cast<const uint32_t*>(lut + byte * 2);
+            for (int b2 = 0; b2 < 4; ++b2) {
+              const uint32_t byte = (w4 >> (8 * b2)) & 255u;
+              out[b2] = lut[(byte >> 4) * 32 + lane] | (lut[(byte & 15u) * 32 + lane] << 16);
             }
           } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int byte_idx = 8 * cc + 2 * b;
-              const uint32_t b0 = (words[byte_idx >> 2] >> (8 * (byte_idx & 3))) & 255u;
-              const uint32_t b1 = (words[(byte_idx + 1) >> 2] >> (8 * ((byte_idx + 1) & 3))) & 255u;
-              out[b] = (uint32_t)lut[b0] | ((uint32_t)lut[b1] << 16);
+            for (int b2 = 0; b2 < 4; ++b2) {
+              const uint32_t w8 = words[2 * c + (b2 >> 1)];
+              const int c0_ = (int)((w8 >> (16 * (b2 & 1))) & 255u) - LVI, c1_ = (int)((w8 >> (16 * (b2 & 1) + 8)) & 255u) - LVI;
+              out[b2] = (uint32_t)__bfloat16_as_ushort(__int2bfloat16_rn(c0_)) |
+                        ((uint32_t)__bfloat16_as_ushort(__int2bfloat16_rn(c1_)) << 16);
             }
           }
-          const int c = 4 * half + cc;                     // chunk position inside the 128-byte row
           *reinterpret_cast<uint4*>(dst + ((c ^ (t & 7)) << 4)) = make_uint4(out[0], out[1], out[2], out[3]);
         }
         fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
@@ -600,8 +625,10 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar(s_)) : "memory");
     }
     // ---- epilogue
+    if (stamps != nullptr && threadIdx.x == 64) stamps[2] = clock64();             // expansion loop done
     const int qd = warp & 3;
     if (!mbar_wait(tmem_full_bar, 0)) ok = false;
+    if (stamps != nullptr && threadIdx.x == 64) stamps[5] = clock64();             // accumulators complete
     ok = __all_sync(0xffffffffu, ok);
     tc_fence_after();
     const int row = m_blk * TC_BM + qd * 32 + lane;
@@ -635,12 +662,14 @@ packed_linear_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   }
   if (!ok && args.error_flag != nullptr) atomicExch(args.error_flag, 1);
+  if (stamps != nullptr && threadIdx.x == 64) stamps[6] = clock64();               // epilogue stores issued
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * PL_BN);
   }
+  if (stamps != nullptr && threadIdx.x == 0) stamps[7] = clock64();               // exit
 }
 
 // Measurement aid (bench / scripts only): back-to-back tcgen05.mma on one resident shared-memory
@@ -1025,18 +1054,19 @@ extern "C" int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const 
                    nullptr, st, &P.sw));
   }
   CUtensorMap tx, tt, tl;
-  CB_TRY(make_tmap_bf16(&tx, P.xb, T, n, n, TC_BM));
+  CB_TRY(make_tmap_bf16_kblocks(&tx, P.xb, T, n, n, TC_BM, PL_KB));
   if (r > 0) {
     CB_TRY(make_tmap_bf16(&tt, P.tb, T, r, r, TC_BM));
     CB_TRY(make_tmap_bf16(&tl, P.Lb, m, r, r, PL_BN));
   } else {
-    tt = tx; tl = tx;
+    CB_TRY(make_tmap_bf16(&tt, P.xb, T, n, n, TC_BM));     // unused placeholders (no rank-r stages)
+    tl = tt;
   }
   PackedLinearArgs a;
   a.T = (int)T; a.m = (int)m; a.n = (int)n; a.r = (int)r;
   a.nkb_codes = (int)(n / TC_BK); a.nkb_lr = (int)((r + TC_BK - 1) / TC_BK);
   a.packed = q_packed; a.q_scale = q_scale; a.gs = global_scale; a.lv = (float)((1 << (q_bits - 1)) - 1);
-  a.y = y; a.ldy = m; a.error_flag = error_flag;
+  a.y = y; a.ldy = m; a.error_flag = error_flag; a.timing = g_timing;
   dim3 grid((unsigned)((m + PL_BN - 1) / PL_BN), (unsigned)((T + TC_BM - 1) / TC_BM));
 #define CB_PL(BITS)                                                                                                  \
   do {                                                                                                               \

@@ -12,6 +12,7 @@ def timeit(fn,n=20):
     e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)/n*1e3
+stamps=torch.zeros(12,dtype=torch.int64,device=dev)
 for T in (16,4096):
     x=torch.randn(T,n,device=dev); y=torch.empty(T,m,device=dev)
     for r in (0,128):
@@ -19,5 +20,9 @@ for T in (16,4096):
         ws=torch.empty(lib.cb_packed_linear_workspace_bytes(T,m,n,r),dtype=torch.uint8,device=dev)
         f=lambda: lib.cb_packed_linear_f32(_lib.ptr(x),T,n,_lib.ptr(packed),2,_lib.ptr(s),_lib.ptr(L) if r else None,_lib.ptr(R) if r else None,m,r,1.0,_lib.ptr(y),_lib.ptr(flag),_lib.ptr(ws),ws.numel(),_lib.stream_ptr())
         print(f"T={T} r={r}: {timeit(f):.0f} us")
+        lib.cb_set_gemm_timing(_lib.ptr(stamps)); f(); torch.cuda.synchronize(); lib.cb_set_gemm_timing(None)
+        t=stamps.tolist(); e=t[0]
+        print(f"    main kernel CTA 0: prologue {t[1]-e}, first stage complete {t[3]-e}, expansion loop done {t[2]-e}, "
+              f"last stage complete {t[4]-e}, accumulators complete {t[5]-e}, epilogue done {t[6]-e}, exit {t[7]-e} clk")
     xb=torch.empty(T,n,device=dev,dtype=torch.bfloat16)
     print(f"T={T} to_bf16(x) alone: {timeit(lambda: lib.cb_convert_bf16(_lib.ptr(x),T,n,n,_lib.ptr(xb),n,None,0,None,_lib.stream_ptr())):.0f} us")
