@@ -442,7 +442,7 @@ def run_ours(args):
                            "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks,
+                "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "clocks": clocks,
                 "errors_last_layer": [round(e, 6) for e in errs]}
         if world == 1:
             probes = roofline_probes(dev, peaks)
