@@ -526,13 +526,22 @@ jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ eval
           be += __shfl_xor_sync(0xffffffffu, be, o);
           ga += __shfl_xor_sync(0xffffffffu, ga, o);
         }
-        if (live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
-          // rotation parameters in fp64: c and s are then rounded independently, so c^2 + s^2 - 1
-          // has no systematic sign and column norms do not drift over the ~q rotations per sweep
+        const bool rotate = live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f;
+        // rotation parameters in fp64: c and s are then rounded independently, so c^2 + s^2 - 1
+        // has no systematic sign and column norms do not drift over the ~q rotations per sweep.
+        // One lane per group runs the fp64 divide / square-root sequences and the others get the result
+        // by shuffle (same bits as computing it on every lane; measured neutral in time: the round is
+        // bound by streaming the matrix through shared memory).
+        float c = 1.f, sn = 0.f;
+        if (rotate && gl == 0) {
           const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
           const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double cd = 1.0 / sqrt(1.0 + tt * tt);
-          const float c = (float)cd, sn = (float)(cd * tt);
+          c = (float)cd; sn = (float)(cd * tt);
+        }
+        c = __shfl_sync(0xffffffffu, c, lane & ~7);
+        sn = __shfl_sync(0xffffffffu, sn, lane & ~7);
+        if (rotate) {
 #pragma unroll
           for (int k = 0; k < JS_V4; ++k) {
             const int i4 = gl + 8 * k;
@@ -593,7 +602,7 @@ jacobi_cluster_kernel(const float* __restrict__ Lc, int q, float* __restrict__ e
   __shared__ int s_rot;
   const int cta = (int)cluster.block_rank();
   const int nthreads = 32 * LPP;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid / LPP, gl = tid % LPP;
   const int groups_per_cta = nthreads / LPP;           // 32
   const int NG = groups_per_cta * JC_CTAS;             // 256 pairs per pass
@@ -639,11 +648,17 @@ jacobi_cluster_kernel(const float* __restrict__ Lc, int q, float* __restrict__ e
           be += __shfl_xor_sync(0xffffffffu, be, o);
           ga += __shfl_xor_sync(0xffffffffu, ga, o);
         }
-        if (live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f) {
+        const bool rotate = live && fabsf(ga) > tol * sqrtf(al * be) && al > 0.f && be > 0.f;
+        float c = 1.f, sn = 0.f;
+        if (rotate && gl == 0) {        // one lane per group runs the fp64 sequences, see jacobi_smem_kernel
           const double zeta = ((double)be - (double)al) / (2.0 * (double)ga);
           const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double cd = 1.0 / sqrt(1.0 + tt * tt);
-          const float c = (float)cd, sn = (float)(cd * tt);
+          c = (float)cd; sn = (float)(cd * tt);
+        }
+        c = __shfl_sync(0xffffffffu, c, lane & ~(LPP - 1));
+        sn = __shfl_sync(0xffffffffu, sn, lane & ~(LPP - 1));
+        if (rotate) {
 #pragma unroll
           for (int k = 0; k < NV4; ++k) {
             const int i4 = gl + LPP * k;
