@@ -21,10 +21,10 @@ def next_power_of_two(n: int) -> int:
 def hadamard_transform(W: torch.Tensor, inverse: bool = False, original_shape: Optional[Tuple[int, int]] = None):
     """Forward: returns (H1 @ pad(W) @ H2, (rows, cols)).  Inverse: W is the padded-size matrix; returns the
     leading `original_shape` block of H1 @ W @ H2 (H is symmetric and orthogonal, main.py:124-129)."""
-    if not W.is_cuda:
-        raise ValueError("hadamard_transform runs on a CUDA device only (there is no CPU fallback)")
     if inverse and original_shape is None:
         raise ValueError("original_shape is required for the inverse transform")
+    if not W.is_cuda:
+        raise ValueError("hadamard_transform runs on a CUDA device only (there is no CPU fallback)")
     lib = _lib.load()
     rows, cols = (int(W.shape[0]), int(W.shape[1])) if not inverse else (int(original_shape[0]), int(original_shape[1]))
     prows, pcols = next_power_of_two(rows), next_power_of_two(cols)
