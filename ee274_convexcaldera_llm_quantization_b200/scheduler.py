@@ -133,12 +133,14 @@ def gather_blobs(blobs: List[torch.Tensor], dst: Optional[int] = 0, group=None) 
     count = torch.tensor([len(blobs)], dtype=torch.int64, device=device)
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(counts, count, group=group)
-    max_count = max(int(c.item()) for c in counts)
+    counts_host = [int(c) for c in torch.cat(counts).tolist()]          # one device read instead of one per rank
+    max_count = max(counts_host)
     size_pad = torch.zeros(max(max_count, 1), dtype=torch.int64, device=device)
     size_pad[:len(blobs)] = sizes
     all_sizes = [torch.zeros_like(size_pad) for _ in range(world)]
     dist.all_gather(all_sizes, size_pad, group=group)
-    totals = [int(s.sum().item()) for s in all_sizes]
+    sizes_host = torch.stack(all_sizes).tolist()                        # [rank][k], one device read
+    totals = [int(sum(row)) for row in sizes_host]
     max_total = max(max(totals), 1)
     payload = torch.zeros(max_total, dtype=torch.uint8, device=device)
     if blobs:
@@ -155,8 +157,8 @@ def gather_blobs(blobs: List[torch.Tensor], dst: Optional[int] = 0, group=None) 
     out: List[List[torch.Tensor]] = []
     for r in range(world):
         off, items = 0, []
-        for k in range(int(counts[r].item())):
-            sz = int(all_sizes[r][k].item())
+        for k in range(counts_host[r]):
+            sz = int(sizes_host[r][k])
             items.append(bufs[r][off:off + sz])
             off += sz
         out.append(items)
