@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {s}")
             with open(os.path.join(OBJ, os.path.basename(s)[:-3] + ".ptxas.log"), "w") as f:
-                f.write(r.stderr)
+                # registers / spills / shared memory per kernel; compile times vary from run to run and are dropped
+                f.write("".join(line for line in r.stderr.splitlines(keepends=True) if "Compile time" not in line))
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if force or jobs or _stale(LIB, objs):
         r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], capture_output=True, text=True)
