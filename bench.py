@@ -4,18 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Metric (BASELINE.json): decomposed matrices / s at 4096 x 4096, rank 128, 2-bit Q
-(config[1]: L/R 16-bit, activation aware, 5 outer iterations, update_order Q,LR).
+(config[1]: L/R 16-bit, activation aware, 5 outer iterations, update_order Q,LR); second half of the metric:
+wall seconds of the full Llama-2-7B-shape job (config[3]), emitted as `full_7b_wall_s` on the same line.
 One step = one batch of `--streams` independent layers (one full caldera() decomposition each).
 
-  value     matrices/s with inputs resident in HBM (cb_caldera_layer enqueued back to back,
-            CUDA-event timed, max over ranks)
-  e2e       the same through the public API with HOST (pinned) inputs: H2D of W and h, the
-            decomposition, D2H of the packed result, all inside the timed region
+  value     matrices/s with inputs resident in HBM (one CUDA-graph replay per layer, CUDA-event timed, max over ranks)
+  e2e       the same through the public API (caldera_async) with HOST (pinned) inputs: H2D of W and h, the
+            decomposition, D2H of the packed result, all inside the timed region; ONE host thread per rank
+  full_7b_wall_s   224 layers layer-sharded over the ranks + gather of the packed blobs on rank 0, for L/R 16-bit and
+            4-bit (inputs generated on the owning GPU before the clock, as SURVEY 8e prescribes)
+  parity    exact-match fraction of the Q codes (iterate 0 and best iterate) and relative difference of the best
+            error against the stored run of the unmodified reference on the same layer (tests/golden/fullsize_c2*)
   roofline  the dominant kernel, timed alone with CUDA events at the workload's shape
-  cpu_baseline  the numpy port of the reference (oracle/) on the host cores, bounded sample
+  cpu_baseline  the reference on the host cores, bounded sample
+  reference_cuda  informational: the unmodified reference with device="cuda" (torch / cuBLAS / cuSOLVER) on this GPU
 
-`--impl reference` times the oracle port only (the Python reference cannot travel to the
-GPU box) and prints the same line with "impl": "reference".
+`--impl reference` times the UNMODIFIED reference's caldera(device="cpu") (oracle/_ref, copied there by
+__graft_entry__.build() in the build container; the numpy port of oracle/ if that copy is absent) and prints the
+same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -97,17 +103,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_reference_sample(threads=None):
-    """One outer iteration (Q update + LR update, exact SVD, four-product error evaluation)
-    of the workload's layer with the numpy port of the reference; scaled linearly to ITERS."""
-    import numpy as np
-    from oracle import caldera_oracle as orc
-    W, h = synth_layer(0)
-    p = orc.OracleParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=1, update_order=["Q", "LR"])
-    t0 = time.perf_counter()
-    d = orc.caldera_oracle(p, W.numpy(), np.diag(h.numpy()))
-    dt = time.perf_counter() - t0
-    return dt, d
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")      # the unmodified reference sources (git-ignored, see oracle/README)
 
 
 def host_threads():
@@ -117,31 +113,113 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def pin_host_threads(cores):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads."""
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = str(cores)
+    import torch
+    torch.set_num_threads(cores)
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "src", "caldera", "decomposition", "alg.py"))
+
+
+def import_reference():
+    """The reference's own modules from oracle/_ref (its `src` package name collides with this repo's drop-in
+    shim, so it is imported under a private name)."""
+    import importlib.util
+    import types
+    if "caldera_ref" in sys.modules:
+        return sys.modules["caldera_ref"]
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF_DIR)
+    try:
+        alg = importlib.import_module("src.caldera.decomposition.alg")
+        dc = importlib.import_module("src.caldera.utils.dataclasses")
+        qz = importlib.import_module("src.caldera.utils.quantization")
+    finally:
+        sys.path.remove(REF_DIR)
+        ref_mods = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+        for k in ref_mods:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    ns = types.SimpleNamespace(caldera=alg.caldera, CalderaParams=dc.CalderaParams, QuantizerFactory=qz.QuantizerFactory,
+                               modules=ref_mods)
+    sys.modules["caldera_ref"] = ns
+    return ns
+
+
+def reference_layer(device, m=M, n=N, rank=RANK, iters=ITERS, idx=0):
+    """One full caldera() call of the UNMODIFIED reference on the workload's layer.  Returns (seconds, result)."""
+    import torch
+    ref = import_reference()
+    W, h = synth_layer(idx, m, n)
+    qf = ref.QuantizerFactory(method="uniform", block_size=64)
+    p = ref.CalderaParams(compute_quantized_component=True, compute_low_rank_factors=True, Q_bits=2, L_bits=16, R_bits=16,
+                          rank=rank, iters=iters, lplr_iters=5, activation_aware_LR=True, update_order=["Q", "LR"],
+                          quant_factory_Q=qf, quant_factory_LR=qf, rand_svd=False, sigma_reg=0.0)
+    H = torch.diag(h)                       # the caller contract of main.py:165
+    torch.manual_seed(42)
+    if device != "cpu":
+        W, H = W.to(device), H.to(device)
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d = ref.caldera(p, W, H, device=device, use_tqdm=False, scale_W=True)
+    if device != "cpu":
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, d
+
+
+def port_sample():
+    """Fallback when oracle/_ref is absent: one outer iteration of the numpy port, scaled linearly to ITERS."""
+    import numpy as np
+    from oracle import caldera_oracle as orc
+    W, h = synth_layer(0)
+    p = orc.OracleParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=1, update_order=["Q", "LR"])
+    t0 = time.perf_counter()
+    orc.caldera_oracle(p, W.numpy(), np.diag(h.numpy()))
+    return (time.perf_counter() - t0) * ITERS
+
+
+def cpu_sample():
+    """(seconds per layer, kind, description) of one bounded CPU sample of the workload."""
+    if reference_available():
+        dt, d = reference_layer("cpu")
+        return dt, "reference", (f"one full caldera(device='cpu') call of the unmodified reference on a {M}x{N} layer "
+                                 f"(all {ITERS} iterations, exact SVD, 4-product error): {dt:.1f} s; best error "
+                                 f"{min(d.errors['LR']):.6f}")
+    dt = port_sample()
+    return dt, "port", (f"oracle/_ref absent: 1 outer iteration of the numpy port on a {M}x{N} layer scaled x{ITERS}: {dt:.1f} s")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    times = []
-    budget = 240.0
+    pin_host_threads(cores)
+    budget = 200.0
     t_start = time.perf_counter()
-    if args.warmup > 0:
-        cpu_reference_sample()      # one warm-up sample is enough for a ~10 s CPU step
+    if args.warmup > 0 and reference_available():
+        reference_layer("cpu", 256, 256, 16, 1)         # pages the libraries in; a full layer is ~1 minute
+    times, kind, desc = [], "port", ""
     for _ in range(max(args.steps, 1)):
-        dt, _ = cpu_reference_sample()
+        dt, kind, desc = cpu_sample()
         times.append(dt)
         if time.perf_counter() - t_start + dt > budget:
             break
-    per_iter = sum(times) / len(times)
-    value = 1.0 / (per_iter * ITERS)
-    sample = (f"{len(times)} sample(s) of 1 outer iteration (Q+LR, exact SVD) of one {M}x{N} layer, "
-              f"{per_iter:.2f} s each, scaled x{ITERS} iterations")
+    per_layer = sum(times) / len(times)
+    value = 1.0 / per_layer
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_iter * ITERS * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_layer * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "steps_measured": len(times)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "steps_measured": len(times),
+                       "step": "one layer (the GPU arm's step is a batch of layers; the metric is per matrix either way)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{len(times)} sample(s); last: {desc}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -281,8 +359,11 @@ def load_peaks():
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from ee274_convexcaldera_llm_quantization_b200 import _lib
-    from ee274_convexcaldera_llm_quantization_b200.alg import make_c_params, caldera
+    from ee274_convexcaldera_llm_quantization_b200 import _lib, parity
+    from ee274_convexcaldera_llm_quantization_b200 import model_job as mj
+    from ee274_convexcaldera_llm_quantization_b200 import scheduler as sch
+    from ee274_convexcaldera_llm_quantization_b200.alg import make_c_params, caldera, caldera_async
+    from ee274_convexcaldera_llm_quantization_b200.engine import get_engine, release_engines
     from ee274_convexcaldera_llm_quantization_b200.runner import CalderaLayerRunner
     from src.caldera.utils.dataclasses import CalderaParams
     from src.caldera.utils.quantization import QuantizerFactory
@@ -301,14 +382,15 @@ def run_ours(args):
     # many independent layers in flight: the library's throughput mode (small contraction grids that
     # overlap across streams, single-CTA eigensolver); "latency" is the single-layer optimum
     _lib.set_execution_mode(args.mode)
-    if args.gemm_ctas > 0:
-        lib.cb_set_gemm_target_ctas(args.gemm_ctas)
 
     fac = QuantizerFactory(method="uniform", block_size=64)
-    qp = CalderaParams(Q_bits=2, L_bits=16, R_bits=16, rank=RANK, iters=ITERS, lplr_iters=5,
-                       activation_aware_LR=True, update_order=["Q", "LR"], quant_factory_Q=fac,
-                       quant_factory_LR=fac, rand_svd=False, sigma_reg=0)
-    cp = make_c_params(qp, True, seed=1000 + rank)
+
+    def params_for(lbits):
+        return CalderaParams(Q_bits=2, L_bits=lbits, R_bits=lbits, rank=RANK, iters=ITERS, lplr_iters=5,
+                             activation_aware_LR=True, update_order=["Q", "LR"], quant_factory_Q=fac,
+                             quant_factory_LR=fac, rand_svd=False, sigma_reg=0)
+    qp = params_for(16)
+    cp = make_c_params(qp, True, seed=0)
 
     # synthetic layers: distinct per rank (weak scaling: per-GPU work is fixed), pinned on the host
     npool = 3
@@ -317,55 +399,48 @@ def run_ours(args):
         W, h = synth_layer(rank * npool + i)
         host_layers.append((W.pin_memory(), h.pin_memory()))
     dev_layers = [(W.to(dev), h.to(dev)) for W, h in host_layers]
-    # One runner (outputs + ~0.5 GiB workspace) per stream.  Layers are independent, so S of them
-    # are kept in flight: the single-CTA factorisation kernels of one layer (Cholesky, Jacobi)
-    # overlap with the bandwidth/tensor-bound kernels of the others.
-    nstreams = max(1, args.streams)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
-    runners = [CalderaLayerRunner(cp, M, N, _lib.CB_H_DIAG, dev, want_packed=True, want_w_scaled=False)
-               for _ in range(nstreams)]
-    runner = runners[0]
-    if not args.no_graph:
-        for s_, r_ in zip(streams, runners):
-            with torch.cuda.stream(s_):
-                r_.capture()
-        torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- resident timing (value): one CUDA-graph replay per layer, `nstreams` layers in flight, one host thread
+    nstreams = max(1, args.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+    runners = [CalderaLayerRunner(cp, M, N, _lib.CB_H_DIAG, dev, want_packed=True, want_w_scaled=False)
+               for _ in range(nstreams)]
+    runner = runners[0]
+    for s_, r_ in zip(streams, runners):
+        with torch.cuda.stream(s_):
+            r_.capture()
+    torch.cuda.synchronize()
+
     def run_resident(first, count):
-        main = torch.cuda.current_stream()
+        main_stream = torch.cuda.current_stream()
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
-        start.record(main)
+        start.record(main_stream)
         for s_ in streams:
             s_.wait_event(start)
         for i in range(count):
             W, h = dev_layers[(first + i) % npool]
             with torch.cuda.stream(streams[i % nstreams]):
-                if args.no_graph:
-                    runners[i % nstreams].enqueue(W, h)
-                else:
-                    runners[i % nstreams].launch(W, h, seed=1000 + rank)
+                runners[i % nstreams].launch(W, h, seed=1000 + rank)
         for s_ in streams:
             ev = torch.cuda.Event()
             ev.record(s_)
-            main.wait_event(ev)
-        stop.record(main)
+            main_stream.wait_event(ev)
+        stop.record(main_stream)
         return start, stop
 
-    # ---- resident timing (value)
-    run_resident(0, args.warmup * nstreams)
+    batch = nstreams                      # one step = one batch of `nstreams` independent layers
+    run_resident(0, args.warmup * batch)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     launches0 = lib.cb_kernel_launch_count()
-    # one step = one batch of `nstreams` independent layers (one per stream)
-    batch = nstreams
     e0, e1 = run_resident(args.warmup * batch, args.steps * batch)
     barrier()
     launches = lib.cb_kernel_launch_count() - launches0
@@ -376,47 +451,49 @@ def run_ours(args):
     torch.cuda.synchronize()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record()
-    if args.no_graph:
-        runner.enqueue(*dev_layers[0])
-    else:
-        runner.launch(*dev_layers[0], seed=1000 + rank)
+    runner.launch(*dev_layers[0], seed=1000 + rank)
     l1.record()
     torch.cuda.synchronize()
     layer_latency_ms = l0.elapsed_time(l1)
+    kernels_per_layer = runner.graph_kernels
+    del runners, runner, streams
+    torch.cuda.empty_cache()
 
-    # ---- end-to-end timing through the public API, host buffers in, packed result out
-    import concurrent.futures as cf
-    auto_workers = min(24, max(4, 3 * host_threads() // (2 * max(world, 1))))
-    nworkers = max(1, min(nstreams, args.e2e_workers if args.e2e_workers > 0 else auto_workers))
+    # ---- end-to-end timing through the public API: ONE host thread, pinned host buffers in, packed result out.
+    # caldera_async() stages W and h with asynchronous H2D copies on the layer's stream, replays the layer's graph,
+    # and the `consume` hook enqueues the D2H copies of the packed codes and the factors into pinned host buffers;
+    # the ~100-byte result record (error trajectory, scales) follows.  `.result()` is called a batch later, so the
+    # host never waits for the layer it has just submitted.
+    engine = get_engine(dev, nstreams)
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
-                 for _ in range(nworkers)]
-    e2e_streams = [torch.cuda.Stream(device=dev) for _ in range(nworkers)]
+                 for _ in range(nstreams)]
 
-    def step_e2e(i):
-        w = i % nworkers
+    def submit_e2e(i):
         W, h = host_layers[i % npool]
-        torch.cuda.set_device(dev)
-        with torch.cuda.stream(e2e_streams[w]):
-            d = caldera(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank,
-                        use_cuda_graph=not args.no_graph, return_dense=not args.e2e_packed_only)
-            out_hosts[w]["Q_packed"].copy_(d.Q_packed, non_blocking=True)
-            out_hosts[w]["L"].copy_(d.L, non_blocking=True)
-            out_hosts[w]["R"].copy_(d.R, non_blocking=True)
-            e2e_streams[w].synchronize()
-        return d.errors["LR"][-1]
+        dst = out_hosts[i % nstreams]
+
+        def to_host(run, kept):
+            dst["Q_packed"].copy_(run.Q_packed, non_blocking=True)
+            dst["L"].copy_(run.L, non_blocking=True)
+            dst["R"].copy_(run.R, non_blocking=True)
+        return caldera_async(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank, return_dense=False,
+                             return_packed=False, consume=to_host, slots=nstreams)
 
     def run_e2e(first, count):
-        # worker w handles steps w, w + nworkers, ... sequentially on its own stream
-        def work(w):
-            return [step_e2e(first + i) for i in range(w, count, nworkers)]
-        with cf.ThreadPoolExecutor(max_workers=nworkers) as ex:
-            return list(ex.map(work, range(nworkers)))
+        pending, last = [], None
+        for i in range(count):
+            pending.append(submit_e2e(first + i))
+            if len(pending) > nstreams:                  # harvest a layer submitted a whole batch ago
+                last = pending.pop(0).result()
+        for hd in pending:
+            last = hd.result()
+        return last
     e2e_steps = max(1, args.steps)
-    run_e2e(0, max(1, min(args.warmup, 2)) * batch)   # every worker warms its stream, workspace and graph
+    run_e2e(0, max(1, min(args.warmup, 2)) * batch)       # every slot captures its graph
     barrier()
     t0 = time.perf_counter()
-    run_e2e(args.warmup * batch, e2e_steps * batch)
+    last_dec = run_e2e(args.warmup * batch, e2e_steps * batch)
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
     barrier()
@@ -426,24 +503,88 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     secs, e2e_secs = (float(x) for x in tmax.tolist())
     h2d = batch * (M * N * 4 + N * 4)
-    d2h = batch * (M * N // 4 + (M + N) * RANK * 4 + runner.small.numel() * 4)
+    d2h = batch * (M * N // 4 + (M + N) * RANK * 4 + 4 * (ITERS * 2 + 20))
+
+    # ---- parity against the stored run of the unmodified reference on this very layer (rank 0, layer seed 1000)
+    parity_rep = None
+    if rank == 0 and not args.no_parity:
+        try:
+            z, _ = parity.load_fullsize_golden("c2")
+            W0, h0 = host_layers[0]
+            qp0 = params_for(16)
+            qp0.iters, qp0.update_order = 1, ["Q"]            # the first Q update alone: iterate 0
+            d0 = caldera(qp0, W0, h0, device=dev, use_tqdm=False, W_copy="none", global_scale=z["global_scale"],
+                         use_cuda_graph=True)
+            dref = caldera(qp, W0, h0, device=dev, use_tqdm=False, W_copy="none", global_scale=z["global_scale"],
+                           use_cuda_graph=True, seed=1000)
+            parity_rep = parity.parity_report(dref, "c2", d0)
+            parity_rep["best_step"], parity_rep["best_step_reference"] = dref.best_step, z["best_step"]
+            del d0, dref
+        except FileNotFoundError:
+            parity_rep = {"unavailable": "tests/golden/fullsize_c2.json not found"}
+
+    # ---- second half of the metric: the full Llama-2-7B-shape job (config 4), L/R 16-bit and 4-bit
+    full7b = None
+    if not args.no_model:
+        release_engines()
+        torch.cuda.empty_cache()
+        names, shapes = mj.llama_shapes(args.model_blocks)
+        full7b = {"layers": len(names), "params": sum(m * n for m, n in shapes), "rank": RANK, "iters": ITERS,
+                  "streams": args.model_streams, "inputs": "generated on the owning GPU before the clock (SURVEY 8e)",
+                  "timed": "barrier -> all layers decomposed -> packed blobs gathered on rank 0 -> device synchronised; "
+                           "max over ranks; second pass (the first one captures the CUDA graphs)"}
+        shards = sch.shard_layout(params_for(16), shapes, world)[0]
+        store = mj.synth_layers(shapes, shards[rank], dev)
+        sch.warm_up_gather(dev, dst=0)
+        for lbits in (16, 4):
+            prm = params_for(lbits)
+            res = None
+            for attempt in range(2):
+                res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams, barrier=barrier)
+                tt = torch.tensor([res["decompose_s"], res["gather_s"], res["wall_s"]], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                if attempt == 0:
+                    first_pass = float(tt[2])
+                    res = None
+            key = f"lr{lbits}"
+            full7b[key] = {"wall_s": float(tt[2]), "decompose_s": float(tt[0]), "gather_s": float(tt[1]),
+                           "gathered_bytes": int(res["gathered_bytes"]), "first_pass_wall_s_incl_graph_capture": first_pass}
+            if rank == 0:
+                parts = sch.split_gathered(res["arena"], res["shards"], res["sizes"])
+                first = sch.unpack_decomposition(parts[0])
+                full7b[key]["layers_gathered"] = len(parts)
+                full7b[key]["first_layer_best_error"] = min(first["errors"]["LR"])
+            res = None
+            release_engines()
+            torch.cuda.empty_cache()
+        del store
+        torch.cuda.empty_cache()
 
     if rank == 0:
         value = world * args.steps * batch / secs
         e2e_value = world * e2e_steps * batch / e2e_secs
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 I/O, bf16 tensor-core operands, f32 accumulate (f32 small factorisations)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "inputs larger than L2: every layer in flight has a ~0.5 GiB working set (126 MB L2), 3 input "
                                  "layers rotated; the roofline probes rotate >= 192 MB of operands",
-                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": nworkers, "e2e_result": "packed Q codes + scale, L, R" if args.e2e_packed_only else "dense + packed",
-                           "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": not args.no_graph, "single_layer_latency_ms": layer_latency_ms,
+                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": 1,
+                           "e2e_result": "packed Q codes + scale, L, R, error trajectory",
+                           "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": True, "single_layer_latency_ms": layer_latency_ms,
+                           "kernels_per_layer": kernels_per_layer,
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "clocks": clocks,
-                "errors_last_layer": [round(e, 6) for e in errs]}
+                "errors_last_layer": [round(e, 6) for e in errs],
+                "e2e_errors_last_layer": {k: [round(e, 6) for e in v] for k, v in last_dec.errors.items()},
+                "parity": parity_rep}
+        if full7b is not None:
+            line["full_7b_wall_s"] = {k: v["wall_s"] for k, v in full7b.items() if isinstance(v, dict)}
+            line["full_7b"] = full7b
         if world == 1:
             probes = roofline_probes(dev, peaks)
             dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_tcgen05")
@@ -458,11 +599,19 @@ def run_ours(args):
             line["roofline_all"] = probes
             if not args.no_cpu:
                 cores = host_threads()
-                dt, _ = cpu_reference_sample()
-                v = 1.0 / (dt * ITERS)
-                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                        "sample": f"1 outer iteration (Q+LR, exact SVD, 4-product error) of one "
-                                                  f"{M}x{N} layer with the numpy port: {dt:.2f} s, scaled x{ITERS}"}
+                pin_host_threads(cores)
+                dt, kind, desc = cpu_sample()
+                line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+            if not args.no_ref_cuda and reference_available():
+                # informational: what a user of the reference gets today on this GPU (torch / cuBLAS / cuSOLVER)
+                try:
+                    reference_layer(str(dev), 512, 512, 16, 1)
+                    dt, dref = reference_layer(str(dev))
+                    line["reference_cuda"] = {"value": 1.0 / dt, "unit": UNIT, "seconds_per_layer": dt,
+                                              "best_error": float(min(dref.errors["LR"])),
+                                              "what": "the unmodified reference's caldera(device='cuda') on the same layer, one call"}
+                except Exception as exc:      # noqa: BLE001  (informational leg must not take the bench down)
+                    line["reference_cuda"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -475,16 +624,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
-    ap.add_argument("--e2e-dense", dest="e2e_packed_only", action="store_false",
-                    help="e2e leg: also materialise the dense fp32 Q / int8 codes copies in the returned decomposition "
-                         "(default: packed codes + factors only, which is what is copied back to the host)")
+    ap.add_argument("--no-model", action="store_true", help="skip the full Llama-2-7B-shape job (full_7b_wall_s)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity report against the stored reference run")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
+    ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
+    ap.add_argument("--model-streams", type=int, default=24, help="layers in flight per GPU in the model-level job")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="library execution mode (cb_set_execution_mode)")
-    ap.add_argument("--gemm-ctas", type=int, default=0, help="grid-size target of the tcgen05 contractions (0 = library default)")
     ap.add_argument("--streams", type=int, default=32, help="independent layers kept in flight per GPU")
-    ap.add_argument("--e2e-workers", type=int, default=0,
-                    help="host threads driving the public API in the e2e leg (0 = min(24, 1.5 x host cores / ranks), at least 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

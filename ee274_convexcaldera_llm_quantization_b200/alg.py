@@ -19,71 +19,40 @@ from .runner import CalderaLayerRunner, workspace_bytes
 
 import os
 import threading
-import time
 
 # Scratch arenas are reused across calls (one per device and calling thread): a layer needs
 # ~0.5 GiB of workspace at 4096 x 4096 and re-allocating it per call costs more than the H2D copy.
 _WS_CACHE = {}
 
 
+_WS_CACHE_MAX_BYTES = int(os.environ.get("CB_WS_CACHE_MAX_BYTES", str(8 << 30)))
+
+
 def _cached_workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
     key = (dev.index, threading.get_ident())
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < nbytes:
-        _WS_CACHE[key] = None
+        _WS_CACHE.pop(key, None)
+        # bounded by bytes, not by entries: arenas of threads that are gone are dropped oldest first
+        while _WS_CACHE and sum(t.numel() for t in _WS_CACHE.values()) + nbytes > _WS_CACHE_MAX_BYTES:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _WS_CACHE[key] = ws
+        if nbytes <= _WS_CACHE_MAX_BYTES:
+            _WS_CACHE[key] = ws
     return ws
 
 
 def release_workspaces() -> None:
     """Drops the cached scratch arenas and captured graphs (otherwise kept for the life of the process)."""
+    from .engine import release_engines
     _WS_CACHE.clear()
-    _GRAPH_CACHE.clear()
+    release_engines()
 
 
-# Captured CUDA graphs of the whole layer.  Runners (graph + fixed input/output buffers + workspace)
-# are pooled per (device, parameters, shape): a call borrows an idle one -- or captures a new one --
-# and hands it back when its results have been copied out, so concurrent callers (threads/streams)
-# each replay their own graph and a warm pool is reused by whoever comes next.
-_GRAPH_CACHE = {}
-_GRAPH_LOCK = threading.Lock()
-_GRAPH_POOL_MAX = 32
-
-
-def _params_signature(p) -> tuple:
-    return tuple(getattr(p, name) if name != "order" else tuple(p.order)
-                 for name, _ in p._fields_ if name != "seed")
-
-
-def _acquire_graph_runner(p, m, n, h_kind, dev, want_packed, want_w_scaled):
-    key = (dev.index, _params_signature(p), m, n, h_kind, want_packed, want_w_scaled, _lib.execution_mode())
-    with _GRAPH_LOCK:
-        pool = _GRAPH_CACHE.setdefault(key, [])
-        if pool:
-            return key, pool.pop()
-    run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=want_packed, want_w_scaled=want_w_scaled)
-    run.capture()
-    return key, run
-
-
-def _release_graph_runner(key, run) -> None:
-    with _GRAPH_LOCK:
-        pool = _GRAPH_CACHE.setdefault(key, [])
-        if len(pool) < _GRAPH_POOL_MAX:
-            pool.append(run)
-
-
+# Captured CUDA graphs of the whole layer live in the per-device LayerEngine (engine.py): slots of
+# stream + workspace arena + graphs, LRU-bounded by bytes; caldera(use_cuda_graph=True) and caldera_async()
+# submit to it.
 _ORDER_CODE = {"Q": 0, "LR": 1}
-
-# optional host-side phase timers of the graph path (CB_CALDERA_TIMES=1): seconds summed over calls/threads
-_PHASE_TIMES = {"acquire": 0.0, "launch": 0.0, "wait": 0.0, "copy_out": 0.0, "calls": 0}
-_PHASE_ON = bool(os.environ.get("CB_CALDERA_TIMES"))
-
-
-def phase_times() -> dict:
-    return dict(_PHASE_TIMES)
-
 
 def _resolve_device(device, W: torch.Tensor) -> torch.device:
     dev = torch.device(device) if device is not None else W.device
@@ -163,6 +132,144 @@ def _check_factories(quant_params: CalderaParams):
                 "(the CALDERA hot path is pinned to method='uniform').")
 
 
+def _validate(quant_params: CalderaParams, W: torch.Tensor):
+    if len(W.shape) != 2:
+        raise ValueError(f"Support only for 2D matrix, but your input has {len(W.shape)} dimensions.")
+    _check_factories(quant_params)
+    quant_factors = bool(quant_params.compute_low_rank_factors) and (quant_params.L_bits < 16 or quant_params.R_bits < 16)
+    if quant_params.compute_quantized_component:
+        assert quant_params.Q_bits in (2, 4, 8, 16), "Bit-width not supported!"
+    if quant_factors:
+        assert quant_params.L_bits in (2, 4, 8, 16) and quant_params.R_bits in (2, 4, 8, 16), "Bit-width not supported!"
+        if quant_params.lplr_iters < 1 and "LR" in quant_params.update_order and quant_params.iters > 0:
+            # the reference dereferences best_L_quant_out = None (alg.py:190)
+            raise AttributeError("'NoneType' object has no attribute 'A_idxs'")
+    return quant_factors
+
+
+def _build_decomposition(quant_params, p, m, n, scale_W, quant_factors, host, nsteps, nerr_pad, t, W_copy, dev):
+    """CalderaDecomposition from the layer's host record (errors | scalars | scales) and its device tensors `t`."""
+    errs = host[:nsteps].tolist()
+    scal = host[nerr_pad:nerr_pad + 8]
+    best_step = int(scal[2].item())
+    errors = {name: [] for name in quant_params.update_order}
+    k = 0
+    for _ in range(p.iters):
+        for name in quant_params.update_order:
+            errors[name].append(errs[k])
+            k += 1
+    taken = best_step >= 0
+    f32 = dict(dtype=torch.float32, device=dev)
+    dec = CalderaDecomposition(Q=t.get("Q"), L=t.get("L"), R=t.get("R"))
+    dec.scaleWH = None
+    dec.SU = torch.ones(n, **f32)
+    dec.SV = torch.ones(m, **f32)
+    if taken and p.compute_q:
+        dec.Q_idxs = t.get("Q_idxs")
+        dec.Q_scale = t["Q_scale"].reshape(1, 1)
+        dec.Q_packed = t.get("Q_packed")
+    if taken and quant_factors:
+        dec.L_idxs, dec.R_idxs = t.get("L_idxs"), t.get("R_idxs")
+        dec.L_scale, dec.R_scale = t["L_scale"].reshape(1, 1), t["R_scale"].reshape(1, 1)
+        dec.L_packed, dec.R_packed = t.get("L_packed"), t.get("R_packed")
+    Wkeep = t.get("W")
+    if W_copy == "cpu":
+        dec.W = Wkeep.cpu()
+    elif W_copy == "device":
+        dec.W = Wkeep
+    else:
+        dec.W = None
+    dec.errors = errors
+    dec.global_scale = float(scal[0].item()) if scale_W else 1
+    dec.best_step = best_step
+    stats = scal[4:8].view(torch.int32).tolist()
+    dec.device_stats = {"lplr_updates_without_iterate": stats[0], "cholesky_retries": stats[1], "jacobi_sweeps": stats[2],
+                        "tc_watchdog": stats[3]}
+    if stats[3] != 0:
+        raise _lib.CalderaRuntimeError(2001, "caldera: tcgen05 pipeline watchdog fired")
+    if stats[1] >= 99:
+        # the analogue of the reference's pinv fallback (alg.py:164-165) ran out: the normal equations stayed
+        # indefinite after the three ridge retries, so L / R hold garbage
+        raise _lib.CalderaRuntimeError(2000, "caldera: Cholesky factorisation failed even after the ridge retries "
+                                             "(rank-deficient or non-finite factors)")
+    if stats[0] != 0:
+        # every inner LPLR error was NaN: the reference dereferences best_L_quant_out = None here (alg.py:190)
+        raise AttributeError("'NoneType' object has no attribute 'A_idxs'")
+    return dec
+
+
+_OUT_FIELDS = ("Q", "L", "R", "Q_idxs", "L_idxs", "R_idxs", "Q_packed", "L_packed", "R_packed", "Q_scale", "L_scale", "R_scale")
+_DENSE_FIELDS = ("Q", "Q_idxs", "L_idxs", "R_idxs")
+
+
+def caldera_async(
+    quant_params: CalderaParams,
+    W: torch.Tensor,
+    H: torch.Tensor = None,
+    device: str = "cuda",
+    use_tqdm: bool = True,
+    scale_W: bool = True,
+    *,
+    W_copy: str = "none",
+    global_scale: Optional[float] = None,
+    sketch_width: int = 0,
+    power_iters: int = -1,
+    power_iters_warm: int = -1,
+    warm_start: bool = True,
+    seed: int = 0,
+    return_packed: bool = True,
+    use_tensor_cores: bool = True,
+    return_dense: bool = True,
+    consume=None,
+    slots: Optional[int] = None,
+):
+    """caldera() without the wait: enqueues the layer on the device's LayerEngine (engine.py) and returns a handle
+    whose `.result()` is the CalderaDecomposition.  One host thread can keep dozens of layers in flight this way
+    (the engine only blocks the caller when all of its slots are busy).  W / H may be pinned host tensors (staged
+    by asynchronous copies) or device tensors.  Arguments are caldera()'s; additionally
+    consume(run, kept)  optional hook called with the layer's stream current right after the layer was enqueued: it
+             may enqueue device-side copies of the runner's outputs (run.Q_packed, run.L, ...) to wherever they
+             are going (a wire-format arena, pinned host buffers); with a hook, and return_dense / return_packed
+             False, no per-layer clones are made at all;
+    slots    layers kept in flight by the engine (first use per device decides; default 32)."""
+    del use_tqdm
+    quant_factors = _validate(quant_params, W)
+    dev = _resolve_device(device, W)
+    _lib.load()
+    m, n = int(W.shape[0]), int(W.shape[1])
+    from .engine import get_engine
+    with torch.cuda.device(dev):
+        if H is not None and not H.is_cuda and H.dim() == 1:
+            # a host-side diagonal (ideally pinned) is staged by the engine's asynchronous copy
+            if H.numel() != n:
+                raise ValueError(f"diagonal Hessian has {H.numel()} entries, expected {n}")
+            h_kind, Hd = _lib.CB_H_DIAG, (H if H.dtype == torch.float32 else H.float())
+        else:
+            h_kind, Hd = _classify_hessian(H, n, dev)
+        p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, 0,
+                          use_tensor_cores, power_iters_warm)
+        want_w = W_copy != "none"
+        keep = [f for f in _OUT_FIELDS if (return_dense or f not in _DENSE_FIELDS) and (return_packed or "packed" not in f)]
+
+        def consume_all(run, kept):
+            for f in keep:
+                t = getattr(run, f)
+                if t is not None:
+                    kept[f] = t.clone()
+            if want_w:
+                kept["W"] = (run.W_scaled if scale_W else run.W_in).clone()
+            if consume is not None:
+                consume(run, kept)
+
+        def finish(run, host, kept):
+            return _build_decomposition(quant_params, p, m, n, scale_W, quant_factors, host, run.nsteps, run.nerr_pad,
+                                        kept, W_copy, dev)
+
+        Wsrc = W if W.dtype == torch.float32 else W.float()
+        return get_engine(dev, slots).submit(p, Wsrc, h_kind, Hd, seed, finish, want_packed=return_packed,
+                                             want_w_scaled=want_w and scale_W, consume=consume_all)
+
+
 def caldera(
     quant_params: CalderaParams,
     W: torch.Tensor,
@@ -194,116 +301,42 @@ def caldera(
              (power iterations of the first, random-start step -- default 12 -- and of the steps warm-started
              from the previous outer iteration's basis -- default 3; rand_svd=True: 2 and 2);
     use_tensor_cores  bf16 tcgen05 contractions for aligned shapes (default) or fp32 SIMT everywhere;
-    use_cuda_graph  replay a captured CUDA graph of the layer (cached per shape/parameters/thread);
+    use_cuda_graph  replay a captured CUDA graph of the layer through the device's LayerEngine
+             (== caldera_async(...).result());
     return_packed  also return bit-packed codes as Q_packed / L_packed / R_packed;
     return_dense  False: leave Q, Q_idxs (and L_idxs / R_idxs) unset -- for callers that only consume the packed
              codes, scales and factors (the model-level job), which saves the m x n fp32 + int8 copies per layer.
     `use_tqdm` is accepted and ignored (the loop runs on the device).
     """
-    if len(W.shape) != 2:
-        raise ValueError(f"Support only for 2D matrix, but your input has {len(W.shape)} dimensions.")
-    _check_factories(quant_params)
+    if use_cuda_graph:
+        return caldera_async(quant_params, W, H, device, use_tqdm, scale_W, W_copy=W_copy, global_scale=global_scale,
+                             sketch_width=sketch_width, power_iters=power_iters, power_iters_warm=power_iters_warm,
+                             warm_start=warm_start, seed=seed, return_packed=return_packed,
+                             use_tensor_cores=use_tensor_cores, return_dense=return_dense).result()
+    quant_factors = _validate(quant_params, W)
     dev = _resolve_device(device, W)
-    lib = _lib.load()
+    _lib.load()
     m, n = int(W.shape[0]), int(W.shape[1])
-    r = int(quant_params.rank)
-    quant_factors = bool(quant_params.compute_low_rank_factors) and (quant_params.L_bits < 16 or quant_params.R_bits < 16)
-    if quant_params.compute_quantized_component:
-        assert quant_params.Q_bits in (2, 4, 8, 16), "Bit-width not supported!"
-    if quant_factors:
-        assert quant_params.L_bits in (2, 4, 8, 16) and quant_params.R_bits in (2, 4, 8, 16), "Bit-width not supported!"
-        if quant_params.lplr_iters < 1 and "LR" in quant_params.update_order and quant_params.iters > 0:
-            # the reference dereferences best_L_quant_out = None (alg.py:190)
-            raise AttributeError("'NoneType' object has no attribute 'A_idxs'")
-
     with torch.cuda.device(dev):
-        # graph mode stages W straight into the captured graph's input buffer (one H2D copy)
-        Wd = None if use_cuda_graph else W.to(dev, torch.float32, non_blocking=True).contiguous()
+        Wd = W.to(dev, torch.float32, non_blocking=True).contiguous()
         h_kind, Hd = _classify_hessian(H, n, dev)
         p = make_c_params(quant_params, scale_W, global_scale, sketch_width, power_iters, warm_start, seed,
                           use_tensor_cores, power_iters_warm)
-
-        f32 = dict(dtype=torch.float32, device=dev)
-        if use_cuda_graph:
-            p.seed = 0
-            t0 = time.perf_counter()
-            graph_key, run = _acquire_graph_runner(p, m, n, h_kind, dev, return_packed, W_copy != "none")
-            t1 = time.perf_counter()
-            run.launch(W, Hd, seed)
-            t2 = time.perf_counter()
-            host = run.read_small()                       # the one synchronisation of the layer
-            t3 = time.perf_counter()
-            clone = lambda t: None if t is None else t.clone()   # noqa: E731  (graph buffers are reused)
-        else:
-            ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
-            run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
-                                     want_w_scaled=(W_copy != "none"), workspace=ws)
-            run.enqueue(Wd, Hd)
-            host = run.read_small()                       # the one synchronisation of the layer
-            clone = lambda t: t                           # noqa: E731
-            run.ws = None                                 # the arena stays in the per-thread cache
-            del ws
-        nsteps = run.nsteps
-        dense = clone if return_dense else (lambda t: None)       # noqa: E731
-        Q, L, R = dense(run.Q), clone(run.L), clone(run.R)
-        Q_idxs, L_idxs, R_idxs = dense(run.Q_idxs), dense(run.L_idxs), dense(run.R_idxs)
-        Q_packed, L_packed, R_packed = clone(run.Q_packed), clone(run.L_packed), clone(run.R_packed)
-        # (cloned here, before the runner goes back to the pool where another thread may replay it)
-        Q_scale, L_scale, R_scale = clone(run.Q_scale), clone(run.L_scale), clone(run.R_scale)
-        W_scaled = clone(run.W_scaled)
-        if use_cuda_graph:
-            if not scale_W:
-                Wd = run.W_in.clone()
-            torch.cuda.current_stream().synchronize()     # copies out of the graph's buffers are done
-            _release_graph_runner(graph_key, run)
-            if _PHASE_ON:
-                t4 = time.perf_counter()
-                with _GRAPH_LOCK:
-                    for key_, dt_ in (("acquire", t1 - t0), ("launch", t2 - t1), ("wait", t3 - t2), ("copy_out", t4 - t3)):
-                        _PHASE_TIMES[key_] += dt_
-                    _PHASE_TIMES["calls"] += 1
-
-    errs = host[:nsteps].tolist()
-    scal = host[run.nerr_pad:run.nerr_pad + 8]
-    best_step = int(scal[2].item())
-    errors = {name: [] for name in quant_params.update_order}
-    k = 0
-    for _ in range(p.iters):
-        for name in quant_params.update_order:
-            errors[name].append(errs[k])
-            k += 1
-
-    taken = best_step >= 0
-    dec = CalderaDecomposition(Q=Q, L=L, R=R)
-    dec.scaleWH = None
-    dec.SU = torch.ones(n, **f32)
-    dec.SV = torch.ones(m, **f32)
-    if taken and p.compute_q:
-        dec.Q_idxs = Q_idxs
-        dec.Q_scale = Q_scale.reshape(1, 1) if use_cuda_graph else Q_scale.clone().reshape(1, 1)
-        dec.Q_packed = Q_packed
-    if taken and quant_factors:
-        dec.L_idxs, dec.R_idxs = L_idxs, R_idxs
-        if use_cuda_graph:
-            dec.L_scale, dec.R_scale = L_scale.reshape(1, 1), R_scale.reshape(1, 1)
-        else:
-            dec.L_scale, dec.R_scale = L_scale.clone().reshape(1, 1), R_scale.clone().reshape(1, 1)
-        dec.L_packed, dec.R_packed = L_packed, R_packed
-    Wkeep = W_scaled if scale_W else Wd
-    if W_copy == "cpu":
-        dec.W = Wkeep.cpu()
-    elif W_copy == "device":
-        dec.W = Wkeep
-    else:
-        dec.W = None
-    dec.errors = errors
-    dec.global_scale = float(scal[0].item()) if scale_W else 1
-    dec.best_step = best_step
-    stats = scal[5:8].view(torch.int32).tolist()
-    dec.device_stats = {"cholesky_retries": stats[0], "jacobi_sweeps": stats[1], "tc_watchdog": stats[2]}
-    if stats[2] != 0:
-        raise _lib.CalderaRuntimeError(2001, "caldera: tcgen05 pipeline watchdog fired")
-    return dec
+        ws = _cached_workspace(workspace_bytes(p, m, n, h_kind), dev)
+        run = CalderaLayerRunner(p, m, n, h_kind, dev, want_packed=return_packed,
+                                 want_w_scaled=(W_copy != "none"), workspace=ws)
+        run.enqueue(Wd, Hd)
+        host = run.read_small()                       # the one synchronisation of the layer
+        run.ws = None                                 # the arena stays in the per-thread cache
+        del ws
+        t = {f: getattr(run, f) for f in _OUT_FIELDS
+             if getattr(run, f) is not None and (return_dense or f not in _DENSE_FIELDS)}
+        for f in ("Q_scale", "L_scale", "R_scale"):   # views into the runner's result record
+            if f in t:
+                t[f] = t[f].clone()
+        t["W"] = run.W_scaled if scale_W else Wd
+        return _build_decomposition(quant_params, p, m, n, scale_W, quant_factors, host, run.nsteps, run.nerr_pad,
+                                    t, W_copy, dev)
 
 
 def activation_aware_error(W: torch.Tensor, H: torch.Tensor, caldera_info: CalderaDecomposition, device: str):

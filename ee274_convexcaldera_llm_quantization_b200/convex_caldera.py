@@ -9,6 +9,14 @@ CPU restatement it is tested against are in oracle/convex_oracle.py.  Steps 3-6
 (round_bit_allocations :244-273, low_rank_factorization :276-339, quantize_residual :342-373,
 compute_certificates :376-419) follow the reference arithmetic.
 
+`params.solver = "SVD"` selects what the reference itself does whenever its solver raises (the `except`
+branch, :233-241: L* = rank-min(128, .) truncated SVD of W, R* = W - L*, b* = b_min, status "failed"); that
+branch is what tests/golden/convex.npz pins end to end against the unmodified reference.
+
+The step functions are also exported under the reference's names (`compute_hessian_and_sensitivities`,
+`round_bit_allocations`, `low_rank_factorization`, `quantize_residual`, `compute_certificates`) and run on
+the GPU; they take torch tensors (any device) or numpy arrays.
+
 Scope of this build: identity or diagonal Hessians (a dense matrix whose off-diagonal entries
 are all zero is accepted); a genuinely dense H or `calibration_data` raises
 NotImplementedError.  There is no CPU fallback.
@@ -83,6 +91,128 @@ def _sum_stats(lib, x: torch.Tensor, y: Optional[torch.Tensor] = None):
     return acc.tolist()
 
 
+def _as_device_f32(x, dev: torch.device) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(dev, torch.float32).contiguous()
+
+
+def compute_hessian_and_sensitivities(W, H=None, calibration_data=None, device: str = "cuda"):
+    """Step 1 (convex_caldera.py:85-125): (H_sqrt, kappa, c).  kappa = ||W||_F and c = 0.1 var(W) come from one
+    fused reduction on the GPU.  H_sqrt is returned as the reference does (dense n x n) for an identity or
+    diagonal Hessian -- the solver itself never forms it (it keeps the diagonal)."""
+    dev = _resolve_device(device, W if torch.is_tensor(W) else torch.empty(0))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        Wd = _as_device_f32(W, dev)
+        n = int(Wd.shape[1])
+        if H is None and calibration_data is not None:
+            raise NotImplementedError("convex_caldera: Hessians from calibration_data (dense X^T X) are not built "
+                                      "in the B200 path yet; pass the diagonal of H")
+        h_kind, Hd = _classify_hessian(None if H is None else _as_device_f32(H, dev), n, dev)
+        if h_kind == _lib.CB_H_DENSE:
+            raise NotImplementedError("convex_caldera: dense (non-diagonal) Hessians are not built in the B200 path yet")
+        hdiag = torch.ones(n, dtype=torch.float32, device=dev) if Hd is None else Hd.clamp_min(1e-8)   # :113
+        s1, s2, _ = _sum_stats(lib, Wd)
+        numel = Wd.numel()
+        kappa = math.sqrt(s2)                                       # torch.norm(W, 'fro') (:120)
+        c = 0.1 * (s2 - s1 * s1 / numel) / max(numel - 1, 1)        # torch.var(W) * 0.1, unbiased (:123)
+        return torch.diag(hdiag.sqrt()), kappa, c
+
+
+def _truncated_svd(lib, A: torch.Tensor, r: int, q: int, power_iters: int, seed: int):
+    """U sqrt(S) (m x r), sqrt(S) V^T (r x n) and S (r) of A by the library's subspace iteration + Rayleigh-Ritz
+    (cb_lowrank_init, not activation aware).  q == min(m, n) makes it a full (not randomized) decomposition."""
+    m, n = int(A.shape[0]), int(A.shape[1])
+    dev = A.device
+    Lf = torch.empty((m, r), dtype=torch.float32, device=dev)
+    Rf = torch.empty((r, n), dtype=torch.float32, device=dev)
+    sig = torch.empty(r, dtype=torch.float32, device=dev)
+    nb = int(lib.cb_lowrank_init_workspace_bytes(m, n, r, q, _lib.CB_H_IDENTITY))
+    if nb == 0:
+        raise ValueError(f"truncated SVD: rank {r} / sketch width {q} not supported for a {m} x {n} matrix (q <= 512)")
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    _lib.check(lib.cb_lowrank_init(_lib.ptr(A), m, n, None, _lib.CB_H_IDENTITY, r, q, int(power_iters), int(seed), 0,
+                                   _lib.ptr(Lf), _lib.ptr(Rf), _lib.ptr(sig), _lib.ptr(ws), nb, _lib.stream_ptr()),
+               "lowrank_init")
+    return Lf, Rf, sig
+
+
+# Singular values are obtained through the q x q Gram matrix of the projected factor (fp32), which resolves them
+# down to ~sqrt(eps_fp32) of the largest one; the reference's "sigma > 1e-6 sigma_1" rank rule (:310-311, applied
+# there to a float64 SVD) is therefore applied with this floor.
+_SIGMA_FLOOR = 1e-3
+
+
+def _rank_rule(s_host: np.ndarray, tau_star: Optional[float]) -> int:
+    """convex_caldera.py:302-311 on singular values that are already at hand."""
+    if len(s_host) == 0 or not s_host[0] > 0:
+        return 0
+    if tau_star is not None:
+        return int(min(np.searchsorted(np.cumsum(s_host), tau_star) + 1, len(s_host)))
+    return int(np.sum(s_host > s_host[0] * max(1e-6, _SIGMA_FLOOR)))
+
+
+def _quantize_factor_(lib, A: torch.Tensor, factor_bits: int) -> None:
+    """In place: round(A / max|A| * lv) / lv * max|A| (convex_caldera.py:326-335), one scale per tensor."""
+    assert factor_bits in (2, 4, 8, 16), "Bit-width not supported!"
+    sc_ = torch.empty(1, dtype=torch.float32, device=A.device)
+    _lib.check(lib.cb_quantize_f32(_lib.ptr(A), A.shape[0], A.shape[1], A.stride(0), A.stride(1), factor_bits, 0, 0.0,
+                                   None, None, _lib.ptr(sc_), _lib.ptr(A), _lib.stream_ptr()), "quantize factors")
+
+
+def low_rank_factorization(L_star, tau_star: Optional[float] = None, mu: Optional[float] = None, quantize: bool = False,
+                           factor_bits: int = 16, *, device: str = "cuda", rank_cap: int = 512, power_iters: int = 4,
+                           seed: int = 0):
+    """Step 4 (convex_caldera.py:276-339): L = U sqrt(S), R = sqrt(S) V^T of L*, truncated by the nuclear-norm
+    bound (constrained form) or the relative threshold (penalty form), optionally re-quantised.  The SVD runs on
+    the GPU (full decomposition when min(m, n) <= rank_cap <= 512, randomized above that).  Returns
+    (L, R, effective_rank) like the reference."""
+    del mu
+    dev = _resolve_device(device, L_star if torch.is_tensor(L_star) else torch.empty(0))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        A = _as_device_f32(L_star, dev)
+        m, n = int(A.shape[0]), int(A.shape[1])
+        r = max(1, min(int(rank_cap), 512, m, n))
+        q = r if r == min(m, n) else min(max(2 * r, r + 32), 512, m, n)
+        Lf, Rf, sig = _truncated_svd(lib, A, r, q, power_iters, seed)
+        rank = _rank_rule(sig.double().cpu().numpy(), tau_star)
+        Lf, Rf = Lf[:, :rank].contiguous(), Rf[:rank, :].contiguous()
+        if quantize and rank > 0:
+            _quantize_factor_(lib, Lf, factor_bits)
+            _quantize_factor_(lib, Rf, factor_bits)
+    return Lf, Rf, rank
+
+
+def quantize_residual(R_star, b_discrete: int, *, device: str = "cuda"):
+    """Step 5 (convex_caldera.py:342-373): (R_quantized, delta) on the residual grid delta = 2 max|R| / (2^b - 1)."""
+    dev = _resolve_device(device, R_star if torch.is_tensor(R_star) else torch.empty(0))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        R = _as_device_f32(R_star, dev)
+        Rq = torch.empty_like(R)
+        dd = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.cb_quantize_residual_f32(_lib.ptr(R), None, R.shape[0], R.shape[1], int(b_discrete), _lib.ptr(Rq),
+                                                None, _lib.ptr(dd[0:1]), _lib.ptr(dd[1:2]), _lib.stream_ptr()),
+                   "quantize_residual")
+        return Rq, float(dd[0].item())
+
+
+def compute_certificates(W, W_compressed, b_discrete: int, effective_rank: float, objective_value: float,
+                         p: float = 1.0, *, device: str = "cuda") -> Dict[str, float]:
+    """Step 6 (convex_caldera.py:376-419)."""
+    del p
+    dev = _resolve_device(device, W if torch.is_tensor(W) else torch.empty(0))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _, w_sq, diff_sq = _sum_stats(lib, _as_device_f32(W, dev), _as_device_f32(W_compressed, dev))
+    residual_norm = math.sqrt(diff_sq)
+    relative_error = residual_norm / math.sqrt(w_sq)
+    return {"avg_bit_width": b_discrete, "effective_rank": effective_rank, "residual_norm": residual_norm,
+            "relative_error": relative_error, "duality_gap": relative_error, "objective_value": objective_value}
+
+
 def convex_caldera(
     W: torch.Tensor,
     H: Optional[torch.Tensor] = None,
@@ -136,52 +266,67 @@ def convex_caldera(
         c = 0.1 * (s2 - s1 * s1 / numel) / max(numel - 1, 1)   # torch.var(W) * 0.1, unbiased (:123)
 
         # ---- Step 2: convex solve (reduced program, oracle/convex_oracle.py)
-        b_star = min(params.b_max, params.B_tot / p)
-        if b_star < params.b_min:
-            raise ValueError(f"convex_caldera: bit budget infeasible (B_tot / p = {params.B_tot / p} < b_min = {params.b_min})")
         constrained = params.tau_star is not None
-        mu = -1.0 if constrained else float(params.mu)
-        tau = float(params.tau_star) if constrained else 0.0
-        q0 = c * math.exp(-params.k * b_star)
-        step_t = 1.0 / (2.0 * lam_max)
-        r = max(1, min(int(rank_cap), m, n))
-        q = int(sketch_width) if sketch_width > 0 else min(max(2 * r, r + 32), m, n)
-        if sketch_width <= 0 and q > 224 and r + 32 <= 224:
-            q = 224
-        q = max(min(q, 512, m, n), r)
         f32 = dict(dtype=torch.float32, device=dev)
-        L, Lp, R, Rp = (torch.zeros((m, n), **f32) for _ in range(4))
-        Lf = torch.empty((m, r), **f32)
-        Rf = torch.empty((r, n), **f32)
-        svals = torch.zeros(2 * r, **f32)
-        scal = torch.zeros(8, dtype=torch.float64, device=dev)
-        ws_bytes = lib.cb_convex_prox_workspace_bytes(m, n, r, q, int(use_tensor_cores))
-        if ws_bytes == 0:
-            raise ValueError("convex_caldera: invalid rank_cap / sketch_width for this shape")
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        theta = C.c_double(1.0)
-        prev_obj, obj, status, done, warm = float("inf"), float("inf"), "max_iters", 0, 0
-        while done < max_iters:
-            step = min(check_every, max_iters - done)
-            st = lib.cb_convex_prox_iters(_lib.ptr(Wd), _lib.ptr(h), m, n, mu, tau, float(params.lambda_reg),
-                                          kappa, q0, step_t, r, q, int(power_iters), int(seed) + done, warm,
-                                          int(use_tensor_cores), step, C.byref(theta), _lib.ptr(L), _lib.ptr(Lp),
-                                          _lib.ptr(R), _lib.ptr(Rp), _lib.ptr(Lf), _lib.ptr(Rf), _lib.ptr(svals),
-                                          _lib.ptr(scal), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-            _lib.check(st, "convex_prox_iters")
-            warm = 1
-            done += step
-            nuc, _alpha, r_sq, smooth = scal[:4].tolist()              # host synchronisation
-            obj = smooth + (0.0 if constrained else mu * nuc) + params.lambda_reg * max(q0, r_sq / kappa)
-            if params.solver_verbose:
-                print(f"[convex_caldera] iter {done}: objective {obj:.6e} nuc {nuc:.4e} ||R||^2 {r_sq:.4e}")
-            if abs(prev_obj - obj) <= params.solver_tol * max(abs(obj), 1e-30) and done > check_every:
-                status = "optimal"
-                break
-            if obj > prev_obj:
-                theta.value = 1.0                                       # adaptive restart
-            prev_obj = obj
-        del ws
+        fallback = str(params.solver).upper() in ("SVD", "FALLBACK")
+        if fallback:
+            # The `except` branch of solve_convex_optimization (:233-241): what the reference returns whenever
+            # its solver raises.  L* = truncated SVD of W with rank min(128, min(m, n)), R* = W - L*.
+            r = min(128, m, n)
+            q = r if r == min(m, n) else (int(sketch_width) if sketch_width > 0 else min(224, m, n))
+            Lf, Rf, sig = _truncated_svd(lib, Wd, r, q, max(int(power_iters), 12), seed)
+            L = torch.empty((m, n), **f32)
+            R = Wd.clone()
+            for dst, alpha, acc in ((L, 1.0, 0), (R, -1.0, 1)):        # L* = (U sqrt S)(sqrt S V^T),  R* = W - L*
+                _lib.check(lib.cb_sgemm_strided(m, n, r, alpha, _lib.ptr(Lf), r, 1, _lib.ptr(Rf), n, 1, _lib.ptr(dst), n, 1,
+                                                acc, _lib.stream_ptr()), "sgemm")
+            b_star, obj, status, done = float(params.b_min), float("inf"), "failed", 0
+            svals = torch.cat([sig, torch.ones_like(sig)])        # sigma and the ratios s'/S (nothing was thresholded)
+        else:
+            b_star = min(params.b_max, params.B_tot / p)
+            if b_star < params.b_min:
+                raise ValueError(f"convex_caldera: bit budget infeasible (B_tot / p = {params.B_tot / p} < b_min = {params.b_min})")
+            mu = -1.0 if constrained else float(params.mu)
+            tau = float(params.tau_star) if constrained else 0.0
+            q0 = c * math.exp(-params.k * b_star)
+            step_t = 1.0 / (2.0 * lam_max)
+            r = max(1, min(int(rank_cap), m, n))
+            q = int(sketch_width) if sketch_width > 0 else min(max(2 * r, r + 32), m, n)
+            if sketch_width <= 0 and q > 224 and r + 32 <= 224:
+                q = 224
+            q = max(min(q, 512, m, n), r)
+            L, Lp, R, Rp = (torch.zeros((m, n), **f32) for _ in range(4))
+            Lf = torch.empty((m, r), **f32)
+            Rf = torch.empty((r, n), **f32)
+            svals = torch.zeros(2 * r, **f32)
+            scal = torch.zeros(8, dtype=torch.float64, device=dev)
+            ws_bytes = lib.cb_convex_prox_workspace_bytes(m, n, r, q, int(use_tensor_cores))
+            if ws_bytes == 0:
+                raise ValueError("convex_caldera: invalid rank_cap / sketch_width for this shape")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            theta = C.c_double(1.0)
+            prev_obj, obj, status, done, warm = float("inf"), float("inf"), "max_iters", 0, 0
+            while done < max_iters:
+                step = min(check_every, max_iters - done)
+                st = lib.cb_convex_prox_iters(_lib.ptr(Wd), _lib.ptr(h), m, n, mu, tau, float(params.lambda_reg),
+                                              kappa, q0, step_t, r, q, int(power_iters), int(seed) + done, warm,
+                                              int(use_tensor_cores), step, C.byref(theta), _lib.ptr(L), _lib.ptr(Lp),
+                                              _lib.ptr(R), _lib.ptr(Rp), _lib.ptr(Lf), _lib.ptr(Rf), _lib.ptr(svals),
+                                              _lib.ptr(scal), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+                _lib.check(st, "convex_prox_iters")
+                warm = 1
+                done += step
+                nuc, _alpha, r_sq, smooth = scal[:4].tolist()              # host synchronisation
+                obj = smooth + (0.0 if constrained else mu * nuc) + params.lambda_reg * max(q0, r_sq / kappa)
+                if params.solver_verbose:
+                    print(f"[convex_caldera] iter {done}: objective {obj:.6e} nuc {nuc:.4e} ||R||^2 {r_sq:.4e}")
+                if abs(prev_obj - obj) <= params.solver_tol * max(abs(obj), 1e-30) and done > check_every:
+                    status = "optimal"
+                    break
+                if obj > prev_obj:
+                    theta.value = 1.0                                       # adaptive restart
+                prev_obj = obj
+            del ws, Lp, Rp
 
         # ---- Step 3: rounding / repair
         b_discrete = round_bit_allocations(b_star, params.discrete_bits, params.B_tot)
@@ -189,11 +334,17 @@ def convex_caldera(
         # ---- Step 4: low-rank factorisation of L* = U diag(s) V^T (convex_caldera.py:276-339)
         sv = svals.cpu()
         s_host, ratio = sv[:r].double().numpy(), svals[r:2 * r]
-        if constrained:
+        if fallback:
+            # the reference re-decomposes L* (:298): singular values S[:r] followed by min(m, n) - r zeros
+            s_rule = np.concatenate([s_host, np.zeros(min(m, n) - r)])
+            rank = min(int(np.searchsorted(np.cumsum(s_rule), params.tau_star) + 1), len(s_rule)) if constrained \
+                else int(np.sum(s_host > s_host[0] * 1e-6))
+            rank = min(rank, r)       # (columns past r would be the zero singular pairs: they add nothing to L R)
+        elif constrained:
             rank = int(min(np.searchsorted(np.cumsum(s_host), params.tau_star) + 1, len(s_host)))
         else:
             rank = int(np.sum(s_host > s_host[0] * 1e-6)) if s_host[0] > 0 else 0
-        rank_capped = bool(s_host[-1] > 0) and r < min(m, n)
+        rank_capped = (not fallback) and bool(s_host[-1] > 0) and r < min(m, n)
         if rank_capped:
             warnings.warn(f"convex_caldera: the thresholded L* saturates rank_cap={r}; increase rank_cap")
         root = ratio.sqrt().contiguous()                   # U sqrt(S) * sqrt(s/S) = U sqrt(s)
@@ -203,12 +354,8 @@ def convex_caldera(
         _lib.check(lib.cb_scale_f32(_lib.ptr(Rf), r, n, _lib.ptr(root), 0, 0, _lib.ptr(Rfac), _lib.stream_ptr()), "scale")
         Lfac, Rfac = Lfac[:, :rank].contiguous(), Rfac[:rank, :].contiguous()
         if params.quantize_factors and rank > 0:
-            assert params.factor_bits in (2, 4, 8, 16), "Bit-width not supported!"
-            for A in (Lfac, Rfac):
-                sc_ = torch.empty(1, **f32)
-                _lib.check(lib.cb_quantize_f32(_lib.ptr(A), A.shape[0], A.shape[1], A.stride(0), A.stride(1),
-                                               params.factor_bits, 0, 0.0, None, None, _lib.ptr(sc_), _lib.ptr(A),
-                                               _lib.stream_ptr()), "quantize factors")
+            _quantize_factor_(lib, Lfac, params.factor_bits)
+            _quantize_factor_(lib, Rfac, params.factor_bits)
 
         # ---- Step 5: quantise the residual; reconstruction uses the full L* (:484-485)
         R_q = torch.empty((m, n), **f32)

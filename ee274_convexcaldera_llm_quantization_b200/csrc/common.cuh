@@ -42,6 +42,28 @@ inline void note_launch(int n = 1) { __atomic_fetch_add(&g_launch_count, (long l
     if (s__ != CB_OK) return s__;      \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting and the library is used on several
+// devices of one process (caldera(device="cuda:N"), one worker thread per stream): remember, per kernel, which
+// devices have been opted in.  Lock-free; a racing second call merely repeats the (idempotent) attribute call.
+struct PerDeviceOnce {
+  unsigned long long mask[4] = {0ull, 0ull, 0ull, 0ull};     // up to 256 devices
+  bool seen(int dev) const {
+    return dev >= 0 && dev < 256 && ((__atomic_load_n(&mask[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) != 0;
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 256) __atomic_fetch_or(&mask[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+  }
+};
+template <typename Kernel>
+inline int opt_in_dynamic_smem(Kernel kernel, int bytes, PerDeviceOnce& once) {
+  int dev = 0;
+  CB_CUDA(cudaGetDevice(&dev));
+  if (once.seen(dev)) return CB_OK;
+  CB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  once.mark(dev);
+  return CB_OK;
+}
+
 constexpr int kNumSMs = 148;  // B200
 
 inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {

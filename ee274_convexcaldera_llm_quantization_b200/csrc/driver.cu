@@ -320,7 +320,11 @@ static int validate_params(const cb_caldera_params* p, int64_t m, int64_t n, int
     if (!bits_ok(p->l_bits) || !bits_ok(p->r_bits)) return CB_ERR_BITS;
     if (p->rank < 1 || p->rank > m || p->rank > n) return CB_ERR_ARG;
     if (p->rank > 512) return CB_ERR_UNSUPPORTED;
-    if ((p->l_bits < 16 || p->r_bits < 16) && p->lplr_iters < 1) return CB_ERR_ARG;
+    // lplr_iters < 1 with quantised factors only fails in the reference when an LR update actually runs
+    // (best_L_quant_out stays None, alg.py:190); update_order = ["Q"] or iters = 0 are fine there and here
+    bool lr_scheduled = false;
+    for (int i = 0; i < p->n_order; ++i) lr_scheduled = lr_scheduled || p->order[i] == 1;
+    if ((p->l_bits < 16 || p->r_bits < 16) && p->lplr_iters < 1 && lr_scheduled && p->iters > 0) return CB_ERR_ARG;
   }
   if (h_kind != CB_H_IDENTITY && h_kind != CB_H_DIAG && h_kind != CB_H_DENSE) return CB_ERR_ARG;
   if (h_kind == CB_H_DENSE && p->aware && p->sigma_reg > 0.f) return CB_ERR_UNSUPPORTED;  // needs lambda_min(H)
@@ -433,84 +437,83 @@ static int lr_product(const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaS
   return lr_product_raw(P.use_tc, P.Lcur, P.Rcur, m, n, r, P.LRbuf, P.Lb16, P.Rtb16, P.flags + 4, st);
 }
 
-static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+// One LPLR iteration (alg.py:161-182) from the current R: weighted least squares for L, quantise L^T, least
+// squares for R, quantise R, inner error sum w_j (res - L R)_ij^2 accumulated into P.dsc[3].  On exit
+// P.Ltmp / P.Rtmp hold the unquantised solutions, P.Lcodes_cur / P.Rcodes_cur + scales the codes (L's in m x r
+// order; the reference's L_idxs order is the transpose), P.Lcur / P.Rcur the dequantised factors.
+static int lplr_step(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
   const int64_t r = p->rank;
   const float* res = (p->aware && !P.dense) ? P.RES : P.Y;  // unweighted residual W - Q
-  for (int k = 0; k < p->lplr_iters; ++k) {
-    // ---- L update: weighted normal equations (alg.py:163 / :167)
-    if (P.dense && p->aware) {
-      CB_TRY(sgemm(n, r, n, 1.f, P.Hs, n, 1, P.Rcur, 1, n, P.HRt, r, 1, false, nullptr, st, &P.lr.sw));   // H R^T
-      CB_TRY(sgemm(r, r, n, 1.f, P.Rcur, n, 1, P.HRt, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));   // R H R^T
-      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, P.HRt, r, 1, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));      // res H R^T
-    } else {
-      const float* Rw = P.Rcur;
-      if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
-      CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));     // R diag(h) R^T
-      CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));        // res diag(h) R^T
-    }
-    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
-    CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));  // alg.py:171-172
-    // ---- R update (alg.py:175)
-    CB_TRY(sgemm(r, r, m, 1.f, P.Lcur, 1, r, P.Lcur, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));  // L^T L
-    CB_TRY(sgemm(r, n, m, 1.f, P.Lcur, 1, r, res, n, 1, P.Br, n, 1, false, nullptr, st, &P.lr.sw));     // L^T res
-    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
-    CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));  // alg.py:179-180
-    // ---- inner error ||(res - L R) H_sqrt||_F and best-so-far (alg.py:182-188)
-    CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st, &P.lr.sw));
-    if (P.dense) CB_TRY(dense_quadratic(P, res, nullptr, 8, nullptr, P.LRbuf, m, n, !p->aware, P.dsc + 3, st));
-    else CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
-    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
-    const int* f = P.flags + 1;
-    CB_TRY(copy_if(f, P.Lb, P.Lcur, sizeof(float) * m * r, st));
-    CB_TRY(copy_if(f, P.Rb, P.Rcur, sizeof(float) * r * n, st));
-    CB_TRY(copy_if(f, P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits), st));
-    CB_TRY(copy_if(f, P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits), st));
-    CB_TRY(copy_if(f, P.Lscale_in, P.Lscale_cur, sizeof(float), st));
-    CB_TRY(copy_if(f, P.Rscale_in, P.Rscale_cur, sizeof(float), st));
+  // ---- L update: weighted normal equations (alg.py:163 / :167)
+  if (P.dense && p->aware) {
+    CB_TRY(sgemm(n, r, n, 1.f, P.Hs, n, 1, P.Rcur, 1, n, P.HRt, r, 1, false, nullptr, st, &P.lr.sw));   // H R^T
+    CB_TRY(sgemm(r, r, n, 1.f, P.Rcur, n, 1, P.HRt, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));   // R H R^T
+    CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, P.HRt, r, 1, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));      // res H R^T
+  } else {
+    const float* Rw = P.Rcur;
+    if (p->aware) { CB_TRY(scale_cols(P.Rcur, r, n, P.h_eff, 0, P.Rw, st)); Rw = P.Rw; }
+    CB_TRY(sgemm(r, r, n, 1.f, Rw, n, 1, P.Rcur, 1, n, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));     // R diag(h) R^T
+    CB_TRY(sgemm(m, r, n, 1.f, res, n, 1, Rw, 1, n, P.Bl, r, 1, false, nullptr, st, &P.lr.sw));        // res diag(h) R^T
   }
-  CB_CUDA(cudaMemcpyAsync(P.Lcur, P.Lb, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(P.Rcur, P.Rb, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+  CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
+  CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));  // alg.py:171-172
+  // ---- R update (alg.py:175)
+  CB_TRY(sgemm(r, r, m, 1.f, P.Lcur, 1, r, P.Lcur, r, 1, P.Gs, r, 1, false, nullptr, st, &P.lr.sw));  // L^T L
+  CB_TRY(sgemm(r, n, m, 1.f, P.Lcur, 1, r, res, n, 1, P.Br, n, 1, false, nullptr, st, &P.lr.sw));     // L^T res
+  CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+  CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
+  CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));  // alg.py:179-180
+  // ---- inner error ||(res - L R) H_sqrt||_F (alg.py:182)
+  CB_TRY(sgemm(m, n, r, 1.f, P.Lcur, r, 1, P.Rcur, n, 1, P.LRbuf, n, 1, false, nullptr, st, &P.lr.sw));
+  if (P.dense) CB_TRY(dense_quadratic(P, res, nullptr, 8, nullptr, P.LRbuf, m, n, !p->aware, P.dsc + 3, st));
+  else CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
   return CB_OK;
 }
 
-// Tensor-core variant of the LPLR loop (diagonal / identity Hessian): the three m x n x r
-// contractions per inner iteration run on gemm_tc against the bf16 operands Yb = res (.) sqrt(h)
-// and Ytb = Yb^T that the rank-r step already built:
+// Tensor-core variant (diagonal / identity Hessian): the three m x n x r contractions of an iteration run on
+// gemm_tc against the bf16 operands Yb = res (.) sqrt(h) and Ytb = Yb^T that the rank-r step already built:
 //   res diag(h) R^T = Yb (R (.) sqrt(h))^T,        L^T res = (L^T Ytb^T) (.) 1/sqrt(h)
 // The r x r Gram matrices are accumulated in fp32 (split-K slices summed in slice order) and factorised in fp32.
-static int lplr_refine_tc(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+static int lplr_step_tc(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
   const int64_t r = p->rank;
   const float* res = p->aware ? P.RES : P.Y;
   int* wd = P.flags + 4;
+  // ---- L update (alg.py:163 / :167)
+  CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st));
+  CB_TRY(gemm_tc(r, r, n, 1.f, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
+  CB_TRY(gemm_tc(m, r, n, 1.f, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
+  CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+  CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
+  CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));
+  // ---- R update (alg.py:175)
+  CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st));
+  CB_TRY(gemm_tc(r, r, m, 1.f, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
+  CB_TRY(gemm_tc(r, n, m, 1.f, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr,
+                 nullptr, 0, wd, nullptr, st, &P.tc.sw));
+  CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
+  CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
+  CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));
+  // ---- inner error (alg.py:182)
+  CB_TRY(lr_product(P, m, n, r, st));
+  CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
+  return CB_OK;
+}
+
+// The LPLR loop (alg.py:160-195): lplr_iters steps, best-so-far kept by predicated device copies.
+static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, bool use_tc, cudaStream_t st) {
+  const int64_t r = p->rank;
   for (int k = 0; k < p->lplr_iters; ++k) {
-    // ---- L update (alg.py:163 / :167)
-    CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st));
-    CB_TRY(gemm_tc(r, r, n, 1.f, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
-    CB_TRY(gemm_tc(m, r, n, 1.f, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
-    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, &P.lr.sw));
-    CB_TRY(quantize_whole(P.Ltmp, m, r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, st));
-    // ---- R update (alg.py:175)
-    CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st));
-    CB_TRY(gemm_tc(r, r, m, 1.f, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, wd, nullptr, st, &P.tc.sw));
-    CB_TRY(gemm_tc(r, n, m, 1.f, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr,
-                   nullptr, 0, wd, nullptr, st, &P.tc.sw));
-    CB_TRY(solve_spd_setup(P.Gs, r, P.Linv, P.Ginv, P.flags + 2, st));
-    CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, &P.lr.sw));
-    CB_TRY(quantize_whole(P.Rtmp, r, n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, st));
-    // ---- inner error and best-so-far (alg.py:182-188)
-    CB_TRY(lr_product(P, m, n, r, st));
-    CB_TRY(err_accum(res, nullptr, 8, nullptr, P.LRbuf, P.w_inner, m, n, P.dsc + 3, st));
-    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, st));
-    const int* f = P.flags + 1;
-    CB_TRY(copy_if(f, P.Lb, P.Lcur, sizeof(float) * m * r, st));
-    CB_TRY(copy_if(f, P.Rb, P.Rcur, sizeof(float) * r * n, st));
-    CB_TRY(copy_if(f, P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits), st));
-    CB_TRY(copy_if(f, P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits), st));
-    CB_TRY(copy_if(f, P.Lscale_in, P.Lscale_cur, sizeof(float), st));
-    CB_TRY(copy_if(f, P.Rscale_in, P.Rscale_cur, sizeof(float), st));
+    CB_TRY(use_tc ? lplr_step_tc(p, P, m, n, st) : lplr_step(p, P, m, n, st));
+    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, k == p->lplr_iters - 1, st));   // alg.py:184-188
+    CopySegments best;
+    best.add(P.Lb, P.Lcur, sizeof(float) * m * r);
+    best.add(P.Rb, P.Rcur, sizeof(float) * r * n);
+    best.add(P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits));
+    best.add(P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits));
+    best.add(P.Lscale_in, P.Lscale_cur, sizeof(float));
+    best.add(P.Rscale_in, P.Rscale_cur, sizeof(float));
+    CB_TRY(copy_if_multi(P.flags + 1, best, st));
   }
   CB_CUDA(cudaMemcpyAsync(P.Lcur, P.Lb, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
   CB_CUDA(cudaMemcpyAsync(P.Rcur, P.Rb, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
@@ -658,7 +661,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
                               warm_valid && p->warm_start, P.Lcur, P.Rcur, P.lr, st));
         }
         warm_valid = true;
-        if (P.quant_factors) CB_TRY(P.use_tc ? lplr_refine_tc(p, P, m, n, st) : lplr_refine(p, P, m, n, st));
+        if (P.quant_factors) CB_TRY(lplr_refine(p, P, m, n, P.use_tc, st));
         have_lr = true;
         CB_TRY(lr_product(P, m, n, r, st));
         lrbuf_valid = true;
@@ -723,6 +726,7 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   // cholesky ridge retries, jacobi sweeps of the last solve, tensor-core pipeline watchdog
   CB_CUDA(cudaMemcpyAsync(out->scalars, P.scalars, sizeof(float) * 8, cudaMemcpyDeviceToDevice, st));
   CB_CUDA(cudaMemcpyAsync(out->scalars + 5, P.flags + 2, sizeof(int) * 3, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(out->scalars + 4, P.flags + 5, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 
@@ -850,6 +854,89 @@ extern "C" int cb_weighted_error(const float* W, int64_t m, int64_t n, const voi
   }
   CB_TRY(err_accum(W, q_codes, q_codes != nullptr ? q_bits : 8, q_scale, LRbuf, hw, m, n, out_num, st));
   if (out_den != nullptr) CB_TRY(err_accum(W, nullptr, 8, nullptr, nullptr, hw, m, n, out_den, st));
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------- one LPLR iteration as a stage (C ABI)
+namespace cb {
+struct LplrStagePlan {
+  LayerPlan P;
+  float* res_w;      // aware: res (.) sqrt(h) in fp32 is not needed; bf16 operands are built straight from res
+  void* Lcodes_t;    // L codes in the reference's order ((L^T).flatten(), alg.py:171)
+};
+static int plan_lplr_stage(Arena& a, int64_t m, int64_t n, int64_t r, int l_bits, int r_bits, bool use_tc, LplrStagePlan& S) {
+  LayerPlan& L = S.P;
+  L.dense = false; L.quant_factors = true; L.use_tc = use_tc; L.q = 0;
+  L.dsc = a.take<double>(4);
+  L.flags = a.take<int>(8);
+  L.scalars = a.take<float>(8);
+  L.h_eff = a.take<float>(n); L.sqrt_h = a.take<float>(n); L.inv_sqrt_h = a.take<float>(n); L.w_inner = a.take<float>(n);
+  L.LRbuf = a.take<float>(m * n);
+  L.Lcur = a.take<float>(m * r); L.Rcur = a.take<float>(r * n);
+  L.Rw = a.take<float>(r * n); L.Gs = a.take<float>(r * r); L.Linv = a.take<float>(r * r); L.Ginv = a.take<float>(r * r);
+  L.Bl = a.take<float>(m * r); L.Br = a.take<float>(r * n); L.Ltmp = a.take<float>(m * r); L.Rtmp = a.take<float>(r * n);
+  L.Lcodes_cur = a.take<uint8_t>(m * r * code_bytes(l_bits));
+  L.Rcodes_cur = a.take<uint8_t>(r * n * code_bytes(r_bits));
+  L.Lscale_cur = a.take<float>(4); L.Rscale_cur = a.take<float>(4);
+  L.lr.sw.buf = a.take<float>(kSplitWsBytes / sizeof(float)); L.lr.sw.bytes = kSplitWsBytes;
+  L.tc.sw = L.lr.sw;
+  if (use_tc) {
+    L.tc.Yb = a.take<bf16>(m * n); L.tc.Ytb = a.take<bf16>(n * m);
+    L.Lb16 = a.take<bf16>(3 * m * r); L.Rtb16 = a.take<bf16>(3 * n * r);
+    L.Rsb16 = a.take<bf16>(r * n); L.Ltb16 = a.take<bf16>(r * m);
+  }
+  S.Lcodes_t = a.take<uint8_t>(m * r * code_bytes(l_bits));
+  return a.ok() ? CB_OK : CB_ERR_WORKSPACE;
+}
+}  // namespace cb
+
+extern "C" size_t cb_lplr_iter_workspace_bytes(int64_t m, int64_t n, int64_t r, int l_bits, int r_bits, int use_tensor_cores) {
+  if (m <= 0 || n <= 0 || r < 1 || r > m || r > n || r > 512 || !bits_ok(l_bits) || !bits_ok(r_bits)) return 0;
+  Arena a{nullptr, 0, 0};
+  LplrStagePlan S{};
+  plan_lplr_stage(a, m, n, r, l_bits, r_bits, use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, 16), S);
+  return a.off + 256;
+}
+
+extern "C" int cb_lplr_iter(const float* res, int64_t m, int64_t n, const float* h, int h_kind, int aware, int64_t r,
+                            int l_bits, int r_bits, const float* R_in, float* L_pre, void* L_idxs, float* L_scale,
+                            float* L_hat, float* R_pre, void* R_idxs, float* R_scale, float* R_hat, double* err_sq,
+                            int use_tensor_cores, int* status, void* ws, size_t ws_bytes, void* stream) {
+  if (res == nullptr || R_in == nullptr || ws == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
+  if (r < 1 || r > m || r > n) return CB_ERR_ARG;
+  if (r > 512) return CB_ERR_UNSUPPORTED;
+  if (!bits_ok(l_bits) || !bits_ok(r_bits)) return CB_ERR_BITS;
+  if (h_kind == CB_H_DENSE) return CB_ERR_UNSUPPORTED;
+  if (h_kind != CB_H_IDENTITY && h_kind != CB_H_DIAG) return CB_ERR_ARG;
+  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool use_tc = use_tensor_cores != 0 && lowrank_tc_usable(m, n, r, 16);
+  Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+  LplrStagePlan S{};
+  CB_TRY(plan_lplr_stage(a, m, n, r, l_bits, r_bits, use_tc, S));
+  LayerPlan& P = S.P;
+  cb_caldera_params prm{};
+  prm.rank = (int32_t)r; prm.l_bits = l_bits; prm.r_bits = r_bits; prm.aware = aware != 0; prm.lplr_iters = 1;
+  CB_CUDA(cudaMemsetAsync(P.dsc, 0, sizeof(double) * 4, st));
+  CB_CUDA(cudaMemsetAsync(P.flags, 0, sizeof(int) * 8, st));
+  CB_TRY(prep_hessian_diag(h_kind == CB_H_DIAG ? h : nullptr, n, 0.f, prm.aware, P.h_eff, P.sqrt_h, P.inv_sqrt_h, P.w_inner,
+                           nullptr, st));
+  // lplr_step reads the unweighted residual through P.RES (aware) / P.Y (not aware)
+  P.RES = const_cast<float*>(res); P.Y = const_cast<float*>(res);
+  if (use_tc) CB_TRY(to_bf16(res, m, n, n, P.tc.Yb, n, P.tc.Ytb, m, prm.aware ? P.sqrt_h : nullptr, st));
+  CB_CUDA(cudaMemcpyAsync(P.Rcur, R_in, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  CB_TRY(use_tc ? lplr_step_tc(&prm, P, m, n, st) : lplr_step(&prm, P, m, n, st));
+  if (L_pre != nullptr) CB_CUDA(cudaMemcpyAsync(L_pre, P.Ltmp, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
+  if (R_pre != nullptr) CB_CUDA(cudaMemcpyAsync(R_pre, P.Rtmp, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  if (L_hat != nullptr) CB_CUDA(cudaMemcpyAsync(L_hat, P.Lcur, sizeof(float) * m * r, cudaMemcpyDeviceToDevice, st));
+  if (R_hat != nullptr) CB_CUDA(cudaMemcpyAsync(R_hat, P.Rcur, sizeof(float) * r * n, cudaMemcpyDeviceToDevice, st));
+  if (L_scale != nullptr) CB_CUDA(cudaMemcpyAsync(L_scale, P.Lscale_cur, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (R_scale != nullptr) CB_CUDA(cudaMemcpyAsync(R_scale, P.Rscale_cur, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (L_idxs != nullptr) CB_TRY(transpose_codes(P.Lcodes_cur, m, r, code_bytes(l_bits), L_idxs, st));
+  if (R_idxs != nullptr)
+    CB_CUDA(cudaMemcpyAsync(R_idxs, P.Rcodes_cur, (size_t)r * n * code_bytes(r_bits), cudaMemcpyDeviceToDevice, st));
+  if (err_sq != nullptr) CB_CUDA(cudaMemcpyAsync(err_sq, P.dsc + 3, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (status != nullptr) CB_CUDA(cudaMemcpyAsync(status, P.flags + 2, sizeof(int) * 3, cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 

@@ -817,11 +817,8 @@ static int make_tmap_bf16_kblocks(CUtensorMap* map, const void* ptr, int64_t row
 template <int BN, int STAGES, int KB>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& args, int splits, cudaStream_t st) {
   using S = TcSmem<BN, STAGES, KB>;
-  static bool attr = false;
-  if (!attr) {
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  CB_TRY(opt_in_dynamic_smem(gemm_tc_kernel<BN, STAGES, KB>, S::TOTAL, once));
   dim3 grid((unsigned)((args.N + BN - 1) / BN), (unsigned)((args.M + TC_BM - 1) / TC_BM), (unsigned)splits);
   gemm_tc_kernel<BN, STAGES, KB><<<grid, TC_THREADS, S::TOTAL, st>>>(ta, tb, args);
   CB_CHECK_LAUNCH();
@@ -1070,11 +1067,8 @@ extern "C" int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const 
   dim3 grid((unsigned)((m + PL_BN - 1) / PL_BN), (unsigned)((T + TC_BM - 1) / TC_BM));
 #define CB_PL(BITS)                                                                                                  \
   do {                                                                                                               \
-    static bool attr = false;                                                                                        \
-    if (!attr) {                                                                                                     \
-      CB_CUDA(cudaFuncSetAttribute(packed_linear_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, PlSmem::TOTAL)); \
-      attr = true;                                                                                                   \
-    }                                                                                                                \
+    static PerDeviceOnce once;                                                                                       \
+    CB_TRY(opt_in_dynamic_smem(packed_linear_kernel<BITS>, PlSmem::TOTAL, once));                                    \
     packed_linear_kernel<BITS><<<grid, PL_THREADS, PlSmem::TOTAL, st>>>(tx, tt, tl, a);                              \
   } while (0)
   if (q_bits == 2) CB_PL(2);

@@ -56,7 +56,7 @@ int err_accum(const float* Ws, const void* codes, int bits, const float* qscale,
               const float* w, int64_t m, int64_t n, double* num, cudaStream_t st, float* amax_next = nullptr);
 int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags,
                  int all_updated, cudaStream_t st);
-int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st);
+int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st);
 int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st);
 // up to 8 (dst, src, bytes) segments copied by one launch when *flag != 0
 struct CopySegments {

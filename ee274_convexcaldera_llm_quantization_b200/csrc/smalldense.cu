@@ -359,11 +359,8 @@ int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st,
   if (G == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
   if (debug_skip() & 1) return CB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem)));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  CB_TRY(opt_in_dynamic_smem(chol_inv_kernel, (int)sizeof(CholSmem), once));
   chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status, g_chol_timing);
   CB_CHECK_LAUNCH();
   return CB_OK;
@@ -747,12 +744,8 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
   }
   if (q <= JS_QMAX && q % 4 == 0) {
     const size_t smem = ((size_t)q * (q + 4) + 2 * (size_t)q) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      CB_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(((size_t)JS_QMAX * (JS_QMAX + 4) + 2 * JS_QMAX) * sizeof(float))));
-      attr_set = true;
-    }
+    static PerDeviceOnce once;
+    CB_TRY(opt_in_dynamic_smem(jacobi_smem_kernel, (int)(((size_t)JS_QMAX * (JS_QMAX + 4) + 2 * JS_QMAX) * sizeof(float)), once));
     jacobi_smem_kernel<<<1, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, kJacobiTol);
     CB_CHECK_LAUNCH();
     return CB_OK;

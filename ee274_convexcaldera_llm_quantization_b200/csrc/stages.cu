@@ -649,13 +649,18 @@ __global__ void select_outer_kernel(double* num, const double* den, float* error
   if (take) { scalars[1] = err; scalars[2] = (float)step; }
   num[0] = 0.0;
 }
-__global__ void select_inner_kernel(double* num, float* scalars, int* flags, int first) {
+__global__ void select_inner_kernel(double* num, float* scalars, int* flags, int first, int last) {
   // alg.py:182-188
   const float err = (float)sqrt(num[0]);
   const float best = first ? __int_as_float(0x7f800000) : scalars[5];
   const int take = err < best;
   flags[1] = take;
   if (take) scalars[5] = err; else if (first) scalars[5] = best;
+  // An LR update in which no inner iterate was ever taken (every error NaN) leaves best_L_quant_out = None in
+  // the reference, which then raises (alg.py:190); count those updates so the caller can raise too.
+  const int any = (first ? 0 : flags[6]) | take;
+  flags[6] = any;
+  if (last && !any) flags[5] += 1;
   num[0] = 0.0;
 }
 
@@ -821,8 +826,8 @@ int select_outer(double* num, const double* den, float* errors, int step, float*
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int select_inner(double* num, float* scalars, int* flags, int first, cudaStream_t st) {
-  select_inner_kernel<<<1, 1, 0, st>>>(num, scalars, flags, first);
+int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st) {
+  select_inner_kernel<<<1, 1, 0, st>>>(num, scalars, flags, first, last);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -56,12 +56,63 @@ def lpt_assign(costs: Sequence[float], world_size: int) -> List[List[int]]:
 
 # ----------------------------------------------------------------------------- wire format
 _FIELDS = ("Q_packed", "Q_scale", "L", "R", "L_packed", "R_packed", "L_scale", "R_scale")
+HEADER_BYTES = 4096          # fixed-size header region at the head of every job blob (magic | length | JSON | padding)
+_FACTOR_DTYPES = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32}
+
+
+def _align(x: int, a: int = 256) -> int:
+    return (x + a - 1) // a * a
+
+
+def blob_layout(params, shape: Tuple[int, int], factor_dtype: str = "float16"):
+    """Byte layout of one layer's blob: a pure function of the layer shape and the parameters, so every rank knows
+    every other rank's blob sizes without exchanging them.  Returns (total_bytes, [(field, dtype, shape, offset,
+    nbytes)]), offsets relative to the blob's start (the payload begins at HEADER_BYTES)."""
+    from . import _lib
+    lib = _lib.load()
+    m, n = int(shape[0]), int(shape[1])
+    r = int(params.rank)
+    secs, off = [], HEADER_BYTES
+
+    def add(field, dtype, shp, nbytes):
+        nonlocal off
+        secs.append((field, dtype, tuple(shp), off, int(nbytes)))
+        off += _align(int(nbytes), 16)
+    if params.compute_quantized_component:
+        nb = int(lib.cb_packed_bytes(m * n, int(params.Q_bits)))
+        add("Q_packed", "uint8", (nb,), nb)
+        add("Q_scale", "float32", (1,), 4)
+    if params.compute_low_rank_factors:
+        if params.L_bits < 16 or params.R_bits < 16:
+            # either factor below 16 bits sends BOTH through the quantiser (alg.py:144): codes of L_bits / R_bits each
+            nl, nr = int(lib.cb_packed_bytes(m * r, int(params.L_bits))), int(lib.cb_packed_bytes(r * n, int(params.R_bits)))
+            add("L_packed", "uint8", (nl,), nl)
+            add("R_packed", "uint8", (nr,), nr)
+            add("L_scale", "float32", (1,), 4)
+            add("R_scale", "float32", (1,), 4)
+        else:
+            es = torch.empty(0, dtype=_FACTOR_DTYPES[factor_dtype]).element_size()
+            add("L", factor_dtype, (m, r), m * r * es)
+            add("R", factor_dtype, (r, n), r * n * es)
+    return _align(off), secs
+
+
+def _header_bytes(meta: dict) -> bytes:
+    header = json.dumps(meta).encode()
+    if len(_MAGIC) + 8 + len(header) > HEADER_BYTES:
+        # an error trajectory this long does not fit the fixed header: keep its tail
+        meta = dict(meta)
+        meta["errors"] = {k: v[-8:] for k, v in meta["errors"].items()}
+        meta["errors_truncated"] = True
+        header = json.dumps(meta).encode()
+    pad = HEADER_BYTES - len(_MAGIC) - 8 - len(header)
+    return _MAGIC + struct.pack("<Q", len(header) + pad) + header + b" " * pad
 
 
 def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, shape: Tuple[int, int],
-                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Serialises what a consumer of the decomposition needs: packed Q codes + scale, and the
-    factors (packed codes + scales when quantised, fp16 otherwise; fp32 if `l_bits` >= 32).
+                       out: Optional[torch.Tensor] = None, factor_dtype: str = "float16") -> torch.Tensor:
+    """Serialises what a consumer of the decomposition needs: packed Q codes + scale, and the factors (packed codes
+    + scales when quantised; `factor_dtype` -- float16 by default, bfloat16 or float32 -- otherwise).
     Layout: magic | u64 header length | JSON header | 16-byte aligned payload sections.
     `out` (uint8, device): write the blob into its head and return that view when it fits."""
     tensors: Dict[str, torch.Tensor] = {}
@@ -75,7 +126,7 @@ def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, sh
     else:
         for f in ("L", "R"):
             if f in tensors:
-                tensors[f] = tensors[f].to(torch.float16)
+                tensors[f] = tensors[f].to(_FACTOR_DTYPES[factor_dtype])
     meta = {"name": name, "shape": list(shape), "q_bits": q_bits, "l_bits": l_bits, "r_bits": r_bits,
             "global_scale": float(dec.global_scale), "best_step": int(getattr(dec, "best_step", -1)),
             "errors": dec.errors, "sections": []}
@@ -102,11 +153,11 @@ def pack_decomposition(name: str, dec, q_bits: int, l_bits: int, r_bits: int, sh
 
 def unpack_decomposition(blob: torch.Tensor) -> dict:
     raw = blob.detach().cpu().contiguous()
-    b = raw.numpy().tobytes()
+    b = raw[:16].numpy().tobytes()
     if b[:8] != _MAGIC:
         raise ValueError("not a caldera-b200 blob")
     (hlen,) = struct.unpack("<Q", b[8:16])
-    meta = json.loads(b[16:16 + hlen].decode())
+    meta = json.loads(raw[16:16 + hlen].numpy().tobytes().decode())
     base = 16 + hlen
     out = dict(meta)
     for sec in meta["sections"]:
@@ -116,173 +167,234 @@ def unpack_decomposition(blob: torch.Tensor) -> dict:
     return out
 
 
+# ----------------------------------------------------------------------------- gather
+def shard_layout(params, shapes: Sequence[Tuple[int, int]], world_size: int, factor_dtype: str = "float16"):
+    """What every rank can compute on its own: the layer -> rank map and the byte offsets of every layer's blob
+    inside its rank's arena and inside the gathered arena (ranks in order, layers in index order within a rank).
+    Returns (shards, sizes, rank_bytes, rank_offsets)."""
+    quantised = params.compute_low_rank_factors and (params.L_bits < 16 or params.R_bits < 16)
+    costs = [layer_cost(m, n, params.rank, params.iters, params.lplr_iters, quantised) for (m, n) in shapes]
+    shards = lpt_assign(costs, world_size)
+    sizes = [blob_layout(params, shp, factor_dtype)[0] for shp in shapes]
+    rank_bytes = [sum(sizes[i] for i in sh) for sh in shards]
+    rank_offsets = [sum(rank_bytes[:r]) for r in range(world_size)]
+    return shards, sizes, rank_bytes, rank_offsets
+
+
+def warm_up_gather(device: torch.device, dst: Optional[int] = 0, group=None) -> None:
+    """Sets up the point-to-point channels the gather uses (NCCL creates them lazily on first use, which costs
+    far more than the gather itself) by exchanging one tiny message along every edge."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    tiny = torch.zeros(world * 256, dtype=torch.uint8, device=device)
+    gather_arena(tiny[rank * 256:(rank + 1) * 256], [256] * world, dst=dst, group=group, out=tiny)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+
+
+def gather_arena(mine: torch.Tensor, rank_bytes: Sequence[int], dst: Optional[int] = 0, group=None,
+                 out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """The one collective of the job: every rank's arena (uint8, rank_bytes[rank] bytes, sizes known to all) lands
+    at its offset in ONE preallocated arena on `dst` (dst=None: on every rank).  Receives are posted straight into
+    their final position -- no padding to the largest shard, no per-rank staging buffers, no size exchange.  Runs
+    as a single group of point-to-point operations (NCCL over NVLink for device arenas, gloo for CPU tensors)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    offs = [sum(rank_bytes[:r]) for r in range(world)]
+    total = sum(rank_bytes)
+    receive = dst is None or rank == dst
+    if receive:
+        if out is None:
+            out = torch.empty(total, dtype=torch.uint8, device=mine.device)
+        own = out[offs[rank]:offs[rank] + rank_bytes[rank]]
+        if own.data_ptr() != mine.data_ptr() and rank_bytes[rank] > 0:
+            own.copy_(mine[:rank_bytes[rank]])
+    if dst is None:
+        # every shard is broadcast from its owner into place (world collectives at full fabric bandwidth)
+        works = [dist.broadcast(out[offs[r]:offs[r] + rank_bytes[r]], src=dist.get_global_rank(group, r) if group else r,
+                                group=group, async_op=True) for r in range(world) if rank_bytes[r] > 0]
+        for w in works:
+            w.wait()
+        return out
+    ops = []
+    if rank == dst:
+        for r in range(world):
+            if r != rank and rank_bytes[r] > 0:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r] + rank_bytes[r]], r, group))
+    elif rank_bytes[rank] > 0:
+        ops.append(dist.P2POp(dist.isend, mine[:rank_bytes[rank]], dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out if receive else None
+
+
+def split_gathered(arena: torch.Tensor, shards: Sequence[Sequence[int]], sizes: Sequence[int]) -> Dict[int, torch.Tensor]:
+    """layer index -> blob view inside a gathered arena (see shard_layout)."""
+    out, off = {}, 0
+    for sh in shards:
+        for i in sh:
+            out[i] = arena[off:off + sizes[i]]
+            off += sizes[i]
+    return out
+
+
 def gather_blobs(blobs: List[torch.Tensor], dst: Optional[int] = 0, group=None) -> Optional[List[List[torch.Tensor]]]:
-    """Gathers every rank's list of blobs.  dst=None -> all ranks receive (all_gather).
-    Two collectives: blob sizes, then one padded payload per rank.  Returns, on receiving
-    ranks, result[rank] = list of that rank's blobs; None elsewhere."""
+    """Gathers every rank's list of variable-length blobs when the sizes are NOT known in advance (free-form blobs
+    from pack_decomposition).  dst=None -> all ranks receive.  One small all_gather of the sizes, then
+    `gather_arena`.  Returns, on receiving ranks, result[rank] = list of that rank's blobs; None elsewhere."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     if blobs:
         device = blobs[0].device
     elif dist.get_backend(group) == "nccl":
         device = torch.device("cuda", torch.cuda.current_device())
     else:
         device = torch.device("cpu")
-    sizes = torch.tensor([b.numel() for b in blobs], dtype=torch.int64, device=device)
-    count = torch.tensor([len(blobs)], dtype=torch.int64, device=device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, count, group=group)
-    counts_host = [int(c) for c in torch.cat(counts).tolist()]          # one device read instead of one per rank
-    max_count = max(counts_host)
-    size_pad = torch.zeros(max(max_count, 1), dtype=torch.int64, device=device)
-    size_pad[:len(blobs)] = sizes
-    all_sizes = [torch.zeros_like(size_pad) for _ in range(world)]
-    dist.all_gather(all_sizes, size_pad, group=group)
-    sizes_host = torch.stack(all_sizes).tolist()                        # [rank][k], one device read
-    totals = [int(sum(row)) for row in sizes_host]
-    max_total = max(max(totals), 1)
-    payload = torch.zeros(max_total, dtype=torch.uint8, device=device)
-    if blobs:
-        payload[:totals[rank]] = torch.cat(blobs)
-    receive = dst is None or rank == dst
-    if dst is None:
-        bufs = [torch.empty(max_total, dtype=torch.uint8, device=device) for _ in range(world)]
-        dist.all_gather(bufs, payload, group=group)
-    else:
-        bufs = [torch.empty(max_total, dtype=torch.uint8, device=device) for _ in range(world)] if receive else None
-        dist.gather(payload, bufs, dst=dst, group=group)
-    if not receive:
+    sizes_obj: List[Optional[List[int]]] = [None] * world
+    dist.all_gather_object(sizes_obj, [int(b.numel()) for b in blobs], group=group)
+    rank_bytes = [sum(sz) for sz in sizes_obj]
+    mine = torch.cat(blobs) if blobs else torch.empty(0, dtype=torch.uint8, device=device)
+    arena = gather_arena(mine, rank_bytes, dst=dst, group=group)
+    if arena is None:
         return None
     out: List[List[torch.Tensor]] = []
+    off = 0
     for r in range(world):
-        off, items = 0, []
-        for k in range(counts_host[r]):
-            sz = int(sizes_host[r][k])
-            items.append(bufs[r][off:off + sz])
+        items = []
+        for sz in sizes_obj[r]:
+            items.append(arena[off:off + sz])
             off += sz
         out.append(items)
     return out
 
 
 # ----------------------------------------------------------------------------- driver
-_WORKER_STREAMS = {}
+class ShardResult:
+    """This rank's part of a job: `indices` (layer indices, ascending), `arena` (uint8 device tensor holding their
+    blobs back to back in that order), `blobs` (views), `records` (per-layer dict: errors, global_scale, ...)."""
 
+    def __init__(self, indices, arena, blobs, records):
+        self.indices, self.arena, self.blobs, self.records = indices, arena, blobs, records
 
-def _worker_streams(dev: torch.device, count: int):
-    """The job's streams, created once per device: torch recycles a pool of 32 streams per device round
-    robin, so making fresh ones on every call would sooner or later alias two workers (or a worker and
-    the graph-capture stream) onto one CUDA stream."""
-    pool = _WORKER_STREAMS.setdefault(dev.index, [])
-    while len(pool) < count:
-        pool.append(torch.cuda.Stream(device=dev))
-    return pool[:count]
+    def __iter__(self):          # (indices, results) like the round-1 return value
+        return iter((self.indices, self.blobs))
 
 
 def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor, Optional[torch.Tensor]]]]],
                      shapes: Sequence[Tuple[int, int]], params, rank: int, world_size: int,
-                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 16,
-                     **caldera_kwargs):
-    """Decomposes this rank's shard of `layers`.
+                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 32,
+                     factor_dtype: str = "float16", arena: Optional[torch.Tensor] = None, **caldera_kwargs):
+    """Decomposes this rank's shard of `layers` (the loop of main.py:147-199, layer-sharded and asynchronous).
 
-    layers[i] = (name, loader) where loader() returns (W, H) -- generated or loaded directly
-    on the owning GPU (or in pinned host memory), so no weight ever crosses ranks.  Returns
-    (indices, results) with results[j] the blob (pack=True) or the CalderaDecomposition of
-    layer indices[j].  The per-layer seed is derived from the layer index only, so the sharded
-    run equals the single-GPU run layer for layer.
+    layers[i] = (name, loader) where loader() returns (W, H) -- generated or loaded directly on the owning GPU (or
+    in pinned host memory), so no weight ever crosses ranks.  ONE host thread submits every layer to the device's
+    LayerEngine (engine.py), which keeps `streams` of them in flight (largest layers first) and never blocks on a
+    layer's result; the packed outputs are copied device-side straight into this rank's wire-format arena and only
+    the ~100-byte result records come back to the host, to be written into the blob headers at the end.
 
-    `streams` layers are kept in flight per GPU (one worker thread + CUDA stream each, largest
-    layers first): the latency-bound factorisation kernels of one layer overlap with the
-    bandwidth- and tensor-bound kernels of the others.  The job always runs in the library's
-    "throughput" execution mode (small contraction grids, single-CTA eigensolver), whatever `streams`
-    and the world size are, so that a sharded run equals the single-GPU run bit for bit; the previous
-    mode is restored on return."""
-    import concurrent.futures as cf
+    pack=True returns a ShardResult (unpacks as (indices, blobs)); pack=False returns (indices, decompositions).
+    The per-layer seed is derived from the layer index only and no kernel on the path uses floating-point atomics
+    for its outputs, so the sharded run equals the single-GPU run bit for bit.  The job runs in the library's
+    "throughput" execution mode whatever `streams` and the world size are; the previous mode is restored on return.
+    `arena`: optional preallocated uint8 device tensor for this rank's blobs (e.g. a slice of the gather target on
+    the destination rank, which makes its own contribution zero-copy)."""
     from . import _lib
-    from .alg import caldera
-    import sys
     previous_mode = _lib.execution_mode()
-    previous_switch = sys.getswitchinterval()
     _lib.set_execution_mode("throughput")
-    # worker threads alternate between short bursts of Python (a few torch calls) and long GIL-free waits on
-    # their stream; with the default 5 ms switch interval a thread that wakes up can sit behind another one's
-    # burst for milliseconds while its GPU stream idles
-    sys.setswitchinterval(float(os.environ.get("CB_SWITCH_INTERVAL", "0.0002")))
     try:
-        return _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, caldera, cf,
+        return _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena,
                                  caldera_kwargs)
     finally:
-        sys.setswitchinterval(previous_switch)
         _lib.set_execution_mode(previous_mode)
 
 
-def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, caldera, cf, caldera_kwargs):
+def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena, caldera_kwargs):
+    from .alg import caldera_async
+    from .engine import get_engine
+    from .runner import workspace_bytes
+    from .alg import make_c_params
+    from . import _lib
+    shards, sizes, rank_bytes, _ = shard_layout(params, shapes, world_size, factor_dtype)
+    mine = shards[rank]
     quantised = params.compute_low_rank_factors and (params.L_bits < 16 or params.R_bits < 16)
-    costs = [layer_cost(m, n, params.rank, params.iters, params.lplr_iters, quantised) for (m, n) in shapes]
-    mine = lpt_assign(costs, world_size)[rank]
+    costs = {i: layer_cost(shapes[i][0], shapes[i][1], params.rank, params.iters, params.lplr_iters, quantised) for i in mine}
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    nworkers = max(1, min(int(streams), len(mine)))
-    order = sorted(range(len(mine)), key=lambda j: (-costs[mine[j]], j))     # big layers first
-    results = [None] * len(mine)
-    cuda_streams = _worker_streams(dev, nworkers)
-    slots = [None] * len(mine)
-    if pack and mine:
-        # The blobs are the only allocations that outlive a layer.  torch's caching allocator keeps free
-        # blocks per stream, so blobs allocated by the workers on their own streams would each be a fresh
-        # cudaMalloc (taking the driver's allocation lock while other threads launch graphs: measured 2.5-5 s
-        # instead of 1.3 s for the 224-layer job).  One arena, sliced per layer, instead.
-        def blob_bytes(m, n):
-            q = m * n * max(params.Q_bits, 1) // 8 if params.compute_quantized_component else 0
-            quantised_lr = params.L_bits < 16 or params.R_bits < 16
-            lr = (m + n) * params.rank * (1 if quantised_lr else 2) if params.compute_low_rank_factors else 0
-            return (q + lr + (1 << 15) + 255) // 256 * 256
-        sizes = [blob_bytes(*shapes[i]) for i in mine]
-        arena = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
-        off = 0
-        for j, sz in enumerate(sizes):
-            slots[j] = arena[off:off + sz]
-            off += sz
-    host_time = [[0.0, 0.0] for _ in range(nworkers)]       # seconds inside caldera() / pack per worker
+    order = sorted(mine, key=lambda i: (-costs[i], i))                     # big layers first
+    engine = get_engine(dev, streams)
+    t_start = time.perf_counter()
+    with torch.cuda.device(dev):
+        offsets, off = {}, 0
+        for i in mine:
+            offsets[i] = off
+            off += sizes[i]
+        if pack:
+            if arena is None:
+                arena = torch.zeros(max(off, 1), dtype=torch.uint8, device=dev)   # padding bytes are part of the blob
+            assert arena.numel() >= off and arena.dtype == torch.uint8
+            if mine:
+                # one arena of the largest layer's workspace per slot, shared by the graphs of every shape
+                scale_w = bool(caldera_kwargs.get("scale_W", True))
+                engine.reserve_workspace(max(workspace_bytes(make_c_params(params, scale_w), m, n, _lib.CB_H_DIAG)
+                                             for (m, n) in {shapes[i] for i in mine}))
+        layouts = {shp: blob_layout(params, shp, factor_dtype)[1] for shp in {shapes[i] for i in mine}}
+        fdt = _FACTOR_DTYPES[factor_dtype]
+        handles = {}
+        for i in order:
+            name, loader = layers[i]
+            W, H = loader()
+            kw = dict(caldera_kwargs)
+            kw.setdefault("seed", 1000 + i)
+            kw.setdefault("W_copy", "none")
+            if pack:
+                blob = arena[offsets[i]:offsets[i] + sizes[i]]
 
-    def work(w):
-        try:
-            _work(w)
-        except BaseException:
-            # ThreadPoolExecutor.map re-raises in worker order, not in time order: show every failure as it happens
-            import sys
-            import traceback
-            sys.stderr.write(f"[decompose_layers] worker {w} failed:\n{traceback.format_exc()}\n")
-            raise
-
-    def _work(w):
-        torch.cuda.set_device(dev)
-        with torch.cuda.stream(cuda_streams[w]):
-            for j in order[w::nworkers]:
-                i = mine[j]
-                name, loader = layers[i]
-                W, H = loader()
-                kw = dict(caldera_kwargs)
-                kw.setdefault("seed", 1000 + i)
-                kw.setdefault("W_copy", "none")
-                kw.setdefault("use_cuda_graph", True)
-                if pack:
-                    kw.setdefault("return_dense", False)       # the blob holds packed codes and factors only
-                t0 = time.perf_counter()
-                dec = caldera(params, W, H, device=dev, use_tqdm=False, **kw)
-                t1 = time.perf_counter()
-                results[j] = pack_decomposition(name, dec, params.Q_bits, params.L_bits, params.R_bits,
-                                                tuple(W.shape), out=slots[j]) if pack else dec
-                host_time[w][0] += t1 - t0
-                host_time[w][1] += time.perf_counter() - t1
-            cuda_streams[w].synchronize()
-
-    if nworkers == 1:
-        work(0)
-    else:
-        with cf.ThreadPoolExecutor(max_workers=nworkers) as ex:
-            list(ex.map(work, range(nworkers)))
+                def consume(run, kept, blob=blob, secs=layouts[tuple(W.shape)]):
+                    # device-side copies of the layer's outputs into its blob (slot stream current)
+                    for field, dtype, shp, o, nb in secs:
+                        src = getattr(run, field)
+                        dst = blob[o:o + nb]
+                        if field in ("L", "R"):
+                            dst.view(fdt).reshape(shp).copy_(src)       # fp32 -> wire dtype
+                            if fdt == torch.float16:
+                                kept["finite"] = kept.get("finite", True) & torch.isfinite(dst.view(fdt)).all()
+                        else:
+                            dst.copy_(src.reshape(-1).view(torch.uint8))
+                kw.update(return_dense=False, return_packed=False, consume=consume)
+            handles[i] = caldera_async(params, W, H, device=dev, use_tqdm=False, slots=streams, **kw)
+        t_submit = time.perf_counter()
+        results, records = {}, {}
+        for i in mine:
+            dec = handles[i].result()
+            if pack:
+                fin = handles[i].kept.get("finite")
+                if fin is not None and not bool(fin):
+                    raise OverflowError(f"layer {layers[i][0]}: a 16-bit factor does not fit float16 on the wire "
+                                        "(pass factor_dtype='bfloat16' or 'float32')")
+                meta = {"name": layers[i][0], "shape": list(shapes[i]), "q_bits": params.Q_bits, "l_bits": params.L_bits,
+                        "r_bits": params.R_bits, "global_scale": float(dec.global_scale), "best_step": int(dec.best_step),
+                        "errors": dec.errors,
+                        "sections": [{"field": f, "dtype": d, "shape": list(shp), "offset": o - HEADER_BYTES, "nbytes": nb}
+                                     for f, d, shp, o, nb in layouts[tuple(shapes[i])]]}
+                records[i] = meta
+                results[i] = arena[offsets[i]:offsets[i] + sizes[i]]
+            else:
+                results[i] = dec
+        if pack and mine:
+            # every header in one pinned staging buffer and one strided device copy
+            heads = torch.empty((len(mine), HEADER_BYTES), dtype=torch.uint8).pin_memory()
+            for j, i in enumerate(mine):
+                heads[j] = torch.frombuffer(bytearray(_header_bytes(records[i])), dtype=torch.uint8)
+            heads_d = heads.to(dev, non_blocking=True)
+            for j, i in enumerate(mine):
+                arena[offsets[i]:offsets[i] + HEADER_BYTES].copy_(heads_d[j], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
     if os.environ.get("CB_SCHEDULER_TIMES"):
         import sys
-        sys.stderr.write(f"[decompose_layers] rank {rank}: per-worker seconds in caldera() "
-                         f"{[round(t[0], 3) for t in host_time]}, in pack {[round(t[1], 3) for t in host_time]}\n")
-    return mine, results
+        sys.stderr.write(f"[decompose_layers] rank {rank}: {len(mine)} layers, submit {t_submit - t_start:.3f} s, "
+                         f"total {time.perf_counter() - t_start:.3f} s\n")
+    if pack:
+        return ShardResult(mine, arena, [results[i] for i in mine], records)
+    return mine, [results[i] for i in mine]

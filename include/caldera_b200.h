@@ -20,6 +20,7 @@
  *                          (maybe_update_Q :253-283, update_LR :128-198, LR_init :201-235,
  *                           quantize_matrix :245-250, activation_aware_error :286-302)
  *   cb_lowrank_init        LR_init                   RCR/caldera/decomposition/alg.py:201-235
+ *   cb_lplr_iter           one pass of the LPLR loop RCR/caldera/decomposition/alg.py:160-188
  *   cb_weighted_error      activation_aware_error    RCR/caldera/decomposition/alg.py:286-302
  *   cb_convex_prox_iters   solve_convex_optimization  RCR/convex_caldera/decomposition/convex_caldera.py:128-241
  *   cb_quantize_residual_f32  quantize_residual        RCR/convex_caldera/decomposition/convex_caldera.py:342-373
@@ -128,6 +129,23 @@ int cb_lowrank_init(const float* A, int64_t m, int64_t n, const float* h, int h_
                     float* L, float* R, float* sigma /* r, optional */,
                     void* ws, size_t ws_bytes, void* stream);
 size_t cb_lowrank_init_workspace_bytes(int64_t m, int64_t n, int64_t r, int64_t q_width, int h_kind);
+
+/* One iteration of the LPLR loop of update_LR (alg.py:160-188) from an injected state -- the stage the
+ * survey's test pyramid asks for.  Given the residual res = W - Q (m x n), the Hessian weights and the
+ * current R (r x n):
+ *   L_pre  = argmin_L ||(res - L R) H^(1/2)||_F   (alg.py:163; normal equations + Cholesky here)
+ *   L_idxs, L_scale, L_hat = whole-tensor quantisation of L_pre^T (alg.py:171-172; L_idxs has r*m codes in the
+ *                            order of (L^T).flatten(), int8 for l_bits <= 8 else int16; L_hat is m x r)
+ *   R_pre  = argmin_R ||res - L_hat R||_F         (alg.py:175)
+ *   R_idxs, R_scale, R_hat = quantisation of R_pre (alg.py:179-180)
+ *   err_sq = ||(res - L_hat R_hat) H_sqrt||_F^2   (alg.py:182; H_sqrt := H when aware == 0, alg.py:50)
+ * Every output pointer may be NULL.  status (3 device ints, optional): Cholesky ridge retries, unused, tcgen05
+ * watchdog.  h_kind: CB_H_IDENTITY or CB_H_DIAG. */
+size_t cb_lplr_iter_workspace_bytes(int64_t m, int64_t n, int64_t r, int l_bits, int r_bits, int use_tensor_cores);
+int cb_lplr_iter(const float* res, int64_t m, int64_t n, const float* h, int h_kind, int aware, int64_t r,
+                 int l_bits, int r_bits, const float* R_in, float* L_pre, void* L_idxs, float* L_scale, float* L_hat,
+                 float* R_pre, void* R_idxs, float* R_scale, float* R_hat, double* err_sq, int use_tensor_cores,
+                 int* status, void* ws, size_t ws_bytes, void* stream);
 
 /* Small dense helpers (exported for tests and for callers that build their own loops). */
 /* G (q x q, symmetric, row-major, destroyed) -> Lc in the lower triangle of G and

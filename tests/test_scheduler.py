@@ -89,6 +89,22 @@ def _worker(rank, world, port, ret):
         else:
             ok = got is None
         ok = ok and sum(len(r) for r in everyone) == 5
+        # fixed-layout job blobs: sizes are a function of (shape, params), so nothing but the payload is exchanged
+        prm = SimpleNamespace(compute_quantized_component=True, compute_low_rank_factors=True, Q_bits=2, L_bits=16,
+                              R_bits=16, rank=2, iters=1, lplr_iters=1)
+        shapes2 = [(8, 12), (16, 12), (8, 12), (8, 24), (16, 12)]
+        shards, sizes, rank_bytes, rank_offs = sch.shard_layout(prm, shapes2, world)
+        arena = torch.cat([torch.full((sizes[i],), i + 1, dtype=torch.uint8) for i in shards[rank]]) \
+            if shards[rank] else torch.empty(0, dtype=torch.uint8)
+        sch.warm_up_gather(torch.device("cpu"), dst=0)
+        for dst in (0, 1, None):
+            full = sch.gather_arena(arena, rank_bytes, dst=dst)
+            if dst is None or rank == dst:
+                parts = sch.split_gathered(full, shards, sizes)
+                ok = ok and sorted(parts) == list(range(5))
+                ok = ok and all(bool((parts[i] == i + 1).all()) and parts[i].numel() == sizes[i] for i in parts)
+            else:
+                ok = ok and full is None
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -101,3 +117,38 @@ def test_gather_gloo_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_blob_layout_and_fixed_header():
+    """The job's blobs have a layout that is a pure function of (shape, parameters): what lets the gather skip the
+    size exchange.  Header region fixed at HEADER_BYTES; sections 16-byte aligned; unpack_decomposition reads it."""
+    for lb, rb in ((16, 16), (4, 4), (16, 4)):
+        prm = SimpleNamespace(compute_quantized_component=True, compute_low_rank_factors=True, Q_bits=2, L_bits=lb,
+                              R_bits=rb, rank=8, iters=2, lplr_iters=2)
+        total, secs = sch.blob_layout(prm, (64, 96))
+        assert total % 256 == 0 and secs[0][3] == sch.HEADER_BYTES
+        names = [s_[0] for s_ in secs]
+        if lb < 16 or rb < 16:
+            assert names == ["Q_packed", "Q_scale", "L_packed", "R_packed", "L_scale", "R_scale"]
+            # a 16-bit factor next to a quantised one travels as 16-bit codes (alg.py:144), 2 bytes per element
+            assert dict((s_[0], s_[4]) for s_ in secs)["L_packed"] == 64 * 8 * lb // 8
+        else:
+            assert names == ["Q_packed", "Q_scale", "L", "R"]
+        for _, _, _, off, nb in secs:
+            assert off % 16 == 0 and off + nb <= total
+        # a blob assembled the way decompose_layers does it
+        blob = torch.zeros(total, dtype=torch.uint8)
+        meta = {"name": "x", "shape": [64, 96], "q_bits": 2, "l_bits": lb, "r_bits": rb, "global_scale": 0.02, "best_step": 1,
+                "errors": {"Q": [0.9], "LR": [0.8]},
+                "sections": [{"field": f, "dtype": d, "shape": list(shp), "offset": o - sch.HEADER_BYTES, "nbytes": nb}
+                             for f, d, shp, o, nb in secs]}
+        blob[:sch.HEADER_BYTES] = torch.frombuffer(bytearray(sch._header_bytes(meta)), dtype=torch.uint8)
+        for f, d, shp, o, nb in secs:
+            blob[o:o + nb] = (hash(f) % 251)
+        out = sch.unpack_decomposition(blob)
+        assert out["name"] == "x" and out["errors"] == meta["errors"]
+        for f, d, shp, o, nb in secs:
+            assert tuple(out[f].shape) == tuple(shp) and str(out[f].dtype) == "torch." + d
+    # a very long error trajectory is truncated rather than overflowing the fixed header
+    long_meta = {"name": "y", "errors": {"Q": [0.123456789] * 400, "LR": [0.5] * 400}, "sections": []}
+    assert len(sch._header_bytes(long_meta)) == sch.HEADER_BYTES
