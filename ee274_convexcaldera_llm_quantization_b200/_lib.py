@@ -78,6 +78,10 @@ _SIGNATURES = {
     "cb_gemm_bf16_tn_bf16out": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cb_gemm_bf16_tn_batched": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
     "cb_quantize_nf_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),

@@ -266,7 +266,8 @@ def caldera_async(
                                         kept, W_copy, dev)
 
         Wsrc = W if W.dtype == torch.float32 else W.float()
-        return get_engine(dev, slots).submit(p, Wsrc, h_kind, Hd, seed, finish, want_packed=return_packed,
+        # a consume hook reads the runner's packed outputs even when no packed clones are returned
+        return get_engine(dev, slots).submit(p, Wsrc, h_kind, Hd, seed, finish, want_packed=return_packed or consume is not None,
                                              want_w_scaled=want_w and scale_W, consume=consume_all)
 
 

@@ -98,6 +98,23 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
             __nv_bfloat16* Ct, int64_t ldct, const float* colscale, const float* rowscale, int splitk,
             int* error_flag, int* splits_used, cudaStream_t st, const SplitWs* sw = nullptr,
             int probe_flags = 0 /* bit 0: loads only (measurement aid) */);
+// gemm_tc2.cu -- batched, persistent CTA-pair variant: C[b] = alpha * A[b] * B[b]^T for b < batch, byte strides between
+// batch items (s*); outputs as in gemm_tc (fp32 C, bf16 Cb, transposed bf16 Ct, any subset)
+struct Gemm2Batch {
+  int64_t batch = 1, M = 0, N = 0, K = 0;
+  float alpha = 1.f;
+  const __nv_bfloat16* A = nullptr; int64_t lda = 0, sA = 0;
+  const __nv_bfloat16* B = nullptr; int64_t ldb = 0, sB = 0;
+  float* C = nullptr; int64_t ldc = 0, sC = 0;
+  __nv_bfloat16* Cb = nullptr; int64_t ldcb = 0, sCb = 0;
+  __nv_bfloat16* Ct = nullptr; int64_t ldct = 0, sCt = 0;
+  const float* colscale = nullptr; int64_t sCol = 0;
+  const float* rowscale = nullptr; int64_t sRow = 0;
+  int max_clusters = 0;          // 0 = one cluster per SM pair
+  int* error_flag = nullptr;
+};
+bool gemm_tc2_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);
+int gemm_tc2(const Gemm2Batch& g, cudaStream_t st);
 int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
             __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st);
 

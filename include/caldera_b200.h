@@ -193,6 +193,19 @@ int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const 
                             int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
                             void* stream);
 void cb_set_gemm_staged_epilogue(int on);
+/* The batched, persistent CTA-pair form of the same contraction (csrc/gemm_tc2.cu): for b < batch,
+ *   C[b] (M x N) = alpha * A[b] (M x K) * B[b] (N x K)^T  [* rowscale[b][i] * colscale[b][j]]
+ * with `tcgen05.mma.cta_group::2` on 256 x N_TILE tiles (N_TILE = min(256, N rounded up to 16)), two accumulators
+ * in tensor memory so that the epilogue of a tile overlaps the main loop of the next, and the batch as a third
+ * tensor-map dimension.  stride_*_bytes: distance between two batch items of each array (multiples of 16 for A and
+ * B).  Any subset of C (fp32), Cb (bf16 row-major), Ct (bf16, N x M) may be given.  max_clusters <= 0: one cluster
+ * per SM pair.  This is what the batched layer driver runs; exported for validation. */
+int cb_gemm_bf16_tn_batched(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
+                            int64_t stride_a_bytes, const void* B_bf16, int64_t ldb, int64_t stride_b_bytes, float* C,
+                            int64_t ldc, int64_t stride_c_bytes, void* Cb_bf16, int64_t ldcb, int64_t stride_cb_bytes,
+                            void* Ct_bf16, int64_t ldct, int64_t stride_ct_bytes, const float* colscale,
+                            int64_t stride_col_bytes, const float* rowscale, int64_t stride_row_bytes, int max_clusters,
+                            int* error_flag, void* stream);
 /* ---- consumer of the packed decomposition (the reference reconstructs a dense matrix,
  * main.py:197 / README.md:182 `W_hat = Q + L @ R`, and multiplies with that) ----
  * y[T, m] = global_scale * x[T, n] * (Q + L R)^T with Q = (codes / levels) * q_scale read from its packed

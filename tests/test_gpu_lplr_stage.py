@@ -74,9 +74,11 @@ def test_lplr_iteration_matches_reference(tc):
             assert de <= (3e-3 if on_tc else 3e-4), (nm, k, "inner error", de)
             # self-consistency: the codes, scales and dequantised factors returned belong together
             lv_l, lv_r = 2 ** (c["lb"] - 1) - 1, 2 ** (c["rb"] - 1) - 1
-            L_from_codes = (o["L_idxs"].float().reshape(r, -1).T / lv_l) * o["L_scale"]
-            assert torch.equal(L_from_codes.contiguous(), o["L_hat"])
-            assert torch.equal((o["R_idxs"].float().reshape(r, -1) / lv_r) * o["R_scale"], o["R_hat"])
+            # (on the CPU: torch's CUDA `tensor / python_scalar` multiplies by a reciprocal; the library and the
+            # reference on CPU use the IEEE divide of quantization.py:105)
+            L_from_codes = (o["L_idxs"].cpu().float().reshape(r, -1).T / lv_l) * o["L_scale"].cpu()
+            assert torch.equal(L_from_codes.contiguous(), o["L_hat"].cpu())
+            assert torch.equal((o["R_idxs"].cpu().float().reshape(r, -1) / lv_r) * o["R_scale"].cpu(), o["R_hat"].cpu())
             R_prev = torch.from_numpy(z[f"{nm}_{k}_R_hat"]).to(DEV)
     print(f"\n[lplr stage, tensor_cores={tc}] case iter |dL_pre| |dR_pre| L-code-mismatch R-code-mismatch |d err|")
     for row in report:
