@@ -6,9 +6,10 @@
 Metric (BASELINE.json): decomposed matrices / s at 4096 x 4096, rank 128, 2-bit Q
 (config[1]: L/R 16-bit, activation aware, 5 outer iterations, update_order Q,LR); second half of the metric:
 wall seconds of the full Llama-2-7B-shape job (config[3]), emitted as `full_7b_wall_s` on the same line.
-One step = one batch of `--streams` independent layers (one full caldera() decomposition each).
+One step = `--slots` x `--batch` independent layers (one full caldera() decomposition each): `--slots` CUDA-graph
+replays in flight, each advancing `--batch` same-shape layers in lock step (cb_caldera_batch).
 
-  value     matrices/s with inputs resident in HBM (one CUDA-graph replay per layer, CUDA-event timed, max over ranks)
+  value     matrices/s with inputs resident in HBM (CUDA-event timed, max over ranks)
   e2e       the same through the public API (caldera_async) with HOST (pinned) inputs: H2D of W and h, the
             decomposition, D2H of the packed result, all inside the timed region; ONE host thread per rank
   full_7b_wall_s   224 layers layer-sharded over the ranks + gather of the packed blobs on rank 0, for L/R 16-bit and
@@ -364,7 +365,7 @@ def run_ours(args):
     from ee274_convexcaldera_llm_quantization_b200 import scheduler as sch
     from ee274_convexcaldera_llm_quantization_b200.alg import make_c_params, caldera, caldera_async
     from ee274_convexcaldera_llm_quantization_b200.engine import get_engine, release_engines
-    from ee274_convexcaldera_llm_quantization_b200.runner import CalderaLayerRunner
+    import ctypes as C
     from src.caldera.utils.dataclasses import CalderaParams
     from src.caldera.utils.quantization import QuantizerFactory
 
@@ -405,18 +406,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident timing (value): one CUDA-graph replay per layer, `nstreams` layers in flight, one host thread
-    nstreams = max(1, args.streams)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
-    runners = [CalderaLayerRunner(cp, M, N, _lib.CB_H_DIAG, dev, want_packed=True, want_w_scaled=False)
-               for _ in range(nstreams)]
-    runner = runners[0]
+    # ---- resident timing (value): `slots` graph replays in flight, each advancing `batch` layers in lock step
+    # (cb_caldera_batch); inputs resident in HBM, staged into the batch's slabs by device-side copies; one host thread
+    nslots, nbatch = max(1, args.slots), max(1, args.batch)
+    nstreams = nslots * nbatch                          # layers in flight
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nslots)]
+    from ee274_convexcaldera_llm_quantization_b200.runner import BatchRunner
+    assert lib.cb_caldera_batch_supported(C.byref(cp), M, N, _lib.CB_H_DIAG), "workload must take the batched driver"
+    runners = [BatchRunner(cp, M, N, _lib.CB_H_DIAG, nbatch, dev, want_packed=True) for _ in range(nslots)]
     for s_, r_ in zip(streams, runners):
         with torch.cuda.stream(s_):
             r_.capture()
     torch.cuda.synchronize()
 
     def run_resident(first, count):
+        """`count` batches (of nbatch layers) round robin over the slots."""
         main_stream = torch.cuda.current_stream()
         start = torch.cuda.Event(enable_timing=True)
         stop = torch.cuda.Event(enable_timing=True)
@@ -424,9 +428,11 @@ def run_ours(args):
         for s_ in streams:
             s_.wait_event(start)
         for i in range(count):
-            W, h = dev_layers[(first + i) % npool]
-            with torch.cuda.stream(streams[i % nstreams]):
-                runners[i % nstreams].launch(W, h, seed=1000 + rank)
+            r_ = runners[i % nslots]
+            with torch.cuda.stream(streams[i % nslots]):
+                for b in range(nbatch):
+                    r_.stage(b, *dev_layers[(first + i * nbatch + b) % npool])
+                r_.replay([1000 + rank] * nbatch)
         for s_ in streams:
             ev = torch.cuda.Event()
             ev.record(s_)
@@ -434,29 +440,41 @@ def run_ours(args):
         stop.record(main_stream)
         return start, stop
 
-    batch = nstreams                      # one step = one batch of `nstreams` independent layers
-    run_resident(0, args.warmup * batch)
+    batch = nstreams                      # one step = `nslots` batches of `nbatch` independent layers
+    run_resident(0, args.warmup * nslots)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     launches0 = lib.cb_kernel_launch_count()
-    e0, e1 = run_resident(args.warmup * batch, args.steps * batch)
+    e0, e1 = run_resident(args.warmup * nslots, args.steps * nslots)
     barrier()
     launches = lib.cb_kernel_launch_count() - launches0
     secs = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
-    errs = runner.read_small()[:runner.nsteps].tolist()
-    # single-stream latency of one layer, for reference
+    v0 = runners[0].layers[0]
+    errs = v0.small[:v0.nsteps].cpu().tolist()
+    # latency of one batch alone, and of a lone layer (batch of one), for reference
     torch.cuda.synchronize()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record()
-    runner.launch(*dev_layers[0], seed=1000 + rank)
+    runners[0].replay([1000 + rank] * nbatch)
+    l1.record()
+    torch.cuda.synchronize()
+    batch_latency_ms = l0.elapsed_time(l1)
+    kernels_per_layer = runners[0].graph_kernels / nbatch
+    del runners, streams, v0
+    torch.cuda.empty_cache()
+    lone = BatchRunner(cp, M, N, _lib.CB_H_DIAG, 1, dev, want_packed=True)
+    lone.capture()
+    lone.stage(0, *dev_layers[0])
+    torch.cuda.synchronize()
+    l0.record()
+    lone.replay([1000 + rank])
     l1.record()
     torch.cuda.synchronize()
     layer_latency_ms = l0.elapsed_time(l1)
-    kernels_per_layer = runner.graph_kernels
-    del runners, runner, streams
+    del lone
     torch.cuda.empty_cache()
 
     # ---- end-to-end timing through the public API: ONE host thread, pinned host buffers in, packed result out.
@@ -464,7 +482,7 @@ def run_ours(args):
     # and the `consume` hook enqueues the D2H copies of the packed codes and the factors into pinned host buffers;
     # the ~100-byte result record (error trajectory, scales) follows.  `.result()` is called a batch later, so the
     # host never waits for the layer it has just submitted.
-    engine = get_engine(dev, nstreams)
+    engine = get_engine(dev, nslots, nbatch)
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
                  for _ in range(nstreams)]
@@ -478,7 +496,7 @@ def run_ours(args):
             dst["L"].copy_(run.L, non_blocking=True)
             dst["R"].copy_(run.R, non_blocking=True)
         return caldera_async(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank, return_dense=False,
-                             return_packed=False, consume=to_host, slots=nstreams)
+                             return_packed=False, consume=to_host, slots=nslots, batch=nbatch)
 
     def run_e2e(first, count):
         pending, last = [], None
@@ -486,6 +504,7 @@ def run_ours(args):
             pending.append(submit_e2e(first + i))
             if len(pending) > nstreams:                  # harvest a layer submitted a whole batch ago
                 last = pending.pop(0).result()
+        engine.flush()
         for hd in pending:
             last = hd.result()
         return last
@@ -540,7 +559,8 @@ def run_ours(args):
             prm = params_for(lbits)
             res = None
             for attempt in range(2):
-                res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams, barrier=barrier)
+                res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams, slots=nslots,
+                                       barrier=barrier)
                 tt = torch.tensor([res["decompose_s"], res["gather_s"], res["wall_s"]], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -570,7 +590,8 @@ def run_ours(args):
                 "dtype": "f32 I/O, bf16 tensor-core operands, f32 accumulate (f32 small factorisations)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "l2": "inputs larger than L2: every layer in flight has a ~0.5 GiB working set (126 MB L2), 3 input "
                                  "layers rotated; the roofline probes rotate >= 192 MB of operands",
-                           "layers_per_step": batch, "layers_in_flight": nstreams, "e2e_host_threads": 1,
+                           "layers_per_step": batch, "layers_in_flight": nstreams, "graph_replays_in_flight": nslots,
+                           "layers_per_replay": nbatch, "e2e_host_threads": 1, "batch_latency_ms": batch_latency_ms,
                            "e2e_result": "packed Q codes + scale, L, R, error trajectory",
                            "hw_queues": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "execution_mode": args.mode, "cuda_graphs": True, "single_layer_latency_ms": layer_latency_ms,
                            "kernels_per_layer": kernels_per_layer,
@@ -628,10 +649,11 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity report against the stored reference run")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
     ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
-    ap.add_argument("--model-streams", type=int, default=24, help="layers in flight per GPU in the model-level job")
+    ap.add_argument("--model-streams", type=int, default=48, help="layers in flight per GPU in the model-level job")
+    ap.add_argument("--slots", type=int, default=3, help="graph replays in flight per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="same-shape layers advancing in lock step per graph replay")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="library execution mode (cb_set_execution_mode)")
-    ap.add_argument("--streams", type=int, default=32, help="independent layers kept in flight per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "cb_cholesky_inverse_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_jacobi_eigh_from_chol_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p]),
+    "cb_min_eig_shift_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "cb_min_eig_shift_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cb_sgemm_strided": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_int, C.c_void_p]),
@@ -116,6 +118,9 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_scale_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_caldera_layer_workspace_bytes": (C.c_size_t, [C.POINTER(cb_caldera_params), C.c_int64, C.c_int64, C.c_int]),
+    "cb_caldera_batch_supported": (C.c_int, [C.POINTER(cb_caldera_params), C.c_int64, C.c_int64, C.c_int]),
+    "cb_caldera_batch": (C.c_int, [C.POINTER(cb_caldera_params), C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_void_p, C.c_int, C.POINTER(cb_caldera_out), C.c_void_p, C.c_size_t, C.c_void_p]),
     "cb_caldera_layer": (C.c_int, [C.POINTER(cb_caldera_params), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                    C.c_int, C.POINTER(cb_caldera_out), C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -222,6 +222,8 @@ def caldera_async(
     return_dense: bool = True,
     consume=None,
     slots: Optional[int] = None,
+    batch: Optional[int] = None,
+    batch_hint: Optional[int] = None,
 ):
     """caldera() without the wait: enqueues the layer on the device's LayerEngine (engine.py) and returns a handle
     whose `.result()` is the CalderaDecomposition.  One host thread can keep dozens of layers in flight this way
@@ -231,7 +233,11 @@ def caldera_async(
              may enqueue device-side copies of the runner's outputs (run.Q_packed, run.L, ...) to wherever they
              are going (a wire-format arena, pinned host buffers); with a hook, and return_dense / return_packed
              False, no per-layer clones are made at all;
-    slots    layers kept in flight by the engine (first use per device decides; default 32)."""
+    slots / batch  geometry of the device's engine: `slots` graph replays in flight, each advancing up to `batch`
+             same-shape layers in lock step (defaults 3 x 16; the batched driver needs the tensor-core path, a
+             diagonal / identity Hessian and rank <= 192 -- other configurations run one layer per replay);
+    batch_hint  how many layers of this shape are about to be submitted (a short job then uses a smaller batch).
+    A handle's layer starts when its batch is full, on `engine.flush()`, or when `.result()` is called."""
     del use_tqdm
     quant_factors = _validate(quant_params, W)
     dev = _resolve_device(device, W)
@@ -267,8 +273,10 @@ def caldera_async(
 
         Wsrc = W if W.dtype == torch.float32 else W.float()
         # a consume hook reads the runner's packed outputs even when no packed clones are returned
-        return get_engine(dev, slots).submit(p, Wsrc, h_kind, Hd, seed, finish, want_packed=return_packed or consume is not None,
-                                             want_w_scaled=want_w and scale_W, consume=consume_all)
+        return get_engine(dev, slots, batch).submit(p, Wsrc, h_kind, Hd, seed, finish,
+                                                    want_packed=return_packed or consume is not None,
+                                                    want_w_scaled=want_w and scale_W, consume=consume_all,
+                                                    batch_hint=batch_hint)
 
 
 def caldera(
@@ -313,7 +321,7 @@ def caldera(
         return caldera_async(quant_params, W, H, device, use_tqdm, scale_W, W_copy=W_copy, global_scale=global_scale,
                              sketch_width=sketch_width, power_iters=power_iters, power_iters_warm=power_iters_warm,
                              warm_start=warm_start, seed=seed, return_packed=return_packed,
-                             use_tensor_cores=use_tensor_cores, return_dense=return_dense).result()
+                             use_tensor_cores=use_tensor_cores, return_dense=return_dense, batch_hint=1).result()
     quant_factors = _validate(quant_params, W)
     dev = _resolve_device(device, W)
     _lib.load()

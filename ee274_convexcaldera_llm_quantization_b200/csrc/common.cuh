@@ -64,6 +64,12 @@ inline int opt_in_dynamic_smem(Kernel kernel, int bytes, PerDeviceOnce& once) {
   return CB_OK;
 }
 
+// Batched launches: layer b of a batch keeps every buffer b * stride bytes after layer 0's (one slab per layer), so
+// a batched kernel takes layer-0 pointers plus that stride and picks its layer from a grid dimension.
+template <typename T> __host__ __device__ __forceinline__ T* boff(T* p, int64_t bytes) {
+  return p == nullptr ? nullptr : reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + (uintptr_t)bytes);
+}
+
 constexpr int kNumSMs = 148;  // B200
 
 inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {

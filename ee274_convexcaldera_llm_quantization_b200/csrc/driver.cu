@@ -132,9 +132,10 @@ static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, 
   return b;
 }
 
-__global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p, int64_t count, uint64_t seed,
-                                                         const uint64_t* __restrict__ seed_dev) {
-  if (seed_dev != nullptr) seed += seed_dev[0];
+__global__ void __launch_bounds__(256) randn_bf16_kernel(bf16* __restrict__ p_, int64_t count, uint64_t seed,
+                                                         const uint64_t* __restrict__ seed_dev, int64_t bstride) {
+  bf16* __restrict__ p = boff(p_, bstride * blockIdx.y);           // one layer of a batch per blockIdx.y
+  if (seed_dev != nullptr) seed += boff(seed_dev, bstride * blockIdx.y)[0];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
     p[i] = __float2bfloat16_rn(gaussian_from(seed, (uint64_t)i));
@@ -157,7 +158,7 @@ static int lowrank_core_tc(int64_t m, int64_t n, int64_t r, int64_t q, int niter
                            const LowrankTcBufs& b, cudaStream_t st) {
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
   if (!warm_valid) {
-    randn_bf16_kernel<<<grid_for(q * n, 256 * 4, 4), 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev);
+    randn_bf16_kernel<<<grid_for(q * n, 256 * 4, 4), 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev, 0);
     CB_CHECK_LAUNCH();
     // Zt[q, m] = Pt[q, K=n] * Y[m, K=n]^T
     CB_TRY(gemm_tc(q, m, n, 1.f, b.Ptb, n, b.Yb, n, nullptr, 0, b.Ztb, m, b.Zb, q, nullptr, nullptr, 1, wd, nullptr, st));
@@ -234,7 +235,7 @@ struct LayerPlan {
   bf16 *Lb16, *Rtb16;   // bf16 hi/lo splits of L (m x 3r) and R^T (n x 3r) for the tensor-core L R product
   bf16 *Rsb16, *Ltb16;  // LPLR operands: R (.) sqrt(h) (r x n) and L^T (r x m)
   // dense (non-diagonal) Hessian
-  float *Hs, *Ebuf, *Tbuf, *HP, *HRt;
+  float *Hs, *Ebuf, *Tbuf, *HP, *HRt, *eigwork;
   int64_t q;
   bool quant_factors;
   bool use_tc;
@@ -300,6 +301,7 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
   }
   if (L.dense) {
     L.Hs = a.take<float>(n * n);
+    L.eigwork = p->aware ? a.take<float>(min_eig_shift_workspace_floats(n)) : nullptr;
     L.Ebuf = a.take<float>(m * n);
     L.Tbuf = a.take<float>(m * n);
     if (p->compute_lr) {
@@ -327,7 +329,6 @@ static int validate_params(const cb_caldera_params* p, int64_t m, int64_t n, int
     if ((p->l_bits < 16 || p->r_bits < 16) && p->lplr_iters < 1 && lr_scheduled && p->iters > 0) return CB_ERR_ARG;
   }
   if (h_kind != CB_H_IDENTITY && h_kind != CB_H_DIAG && h_kind != CB_H_DENSE) return CB_ERR_ARG;
-  if (h_kind == CB_H_DENSE && p->aware && p->sigma_reg > 0.f) return CB_ERR_UNSUPPORTED;  // needs lambda_min(H)
   if (p->q_block != 0) return CB_ERR_UNSUPPORTED;
   return CB_OK;
 }
@@ -400,8 +401,10 @@ static int dense_quadratic(const LayerPlan& P, const float* A, const void* codes
 // so the product carries ~16 mantissa bits: the residual W - L R that the Q update quantises
 // and the reported error then agree with the fp32 factors that are returned.
 __global__ void __launch_bounds__(256)
-split3_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int transpose, int second_is_lo,
-              bf16* __restrict__ out /* rows_out x 3*inner */) {
+split3_kernel(const float* __restrict__ X_, int64_t rows, int64_t cols, int transpose, int second_is_lo,
+              bf16* __restrict__ out_ /* rows_out x 3*inner */, int64_t bstride = 0) {
+  const float* __restrict__ X = boff(X_, bstride * blockIdx.y);
+  bf16* __restrict__ out = boff(out_, bstride * blockIdx.y);
   // transpose == 0: X is rows x cols, out row i = [hi(i,:) | (lo or hi)(i,:) | (hi or lo)(i,:)] with inner = cols
   // transpose == 1: X is rows x cols, out row j (of cols) built from column j, inner = rows
   const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
@@ -520,6 +523,160 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
   return CB_OK;
 }
 
+// ================================================================ batched layers
+// B same-shape layers advancing in lock step (Bt: layer b's buffers sit b * stride bytes after layer 0's).  Every
+// contraction of the rank-r step, the small factorisations and the bookkeeping kernels are ONE launch for the whole
+// batch -- the batched CTA-pair contraction of gemm_tc2.cu (hundreds of tiles per launch instead of 16-32), one CTA
+// per layer for Cholesky / Jacobi -- and only the HBM-bound full-matrix passes, which fill the machine on their own,
+// are launched layer by layer.  Orientation: gemm_tc2 owns 256-row tiles of its M, so the long dimension of every
+// skinny contraction goes to M and the sketch width q (224) becomes the instruction's N.
+static int g2(const Bt& bt, int64_t M, int64_t N, int64_t K, const bf16* A, int64_t lda, const bf16* B, int64_t ldb,
+              float* C, int64_t ldc, bf16* Cb, int64_t ldcb, bf16* Ct, int64_t ldct, const float* colscale, int* wd,
+              cudaStream_t st) {
+  Gemm2Batch g;
+  g.batch = bt.n; g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.sA = bt.stride; g.B = B; g.ldb = ldb; g.sB = bt.stride;
+  g.C = C; g.ldc = ldc; g.sC = bt.stride; g.Cb = Cb; g.ldcb = ldcb; g.sCb = bt.stride; g.Ct = Ct; g.ldct = ldct; g.sCt = bt.stride;
+  g.colscale = colscale; g.sCol = bt.stride; g.error_flag = wd;
+  return gemm_tc2(g, st);
+}
+
+// Xt (q x N) and X (N x q) hold the same raw sketch; writes its orthonormalised form as Xot (q x N) and/or Xo (N x q)
+static int orthonormalize_b(const Bt& bt, const bf16* Xt, const bf16* X, int64_t N, int64_t q, bf16* Xot, bf16* Xo,
+                            const LowrankTcBufs& b, cudaStream_t st) {
+  int* wd = b.status != nullptr ? b.status + 2 : nullptr;
+  CB_TRY(g2(bt, q, q, N, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st));              // G = X^T X
+  CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st, b.Linvb, bt));
+  return g2(bt, N, q, q, X, q, b.Linvb, q, nullptr, 0, Xo, q, Xot, N, nullptr, wd, st);                // Xo = X Linv^T
+}
+
+static int copy_b(const Bt& bt, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  CopySegments c;
+  c.add(dst, src, bytes);
+  return copy_if_multi(nullptr, c, st, bt);
+}
+
+static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t q, int niter, uint64_t seed, int aware,
+                          const float* inv_sqrt_h, bool warm_valid, float* L, float* R, const LowrankTcBufs& b, cudaStream_t st) {
+  int* wd = b.status != nullptr ? b.status + 2 : nullptr;
+  if (!warm_valid) {
+    dim3 grid((unsigned)grid_for(q * n, 256 * 4, 1), (unsigned)bt.n);
+    randn_bf16_kernel<<<grid, 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev, bt.stride);
+    CB_CHECK_LAUNCH();
+    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Ptb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));        // Z = Y P
+    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  }
+  for (int it = 0; it < niter; ++it) {
+    CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Pb, q, b.Ptb, n, nullptr, wd, st));      // P = Y^T Zo
+    CB_TRY(orthonormalize_b(bt, b.Ptb, b.Pb, n, q, b.Potb, nullptr, b, st));
+    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Potb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));       // Z = Y Po
+    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  }
+  // CholeskyQR2 on the (bf16-rounded) basis itself
+  {
+    CopySegments c;
+    c.add(b.Ztb, b.Zotb, sizeof(bf16) * q * m);
+    c.add(b.Zb, b.Zob, sizeof(bf16) * q * m);
+    CB_TRY(copy_if_multi(nullptr, c, st, bt));
+  }
+  CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+  // B = Zo^T Y (q x n) in both orientations; G = B B^T in fp32
+  CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Btb, q, b.Bb, n, nullptr, wd, st));
+  CB_TRY(g2(bt, q, q, n, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st, nullptr, bt));
+  CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st, bt));
+  CB_TRY(to_bf16(b.V, q, q, q, b.Vb, q, nullptr, 0, nullptr, st, bt));
+  // L[m, r] = Zo V_r^T ;  R[r, n] = V_r B (column-scaled by 1 / sqrt(h))
+  CB_TRY(g2(bt, m, r, q, b.Zob, q, b.Vb, q, L, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(g2(bt, r, n, q, b.Vb, q, b.Btb, q, R, n, nullptr, 0, nullptr, 0, aware ? inv_sqrt_h : nullptr, wd, st));
+  if (!aware) {
+    for (int k = 0; k < bt.n; ++k) {
+      CB_TRY(scale_cols(at(L, bt, k), m, r, at(b.evals, bt, k), 2, at(L, bt, k), st));
+      CB_TRY(scale_rows(at(R, bt, k), r, n, at(b.evals, bt, k), 3, at(R, bt, k), st));
+    }
+  }
+  // rotate the stored basis into its Ritz vectors for the next warm start
+  CB_TRY(g2(bt, m, q, q, b.Zob, q, b.Vb, q, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));
+  CopySegments c;
+  c.add(b.Zob, b.Zb, sizeof(bf16) * m * q);
+  c.add(b.Zotb, b.Ztb, sizeof(bf16) * m * q);
+  return copy_if_multi(nullptr, c, st, bt);
+}
+
+static int lr_product_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
+  dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
+  split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
+  CB_CHECK_LAUNCH();
+  split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
+  CB_CHECK_LAUNCH();
+  return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st);
+}
+
+// lplr_step_tc for a batch: contractions batched, the fp32 r x r solves and the whole-tensor quantiser per layer
+static int lplr_step_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+  const int64_t r = p->rank;
+  const float* res = p->aware ? P.RES : P.Y;
+  int* wd = P.flags + 4;
+  auto spd = [&](cudaStream_t s_) -> int {
+    CB_TRY(cholesky_inverse(P.Gs, (int)r, P.Linv, P.flags + 2, s_, nullptr, bt));
+    for (int k = 0; k < bt.n; ++k)
+      CB_TRY(sgemm(r, r, r, 1.f, at(P.Linv, bt, k), 1, r, at(P.Linv, bt, k), r, 1, at(P.Ginv, bt, k), r, 1, false, nullptr, s_));
+    return CB_OK;
+  };
+  // ---- L update (alg.py:163 / :167)
+  CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st, bt));
+  CB_TRY(g2(bt, r, r, n, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(g2(bt, m, r, n, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(spd(st));
+  for (int k = 0; k < bt.n; ++k) {
+    CB_TRY(sgemm(m, r, r, 1.f, at(P.Bl, bt, k), r, 1, at(P.Ginv, bt, k), r, 1, at(P.Ltmp, bt, k), r, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(at(P.Ltmp, bt, k), m, r, p->l_bits, at(P.Lcodes_cur, bt, k), at(P.Lscale_cur, bt, k), at(P.Lcur, bt, k), st));
+  }
+  // ---- R update (alg.py:175)
+  CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st, bt));
+  CB_TRY(g2(bt, r, r, m, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(g2(bt, r, n, m, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr, wd, st));
+  CB_TRY(spd(st));
+  for (int k = 0; k < bt.n; ++k) {
+    CB_TRY(sgemm(r, n, r, 1.f, at(P.Ginv, bt, k), r, 1, at(P.Br, bt, k), n, 1, at(P.Rtmp, bt, k), n, 1, false, nullptr, st));
+    CB_TRY(quantize_whole(at(P.Rtmp, bt, k), r, n, p->r_bits, at(P.Rcodes_cur, bt, k), at(P.Rscale_cur, bt, k), at(P.Rcur, bt, k), st));
+  }
+  // ---- inner error (alg.py:182)
+  CB_TRY(lr_product_b(bt, P, m, n, r, st));
+  for (int k = 0; k < bt.n; ++k)
+    CB_TRY(err_accum(at(res, bt, k), nullptr, 8, nullptr, at(P.LRbuf, bt, k), at(P.w_inner, bt, k), m, n, at(P.dsc, bt, k) + 3, st));
+  return CB_OK;
+}
+
+static int lplr_refine_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, cudaStream_t st) {
+  const int64_t r = p->rank;
+  for (int k = 0; k < p->lplr_iters; ++k) {
+    CB_TRY(lplr_step_b(bt, p, P, m, n, st));
+    CB_TRY(select_inner(P.dsc + 3, P.scalars, P.flags, k == 0, k == p->lplr_iters - 1, st, bt));
+    CopySegments best;
+    best.add(P.Lb, P.Lcur, sizeof(float) * m * r);
+    best.add(P.Rb, P.Rcur, sizeof(float) * r * n);
+    best.add(P.Lcodes_in, P.Lcodes_cur, (size_t)m * r * code_bytes(p->l_bits));
+    best.add(P.Rcodes_in, P.Rcodes_cur, (size_t)r * n * code_bytes(p->r_bits));
+    best.add(P.Lscale_in, P.Lscale_cur, sizeof(float));
+    best.add(P.Rscale_in, P.Rscale_cur, sizeof(float));
+    CB_TRY(copy_if_multi(P.flags + 1, best, st, bt));
+  }
+  CopySegments c;
+  c.add(P.Lcur, P.Lb, sizeof(float) * m * r);
+  c.add(P.Rcur, P.Rb, sizeof(float) * r * n);
+  return copy_if_multi(nullptr, c, st, bt);
+}
+
+// Which layers the batched driver takes: the production path (tensor-core contractions, identity / diagonal Hessian,
+// a sketch the one-CTA-per-layer eigensolver holds).  Everything else runs through cb_caldera_layer.
+static bool batch_supported(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
+  if (validate_params(p, m, n, h_kind) != CB_OK) return false;
+  if (h_kind == CB_H_DENSE || !p->compute_lr || !p->compute_q || !p->use_tensor_cores) return false;
+  const int64_t q = default_sketch_width(p, m, n);
+  return lowrank_tc_usable(m, n, p->rank, q) && m % 4 == 0 && n % 4 == 0 && q <= 224 && q % 4 == 0;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -584,8 +741,13 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   const float* Ws = scale_w ? P.Ws : W;
   if (P.dense) {
     // alg.py:54 symmetrises only in the activation-aware branch; otherwise H is used as given
-    if (p->aware) CB_TRY(symmetrize(h, n, P.Hs, st));
-    else CB_CUDA(cudaMemcpyAsync(P.Hs, h, sizeof(float) * n * n, cudaMemcpyDeviceToDevice, st));
+    if (p->aware) {
+      CB_TRY(symmetrize(h, n, P.Hs, st));
+      // alg.py:57-64: lift the spectrum to sigma_reg when its lower end is below it
+      CB_TRY(min_eig_shift(P.Hs, n, p->sigma_reg, P.eigwork, nullptr, st));
+    } else {
+      CB_CUDA(cudaMemcpyAsync(P.Hs, h, sizeof(float) * n * n, cudaMemcpyDeviceToDevice, st));
+    }
     CB_CUDA(cudaMemsetAsync(P.dsc + 1, 0, sizeof(double), st));
     CB_TRY(dense_quadratic(P, Ws, nullptr, 8, nullptr, nullptr, m, n, false, P.dsc + 1, st));   // tr(W H W^T)
   }
@@ -728,6 +890,176 @@ extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int6
   CB_CUDA(cudaMemcpyAsync(out->scalars + 5, P.flags + 2, sizeof(int) * 3, cudaMemcpyDeviceToDevice, st));
   CB_CUDA(cudaMemcpyAsync(out->scalars + 4, P.flags + 5, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return CB_OK;
+}
+
+// ---------------------------------------------------------------- batched layer driver
+// cb_caldera_layer for `batch` same-shape layers in lock step on one stream.  Layer b reads W + b * stride, h + b *
+// stride and writes through out-> pointers + b * stride; its workspace starts at ws + b * stride (stride in bytes, a
+// multiple of 256; one slab per layer holds all of these).  Same arithmetic per layer as the single-layer driver with
+// the batched contraction engine; results do not depend on the batch size or on a layer's position in the batch.
+extern "C" int cb_caldera_batch_supported(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
+  return (p != nullptr && batch_supported(p, m, n, h_kind)) ? 1 : 0;
+}
+
+extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t stride_bytes, const float* W, int64_t m,
+                                int64_t n, const float* h, int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  CB_TRY(validate_params(p, m, n, h_kind));
+  if (batch < 1 || (batch > 1 && (stride_bytes <= 0 || stride_bytes % 256 != 0))) return CB_ERR_ARG;
+  if (!batch_supported(p, m, n, h_kind)) return CB_ERR_UNSUPPORTED;
+  if (W == nullptr || out == nullptr || ws == nullptr) return CB_ERR_ARG;
+  if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
+  if (out->Q == nullptr || out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr ||
+      out->Q_idxs == nullptr || out->Q_scale == nullptr)
+    return CB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Bt bt;
+  bt.n = batch; bt.stride = batch > 1 ? stride_bytes : 0;
+  const int64_t r = p->rank;
+  const int64_t numel = m * n;
+  const bool scale_w = p->scale_w != 0;
+
+  Arena a{reinterpret_cast<uint8_t*>(ws), 0, ws_bytes};
+  LayerPlan P{};
+  CB_TRY(plan_layer(a, p, m, n, scale_w, h_kind, P));
+  if (P.quant_factors && (out->L_idxs == nullptr || out->R_idxs == nullptr || out->L_scale == nullptr || out->R_scale == nullptr))
+    return CB_ERR_ARG;
+  P.lr.status = P.flags + 2; P.tc.status = P.flags + 2;
+  P.lr.seed_dev = out->seed_dev; P.tc.seed_dev = out->seed_dev;
+  const int qcb = code_bytes(p->q_bits), lcb = code_bytes(p->l_bits), rcb = code_bytes(p->r_bits);
+
+  // ---- initial state: Q = 0, L = 0, R = 0 (alg.py:71-75)
+  {
+    CopySegments z;
+    z.add(P.dsc, nullptr, sizeof(double) * 4);
+    z.add(P.flags, nullptr, sizeof(int) * 8);
+    z.add(out->L, nullptr, sizeof(float) * m * r);
+    z.add(out->R, nullptr, sizeof(float) * r * n);
+    z.add(out->Q_idxs, nullptr, (size_t)numel * qcb);
+    z.add(out->Q_scale, nullptr, sizeof(float));
+    if (p->iters * p->n_order > 0) z.add(out->errors, nullptr, sizeof(float) * p->iters * p->n_order);
+    CB_TRY(copy_if_multi(nullptr, z, st, bt));
+    CopySegments z2;
+    z2.add(P.Lcur, nullptr, sizeof(float) * m * r);
+    z2.add(P.Rcur, nullptr, sizeof(float) * r * n);
+    if (P.quant_factors) {
+      z2.add(P.Lcodes_out, nullptr, (size_t)m * r * lcb);
+      z2.add(out->R_idxs, nullptr, (size_t)r * n * rcb);
+    }
+    CB_TRY(copy_if_multi(nullptr, z2, st, bt));
+  }
+  // ---- global scale, scaled W, error denominator, Hessian vectors
+  if (scale_w && !(p->global_scale_in > 0.f))
+    for (int b = 0; b < bt.n; ++b) CB_TRY(sumsq(at(W, bt, b), numel, at(P.dsc, bt, b), st));
+  CB_TRY(finalize_global_scale(P.dsc + 0, numel, p->global_scale_in, scale_w, P.scalars, st, bt));
+  CB_TRY(prep_hessian_diag(h_kind == CB_H_DIAG ? h : nullptr, n, p->sigma_reg, p->aware, P.h_eff, P.sqrt_h, P.inv_sqrt_h,
+                           P.w_inner, nullptr, st, bt));
+  for (int b = 0; b < bt.n; ++b)
+    CB_TRY(scale_and_den(at(W, bt, b), at(P.Ws, bt, b), m, n, at(P.scalars, bt, b), at(P.h_eff, bt, b), at(P.dsc, bt, b) + 1, st));
+  const float* Ws = scale_w ? P.Ws : W;
+  if (out->W_scaled != nullptr) CB_TRY(copy_b(bt, out->W_scaled, Ws, sizeof(float) * numel, st));
+
+  const int niter_cold = p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 12);
+  const int niter_warm = p->power_iters_warm >= 0 ? p->power_iters_warm
+                                                  : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
+  bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
+  bool y_valid = false, amax_valid = false;
+  bool updated[8] = {false, false, false, false, false, false, false, false};
+  float* res_out = P.quant_factors ? (p->aware ? P.RES : P.Y) : nullptr;   // fp32 residual W - Q for the LPLR loop
+  int step = 0;
+  for (int it = 0; it < p->iters; ++it) {
+    for (int oi = 0; oi < p->n_order; ++oi, ++step) {
+      const int which = p->order[oi];
+      bool num_ready = false;
+      if (which == 0) {
+        // ---- Q update (maybe_update_Q, alg.py:253-283) fused with the bf16 operand builder of the next rank-r step
+        const float* lrp = nullptr;
+        if (have_lr) {
+          if (!lrbuf_valid) CB_TRY(lr_product_b(bt, P, m, n, r, st));
+          lrbuf_valid = true;
+          lrp = P.LRbuf;
+        }
+        for (int b = 0; b < bt.n; ++b) {
+          if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(at(Ws, bt, b), at(lrp, bt, b), numel, at(P.amax, bt, b), st));
+          CB_TRY(quant_form_y_bf16(at(Ws, bt, b), at(lrp, bt, b), at(P.h_eff, bt, b), p->aware ? at(P.sqrt_h, bt, b) : nullptr, m, n,
+                                   at(P.amax, bt, b), 1e-8f, p->q_bits, at(P.codes_cur, bt, b), at(P.qscale_cur, bt, b),
+                                   at(P.dsc, bt, b) + 2, at(P.tc.Yb, bt, b), at(P.tc.Ytb, bt, b), at(res_out, bt, b), st));
+        }
+        y_valid = true;
+        have_q = true;
+        num_ready = true;
+      } else {
+        // ---- LR update (maybe_update_LR / update_LR, alg.py:115-198)
+        if (y_valid) {
+          y_valid = false;       // the Q update that produced the current codes already wrote Yb / Ytb (and the residual)
+        } else {
+          for (int b = 0; b < bt.n; ++b)
+            CB_TRY(form_y_bf16(at(Ws, bt, b), have_q ? at(P.codes_cur, bt, b) : nullptr, p->q_bits, at(P.qscale_cur, bt, b),
+                               p->aware ? at(P.sqrt_h, bt, b) : nullptr, m, n, at(P.tc.Yb, bt, b), at(P.tc.Ytb, bt, b),
+                               at(res_out, bt, b), st));
+        }
+        const int niter = (warm_valid && p->warm_start && basis_saw_q) ? niter_warm : niter_cold;
+        basis_saw_q = have_q;
+        CB_TRY(lowrank_core_b(bt, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
+                              warm_valid && p->warm_start, P.Lcur, P.Rcur, P.tc, st));
+        warm_valid = true;
+        if (P.quant_factors) CB_TRY(lplr_refine_b(bt, p, P, m, n, st));
+        have_lr = true;
+        CB_TRY(lr_product_b(bt, P, m, n, r, st));
+        lrbuf_valid = true;
+        amax_valid = false;
+      }
+      if (!num_ready) {
+        // right after an LR update this pass also delivers the abs-max the next Q update needs
+        const bool want_amax = which == 1;
+        for (int b = 0; b < bt.n; ++b)
+          CB_TRY(err_accum(at(Ws, bt, b), have_q ? at(P.codes_cur, bt, b) : nullptr, p->q_bits, at(P.qscale_cur, bt, b),
+                           (have_lr && lrbuf_valid) ? at(P.LRbuf, bt, b) : nullptr, at(P.h_eff, bt, b), m, n, at(P.dsc, bt, b) + 2, st,
+                           want_amax ? at(P.amax, bt, b) : nullptr));
+        if (want_amax) amax_valid = true;
+      }
+      updated[oi] = true;
+      bool all_updated = true;
+      for (int k = 0; k < p->n_order; ++k) {
+        bool u = false;
+        for (int j = 0; j < p->n_order; ++j) u = u || (updated[j] && p->order[j] == p->order[k]);
+        all_updated = all_updated && u;
+      }
+      CB_TRY(select_outer(P.dsc + 2, P.dsc + 1, out->errors, step, P.scalars, P.flags, all_updated ? 1 : 0, st, bt));
+      // ---- best_decomp = deepcopy(curr_decomp) (alg.py:107), device side
+      CopySegments best;
+      if (have_q) {
+        best.add(out->Q_idxs, P.codes_cur, (size_t)numel * qcb);
+        best.add(out->Q_scale, P.qscale_cur, sizeof(float));
+      }
+      if (have_lr) {
+        best.add(out->L, P.Lcur, sizeof(float) * m * r);
+        best.add(out->R, P.Rcur, sizeof(float) * r * n);
+        if (P.quant_factors) {
+          best.add(P.Lcodes_out, P.Lcodes_in, (size_t)m * r * lcb);
+          best.add(out->R_idxs, P.Rcodes_in, (size_t)r * n * rcb);
+          best.add(out->L_scale, P.Lscale_in, sizeof(float));
+          best.add(out->R_scale, P.Rscale_in, sizeof(float));
+        }
+      }
+      CB_TRY(copy_if_multi(P.flags, best, st, bt));
+    }
+  }
+  // ---- materialise the best iterate
+  for (int b = 0; b < bt.n; ++b) {
+    CB_TRY(cb_dequantize_f32(at(out->Q_idxs, bt, b), nullptr, at(out->Q_scale, bt, b), numel, p->q_bits, 0, at(out->Q, bt, b), stream));
+    if (out->Q_packed != nullptr) CB_TRY(cb_pack_codes(at(out->Q_idxs, bt, b), numel, p->q_bits, at(out->Q_packed, bt, b), stream));
+    if (P.quant_factors) {
+      CB_TRY(transpose_codes(at(P.Lcodes_out, bt, b), m, r, lcb, at(out->L_idxs, bt, b), st));
+      if (out->L_packed != nullptr) CB_TRY(cb_pack_codes(at(out->L_idxs, bt, b), m * r, p->l_bits, at(out->L_packed, bt, b), stream));
+      if (out->R_packed != nullptr) CB_TRY(cb_pack_codes(at(out->R_idxs, bt, b), r * n, p->r_bits, at(out->R_packed, bt, b), stream));
+    }
+  }
+  CopySegments fin;
+  fin.add(out->scalars, P.scalars, sizeof(float) * 4);
+  fin.add(out->scalars + 5, P.flags + 2, sizeof(int) * 3);
+  fin.add(out->scalars + 4, P.flags + 5, sizeof(int));
+  return copy_if_multi(nullptr, fin, st, bt);
 }
 
 // ---------------------------------------------------------------- Hessian accumulation

@@ -828,8 +828,12 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
 
 // fp32 -> bf16 (optionally transposed and/or scaled) conversions around the tensor-core path
 __global__ void __launch_bounds__(256)
-to_bf16_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* __restrict__ Y,
-               int64_t ldy, const float* __restrict__ colscale) {
+to_bf16_kernel(const float* __restrict__ X_, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* __restrict__ Y_,
+               int64_t ldy, const float* __restrict__ colscale_, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.y;
+  const float* __restrict__ X = boff(X_, bo);
+  __nv_bfloat16* __restrict__ Y = boff(Y_, bo);
+  const float* __restrict__ colscale = boff(colscale_, bo);
   const int64_t total = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / cols, c = i - r * cols;
@@ -840,8 +844,12 @@ to_bf16_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t 
 }
 // Yt (cols x rows, bf16) = X^T, tiled through shared memory
 __global__ void __launch_bounds__(256)
-to_bf16_t_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* __restrict__ Yt,
-                 int64_t ldyt, const float* __restrict__ colscale) {
+to_bf16_t_kernel(const float* __restrict__ X_, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* __restrict__ Yt_,
+                 int64_t ldyt, const float* __restrict__ colscale_, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.z;
+  const float* __restrict__ X = boff(X_, bo);
+  __nv_bfloat16* __restrict__ Yt = boff(Yt_, bo);
+  const float* __restrict__ colscale = boff(colscale_, bo);
   __shared__ float tile[32][33];
   const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -859,14 +867,15 @@ to_bf16_t_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_
 }
 
 int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
-            __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st) {
+            __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st, const Bt& bt) {
   if (Y != nullptr) {
-    to_bf16_kernel<<<grid_for(rows * cols, 256 * 4, 8), 256, 0, st>>>(X, rows, cols, ldx, Y, ldy, colscale);
+    dim3 grid1((unsigned)grid_for(rows * cols, 256 * 4, bt.n > 1 ? 2 : 8), (unsigned)bt.n);
+    to_bf16_kernel<<<grid1, 256, 0, st>>>(X, rows, cols, ldx, Y, ldy, colscale, bt.stride);
     CB_CHECK_LAUNCH();
   }
   if (Yt != nullptr) {
-    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-    to_bf16_t_kernel<<<grid, 256, 0, st>>>(X, rows, cols, ldx, Yt, ldyt, colscale);
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)bt.n);
+    to_bf16_t_kernel<<<grid, 256, 0, st>>>(X, rows, cols, ldx, Yt, ldyt, colscale, bt.stride);
     CB_CHECK_LAUNCH();
   }
   return CB_OK;

@@ -59,10 +59,6 @@ struct Gemm2Args {
   int* error_flag; int64_t sFlag;
 };
 
-template <typename T> __device__ __forceinline__ T* boff(T* p, int64_t bytes) {
-  return p == nullptr ? nullptr : reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + bytes);
-}
-
 // 32 consecutive output columns of one row: scaling, then the fp32 / bf16 / transposed-bf16 stores asked for
 __device__ __forceinline__ void g2_store_chunk(const Gemm2Args& a, int b, int row, int col0, float rs, float (&v)[32]) {
   if (row >= a.M || col0 >= a.N) return;

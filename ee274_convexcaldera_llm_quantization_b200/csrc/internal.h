@@ -6,6 +6,16 @@
 
 namespace cb {
 
+// A batch of same-shape layers advancing in lock step: layer b's buffers (inputs, outputs, workspace) sit b * stride
+// bytes after layer 0's.  Stage functions take layer-0 pointers; n == 1 is the single-layer case.
+struct Bt {
+  int n = 1;
+  int64_t stride = 0;
+};
+template <typename T> inline T* at(T* p, const Bt& bt, int b) {
+  return (p == nullptr || b == 0) ? p : reinterpret_cast<T*>(reinterpret_cast<uintptr_t>(p) + (uintptr_t)((int64_t)b * bt.stride));
+}
+
 // Scratch for split-K: the partial tiles of every K slice, summed in slice order by a reduce launch
 // that follows the contraction on the same stream (no floating-point atomics).  Without it, or when
 // it is too small, the contraction runs unsplit.
@@ -28,9 +38,14 @@ int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t 
 
 // smalldense.cu
 int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st,
-                     __nv_bfloat16* Linv_bf16 = nullptr);
+                     __nv_bfloat16* Linv_bf16 = nullptr, const Bt& bt = Bt());
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
-                          cudaStream_t st);
+                          cudaStream_t st, const Bt& bt = Bt());
+
+// Hs (n x n symmetric, in place) += max(0, sigma_reg - lambda_min(Hs)) I with lambda_min from a Lanczos run
+// (alg.py:57-64); work: min_eig_shift_workspace_floats(n) floats; stats (optional): shift, lambda_min
+size_t min_eig_shift_workspace_floats(int64_t n);
+int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st);
 
 // stages.cu -- fused element-wise stages of the outer loop (all asynchronous on `st`)
 struct HessianVecs {
@@ -42,11 +57,11 @@ struct HessianVecs {
 
 int sumsq(const float* x, int64_t numel, double* out, cudaStream_t st);
 int finalize_global_scale(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars,
-                          cudaStream_t st);
+                          cudaStream_t st, const Bt& bt = Bt());
 int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h,
                   double* den, cudaStream_t st);
 int prep_hessian_diag(const float* h_in, int64_t n, float sigma_reg, int aware, float* h_eff, float* sqrt_h,
-                      float* inv_sqrt_h, float* w_inner, float* scratch, cudaStream_t st);
+                      float* inv_sqrt_h, float* w_inner, float* scratch, cudaStream_t st, const Bt& bt = Bt());
 int resid_absmax(const float* Ws, const float* LR, int64_t numel, float* amax, cudaStream_t st);
 int quant_err(const float* Ws, const float* LR, const float* h, int64_t m, int64_t n, const float* amax,
               float eps, int bits, void* codes, float* qscale, double* num, cudaStream_t st);
@@ -55,8 +70,8 @@ int form_y(const float* Ws, const void* codes, int bits, const float* qscale, co
 int err_accum(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR,
               const float* w, int64_t m, int64_t n, double* num, cudaStream_t st, float* amax_next = nullptr);
 int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags,
-                 int all_updated, cudaStream_t st);
-int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st);
+                 int all_updated, cudaStream_t st, const Bt& bt = Bt());
+int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st, const Bt& bt = Bt());
 int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStream_t st);
 // up to 8 (dst, src, bytes) segments copied by one launch when *flag != 0
 struct CopySegments {
@@ -65,11 +80,12 @@ struct CopySegments {
   size_t bytes[8];
   int count = 0;
   void add(void* d, const void* s_, size_t b) {
-    if (b == 0 || count >= 8) return;
+    if (b == 0 || count >= 8 || d == nullptr) return;
     dst[count] = d; src[count] = s_; bytes[count] = b; ++count;
   }
 };
-int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st);
+// flag == nullptr: unconditional; a segment with src == nullptr is zero-filled
+int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st, const Bt& bt = Bt());
 int fill_randn(float* p, int64_t count, uint64_t seed, const uint64_t* seed_dev, cudaStream_t st);
 int scale_cols(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
 int scale_rows(const float* X, int64_t rows, int64_t cols, const float* v, int mode, float* out, cudaStream_t st);
@@ -116,7 +132,7 @@ struct Gemm2Batch {
 bool gemm_tc2_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);
 int gemm_tc2(const Gemm2Batch& g, cudaStream_t st);
 int to_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, __nv_bfloat16* Y, int64_t ldy,
-            __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st);
+            __nv_bfloat16* Yt, int64_t ldyt, const float* colscale, cudaStream_t st, const Bt& bt = Bt());
 
 // quant.cu (C ABI, reused internally)
 }  // namespace cb

@@ -309,8 +309,15 @@ constexpr int CHOL_THREADS = 512;   // 128 registers/thread: the 32x32 diagonal 
 long long* g_chol_timing = nullptr;   // measurement aid (cb_set_chol_timing): 4 clock64 stamps
 
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
-chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfloat16* __restrict__ Linv_bf16,
-                int* __restrict__ status, long long* __restrict__ stamps) {
+chol_inv_kernel(float* __restrict__ G_, int q, float* __restrict__ Linv_, __nv_bfloat16* __restrict__ Linv_bf16_,
+                int* __restrict__ status_, long long* __restrict__ stamps, int64_t bstride) {
+  // one CTA per layer of a batch (blockIdx.x); layer b's buffers sit b * bstride bytes after layer 0's
+  const int64_t bo = bstride * blockIdx.x;
+  float* __restrict__ G = boff(G_, bo);
+  float* __restrict__ Linv = boff(Linv_, bo);
+  __nv_bfloat16* __restrict__ Linv_bf16 = boff(Linv_bf16_, bo);
+  int* __restrict__ status = boff(status_, bo);
+  if (blockIdx.x != 0) stamps = nullptr;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CholSmem& s = *reinterpret_cast<CholSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -355,13 +362,13 @@ chol_inv_kernel(float* __restrict__ G, int q, float* __restrict__ Linv, __nv_bfl
   if (tid == 0 && status != nullptr) atomicMax(status, retries);
 }
 
-int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st, __nv_bfloat16* Linv_bf16) {
+int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st, __nv_bfloat16* Linv_bf16, const Bt& bt) {
   if (G == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
   if (debug_skip() & 1) return CB_OK;
   static PerDeviceOnce once;
   CB_TRY(opt_in_dynamic_smem(chol_inv_kernel, (int)sizeof(CholSmem), once));
-  chol_inv_kernel<<<1, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status, g_chol_timing);
+  chol_inv_kernel<<<bt.n, CHOL_THREADS, sizeof(CholSmem), st>>>(G, q, Linv, Linv_bf16, status, g_chol_timing, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -474,8 +481,14 @@ constexpr int JS_THREADS = 512;
 constexpr int JS_V4 = JS_QMAX / 32;   // float4 per lane and vector
 
 __global__ void __launch_bounds__(JS_THREADS, 1)
-jacobi_smem_kernel(const float* __restrict__ Lc, int q, float* __restrict__ evals, float* __restrict__ evecs,
-                   int* __restrict__ sweeps_out, int max_sweeps, float tol) {
+jacobi_smem_kernel(const float* __restrict__ Lc_, int q, float* __restrict__ evals_, float* __restrict__ evecs_,
+                   int* __restrict__ sweeps_out_, int max_sweeps, float tol, int64_t bstride) {
+  // one CTA per layer of a batch (blockIdx.x)
+  const int64_t bo = bstride * blockIdx.x;
+  const float* __restrict__ Lc = boff(Lc_, bo);
+  float* __restrict__ evals = boff(evals_, bo);
+  float* __restrict__ evecs = boff(evecs_, bo);
+  int* __restrict__ sweeps_out = boff(sweeps_out_, bo);
   extern __shared__ __align__(16) float js_smem[];
   const int stride = q + 4;
   float* V = js_smem;                       // V[v * stride + i] = component i of vector v
@@ -720,7 +733,7 @@ constexpr float kJacobiTol = 3e-5f;
 int g_jacobi_single = -1;
 
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
-                          cudaStream_t st) {
+                          cudaStream_t st, const Bt& bt) {
   if (Lc == nullptr || evals == nullptr || evecs == nullptr || work == nullptr || q <= 0) return CB_ERR_ARG;
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
   if (debug_skip() & 2) return CB_OK;
@@ -731,7 +744,8 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
     const char* e = getenv("CB_JACOBI_SINGLE");
     g_jacobi_single = (e != nullptr && atoi(e) == 1) ? 1 : 0;
   }
-  const bool prefer_single = g_jacobi_single == 1 && q <= JS_QMAX;
+  if (bt.n > 1 && !(q <= JS_QMAX && q % 4 == 0)) return CB_ERR_UNSUPPORTED;   // batches run the one-CTA-per-layer kernel
+  const bool prefer_single = (g_jacobi_single == 1 || bt.n > 1) && q <= JS_QMAX;
   if (!prefer_single && q % 4 == 0 && q >= 64 && aligned16(work) && aligned16(evecs)) {
     // cluster kernel: `work` holds q*q floats of column storage followed by q floats of norms and 2 counters
     float* lam_buf = work + (size_t)q * q;
@@ -746,12 +760,156 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
     const size_t smem = ((size_t)q * (q + 4) + 2 * (size_t)q) * sizeof(float);
     static PerDeviceOnce once;
     CB_TRY(opt_in_dynamic_smem(jacobi_smem_kernel, (int)(((size_t)JS_QMAX * (JS_QMAX + 4) + 2 * JS_QMAX) * sizeof(float)), once));
-    jacobi_smem_kernel<<<1, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, kJacobiTol);
+    jacobi_smem_kernel<<<bt.n, JS_THREADS, smem, st>>>(Lc, q, evals, evecs, sweeps, 30, kJacobiTol, bt.stride);
     CB_CHECK_LAUNCH();
     return CB_OK;
   }
   jacobi_kernel<<<1, 1024, 0, st>>>(Lc, q, evals, evecs, work, sweeps, 30, kJacobiTol);
   CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+// ---------------------------------------------------------------- smallest eigenvalue of a dense symmetric matrix
+// alg.py:57-64 shifts a Hessian whose smallest eigenvalue is below sigma_reg: H += (sigma_reg - lambda_min) I.  The
+// reference reads lambda_min off a full eigendecomposition; here it comes from a Lanczos run with full
+// reorthogonalisation (k <= 96 steps, each one symmetric matrix-vector product over all SMs plus a single-CTA
+// orthogonalisation step), followed by bisection on the k x k tridiagonal matrix.  The smallest Ritz value converges
+// to lambda_min from above: geometrically when lambda_min is separated from the rest of the spectrum (the rank-deficient
+// Hessians sigma_reg exists for: lambda_min = 0 with the non-zero eigenvalues bounded away), like range / k^2 otherwise.
+constexpr int kLanczosMax = 96;
+
+__global__ void __launch_bounds__(256) symv_kernel(const float* __restrict__ A, const float* __restrict__ v,
+                                                    float* __restrict__ y, int n) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* row = A + (size_t)warp * n;
+  float acc = 0.f;
+  for (int j = lane; j < n; j += 32) acc = fmaf(row[j], v[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[warp] = acc;
+}
+
+// work layout: V[(kLanczosMax + 1) x n] | y[n] | alpha[kLanczosMax] | beta[kLanczosMax] | kdone (int) | shift (float)
+__global__ void __launch_bounds__(1024) lanczos_init_kernel(float* __restrict__ V, int n, int* __restrict__ kdone) {
+  __shared__ double red[32];
+  double ss = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float g = gaussian_from(0x1A2B3C4Dull, (uint64_t)i);
+    V[i] = g;
+    ss += (double)g * (double)g;
+  }
+  ss = block_sum(ss, red);
+  __shared__ float s_inv;
+  if (threadIdx.x == 0) { s_inv = (float)(1.0 / sqrt(ss)); kdone[0] = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) V[i] *= s_inv;
+}
+
+__global__ void __launch_bounds__(1024)
+lanczos_step_kernel(float* __restrict__ V, float* __restrict__ y, float* __restrict__ alpha, float* __restrict__ beta,
+                    int* __restrict__ kdone, int j, int n) {
+  if (kdone[0] != 0) return;                       // an invariant subspace was found at an earlier step
+  __shared__ double red[32];
+  __shared__ float s_c;
+  const float* vj = V + (size_t)j * n;
+  // w = y - sum_i <V_i, y> V_i over the whole basis, twice (classical "twice is enough" reorthogonalisation); the
+  // coefficient along V_j of the first pass is alpha_j
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i <= j; ++i) {
+      const float* vi = V + (size_t)i * n;
+      double d = 0.0;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) d += (double)vi[e] * (double)y[e];
+      d = block_sum(d, red);
+      if (threadIdx.x == 0) { s_c = (float)d; if (pass == 0 && i == j) alpha[j] = (float)d; }
+      __syncthreads();
+      const float c = s_c;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) y[e] = fmaf(-c, vi[e], y[e]);
+      __syncthreads();
+    }
+  }
+  (void)vj;
+  double ss = 0.0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) ss += (double)y[e] * (double)y[e];
+  ss = block_sum(ss, red);
+  __shared__ float s_beta;
+  if (threadIdx.x == 0) {
+    s_beta = (float)sqrt(ss);
+    beta[j] = s_beta;
+    // breakdown: the Krylov space is invariant, the tridiagonal matrix of order j + 1 already holds exact eigenvalues
+    if (!(s_beta > 1e-6f * fmaxf(fabsf(alpha[j]), 1e-30f))) kdone[0] = j + 1;
+  }
+  __syncthreads();
+  if (kdone[0] != 0) return;
+  const float inv = 1.f / s_beta;
+  float* vn = V + (size_t)(j + 1) * n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) vn[e] = y[e] * inv;
+}
+
+// smallest eigenvalue of the k x k tridiagonal matrix (alpha, beta) by bisection on the Sturm count; one thread
+__global__ void lanczos_finish_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const int* __restrict__ kdone,
+                                      int kmax, float sigma_reg, float* __restrict__ out /* [0] shift, [1] lambda_min */) {
+  const int k = kdone[0] != 0 ? kdone[0] : kmax;
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < k; ++i) {
+    const double off = (i > 0 ? fabs((double)beta[i - 1]) : 0.0) + (i + 1 < k ? fabs((double)beta[i]) : 0.0);
+    lo = fmin(lo, (double)alpha[i] - off);
+    hi = fmax(hi, (double)alpha[i] + off);
+  }
+  // count of eigenvalues < x
+  auto count_below = [&](double x) {
+    int c = 0;
+    double d = 1.0;
+    for (int i = 0; i < k; ++i) {
+      const double b2 = i > 0 ? (double)beta[i - 1] * (double)beta[i - 1] : 0.0;
+      d = ((double)alpha[i] - x) - (i > 0 ? b2 / d : 0.0);
+      if (d == 0.0) d = -1e-300;
+      if (d < 0.0) ++c;
+    }
+    return c;
+  };
+  for (int it = 0; it < 200 && hi - lo > 1e-14 * fmax(fabs(lo), fabs(hi)) + 1e-300; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (count_below(mid) >= 1) hi = mid; else lo = mid;
+  }
+  const float lam = (float)(0.5 * (lo + hi));
+  out[1] = lam;
+  out[0] = lam < sigma_reg ? sigma_reg - lam : 0.f;      // alg.py:59-63
+}
+
+__global__ void __launch_bounds__(256) add_diag_kernel(float* __restrict__ A, int n, const float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = shift[0];
+  if (i < n && s != 0.f) A[(size_t)i * n + i] += s;
+}
+
+size_t min_eig_shift_workspace_floats(int64_t n) {
+  const int64_t k = n < kLanczosMax ? n : kLanczosMax;
+  return (size_t)((k + 2) * n + 2 * kLanczosMax + 8);
+}
+
+// Hs (n x n symmetric, in place) += max(0, sigma_reg - lambda_min(Hs)) I; stats (optional, 2 floats): shift, lambda_min
+int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st) {
+  if (Hs == nullptr || work == nullptr || n <= 0) return CB_ERR_ARG;
+  const int k = (int)(n < kLanczosMax ? n : kLanczosMax);
+  float* V = work;
+  float* y = V + (size_t)(k + 1) * n;
+  float* alpha = y + n;
+  float* beta = alpha + kLanczosMax;
+  int* kdone = reinterpret_cast<int*>(beta + kLanczosMax);
+  float* out = reinterpret_cast<float*>(kdone + 2);
+  lanczos_init_kernel<<<1, 1024, 0, st>>>(V, (int)n, kdone);
+  CB_CHECK_LAUNCH();
+  for (int j = 0; j < k; ++j) {
+    symv_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(Hs, V + (size_t)j * n, y, (int)n);
+    CB_CHECK_LAUNCH();
+    lanczos_step_kernel<<<1, 1024, 0, st>>>(V, y, alpha, beta, kdone, j, (int)n);
+    CB_CHECK_LAUNCH();
+  }
+  lanczos_finish_kernel<<<1, 1, 0, st>>>(alpha, beta, kdone, k, sigma_reg, out);
+  CB_CHECK_LAUNCH();
+  add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Hs, (int)n, out);
+  CB_CHECK_LAUNCH();
+  if (stats != nullptr) CB_CUDA(cudaMemcpyAsync(stats, out, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 
@@ -761,6 +919,15 @@ extern "C" void cb_set_chol_timing(void* stamps_dev) { cb::g_chol_timing = reint
 
 extern "C" int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream) {
   return cb::cholesky_inverse(G, (int)q, Linv, status, (cudaStream_t)stream);
+}
+
+extern "C" size_t cb_min_eig_shift_workspace_bytes(int64_t n) {
+  return n > 0 ? cb::min_eig_shift_workspace_floats(n) * sizeof(float) : 0;
+}
+extern "C" int cb_min_eig_shift_f32(float* H, int64_t n, float sigma_reg, float* stats, void* ws, size_t ws_bytes, void* stream) {
+  if (H == nullptr || ws == nullptr || n <= 0) return CB_ERR_ARG;
+  if (ws_bytes < cb_min_eig_shift_workspace_bytes(n)) return CB_ERR_WORKSPACE;
+  return cb::min_eig_shift(H, n, sigma_reg, reinterpret_cast<float*>(ws), stats, (cudaStream_t)stream);
 }
 
 extern "C" int cb_jacobi_eigh_from_chol_f32(const float* Lc, int64_t q, float* evals, float* evecs, float* work,

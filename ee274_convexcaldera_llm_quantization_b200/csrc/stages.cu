@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
-__global__ void finalize_gs_kernel(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars) {
+__global__ void finalize_gs_kernel(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars,
+                                   int64_t bstride) {
+  sumsq = boff(sumsq, bstride * blockIdx.x); scalars = boff(scalars, bstride * blockIdx.x);
   // alg.py:38-41: W.square().mean().sqrt().item(), fp32
   float gs = 1.f;
   if (scale_w) gs = gs_in > 0.f ? gs_in : sqrtf((float)(sumsq[0] / (double)numel));
@@ -129,8 +131,11 @@ scale_den_kernel(const float* __restrict__ W, float* __restrict__ Ws, int64_t nu
 
 // ---------------------------------------------------------------- diagonal Hessian prep
 __global__ void __launch_bounds__(1024)
-prep_h_kernel(const float* __restrict__ h_in, int n, float sigma_reg, int aware, float* __restrict__ h_eff,
-              float* __restrict__ sqrt_h, float* __restrict__ inv_sqrt_h, float* __restrict__ w_inner) {
+prep_h_kernel(const float* __restrict__ h_in_, int n, float sigma_reg, int aware, float* __restrict__ h_eff_,
+              float* __restrict__ sqrt_h_, float* __restrict__ inv_sqrt_h_, float* __restrict__ w_inner_, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.x;
+  const float* h_in = boff(h_in_, bo);
+  float *h_eff = boff(h_eff_, bo), *sqrt_h = boff(sqrt_h_, bo), *inv_sqrt_h = boff(inv_sqrt_h_, bo), *w_inner = boff(w_inner_, bo);
   __shared__ float red[32];
   __shared__ float s_shift;
   float mn = __int_as_float(0x7f800000);
@@ -640,7 +645,9 @@ stats_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n
 
 // ---------------------------------------------------------------- selection / bookkeeping
 __global__ void select_outer_kernel(double* num, const double* den, float* errors, int step, float* scalars,
-                                    int* flags, int all_updated) {
+                                    int* flags, int all_updated, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.x;
+  num = boff(num, bo); den = boff(den, bo); errors = boff(errors, bo); scalars = boff(scalars, bo); flags = boff(flags, bo);
   // alg.py:104-107: strict '<' and only once every component has been updated
   const float err = (float)sqrt(num[0] / den[0]);
   errors[step] = err;
@@ -649,7 +656,9 @@ __global__ void select_outer_kernel(double* num, const double* den, float* error
   if (take) { scalars[1] = err; scalars[2] = (float)step; }
   num[0] = 0.0;
 }
-__global__ void select_inner_kernel(double* num, float* scalars, int* flags, int first, int last) {
+__global__ void select_inner_kernel(double* num, float* scalars, int* flags, int first, int last, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.x;
+  num = boff(num, bo); scalars = boff(scalars, bo); flags = boff(flags, bo);
   // alg.py:182-188
   const float err = (float)sqrt(num[0]);
   const float best = first ? __int_as_float(0x7f800000) : scalars[5];
@@ -681,14 +690,26 @@ copy_if_kernel(const int* __restrict__ flag, uint8_t* __restrict__ dst, const ui
 }
 
 // best_decomp = deepcopy(curr_decomp) for all its parts in one launch: blockIdx.y selects the segment
-__global__ void __launch_bounds__(256) copy_if_multi_kernel(const int* __restrict__ flag, const CopySegments segs) {
-  if (flag != nullptr && flag[0] == 0) return;
+__global__ void __launch_bounds__(256) copy_if_multi_kernel(const int* __restrict__ flag, const CopySegments segs, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.z;
+  if (flag != nullptr && boff(flag, bo)[0] == 0) return;
   const int k = blockIdx.y;
   const size_t bytes = segs.bytes[k];
-  uint8_t* __restrict__ dst = reinterpret_cast<uint8_t*>(segs.dst[k]);
-  const uint8_t* __restrict__ src = reinterpret_cast<const uint8_t*>(segs.src[k]);
+  uint8_t* __restrict__ dst = boff(reinterpret_cast<uint8_t*>(segs.dst[k]), bo);
+  const uint8_t* __restrict__ src = boff(reinterpret_cast<const uint8_t*>(segs.src[k]), bo);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (src == nullptr) {                      // zero fill
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      const size_t n16 = bytes >> 4;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (size_t i = t0; i < n16; i += stride) d4[i] = make_uint4(0, 0, 0, 0);
+      for (size_t i = (n16 << 4) + t0; i < bytes; i += stride) dst[i] = 0;
+    } else {
+      for (size_t i = t0; i < bytes; i += stride) dst[i] = 0;
+    }
+    return;
+  }
   if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
     const size_t n16 = bytes >> 4;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -751,8 +772,8 @@ int sumsq(const float* x, int64_t numel, double* out, cudaStream_t st) {
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int finalize_global_scale(const double* ss, int64_t numel, float gs_in, int scale_w, float* scalars, cudaStream_t st) {
-  finalize_gs_kernel<<<1, 1, 0, st>>>(ss, numel, gs_in, scale_w, scalars);
+int finalize_global_scale(const double* ss, int64_t numel, float gs_in, int scale_w, float* scalars, cudaStream_t st, const Bt& bt) {
+  finalize_gs_kernel<<<bt.n, 1, 0, st>>>(ss, numel, gs_in, scale_w, scalars, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -766,8 +787,9 @@ int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* 
   return CB_OK;
 }
 int prep_hessian_diag(const float* h_in, int64_t n, float sigma_reg, int aware, float* h_eff, float* sqrt_h,
-                      float* inv_sqrt_h, float* w_inner, float*, cudaStream_t st) {
-  prep_h_kernel<<<1, 1024, 0, st>>>(h_in, (int)n, sigma_reg, aware, h_eff, sqrt_h, inv_sqrt_h, w_inner);
+                      float* inv_sqrt_h, float* w_inner, float* scratch, cudaStream_t st, const Bt& bt) {
+  (void)scratch;
+  prep_h_kernel<<<bt.n, 1024, 0, st>>>(h_in, (int)n, sigma_reg, aware, h_eff, sqrt_h, inv_sqrt_h, w_inner, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -821,13 +843,14 @@ int err_accum(const float* Ws, const void* codes, int bits, const float* qscale,
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags, int all_updated, cudaStream_t st) {
-  select_outer_kernel<<<1, 1, 0, st>>>(num, den, errors, step, scalars, flags, all_updated);
+int select_outer(double* num, const double* den, float* errors, int step, float* scalars, int* flags, int all_updated, cudaStream_t st,
+                 const Bt& bt) {
+  select_outer_kernel<<<bt.n, 1, 0, st>>>(num, den, errors, step, scalars, flags, all_updated, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st) {
-  select_inner_kernel<<<1, 1, 0, st>>>(num, scalars, flags, first, last);
+int select_inner(double* num, float* scalars, int* flags, int first, int last, cudaStream_t st, const Bt& bt) {
+  select_inner_kernel<<<bt.n, 1, 0, st>>>(num, scalars, flags, first, last, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -839,13 +862,13 @@ int copy_if(const int* flag, void* dst, const void* src, size_t bytes, cudaStrea
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st) {
+int copy_if_multi(const int* flag, const CopySegments& segs, cudaStream_t st, const Bt& bt) {
   if (segs.count <= 0) return CB_OK;
   size_t biggest = 0;
   for (int k = 0; k < segs.count; ++k) biggest = segs.bytes[k] > biggest ? segs.bytes[k] : biggest;
   if (biggest == 0) return CB_OK;
-  dim3 grid((unsigned)grid_for((int64_t)(biggest / 16 + 1), 256 * 4, 4), (unsigned)segs.count);
-  copy_if_multi_kernel<<<grid, 256, 0, st>>>(flag, segs);
+  dim3 grid((unsigned)grid_for((int64_t)(biggest / 16 + 1), 256 * 4, bt.n > 1 ? 1 : 4), (unsigned)segs.count, (unsigned)bt.n);
+  copy_if_multi_kernel<<<grid, 256, 0, st>>>(flag, segs, bt.stride);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

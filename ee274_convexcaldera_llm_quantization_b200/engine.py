@@ -1,33 +1,36 @@
 """Asynchronous layer engine: many decompositions in flight on one GPU, driven by ONE host thread.
 
-The reference decomposes layers one after the other and blocks on every one (main.py:147-199; host syncs
-at alg.py:39, :59, :300).  A layer here is a single CUDA-graph replay (runner.py) whose only latency-bound part
-is a chain of single-CTA factorisation kernels, so throughput comes from keeping many independent layers in
-flight.  Round 1 did that with one blocked host thread per layer in flight, which made the end-to-end rate
-`threads / layer latency` and capped it by the host's core count.  The engine decouples the two:
+The reference decomposes layers one after the other and blocks on every one (main.py:147-199; host syncs at
+alg.py:39, :59, :300).  Here a layer is part of a CUDA-graph replay whose only latency-bound part is a chain of
+single-CTA factorisation kernels, so throughput comes from keeping many independent layers in flight.  Round 1 did
+that with one blocked host thread per layer, which made the end-to-end rate `threads / layer latency` and capped it
+by the host's core count.  The engine decouples the two:
 
-  submit()   picks a free slot (stream + workspace arena + captured graph for this shape/parameters), enqueues
-             H2D staging of W and h, the graph replay, the caller's device-side `consume` copies (e.g. straight
-             into a wire-format arena or pinned host buffers) and the D2H copy of the ~100-byte result record,
-             records an event and returns a LayerHandle at once.  It only blocks when every slot is busy.
-  LayerHandle.result()  waits for that event and builds the CalderaDecomposition.
+  submit()   stages W and h (asynchronous H2D copies when they are pinned host tensors) into a free slot and returns
+             a LayerHandle at once.  Layers that the batched driver supports (csrc/driver.cu: cb_caldera_batch) are
+             collected until a slot's batch is full -- `batch` same-shape layers then advance in lock step as ONE
+             graph replay, each contraction / factorisation being one launch for all of them -- other configurations
+             replay a single-layer graph.  After the replay the caller's device-side `consume` copies (e.g. straight
+             into a wire-format arena or pinned host buffers) and the D2H copy of the ~100-byte result records are
+             enqueued and an event is recorded.  submit() only blocks when every slot is busy.
+  LayerHandle.result()  launches the handle's batch if it is still filling, waits for its event and builds the
+             CalderaDecomposition.
 
-Slots own their stream and workspace; the graphs of different shapes captured in one slot share its arena, so
-device memory is slots x (largest layer footprint), whatever the number of distinct shapes.  Captured runners are
-kept per slot in LRU order under a byte budget (`CB_ENGINE_MAX_BYTES`, default 70 % of the device memory that is
-free when the engine is created).
+Slots own a stream and one device arena that the graphs of every shape captured in that slot share (they are never in
+flight together), so device memory is slots x (largest batch footprint) whatever the number of distinct shapes; the
+arena is bounded by `CB_ENGINE_MAX_BYTES` (default 60 % of the device memory free at creation) through the batch size.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import threading
-from collections import OrderedDict
-from typing import Callable, Optional
+from typing import Callable, Dict, List, Optional
 
 import torch
 
 from . import _lib
-from .runner import CalderaLayerRunner, workspace_bytes
+from .runner import BatchRunner, CalderaLayerRunner, workspace_bytes
 
 
 def _params_signature(p) -> tuple:
@@ -35,40 +38,41 @@ def _params_signature(p) -> tuple:
                  for name, _ in p._fields_ if name != "seed")
 
 
-def _tensor_bytes(*tensors) -> int:
-    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
-
-
 class LayerHandle:
     """One layer in flight.  `result()` blocks until it is done and returns what `finish` builds."""
 
-    def __init__(self, engine: "LayerEngine", slot: "_Slot", run: CalderaLayerRunner, finish: Callable):
-        self._engine, self._slot, self.run, self._finish = engine, slot, run, finish
-        self._host = None
+    def __init__(self, group: "_Group", index: int, finish: Callable, consume: Optional[Callable], seed: int):
+        self._group, self._index, self._finish, self._consume, self._seed = group, index, finish, consume, seed
         self._value = None
         self._done = False
-        self.kept = {}           # device tensors produced by `consume` that belong to this layer
+        self.kept: dict = {}           # device tensors produced by `consume` that belong to this layer
 
-    def _collect(self) -> None:
-        """Waits for the layer and frees its slot (idempotent; called by result() or when the slot is reused)."""
-        if self._host is not None:
-            return
-        slot = self._slot
-        slot.event.synchronize()
-        self._host = slot.host_small[:self.run.small.numel()].clone()
-        slot.handle = None
-        self._engine._release(slot)
+    @property
+    def run(self):
+        return self._group.views[self._index]
 
     def done(self) -> bool:
-        return self._host is not None or self._slot.event.query()
+        g = self._group
+        return g.host is not None or (g.launched and g.slot.event.query())
 
     def result(self):
         if not self._done:
-            self._collect()
-            self._value = self._finish(self.run, self._host, self.kept)
+            g = self._group
+            g.engine._collect(g)
+            self._value = self._finish(g.views[self._index], g.host[self._index], self.kept)
             self._done = True
-            self._finish = None
+            self._finish = self._consume = None
         return self._value
+
+
+class _Group:
+    """The layers sharing one graph replay in one slot (a full or partial batch, or a single layer)."""
+
+    def __init__(self, engine, slot, runner, views, key):
+        self.engine, self.slot, self.runner, self.views, self.key = engine, slot, runner, views, key
+        self.handles: List[LayerHandle] = []
+        self.launched = False
+        self.host = None
 
 
 class _Slot:
@@ -76,132 +80,182 @@ class _Slot:
         self.index = index
         self.stream = torch.cuda.Stream(device=device)
         self.event = torch.cuda.Event()
-        self.ws: Optional[torch.Tensor] = None
-        self.runners: "OrderedDict[tuple, CalderaLayerRunner]" = OrderedDict()
-        self.host_small = torch.empty(4096, dtype=torch.float32).pin_memory()
-        self.handle: Optional[LayerHandle] = None
+        self.arena: Optional[torch.Tensor] = None
+        self.runners: Dict[tuple, object] = {}
+        self.host_small: Optional[torch.Tensor] = None
+        self.group: Optional[_Group] = None
 
 
 class LayerEngine:
-    def __init__(self, device: torch.device, slots: int = 32, max_bytes: Optional[int] = None):
+    def __init__(self, device: torch.device, slots: int = 3, batch: int = 16, max_bytes: Optional[int] = None):
         self.device = device
         self.lock = threading.RLock()
+        self.batch = max(1, int(batch))
         with torch.cuda.device(device):
             self.slots = [_Slot(device, i) for i in range(max(1, int(slots)))]
             if max_bytes is None:
                 env = os.environ.get("CB_ENGINE_MAX_BYTES")
-                max_bytes = int(env) if env else int(0.7 * torch.cuda.mem_get_info(device)[0])
+                max_bytes = int(env) if env else int(0.6 * torch.cuda.mem_get_info(device)[0])
         self.max_bytes = int(max_bytes)
         self.free = list(reversed(self.slots))       # pop() hands out slot 0 first
-        self.inflight = []                           # slots in submission order
-        self.bytes = 0
+        self.inflight: List[_Slot] = []              # launched, in launch order
+        self.filling: Dict[tuple, _Group] = {}       # key -> group still collecting layers
         self.kernels_replayed = 0
 
-    # ------------------------------------------------------------------ memory accounting
-    @staticmethod
-    def _runner_bytes(run: CalderaLayerRunner) -> int:
-        return _tensor_bytes(run.Q, run.L, run.R, run.Q_idxs, run.L_idxs, run.R_idxs, run.Q_packed, run.L_packed,
-                             run.R_packed, run.W_scaled, run.W_in, run.h_in, run.small)
-
-    def _evict(self, need: int, keep_slot: _Slot) -> None:
-        """Drops least-recently-used runners of idle slots until `need` more bytes fit the budget."""
-        for slot in self.slots:
-            if self.bytes + need <= self.max_bytes:
-                return
-            if slot.handle is not None and slot is not keep_slot:
-                continue
-            while slot.runners and self.bytes + need > self.max_bytes:
-                _, old = slot.runners.popitem(last=False)
-                self.bytes -= self._runner_bytes(old)
-                if old.ws is not slot.ws:
-                    self.bytes -= _tensor_bytes(old.ws)
-
-    def reserve_workspace(self, nbytes: int) -> None:
-        """Sizes every slot's arena for the largest layer of a job up front (graphs captured later share it)."""
-        with self.lock, torch.cuda.device(self.device):
-            for slot in self.slots:
-                if slot.ws is None or slot.ws.numel() < nbytes:
-                    if slot.handle is not None:
-                        slot.handle._collect()
-                    self._grow(slot, nbytes)
-
-    def _grow(self, slot: _Slot, nbytes: int) -> None:
-        # runners captured against the old arena keep it alive through their own reference and stay valid
-        if slot.ws is not None and not any(r.ws is slot.ws for r in slot.runners.values()):
-            self.bytes -= _tensor_bytes(slot.ws)
-        self._evict(nbytes, slot)
-        slot.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        self.bytes += nbytes
-
     # ------------------------------------------------------------------ slots
+    def _slot_bytes(self) -> int:
+        return self.max_bytes // len(self.slots)
+
     def _acquire(self) -> _Slot:
         if not self.free:
-            oldest = self.inflight[0]
-            oldest.handle._collect()             # blocks until the oldest layer in flight is done
+            if self.inflight:
+                self._collect(self.inflight[0].group)           # blocks until the oldest group in flight is done
+            else:
+                # every slot is filling a different shape: launch the fullest partial batch to make room
+                g = max(self.filling.values(), key=lambda g_: len(g_.handles))
+                self._launch(g)
+                self._collect(g)
         return self.free.pop()
 
-    def _release(self, slot: _Slot) -> None:
-        with self.lock:
-            if slot in self.inflight:
-                self.inflight.remove(slot)
-            self.free.append(slot)
+    def _arena(self, slot: _Slot, nbytes: int) -> torch.Tensor:
+        if slot.arena is None or slot.arena.numel() < nbytes:
+            slot.runners.clear()                                 # graphs captured against the old arena die with it
+            slot.arena = None
+            slot.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return slot.arena
 
-    def _runner(self, slot: _Slot, p, m: int, n: int, h_kind: int, want_packed: bool, want_w_scaled: bool):
-        key = (_params_signature(p), m, n, h_kind, want_packed, want_w_scaled, _lib.execution_mode())
-        run = slot.runners.get(key)
-        if run is not None:
-            slot.runners.move_to_end(key)
-            return run
-        need = workspace_bytes(p, m, n, h_kind)
-        if slot.ws is None or slot.ws.numel() < need:
-            self._grow(slot, need)
-        run = CalderaLayerRunner(p, m, n, h_kind, self.device, want_packed=want_packed, want_w_scaled=want_w_scaled,
-                                 workspace=slot.ws)
-        with torch.cuda.stream(slot.stream):
-            run.capture()
-        self._evict(self._runner_bytes(run), slot)
-        self.bytes += self._runner_bytes(run)
-        slot.runners[key] = run
-        if run.small.numel() > slot.host_small.numel():
-            slot.host_small = torch.empty(run.small.numel(), dtype=torch.float32).pin_memory()
-        return run
+    def reserve(self, nbytes: int) -> None:
+        """Sizes every slot's arena for the largest batch of a job up front (graphs captured later share it)."""
+        with self.lock, torch.cuda.device(self.device):
+            self.drain()
+            for slot in self.slots:
+                self._arena(slot, min(nbytes, self._slot_bytes()))
+
+    def batch_for(self, p, m: int, n: int, h_kind: int, want_packed: bool, want_w_scaled: bool, hint: Optional[int]) -> int:
+        """Layers per graph replay for this configuration: 0 = not batchable (single-layer graph)."""
+        lib = _lib.load()
+        if self.batch <= 1 or not lib.cb_caldera_batch_supported(C.byref(p), m, n, h_kind):
+            return 0
+        b = self.batch if not hint else max(1, min(self.batch, int(hint)))
+        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled)
+        return max(1, min(b, self._slot_bytes() // stride))
+
+    def _group_for(self, p, m, n, h_kind, want_packed, want_w_scaled, hint) -> _Group:
+        nb = self.batch_for(p, m, n, h_kind, want_packed, want_w_scaled, hint)
+        key = (_params_signature(p), m, n, h_kind, want_packed, want_w_scaled, _lib.execution_mode(), nb)
+        g = self.filling.get(key)
+        if g is not None:
+            return g
+        slot = self._acquire()
+        try:
+            run = slot.runners.get(key)
+            if run is None:
+                with torch.cuda.stream(slot.stream):
+                    if nb > 0:
+                        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled)
+                        run = BatchRunner(p, m, n, h_kind, nb, self.device, want_packed=want_packed, want_w_scaled=want_w_scaled,
+                                          slab=self._arena(slot, max(stride * nb, slot.arena.numel() if slot.arena is not None else 0)))
+                    else:
+                        need = workspace_bytes(p, m, n, h_kind)
+                        run = CalderaLayerRunner(p, m, n, h_kind, self.device, want_packed=want_packed, want_w_scaled=want_w_scaled,
+                                                 workspace=self._arena(slot, max(need, slot.arena.numel() if slot.arena is not None else 0)))
+                    run.capture()
+                slot.runners[key] = run
+            views = run.layers if nb > 0 else [run]
+            nsmall = views[0].small.numel()
+            if slot.host_small is None or slot.host_small.numel() < len(views) * nsmall:
+                slot.host_small = torch.empty(len(views) * nsmall, dtype=torch.float32).pin_memory()
+        except BaseException:
+            self.free.append(slot)
+            raise
+        g = _Group(self, slot, run, views, key)
+        slot.group = g
+        self.filling[key] = g
+        return g
 
     # ------------------------------------------------------------------ submission
     def submit(self, p, W: torch.Tensor, h_kind: int, H: Optional[torch.Tensor], seed: int, finish: Callable,
                want_packed: bool = True, want_w_scaled: bool = False,
-               consume: Optional[Callable[[CalderaLayerRunner, dict], None]] = None) -> LayerHandle:
-        """Enqueues one layer and returns immediately.  W / H: device tensors or pinned host tensors (staged with
-        an asynchronous copy on the slot's stream).  `consume(run, kept)` runs right after the replay with the
-        slot's stream current and must only enqueue device work (copies of the outputs to where they are going);
-        tensors it stores in `kept` travel with the handle.  `finish(run, host_record, kept)` builds the result
-        once the layer is done (host side, inside LayerHandle.result())."""
+               consume: Optional[Callable] = None, batch_hint: Optional[int] = None) -> LayerHandle:
+        """Stages one layer and returns immediately.  W / H: device tensors or pinned host tensors.  `consume(view,
+        kept)` runs right after the layer's graph replay was enqueued, with the slot's stream current, and must only
+        enqueue device work (copies of view.Q_packed, view.L, ... to where they are going); tensors it stores in
+        `kept` travel with the handle.  `finish(view, host_record, kept)` builds the result once the layer is done
+        (host side, inside LayerHandle.result()).  `batch_hint`: how many layers of this shape the caller is about
+        to submit (bounds the batch size so that a short job does not run a mostly empty batch)."""
         m, n = int(W.shape[0]), int(W.shape[1])
         with self.lock, torch.cuda.device(self.device):
-            slot = self._acquire()
-            try:
-                run = self._runner(slot, p, m, n, h_kind, want_packed, want_w_scaled)
-                handle = LayerHandle(self, slot, run, finish)
-                caller = torch.cuda.current_stream()
-                slot.stream.wait_stream(caller)          # W / H may have been produced on the caller's stream
-                with torch.cuda.stream(slot.stream):
-                    run.launch(W, H, seed)
-                    self.kernels_replayed += run.graph_kernels
-                    if consume is not None:
-                        consume(run, handle.kept)
-                    slot.host_small[:run.small.numel()].copy_(run.small, non_blocking=True)
-                    slot.event.record(slot.stream)
-            except BaseException:
-                self.free.append(slot)
-                raise
-            slot.handle = handle
-            self.inflight.append(slot)
+            g = self._group_for(p, m, n, h_kind, want_packed, want_w_scaled, batch_hint)
+            idx = len(g.handles)
+            handle = LayerHandle(g, idx, finish, consume, seed)
+            caller = torch.cuda.current_stream()
+            g.slot.stream.wait_stream(caller)              # W / H may have been produced on the caller's stream
+            with torch.cuda.stream(g.slot.stream):
+                if isinstance(g.runner, BatchRunner):
+                    g.runner.stage(idx, W, H)
+                else:
+                    g.runner.W_in.copy_(W, non_blocking=True)
+                    if g.runner.h_in is not None and H is not None:
+                        g.runner.h_in.copy_(H, non_blocking=True)
+            g.handles.append(handle)
+            if len(g.handles) == len(g.views):
+                self._launch(g)
             return handle
+
+    def _launch(self, g: _Group) -> None:
+        if g.launched:
+            return
+        slot = g.slot
+        with torch.cuda.device(self.device), torch.cuda.stream(slot.stream):
+            seeds = [h._seed for h in g.handles]
+            if isinstance(g.runner, BatchRunner):
+                g.runner.replay(seeds)
+            else:
+                g.runner.seed_dev.fill_(int(seeds[0]))
+                g.runner.graph.replay()
+                g.runner.lib.cb_note_launches(g.runner.graph_kernels)
+            self.kernels_replayed += g.runner.graph_kernels
+            for h in g.handles:
+                if h._consume is not None:
+                    h._consume(g.views[h._index], h.kept)
+            nsmall = g.views[0].small.numel()
+            dst = slot.host_small[:len(g.views) * nsmall].view(len(g.views), nsmall)
+            if isinstance(g.runner, BatchRunner):
+                dst.copy_(g.runner.small_all, non_blocking=True)
+            else:
+                dst[0].copy_(g.runner.small, non_blocking=True)
+            slot.event.record(slot.stream)
+        g.launched = True
+        self.filling.pop(g.key, None)
+        self.inflight.append(slot)
+
+    def _collect(self, g: _Group) -> None:
+        """Waits for a group and frees its slot (idempotent)."""
+        with self.lock:
+            if g.host is not None:
+                return
+            self._launch(g)
+            slot = g.slot
+            slot.event.synchronize()
+            nsmall = g.views[0].small.numel()
+            g.host = slot.host_small[:len(g.views) * nsmall].view(len(g.views), nsmall).clone()
+            slot.group = None
+            if slot in self.inflight:
+                self.inflight.remove(slot)
+            self.free.append(slot)
+
+    def flush(self) -> None:
+        """Launches every partially filled batch."""
+        with self.lock:
+            for g in list(self.filling.values()):
+                self._launch(g)
 
     def drain(self) -> None:
         with self.lock:
+            self.flush()
             for slot in list(self.inflight):
-                if slot.handle is not None:
-                    slot.handle._collect()
+                if slot.group is not None:
+                    self._collect(slot.group)
 
     def release(self) -> None:
         """Drops every captured graph and arena (the engine stays usable)."""
@@ -209,28 +263,26 @@ class LayerEngine:
         with self.lock:
             for slot in self.slots:
                 slot.runners.clear()
-                slot.ws = None
-            self.bytes = 0
+                slot.arena = None
 
 
-_ENGINES = {}
+_ENGINES: Dict[int, LayerEngine] = {}
 _ENGINES_LOCK = threading.Lock()
 
 
-def get_engine(device: torch.device, slots: Optional[int] = None) -> LayerEngine:
-    """The per-device engine (created on first use; `slots` only takes effect then or when larger)."""
+def get_engine(device: torch.device, slots: Optional[int] = None, batch: Optional[int] = None) -> LayerEngine:
+    """The per-device engine, created on first use: `slots` groups in flight (default CB_ENGINE_SLOTS or 3) of up to
+    `batch` layers each (default CB_ENGINE_BATCH or 16).  Asking for a different geometry later rebuilds it."""
     key = device.index if device.index is not None else torch.cuda.current_device()
     with _ENGINES_LOCK:
         eng = _ENGINES.get(key)
-        want = int(slots) if slots else int(os.environ.get("CB_ENGINE_SLOTS", "32"))
+        want_slots = int(slots) if slots else int(os.environ.get("CB_ENGINE_SLOTS", "3"))
+        want_batch = int(batch) if batch else int(os.environ.get("CB_ENGINE_BATCH", "16"))
+        if eng is not None and ((slots and want_slots != len(eng.slots)) or (batch and want_batch != eng.batch)):
+            eng.release()
+            eng = None
         if eng is None:
-            eng = _ENGINES[key] = LayerEngine(torch.device("cuda", key), want)
-        elif slots and want > len(eng.slots):
-            with eng.lock, torch.cuda.device(eng.device):
-                for i in range(len(eng.slots), want):
-                    s = _Slot(eng.device, i)
-                    eng.slots.append(s)
-                    eng.free.insert(0, s)
+            eng = _ENGINES[key] = LayerEngine(torch.device("cuda", key), want_slots, want_batch)
         return eng
 
 

@@ -36,8 +36,8 @@ def synth_layers(shapes: Sequence[Tuple[int, int]], indices: Sequence[int], dev:
     return store
 
 
-def run_model_job(params, names, shapes, store, rank: int, world: int, dev: torch.device, streams: int = 32,
-                  dst: int = 0, factor_dtype: str = "float16", barrier=None) -> dict:
+def run_model_job(params, names, shapes, store, rank: int, world: int, dev: torch.device, streams: int = 48,
+                  dst: int = 0, factor_dtype: str = "float16", barrier=None, slots: int = 3) -> dict:
     """One timed pass: decompose this rank's shard (inputs already on its GPU) and gather the packed blobs on `dst`.
     Wall clock from a barrier to the end of the gather, device synchronised on both sides; the caller takes the
     max over ranks.  Returns the timings, the gathered arena (on `dst`) and this rank's ShardResult."""
@@ -53,7 +53,7 @@ def run_model_job(params, names, shapes, store, rank: int, world: int, dev: torc
         if barrier is not None:
             barrier()
         t0 = time.perf_counter()
-        shard = sch.decompose_layers(layers, shapes, params, rank, world, device=dev, streams=streams,
+        shard = sch.decompose_layers(layers, shapes, params, rank, world, device=dev, streams=streams, slots=slots,
                                      factor_dtype=factor_dtype, arena=arena)
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()

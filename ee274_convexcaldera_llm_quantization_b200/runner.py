@@ -134,3 +134,154 @@ class CalderaLayerRunner:
     def read_small(self) -> torch.Tensor:
         """The one host synchronisation of a layer: error trajectory, scalars, scales."""
         return self.small.cpu()
+
+
+# ----------------------------------------------------------------------------- batched layers
+class _LayerView:
+    """One layer of a BatchRunner, with the attribute names of CalderaLayerRunner (views into the layer's slab)."""
+    __slots__ = ("Q", "L", "R", "Q_idxs", "L_idxs", "R_idxs", "Q_packed", "L_packed", "R_packed", "Q_scale", "L_scale",
+                 "R_scale", "W_scaled", "W_in", "h_in", "small", "nsteps", "nerr_pad", "graph_kernels")
+
+
+class BatchRunner:
+    """`batch` same-shape layers decomposed in lock step by ONE captured CUDA graph of cb_caldera_batch.
+
+    Every per-layer buffer (input staging, outputs, result record, seed, workspace) lives in that layer's slab;
+    slabs are `stride` bytes apart inside one allocation, which is what lets a single kernel launch serve the whole
+    batch (csrc/driver.cu).  `slab` may be passed in (and shared with the runners of other shapes that are never
+    in flight at the same time)."""
+
+    def __init__(self, c_params: "_lib.cb_caldera_params", m: int, n: int, h_kind: int, batch: int, device: torch.device,
+                 want_packed: bool = True, want_w_scaled: bool = False, slab: Optional[torch.Tensor] = None):
+        self.lib = _lib.load()
+        self.p = c_params
+        p = c_params
+        self.m, self.n, self.h_kind, self.device, self.batch = int(m), int(n), int(h_kind), device, int(batch)
+        r = int(p.rank)
+        self.quant_factors = bool(p.compute_lr) and (p.l_bits < 16 or p.r_bits < 16)
+        self.nsteps = p.iters * p.n_order
+        self.nerr_pad = (self.nsteps + 3) // 4 * 4
+        self.nsmall = self.nerr_pad + 8 + 12
+        self.off, self.stride, self.ws_bytes = self._layout(p, m, n, h_kind, want_packed, want_w_scaled)
+        total = self.stride * self.batch
+        with torch.cuda.device(device):
+            if slab is not None and slab.numel() >= total and slab.device == device:
+                self.slab = slab
+            else:
+                self.slab = torch.empty(total, dtype=torch.uint8, device=device)
+        base = self.slab.data_ptr()
+        assert base % 256 == 0
+        self.out = _lib.cb_caldera_out()
+        for name in ("Q", "L", "R", "Q_idxs", "Q_packed", "L_idxs", "R_idxs", "L_packed", "R_packed", "W_scaled"):
+            setattr(self.out, name, base + self.off[name][0] if name in self.off else None)
+        so = self.off["small"][0]
+        self.out.errors = base + so
+        self.out.scalars = base + so + 4 * self.nerr_pad
+        self.out.Q_scale = base + so + 4 * (self.nerr_pad + 8)
+        self.out.L_scale = base + so + 4 * (self.nerr_pad + 12)
+        self.out.R_scale = base + so + 4 * (self.nerr_pad + 16)
+        self.out.seed_dev = base + self.off["seed"][0]
+        # strided views over all layers: seeds (int64) and result records (float32)
+        self.seeds = torch.as_strided(self.slab.view(torch.int64), (self.batch,), (self.stride // 8,), self.off["seed"][0] // 8)
+        self.small_all = torch.as_strided(self.slab.view(torch.float32), (self.batch, self.nsmall), (self.stride // 4, 1), so // 4)
+        cd = lambda b: torch.int8 if b <= 8 else torch.int16  # noqa: E731
+        shapes = {"W_in": (torch.float32, (m, n)), "h_in": (torch.float32, (n,)), "Q": (torch.float32, (m, n)),
+                  "L": (torch.float32, (m, r)), "R": (torch.float32, (r, n)), "Q_idxs": (cd(p.q_bits), (1, m * n)),
+                  "L_idxs": (cd(p.l_bits), (1, r * m)), "R_idxs": (cd(p.r_bits), (1, r * n)), "Q_packed": (torch.uint8, None),
+                  "L_packed": (torch.uint8, None), "R_packed": (torch.uint8, None), "W_scaled": (torch.float32, (m, n))}
+        self.layers = []
+        for b in range(self.batch):
+            v = _LayerView()
+            for name, (dt, shp) in shapes.items():
+                if name in self.off:
+                    o0, nb = self.off[name]
+                    t = self.slab[b * self.stride + o0: b * self.stride + o0 + nb].view(dt)
+                    setattr(v, name, t.reshape(shp) if shp is not None else t)
+                else:
+                    setattr(v, name, None)
+            v.small = self.small_all[b]
+            k = self.nerr_pad + 8
+            v.Q_scale, v.L_scale, v.R_scale = v.small[k:k + 1], v.small[k + 4:k + 5], v.small[k + 8:k + 9]
+            v.nsteps, v.nerr_pad = self.nsteps, self.nerr_pad
+            self.layers.append(v)
+        self.graph = None
+        self.graph_kernels = 0
+        self.seeds_host = torch.zeros(self.batch, dtype=torch.int64).pin_memory()
+
+    @staticmethod
+    def _layout(p, m, n, h_kind, want_packed, want_w_scaled):
+        """Byte offsets of one layer's buffers inside its slab: ({name: (offset, nbytes)}, stride, workspace bytes)."""
+        lib = _lib.load()
+        r = int(p.rank)
+        quant_factors = bool(p.compute_lr) and (p.l_bits < 16 or p.r_bits < 16)
+        nsmall = (p.iters * p.n_order + 3) // 4 * 4 + 8 + 12
+        cb = lambda b: 1 if b <= 8 else 2  # noqa: E731
+        ws_bytes = int(lib.cb_caldera_layer_workspace_bytes(C.byref(p), m, n, h_kind)) or 256
+        fields = [("W_in", 4 * m * n), ("h_in", 4 * n if h_kind == _lib.CB_H_DIAG else 0), ("small", 4 * nsmall),
+                  ("seed", 8), ("Q", 4 * m * n), ("L", 4 * m * r), ("R", 4 * r * n), ("Q_idxs", m * n * cb(p.q_bits)),
+                  ("Q_packed", int(lib.cb_packed_bytes(m * n, p.q_bits)) if want_packed else 0),
+                  ("L_idxs", r * m * cb(p.l_bits) if quant_factors else 0),
+                  ("R_idxs", r * n * cb(p.r_bits) if quant_factors else 0),
+                  ("L_packed", int(lib.cb_packed_bytes(m * r, p.l_bits)) if (want_packed and quant_factors) else 0),
+                  ("R_packed", int(lib.cb_packed_bytes(r * n, p.r_bits)) if (want_packed and quant_factors) else 0),
+                  ("W_scaled", 4 * m * n if (p.scale_w and want_w_scaled) else 0), ("ws", ws_bytes)]
+        off, o = {}, 0
+        for name, nbytes in fields:
+            if nbytes > 0:
+                off[name] = (o, nbytes)
+                o += (nbytes + 255) // 256 * 256
+        return off, o, ws_bytes
+
+    @staticmethod
+    def slab_stride(p, m, n, h_kind, want_packed=True, want_w_scaled=False) -> int:
+        return BatchRunner._layout(p, m, n, h_kind, want_packed, want_w_scaled)[1]
+
+    def _ptr(self, name):
+        return C.c_void_p(self.slab.data_ptr() + self.off[name][0]) if name in self.off else None
+
+    def enqueue(self) -> None:
+        """Asynchronous: the whole batch on the current stream, reading the staged inputs of every slab."""
+        with torch.cuda.device(self.device):
+            st = self.lib.cb_caldera_batch(C.byref(self.p), self.batch, self.stride, self._ptr("W_in"), self.m, self.n,
+                                           self._ptr("h_in"), self.h_kind, C.byref(self.out), self._ptr("ws"), self.ws_bytes,
+                                           _lib.stream_ptr())
+        _lib.check(st, "caldera_batch")
+
+    def capture(self) -> None:
+        if self.graph is not None:
+            return
+        with _CAPTURE_LOCK, torch.cuda.device(self.device):
+            for v in self.layers:
+                v.W_in.normal_(0.0, 0.02)
+                if v.h_in is not None:
+                    v.h_in.fill_(1.0)
+            self.seeds.zero_()
+            self.enqueue()                                # eager warm-up: one-time attribute setup outside capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.lib.cb_kernel_launch_count()
+            with torch.cuda.graph(g, stream=_capture_stream(self.device), capture_error_mode="thread_local"):
+                self.enqueue()
+            self.graph_kernels = int(self.lib.cb_kernel_launch_count() - n0)
+            for v in self.layers:
+                v.graph_kernels = self.graph_kernels / self.batch
+            self.graph = g
+
+    def stage(self, b: int, W: torch.Tensor, h: Optional[torch.Tensor]) -> None:
+        """Asynchronous copy of one layer's inputs (device or pinned host tensors) into slab b."""
+        v = self.layers[b]
+        v.W_in.copy_(W, non_blocking=True)
+        if v.h_in is not None and h is not None:
+            v.h_in.copy_(h, non_blocking=True)
+
+    def replay(self, seeds) -> None:
+        """Asynchronous on the current stream: set the per-layer seeds and replay the batch's graph (capture() first:
+        capturing overwrites the staged inputs with its warm-up data)."""
+        if self.graph is None:
+            raise RuntimeError("BatchRunner.replay(): call capture() before staging inputs")
+        with torch.cuda.device(self.device):
+            # (pinned staging: a pageable source would make the copy wait for everything queued on this stream)
+            self.seeds_host[:len(seeds)] = torch.tensor(list(seeds), dtype=torch.int64)
+            self.seeds.copy_(self.seeds_host, non_blocking=True)
+            self.graph.replay()
+            self.lib.cb_note_launches(self.graph_kernels)

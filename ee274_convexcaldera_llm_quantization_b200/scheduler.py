@@ -285,15 +285,17 @@ class ShardResult:
 
 def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor, Optional[torch.Tensor]]]]],
                      shapes: Sequence[Tuple[int, int]], params, rank: int, world_size: int,
-                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 32,
-                     factor_dtype: str = "float16", arena: Optional[torch.Tensor] = None, **caldera_kwargs):
+                     device: Optional[torch.device] = None, pack: bool = True, streams: int = 48,
+                     factor_dtype: str = "float16", arena: Optional[torch.Tensor] = None, slots: int = 3,
+                     **caldera_kwargs):
     """Decomposes this rank's shard of `layers` (the loop of main.py:147-199, layer-sharded and asynchronous).
 
     layers[i] = (name, loader) where loader() returns (W, H) -- generated or loaded directly on the owning GPU (or
     in pinned host memory), so no weight ever crosses ranks.  ONE host thread submits every layer to the device's
-    LayerEngine (engine.py), which keeps `streams` of them in flight (largest layers first) and never blocks on a
-    layer's result; the packed outputs are copied device-side straight into this rank's wire-format arena and only
-    the ~100-byte result records come back to the host, to be written into the blob headers at the end.
+    LayerEngine (engine.py), which keeps up to `streams` of them in flight -- `slots` graph replays of `streams /
+    slots` same-shape layers advancing in lock step (largest layers first) -- and never blocks on a layer's result;
+    the packed outputs are copied device-side straight into this rank's wire-format arena and only the ~100-byte
+    result records come back to the host, to be written into the blob headers at the end.
 
     pack=True returns a ShardResult (unpacks as (indices, blobs)); pack=False returns (indices, decompositions).
     The per-layer seed is derived from the layer index only and no kernel on the path uses floating-point atomics
@@ -306,24 +308,27 @@ def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor
     _lib.set_execution_mode("throughput")
     try:
         return _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena,
-                                 caldera_kwargs)
+                                 slots, caldera_kwargs)
     finally:
         _lib.set_execution_mode(previous_mode)
 
 
-def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena, caldera_kwargs):
+def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena, slots,
+                      caldera_kwargs):
     from .alg import caldera_async
     from .engine import get_engine
-    from .runner import workspace_bytes
-    from .alg import make_c_params
-    from . import _lib
     shards, sizes, rank_bytes, _ = shard_layout(params, shapes, world_size, factor_dtype)
     mine = shards[rank]
     quantised = params.compute_low_rank_factors and (params.L_bits < 16 or params.R_bits < 16)
     costs = {i: layer_cost(shapes[i][0], shapes[i][1], params.rank, params.iters, params.lplr_iters, quantised) for i in mine}
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    order = sorted(mine, key=lambda i: (-costs[i], i))                     # big layers first
-    engine = get_engine(dev, streams)
+    order = sorted(mine, key=lambda i: (-costs[i], shapes[i], i))          # big layers first, equal shapes together
+    slots = max(1, int(slots))
+    batch = max(1, int(streams) // slots)
+    engine = get_engine(dev, slots, batch)
+    per_shape = {}
+    for i in mine:
+        per_shape[tuple(shapes[i])] = per_shape.get(tuple(shapes[i]), 0) + 1
     t_start = time.perf_counter()
     with torch.cuda.device(dev):
         offsets, off = {}, 0
@@ -334,11 +339,6 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
             if arena is None:
                 arena = torch.zeros(max(off, 1), dtype=torch.uint8, device=dev)   # padding bytes are part of the blob
             assert arena.numel() >= off and arena.dtype == torch.uint8
-            if mine:
-                # one arena of the largest layer's workspace per slot, shared by the graphs of every shape
-                scale_w = bool(caldera_kwargs.get("scale_W", True))
-                engine.reserve_workspace(max(workspace_bytes(make_c_params(params, scale_w), m, n, _lib.CB_H_DIAG)
-                                             for (m, n) in {shapes[i] for i in mine}))
         layouts = {shp: blob_layout(params, shp, factor_dtype)[1] for shp in {shapes[i] for i in mine}}
         fdt = _FACTOR_DTYPES[factor_dtype]
         handles = {}
@@ -363,7 +363,10 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
                         else:
                             dst.copy_(src.reshape(-1).view(torch.uint8))
                 kw.update(return_dense=False, return_packed=False, consume=consume)
-            handles[i] = caldera_async(params, W, H, device=dev, use_tqdm=False, slots=streams, **kw)
+            # a shape with fewer layers than a batch runs a batch of exactly that many
+            handles[i] = caldera_async(params, W, H, device=dev, use_tqdm=False, slots=slots, batch=batch,
+                                       batch_hint=per_shape[tuple(shapes[i])], **kw)
+        engine.flush()
         t_submit = time.perf_counter()
         results, records = {}, {}
         for i in mine:

@@ -162,6 +162,12 @@ void cb_set_chol_timing(void* stamps_dev);
  * work: q*q + q + 8 floats of scratch (column storage, norms, sweep counters). */
 int cb_jacobi_eigh_from_chol_f32(const float* Lc, int64_t q, float* evals, float* evecs,
                                  float* work, int* sweeps, void* stream);
+/* The sigma_reg shift of alg.py:57-64 for a dense symmetric H (n x n, row-major, in place):
+ * H += max(0, sigma_reg - lambda_min(H)) I.  lambda_min comes from <= 96 Lanczos steps with full reorthogonalisation
+ * and bisection on the tridiagonal matrix (the reference reads it off a full eigh).  stats (2 device floats, optional):
+ * the shift applied and the lambda_min estimate. */
+size_t cb_min_eig_shift_workspace_bytes(int64_t n);
+int cb_min_eig_shift_f32(float* H, int64_t n, float sigma_reg, float* stats, void* ws, size_t ws_bytes, void* stream);
 /* C = alpha * op(A) op(B) (+ C) with arbitrary element strides: A(i,k) = A[i*a_rs + k*a_cs],
  * B(k,j) = B[k*b_rs + j*b_cs], C(i,j) = C[i*c_rs + j*c_cs].  fp32 SIMT kernel: the path for
  * shapes the tcgen05 tiles do not cover and the in-library reference for them. */
@@ -324,6 +330,19 @@ size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, int64_t m, i
 int cb_caldera_layer(const cb_caldera_params* p, const float* W, int64_t m, int64_t n,
                      const float* h, int h_kind, const cb_caldera_out* out,
                      void* ws, size_t ws_bytes, void* stream);
+
+/* The same decomposition for `batch` same-shape layers advancing in lock step on one stream (the model-level job:
+ * a 7B model has 128 + 64 + 32 layers of three shapes).  Layer b reads W + b * stride_bytes and h + b * stride_bytes,
+ * writes through every pointer of `out` + b * stride_bytes and uses the workspace ws + b * stride_bytes
+ * (cb_caldera_layer_workspace_bytes() each): one slab per layer, stride_bytes a multiple of 256.  Each contraction of
+ * the rank-r step, each small factorisation and each bookkeeping step is then ONE launch for the whole batch (the
+ * batched CTA-pair tcgen05 contraction; one CTA per layer for Cholesky / Jacobi).  A layer's result does not depend
+ * on the batch size or on its position in the batch.  Supported (cb_caldera_batch_supported() != 0): tensor-core
+ * path, Q and LR both computed, identity / diagonal Hessian, rank <= 192; other configurations return
+ * CB_ERR_UNSUPPORTED and go through cb_caldera_layer. */
+int cb_caldera_batch_supported(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind);
+int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t stride_bytes, const float* W, int64_t m, int64_t n,
+                     const float* h, int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- Convex-CALDERA */
 

@@ -29,7 +29,7 @@ ap.add_argument("--blocks", type=int, default=32)
 ap.add_argument("--rank", type=int, default=128)
 ap.add_argument("--lbits", type=int, default=16)
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--streams", type=int, default=32)
+ap.add_argument("--streams", type=int, default=48)
 ap.add_argument("--repeats", type=int, default=2, help="timed passes after the warm-up pass")
 ap.add_argument("--hidden", type=int, default=4096)
 ap.add_argument("--ffn", type=int, default=11008)

@@ -94,6 +94,11 @@ def make_inputs(m, n, seed, hkind):
     elif hkind == "dense":
         X = torch.randn(4 * n, n, generator=g) * (0.25 + torch.rand(n, generator=g))[None, :]
         H = X.T @ X / (4 * n)
+    elif hkind == "dense_lowrank":
+        # fewer samples than features: H = X^T X / T is rank deficient (lambda_min = 0 up to rounding), the case
+        # sigma_reg exists for (alg.py:59-64)
+        X = torch.randn(n // 2, n, generator=g) * (0.25 + torch.rand(n, generator=g))[None, :]
+        H = X.T @ X / (n // 2)
     elif hkind == "zero_entry":
         h = 0.5 + torch.rand(n, generator=g)
         h[7] = 0.0
@@ -143,6 +148,12 @@ CASES = {
     "lr_only": (96, 128, 1012, "diag",
                 dict(L_bits=16, R_bits=16, compute_quantized_component=False, rank=8, iters=2,
                      update_order=["LR"]), True),
+    "q4_lr8_dense_sigma_reg": (96, 128, 1015, "dense_lowrank",
+                               dict(Q_bits=4, L_bits=8, R_bits=8, rank=8, iters=3, lplr_iters=2,
+                                    sigma_reg=1e-3, update_order=["Q", "LR"]), True),
+    "q2_lr16_dense_sigma_reg": (128, 160, 1016, "dense_lowrank",
+                                dict(Q_bits=2, L_bits=16, R_bits=16, rank=12, iters=3,
+                                     sigma_reg=5e-2, update_order=["Q", "LR"]), True),
     "q2_lr16_mid": (384, 512, 1013, "diag",
                     dict(Q_bits=2, L_bits=16, R_bits=16, rank=32, iters=5,
                          update_order=["Q", "LR"]), True),
@@ -152,8 +163,10 @@ CASES = {
 }
 
 
-def caldera_cases():
+def caldera_cases(only=None):
     for name, (m, n, seed, hkind, kw, scale_W) in CASES.items():
+        if only and name not in only:
+            continue
         W, H = make_inputs(m, n, seed, hkind)
         params = CalderaParams(quant_factory_Q=QuantizerFactory(method="uniform", block_size=64),
                                quant_factory_LR=QuantizerFactory(method="uniform", block_size=64),
@@ -186,6 +199,10 @@ def caldera_cases():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    import sys
+    if len(sys.argv) > 1:                 # regenerate the named caldera cases only
+        caldera_cases(set(sys.argv[1:]))
+        raise SystemExit(0)
     quantizer_cases()
     caldera_cases()
     with open(os.path.join(OUT, "meta.json"), "w") as f:

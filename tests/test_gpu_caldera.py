@@ -102,6 +102,10 @@ def test_golden(path):
     if "H" in z:
         Hd = H.to(DEV).double()
         Hd = (Hd + Hd.T) / 2
+        if kw.get("sigma_reg", 0) and p.activation_aware_LR:
+            lam_min = float(torch.linalg.eigvalsh(Hd)[0])
+            if lam_min < kw["sigma_reg"]:                       # alg.py:59-63
+                Hd = Hd + (kw["sigma_reg"] - lam_min) * torch.eye(Hd.shape[0], device=DEV, dtype=torch.float64)
         Wd64 = d.W.to(DEV).double()
         E64 = (d.Q + d.L @ d.R).double() - Wd64
         consistent = float((torch.trace(E64 @ Hd @ E64.T) / torch.trace(Wd64 @ Hd @ Wd64.T)).sqrt())
@@ -248,25 +252,54 @@ def test_tensor_core_path_agrees_with_simt():
                                rtol=5e-5)
 
 
-def test_dense_hessian_sigma_reg_not_supported():
-    """A dense H with sigma_reg > 0 needs lambda_min(H) (alg.py:59-63); not built: fails loudly."""
-    W = torch.randn(64, 48)
-    X = torch.randn(200, 48)
-    with pytest.raises(NotImplementedError):
-        caldera(_params(dict(rank=4, iters=1, L_bits=16, R_bits=16, sigma_reg=1e-3, update_order=["Q", "LR"])),
-                W, X.T @ X / 200, device=DEV, use_tqdm=False)
+@pytest.mark.parametrize("n,kind", [(48, "lowrank"), (160, "lowrank"), (512, "lowrank"), (96, "full"), (640, "indefinite"),
+                                    (2048, "lowrank")])
+def test_dense_hessian_min_eig_shift(n, kind):
+    """alg.py:57-64 for a dense H: lambda_min by Lanczos on the device against torch.linalg.eigvalsh, and the shift
+    H += (sigma_reg - lambda_min) I.  (The golden cases *_dense_sigma_reg run the whole decomposition with it.)"""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n)
+    if kind == "lowrank":
+        X = torch.randn(n // 2, n, generator=g) * (0.25 + torch.rand(n, generator=g))[None, :]
+        H = X.T @ X / (n // 2)
+    elif kind == "full":
+        X = torch.randn(4 * n, n, generator=g)
+        H = X.T @ X / (4 * n)
+    else:
+        A = torch.randn(n, n, generator=g)
+        H = (A + A.T) / (2 * n ** 0.5)                      # Wigner matrix: lambda_min ~ -sqrt(2)
+    lam = torch.linalg.eigvalsh(H.double())
+    lam_min, lam_max = float(lam[0]), float(lam[-1])
+    for sigma_reg in (0.0, 1e-3, 0.5):
+        Hd = H.to(DEV).contiguous()
+        ws = torch.empty(lib.cb_min_eig_shift_workspace_bytes(n), dtype=torch.uint8, device=DEV)
+        stats = torch.zeros(2, device=DEV)
+        _lib.check(lib.cb_min_eig_shift_f32(_lib.ptr(Hd), n, sigma_reg, _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr()), "min_eig_shift")
+        shift, est = (float(x) for x in stats.tolist())
+        # a separated lower end (rank-deficient Gram matrix, small n) is found to fp32 accuracy; the edge of a
+        # continuous spectrum converges like range / k^2 from above
+        tol = 2e-5 * lam_max if kind == "lowrank" or n <= 96 else 2e-2 * (lam_max - lam_min)
+        assert abs(est - lam_min) <= tol + 1e-6, (kind, n, est, lam_min)
+        assert est >= lam_min - 1e-5 * max(abs(lam_max), 1.0)
+        want = max(0.0, sigma_reg - est)
+        np.testing.assert_allclose(shift, want, rtol=1e-6, atol=1e-9)
+        assert torch.allclose(Hd.cpu(), H + shift * torch.eye(n), atol=1e-6 * max(1.0, lam_max))
 
 
 def test_cuda_graph_replay_matches_eager():
     """caldera(use_cuda_graph=True) replays a captured graph of the layer: same numbers as the eager
-    launch sequence, for different inputs and seeds through the same cached graph."""
+    launch sequence, for different inputs and seeds through the same cached graph.  (fp32 SIMT contractions: with
+    tensor cores the graph path runs the batched driver, whose contraction kernel sums in a different order --
+    tests/test_gpu_batch.py compares those two.)"""
     g = torch.Generator().manual_seed(21)
     kw = dict(Q_bits=2, L_bits=4, R_bits=4, rank=16, iters=2, lplr_iters=2, update_order=["Q", "LR"])
     for trial in range(3):
         W = 0.02 * torch.randn(512, 384, generator=g)
         h = 0.5 + torch.rand(384, generator=g)
-        a = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=False)
-        b = caldera(_params(kw), W.pin_memory(), h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=True)
+        a = caldera(_params(kw), W, h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=False, use_tensor_cores=False)
+        b = caldera(_params(kw), W.pin_memory(), h, device=DEV, use_tqdm=False, seed=trial, use_cuda_graph=True,
+                    use_tensor_cores=False)
         assert a.errors == b.errors
         assert torch.equal(a.Q_idxs, b.Q_idxs) and torch.equal(a.L, b.L) and torch.equal(a.R_idxs, b.R_idxs)
         assert torch.equal(a.Q_packed, b.Q_packed) and torch.equal(a.W, b.W)

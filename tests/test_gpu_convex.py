@@ -169,12 +169,15 @@ def test_golden_whole_pipeline_fallback_branch(gold):
         Lg, Rg = z[f"e2e_{k}_L_star"], z[f"e2e_{k}_R_star"]
         # (fp32 Rayleigh-Ritz through a Gram matrix; the cut at rank 128 falls inside a slowly decaying spectrum)
         assert np.abs(d.L_star.cpu().numpy() - Lg).max() <= 6e-5 * np.abs(Lg).max(), c
-        np.testing.assert_allclose(d.group_info["delta"], c["delta"], rtol=2e-4)
+        # (atol: when rank 128 >= min(m, n) the "residual" W - L* is pure rounding noise and so is its grid step)
+        np.testing.assert_allclose(d.group_info["delta"], c["delta"], rtol=2e-4, atol=1e-5 * float(W.abs().max()))
         # the residual lives on the reference's grid; codes differ only where an SVD rounding difference crosses a
         # rounding boundary (R* = W - L* is the small tail of the spectrum, so those differences are relatively large)
         # R* = W - L* inherits the absolute error of L*
         assert np.abs(d.R_star.cpu().numpy() - Rg).max() <= 6e-5 * np.abs(Lg).max() + c["delta"], c
-        if c["b_discrete"] <= 8:      # (a 16-bit grid is finer than the fp32 error of L* itself)
+        # (a 16-bit grid is finer than the fp32 error of L* itself; with min(m, n) <= 128 the fallback keeps every
+        #  singular value and the "residual" is rounding noise)
+        if c["b_discrete"] <= 8 and min(c["m"], c["n"]) > 128:
             ci, cg = np.rint(d.R_star.cpu().numpy() / d.group_info["delta"]), np.rint(Rg / c["delta"])
             assert np.abs(ci - cg).max() <= 1 and np.mean(ci != cg) <= 0.02, (c, np.mean(ci != cg))
         assert torch.equal(d.W_compressed, d.L_star + d.R_star)
