@@ -241,10 +241,9 @@ def time_kernel(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-def roofline_probes(dev, peaks):
-    """Dominant kernel classes timed alone (CUDA events on the launching stream) at the
-    workload's shapes.  Inputs (64 MiB W, 192 MiB rotating) exceed nothing smaller than L2,
-    so three tensors are rotated to defeat the 126 MB L2."""
+def roofline_probes(dev, peaks, nbatch):
+    """Dominant kernel classes timed alone (CUDA events on the launching stream) at the workload's shapes; operands
+    are rotated so that consecutive launches never find their input in the 126 MB L2."""
     import torch
     from ee274_convexcaldera_llm_quantization_b200 import _lib
     lib = _lib.load()
@@ -266,74 +265,8 @@ def roofline_probes(dev, peaks):
     out["quantize_pack_b2_bs64"] = {"bound": "hbm", "achieved": bytes_q / t / 1e9, "peak": peaks["hbm_gbs"],
                                     "unit": "GB/s", "frac": bytes_q / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                     "seconds": t, "algorithmic_bytes": bytes_q}
-    # (b) sketch contraction Zt[q, m] = Pt[q, K=n] * Y[m, K=n]^T on the tcgen05 kernel: the kernel with
-    #     the largest share of GPU time per layer (ncu launch list, profiles/).  bf16 operands in HBM.
-    q = 224
-    # six bf16 operands (6 x 32 MiB = 192 MiB) so that the rotation does not fit in the 126 MB L2
-    ys = [x.bfloat16() for x in xs] + [(0.02 * torch.randn(M, N, device=dev)).bfloat16() for _ in range(3)]
-    Pt = torch.randn(q, N, device=dev).bfloat16()
-    Zt = torch.empty(q, M, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    # outputs as in the layer: bf16 row-major (q x m) and transposed (m x q), no fp32 copy
-    Zts = [torch.empty(q, M, device=dev, dtype=torch.bfloat16) for _ in range(4)]
-    Zs = [torch.empty(M, q, device=dev, dtype=torch.bfloat16) for _ in range(4)]
-    flops = 2.0 * M * N * q
-
-    def sketch(j=0):
-        y = ys[k[0] % 6]
-        k[0] += 1
-        lib.cb_gemm_bf16_tn_bf16out(q, M, N, 1.0, _lib.ptr(Pt), N, _lib.ptr(y), N, _lib.ptr(Zts[j]), M, _lib.ptr(Zs[j]), q,
-                                    None, None, _lib.ptr(flag), _lib.stream_ptr())
-
-    def entry(t, note, **extra):
-        e = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-             "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None, "seconds": t,
-             "algorithmic_flops": flops, "hbm_gbs": (2 * M * N + 2 * q * N + 2 * 2 * q * M) / t / 1e9, "note": note}
-        e.update(extra)
-        return e
-    skinny = ("skinny: 2q flop per 2-byte element of Y = 224 flop/B, so min(tensor peak, AI x HBM) = "
-              "min(1662.7, 224 x 6.54) = 1465 TFLOP/s; N = 256 tiles run the tensor pipe at its rate, the rest is "
-              "prologue + epilogue of a 64-K-block tile")
-    # as it runs in the timed region (throughput mode): 32-CTA grids of 128 x 256 tiles, four of them
-    # side by side on different streams; seconds = elapsed / launches
-    lib.cb_set_gemm_target_ctas(32)
-    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
-    for j, s_ in enumerate(side):
-        with torch.cuda.stream(s_):
-            for _ in range(3):
-                sketch(j)
-    torch.cuda.synchronize()
-    rounds = 20
-    # fork-join graph: 4 streams x `rounds` launches, so that the host's launch rate is not what is timed
-    cap = torch.cuda.Stream(device=dev)
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
-        for j, s_ in enumerate(side):
-            s_.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s_):
-                for _ in range(rounds):
-                    sketch(j)
-        for s_ in side:
-            torch.cuda.current_stream().wait_stream(s_)
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    t4 = e0.elapsed_time(e1) * 1e-3 / (rounds * 4)
-    out["sketch_gemm_tcgen05"] = entry(t4, skinny + "; 32-CTA grid, 4 launches in flight (as in the timed region)",
-                                       grid_ctas=32, in_flight=4)
-    out["sketch_gemm_tcgen05_32cta_alone"] = entry(time_kernel(sketch, iters=20), skinny + "; 32-CTA grid alone "
-                                                   "(occupies 32 of 148 SMs)", grid_ctas=32, in_flight=1)
-    lib.cb_set_gemm_target_ctas(120)
-    out["sketch_gemm_tcgen05_128cta_alone"] = entry(time_kernel(sketch, iters=20), skinny + "; latency-mode grid "
-                                                    "(128 x 64 tiles, 128 CTAs) alone", grid_ctas=128, in_flight=1)
-    _lib.set_execution_mode(_lib.execution_mode())     # restore the grid policy of the current mode
-    assert int(flag.item()) == 0
-    # (c) whole-tensor quantise + pack (the form caldera() itself uses, alg.py:247): two passes
+    # (b) whole-tensor quantise + pack (the form caldera() itself uses, alg.py:247): two passes
     def quant_whole():
         x = xs[k[0] % 3]
         k[0] += 1
@@ -344,6 +277,38 @@ def roofline_probes(dev, peaks):
     out["quantize_pack_b2_whole"] = {"bound": "hbm", "achieved": bytes_w / t / 1e9, "peak": peaks["hbm_gbs"],
                                      "unit": "GB/s", "frac": bytes_w / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                      "seconds": t, "algorithmic_bytes": bytes_w}
+    del xs
+    # (c) the sketch contraction Z[m, q] = Y[m, K = n] * P[q, K = n]^T of the rank-r step as the batched driver
+    #     launches it: ONE launch of the CTA-pair tcgen05 kernel for all layers of a batch (bf16 operands in HBM,
+    #     bf16 outputs in both orientations) -- the kernel with the largest share of GPU time (profiles/).
+    q = 224
+    skinny = ("skinny: 2q flop per 2-byte element of Y = 224 flop/B, so min(tensor peak, AI x HBM) = "
+              "min(1662.7, 224 x 6.54) = 1465 TFLOP/s; 256 x 224 tiles on CTA pairs (cta_group::2), persistent, two TMEM "
+              "accumulators")
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    for label, nb in (("sketch_gemm_tcgen05", nbatch), ("sketch_gemm_tcgen05_batch32", 32), ("sketch_gemm_tcgen05_batch1", 1)):
+        nrot = 2 if nb >= 8 else 8            # >= 2 x nb x 32 MiB of A operands: never L2 resident across launches
+        As = [(0.02 * torch.randn(nb, M, N, device=dev)).bfloat16() for _ in range(nrot)]
+        B = torch.randn(nb, q, N, device=dev).bfloat16()
+        Cb = torch.empty(nb, M, q, device=dev, dtype=torch.bfloat16)
+        Ct = torch.empty(nb, q, M, device=dev, dtype=torch.bfloat16)
+
+        def sketch():
+            A = As[k[0] % nrot]
+            k[0] += 1
+            lib.cb_gemm_bf16_tn_batched(nb, M, q, N, 1.0, _lib.ptr(A), N, A.stride(0) * 2, _lib.ptr(B), N, B.stride(0) * 2,
+                                        None, 0, 0, _lib.ptr(Cb), q, Cb.stride(0) * 2, _lib.ptr(Ct), M, Ct.stride(0) * 2,
+                                        None, 0, None, 0, 0, _lib.ptr(counter), _lib.ptr(flag), _lib.stream_ptr())
+        t = time_kernel(sketch, iters=10)
+        flops = 2.0 * nb * M * N * q
+        out[label] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                      "frac": flops / t / 1e12 / peaks["bf16_tflops"], "traffic": None, "seconds": t,
+                      "algorithmic_flops": flops, "layers_per_launch": nb,
+                      "hbm_gbs": nb * (2 * M * N + 2 * q * N + 2 * 2 * q * M) / t / 1e9, "note": skinny}
+        del As, B, Cb, Ct
+        torch.cuda.empty_cache()
+    assert int(flag.item()) == 0
     return out
 
 
@@ -607,7 +572,7 @@ def run_ours(args):
             line["full_7b_wall_s"] = {k: v["wall_s"] for k, v in full7b.items() if isinstance(v, dict)}
             line["full_7b"] = full7b
         if world == 1:
-            probes = roofline_probes(dev, peaks)
+            probes = roofline_probes(dev, peaks, nbatch)
             dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_tcgen05")
             tpath = os.path.join(ROOT, "profiles", "traffic.json")      # ncu --set full, DRAM bytes per launch
             if os.path.exists(tpath):
@@ -653,7 +618,7 @@ def main():
     ap.add_argument("--slots", type=int, default=3, help="graph replays in flight per GPU")
     ap.add_argument("--batch", type=int, default=16, help="same-shape layers advancing in lock step per graph replay")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
-                    help="library execution mode (cb_set_execution_mode)")
+                    help="execution mode written into cb_caldera_params.exec_mode (single-layer driver only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcaldera_b200.so")
+# CB_LIBRARY selects another build of the same sources (scripts/probe_*.py use libcaldera_b200_measure.so, built with
+# -DCB_MEASURE by `python -m ee274_convexcaldera_llm_quantization_b200.build --measure`)
+LIB_PATH = os.path.join(_PKG, os.environ.get("CB_LIBRARY", "libcaldera_b200.so"))
 
 CB_OK = 0
 CB_ERR_ARG, CB_ERR_BITS, CB_ERR_BLOCK, CB_ERR_WORKSPACE, CB_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -29,7 +31,7 @@ class cb_caldera_params(C.Structure):
         ("rand_svd", C.c_int32), ("sigma_reg", C.c_float), ("scale_w", C.c_int32),
         ("global_scale_in", C.c_float), ("q_block", C.c_int64),
         ("sketch_width", C.c_int32), ("power_iters", C.c_int32), ("power_iters_warm", C.c_int32), ("warm_start", C.c_int32),
-        ("use_tensor_cores", C.c_int32), ("seed", C.c_uint64),
+        ("use_tensor_cores", C.c_int32), ("exec_mode", C.c_int32), ("seed", C.c_uint64),
     ]
 
 
@@ -79,12 +81,11 @@ _SIGNATURES = {
                                   C.c_size_t, C.c_void_p]),
     "cb_gemm_bf16_tn_bf16out": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_gemm_bf16_tn_batched": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int64,
                                           C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                           C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
-                                          C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
-    "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
+                                          C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cb_quantize_nf_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "cb_dequantize_nf_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
@@ -99,12 +100,6 @@ _SIGNATURES = {
     "cb_packed_linear_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]),
-    "cb_set_gemm_target_ctas": (None, [C.c_int]),
-    "cb_set_execution_mode": (C.c_int, [C.c_int]),
-    "cb_set_gemm_kblocks": (None, [C.c_int]),
-    "cb_set_gemm_timing": (None, [C.c_void_p]),
-    "cb_set_chol_timing": (None, [C.c_void_p]),
-    "cb_probe_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cb_convert_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "cb_sum_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -125,6 +120,15 @@ _SIGNATURES = {
                                    C.c_int, C.POINTER(cb_caldera_out), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
+# measurement aids: exported by libcaldera_b200_measure.so only (include/caldera_b200.h, CB_MEASURE section)
+_MEASURE_SIGNATURES = {
+    "cb_set_gemm_staged_epilogue": (None, [C.c_int]),
+    "cb_set_gemm_kblocks": (None, [C.c_int]),
+    "cb_set_gemm_timing": (None, [C.c_void_p]),
+    "cb_set_chol_timing": (None, [C.c_void_p]),
+    "cb_probe_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
 _lib = None
 
 
@@ -142,6 +146,11 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in _MEASURE_SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
 
@@ -151,18 +160,21 @@ _mode = "latency"
 
 
 def set_execution_mode(mode: str) -> None:
-    """"latency" (default): a single layer finishes as early as possible.  "throughput": many layers are
-    in flight on different streams (include/caldera_b200.h, cb_set_execution_mode).  Process-wide;
-    captured CUDA graphs are keyed by the mode they were captured in."""
+    """Default execution mode that `make_c_params` writes into cb_caldera_params.exec_mode: "latency" (a single layer
+    finishes as early as possible) or "throughput" (many layers in flight on different streams; see
+    include/caldera_b200.h).  Host-side default only: the library itself keeps no mode -- it is part of every call."""
     global _mode
     if mode not in _MODES:
         raise ValueError(f"execution mode must be one of {sorted(_MODES)}, got {mode!r}")
-    check(load().cb_set_execution_mode(_MODES[mode]), "set_execution_mode")
     _mode = mode
 
 
 def execution_mode() -> str:
     return _mode
+
+
+def execution_mode_code(mode=None) -> int:
+    return _MODES[mode if mode is not None else _mode]
 
 
 def exported_symbols():

@@ -119,6 +119,7 @@ def make_c_params(quant_params: CalderaParams, scale_W: bool, global_scale: Opti
     p.power_iters_warm = int(power_iters_warm)
     p.warm_start = int(bool(warm_start))
     p.use_tensor_cores = int(bool(use_tensor_cores))
+    p.exec_mode = _lib.execution_mode_code()
     p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return p
 

@@ -31,7 +31,16 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, measure: bool = False) -> str:
+    """measure=True builds libcaldera_b200_measure.so instead: the same sources with -DCB_MEASURE, i.e. with the timing
+    stamps, knock-out switch and probe entry points that scripts/probe_*.py use (never loaded by the package itself)."""
+    if measure:
+        return _build(force, verbose, os.path.join(CSRC, "_build_measure"), os.path.join(PKG, "libcaldera_b200_measure.so"),
+                      FLAGS + ["-DCB_MEASURE"])
+    return _build(force, verbose, OBJ, LIB, FLAGS)
+
+
+def _build(force, verbose, OBJ, LIB, FLAGS) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
@@ -66,4 +75,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, measure="--measure" in sys.argv))

@@ -9,14 +9,19 @@
 
 namespace cb {
 
-// Measurement aid (never set in production): CB_DEBUG_SKIP is a bit mask of kernel classes whose
+// Measurement aid, compiled only with -DCB_MEASURE (python -m ...build --measure -> libcaldera_b200_measure.so):
+// CB_DEBUG_SKIP is a bit mask of kernel classes whose
 // launches are dropped so that their share of a multi-stream run can be read off the change in
 // throughput (results are then garbage).  1: Cholesky, 2: Jacobi, 4: tcgen05 contractions.
+#ifdef CB_MEASURE
 inline int debug_skip() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("CB_DEBUG_SKIP"); v = e != nullptr ? atoi(e) : 0; }
   return v;
 }
+#else
+constexpr int debug_skip() { return 0; }     // the release library has no knock-out switch
+#endif
 
 
 // ---------------------------------------------------------------- launch bookkeeping

@@ -113,6 +113,7 @@ struct LowrankTcBufs {
   int* status;                    // [0] cholesky retries, [1] jacobi sweeps, [2] gemm watchdog
   const uint64_t* seed_dev = nullptr;
   SplitWs sw;                     // the layer's split-K scratch (same one as LowrankBufs::sw)
+  int* tile_counter = nullptr;    // dynamic tile scheduler of the batched contraction (2 zeroed ints)
 };
 
 static bool lowrank_tc_usable(int64_t m, int64_t n, int64_t r, int64_t q) {
@@ -127,6 +128,7 @@ static LowrankTcBufs plan_lowrank_tc(Arena& a, int64_t m, int64_t n, int64_t q, 
   b.Linvb = a.take<bf16>(q * q); b.Bb = a.take<bf16>(q * n); b.Btb = a.take<bf16>(n * q); b.Vb = a.take<bf16>(q * q);
   b.G = a.take<float>(q * q); b.Linv = a.take<float>(q * q); b.work = a.take<float>(q * q + q + 8);
   b.evals = a.take<float>(q); b.V = a.take<float>(q * q);
+  b.tile_counter = a.take<int>(4);
   b.sw = sw;
   b.status = status;
   return b;
@@ -315,6 +317,7 @@ static int plan_layer(Arena& a, const cb_caldera_params* p, int64_t m, int64_t n
 static int validate_params(const cb_caldera_params* p, int64_t m, int64_t n, int h_kind) {
   if (p == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
   if (p->n_order < 0 || p->n_order > 8 || p->iters < 0) return CB_ERR_ARG;
+  if (p->exec_mode != CB_MODE_LATENCY && p->exec_mode != CB_MODE_THROUGHPUT) return CB_ERR_ARG;
   for (int i = 0; i < p->n_order; ++i)
     if (p->order[i] != 0 && p->order[i] != 1) return CB_ERR_ARG;
   if (p->compute_q && !bits_ok(p->q_bits)) return CB_ERR_BITS;
@@ -532,8 +535,9 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
 // skinny contraction goes to M and the sketch width q (224) becomes the instruction's N.
 static int g2(const Bt& bt, int64_t M, int64_t N, int64_t K, const bf16* A, int64_t lda, const bf16* B, int64_t ldb,
               float* C, int64_t ldc, bf16* Cb, int64_t ldcb, bf16* Ct, int64_t ldct, const float* colscale, int* wd,
-              cudaStream_t st) {
+              cudaStream_t st, int* tile_counter = nullptr) {
   Gemm2Batch g;
+  g.tile_counter = tile_counter;
   g.batch = bt.n; g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = lda; g.sA = bt.stride; g.B = B; g.ldb = ldb; g.sB = bt.stride;
   g.C = C; g.ldc = ldc; g.sC = bt.stride; g.Cb = Cb; g.ldcb = ldcb; g.sCb = bt.stride; g.Ct = Ct; g.ldct = ldct; g.sCt = bt.stride;
@@ -545,9 +549,9 @@ static int g2(const Bt& bt, int64_t M, int64_t N, int64_t K, const bf16* A, int6
 static int orthonormalize_b(const Bt& bt, const bf16* Xt, const bf16* X, int64_t N, int64_t q, bf16* Xot, bf16* Xo,
                             const LowrankTcBufs& b, cudaStream_t st) {
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
-  CB_TRY(g2(bt, q, q, N, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st));              // G = X^T X
+  CB_TRY(g2(bt, q, q, N, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter));              // G = X^T X
   CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st, b.Linvb, bt));
-  return g2(bt, N, q, q, X, q, b.Linvb, q, nullptr, 0, Xo, q, Xot, N, nullptr, wd, st);                // Xo = X Linv^T
+  return g2(bt, N, q, q, X, q, b.Linvb, q, nullptr, 0, Xo, q, Xot, N, nullptr, wd, st, b.tile_counter);                // Xo = X Linv^T
 }
 
 static int copy_b(const Bt& bt, void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -563,13 +567,13 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
     dim3 grid((unsigned)grid_for(q * n, 256 * 4, 1), (unsigned)bt.n);
     randn_bf16_kernel<<<grid, 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev, bt.stride);
     CB_CHECK_LAUNCH();
-    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Ptb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));        // Z = Y P
+    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Ptb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st, b.tile_counter));        // Z = Y P
     CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
   }
   for (int it = 0; it < niter; ++it) {
-    CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Pb, q, b.Ptb, n, nullptr, wd, st));      // P = Y^T Zo
+    CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Pb, q, b.Ptb, n, nullptr, wd, st, b.tile_counter));      // P = Y^T Zo
     CB_TRY(orthonormalize_b(bt, b.Ptb, b.Pb, n, q, b.Potb, nullptr, b, st));
-    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Potb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));       // Z = Y Po
+    CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Potb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st, b.tile_counter));       // Z = Y Po
     CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
   }
   // CholeskyQR2 on the (bf16-rounded) basis itself
@@ -581,14 +585,14 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
   }
   CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
   // B = Zo^T Y (q x n) in both orientations; G = B B^T in fp32
-  CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Btb, q, b.Bb, n, nullptr, wd, st));
-  CB_TRY(g2(bt, q, q, n, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Btb, q, b.Bb, n, nullptr, wd, st, b.tile_counter));
+  CB_TRY(g2(bt, q, q, n, b.Bb, n, b.Bb, n, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter));
   CB_TRY(cholesky_inverse(b.G, (int)q, nullptr, b.status, st, nullptr, bt));
   CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st, bt));
   CB_TRY(to_bf16(b.V, q, q, q, b.Vb, q, nullptr, 0, nullptr, st, bt));
   // L[m, r] = Zo V_r^T ;  R[r, n] = V_r B (column-scaled by 1 / sqrt(h))
-  CB_TRY(g2(bt, m, r, q, b.Zob, q, b.Vb, q, L, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
-  CB_TRY(g2(bt, r, n, q, b.Vb, q, b.Btb, q, R, n, nullptr, 0, nullptr, 0, aware ? inv_sqrt_h : nullptr, wd, st));
+  CB_TRY(g2(bt, m, r, q, b.Zob, q, b.Vb, q, L, r, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter));
+  CB_TRY(g2(bt, r, n, q, b.Vb, q, b.Btb, q, R, n, nullptr, 0, nullptr, 0, aware ? inv_sqrt_h : nullptr, wd, st, b.tile_counter));
   if (!aware) {
     for (int k = 0; k < bt.n; ++k) {
       CB_TRY(scale_cols(at(L, bt, k), m, r, at(b.evals, bt, k), 2, at(L, bt, k), st));
@@ -596,7 +600,7 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
     }
   }
   // rotate the stored basis into its Ritz vectors for the next warm start
-  CB_TRY(g2(bt, m, q, q, b.Zob, q, b.Vb, q, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st));
+  CB_TRY(g2(bt, m, q, q, b.Zob, q, b.Vb, q, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st, b.tile_counter));
   CopySegments c;
   c.add(b.Zob, b.Zb, sizeof(bf16) * m * q);
   c.add(b.Zotb, b.Ztb, sizeof(bf16) * m * q);
@@ -609,7 +613,54 @@ static int lr_product_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, 
   CB_CHECK_LAUNCH();
   split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
   CB_CHECK_LAUNCH();
-  return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st);
+  return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st, P.tc.tile_counter);
+}
+
+// The split-bf16 operands of L R ([Lh | Lh | Ll] and [Rh^T | Rl^T | Rh^T], K = 3r) for the fused contractions below
+static int lr_operands_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
+  dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
+  split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
+  CB_CHECK_LAUNCH();
+  split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
+static Gemm2Batch lr_gemm_desc(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r) {
+  Gemm2Batch g;
+  g.batch = bt.n; g.M = m; g.N = n; g.K = 3 * r;
+  g.A = P.Lb16; g.lda = 3 * r; g.sA = bt.stride; g.B = P.Rtb16; g.ldb = 3 * r; g.sB = bt.stride;
+  g.error_flag = P.flags + 4; g.sE = bt.stride; g.tile_counter = P.tc.tile_counter;
+  return g;
+}
+
+// num += sum_ij hvec_j (Wsrc - Q - L R)_ij^2 and (optionally) amax = max |Wsrc - L R| with L R computed tile by tile in
+// tensor memory and consumed in the contraction's epilogue: the m x n product never exists in HBM (alg.py:293-301,
+// and :182 for the LPLR inner error with Wsrc = residual, no codes)
+static int lr_error_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, const float* Wsrc, void* codes,
+                      int cbytes, int bits, float* qscale, const float* hvec, double* num, float* amax, cudaStream_t st) {
+  Gemm2Batch g = lr_gemm_desc(bt, P, m, n, r);
+  g.epi = 1; g.code_bytes = cbytes; g.lv = (float)((1 << (bits - 1)) - 1);
+  g.Wsrc = Wsrc; g.ldw = n; g.codes = codes; g.ldcodes = n; g.qscale = qscale; g.hvec = hvec; g.num = num; g.amax = amax;
+  if (amax != nullptr) {
+    CopySegments z;
+    z.add(amax, nullptr, sizeof(float));
+    CB_TRY(copy_if_multi(nullptr, z, st, bt));
+  }
+  return gemm_tc2(g, st);
+}
+
+// The Q update (maybe_update_Q, alg.py:253-283) as the epilogue of the same contraction: quantise Ws - L R with the
+// abs-max already known, write the codes, the bf16 operands of the next rank-r step (and the fp32 residual for the
+// LPLR loop) and accumulate the weighted error of the new iterate.
+static int lr_quant_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, int64_t r,
+                      const float* Ws, float* res_out, cudaStream_t st) {
+  Gemm2Batch g = lr_gemm_desc(bt, P, m, n, r);
+  g.epi = 2; g.code_bytes = code_bytes(p->q_bits); g.lv = (float)((1 << (p->q_bits - 1)) - 1); g.eps = 1e-8f;
+  g.Wsrc = Ws; g.ldw = n; g.codes = P.codes_cur; g.ldcodes = n; g.qscale = P.qscale_cur; g.hvec = P.h_eff;
+  g.sqrt_h = p->aware ? P.sqrt_h : nullptr; g.amax = P.amax; g.num = P.dsc + 2;
+  g.Yb = P.tc.Yb; g.Ytb = P.tc.Ytb; g.RES = res_out;
+  return gemm_tc2(g, st);
 }
 
 // lplr_step_tc for a batch: contractions batched, the fp32 r x r solves and the whole-tensor quantiser per layer
@@ -625,8 +676,8 @@ static int lplr_step_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan
   };
   // ---- L update (alg.py:163 / :167)
   CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st, bt));
-  CB_TRY(g2(bt, r, r, n, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
-  CB_TRY(g2(bt, m, r, n, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
+  CB_TRY(g2(bt, r, r, n, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
+  CB_TRY(g2(bt, m, r, n, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(spd(st));
   for (int k = 0; k < bt.n; ++k) {
     CB_TRY(sgemm(m, r, r, 1.f, at(P.Bl, bt, k), r, 1, at(P.Ginv, bt, k), r, 1, at(P.Ltmp, bt, k), r, 1, false, nullptr, st));
@@ -634,14 +685,18 @@ static int lplr_step_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan
   }
   // ---- R update (alg.py:175)
   CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st, bt));
-  CB_TRY(g2(bt, r, r, m, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st));
-  CB_TRY(g2(bt, r, n, m, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr, wd, st));
+  CB_TRY(g2(bt, r, r, m, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
+  CB_TRY(g2(bt, r, n, m, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(spd(st));
   for (int k = 0; k < bt.n; ++k) {
     CB_TRY(sgemm(r, n, r, 1.f, at(P.Ginv, bt, k), r, 1, at(P.Br, bt, k), n, 1, at(P.Rtmp, bt, k), n, 1, false, nullptr, st));
     CB_TRY(quantize_whole(at(P.Rtmp, bt, k), r, n, p->r_bits, at(P.Rcodes_cur, bt, k), at(P.Rscale_cur, bt, k), at(P.Rcur, bt, k), st));
   }
-  // ---- inner error (alg.py:182)
+  // ---- inner error (alg.py:182), fused into the L R contraction when the shape allows
+  if (n % 32 == 0) {
+    CB_TRY(lr_operands_b(bt, P, m, n, r, st));
+    return lr_error_b(bt, P, m, n, r, res, nullptr, 1, 8, nullptr, P.w_inner, P.dsc + 3, nullptr, st);
+  }
   CB_TRY(lr_product_b(bt, P, m, n, r, st));
   for (int k = 0; k < bt.n; ++k)
     CB_TRY(err_accum(at(res, bt, k), nullptr, 8, nullptr, at(P.LRbuf, bt, k), at(P.w_inner, bt, k), m, n, at(P.dsc, bt, k) + 3, st));
@@ -692,6 +747,7 @@ extern "C" size_t cb_caldera_layer_workspace_bytes(const cb_caldera_params* p, i
 extern "C" int cb_caldera_layer(const cb_caldera_params* p, const float* W, int64_t m, int64_t n, const float* h,
                                 int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes, void* stream) {
   CB_TRY(validate_params(p, m, n, h_kind));
+  PolicyScope policy(p->exec_mode);
   if (W == nullptr || out == nullptr || ws == nullptr) return CB_ERR_ARG;
   if ((h_kind == CB_H_DIAG || h_kind == CB_H_DENSE) && h == nullptr) return CB_ERR_ARG;
   if (out->Q == nullptr || out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr)
@@ -942,6 +998,7 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
     CopySegments z2;
     z2.add(P.Lcur, nullptr, sizeof(float) * m * r);
     z2.add(P.Rcur, nullptr, sizeof(float) * r * n);
+    z2.add(P.tc.tile_counter, nullptr, sizeof(int) * 4);
     if (P.quant_factors) {
       z2.add(P.Lcodes_out, nullptr, (size_t)m * r * lcb);
       z2.add(out->R_idxs, nullptr, (size_t)r * n * rcb);
@@ -964,6 +1021,8 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
                                                   : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
   bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
   bool y_valid = false, amax_valid = false;
+  bool lr16_valid = false;                 // P.Lb16 / P.Rtb16 hold the split-bf16 operands of the current L, R
+  const bool fused = n % 32 == 0 && m % 2 == 0;   // fused L R epilogues (whole 32-column chunks per thread)
   bool updated[8] = {false, false, false, false, false, false, false, false};
   float* res_out = P.quant_factors ? (p->aware ? P.RES : P.Y) : nullptr;   // fp32 residual W - Q for the LPLR loop
   int step = 0;
@@ -973,17 +1032,22 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
       bool num_ready = false;
       if (which == 0) {
         // ---- Q update (maybe_update_Q, alg.py:253-283) fused with the bf16 operand builder of the next rank-r step
-        const float* lrp = nullptr;
-        if (have_lr) {
-          if (!lrbuf_valid) CB_TRY(lr_product_b(bt, P, m, n, r, st));
-          lrbuf_valid = true;
-          lrp = P.LRbuf;
-        }
-        for (int b = 0; b < bt.n; ++b) {
-          if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(at(Ws, bt, b), at(lrp, bt, b), numel, at(P.amax, bt, b), st));
-          CB_TRY(quant_form_y_bf16(at(Ws, bt, b), at(lrp, bt, b), at(P.h_eff, bt, b), p->aware ? at(P.sqrt_h, bt, b) : nullptr, m, n,
-                                   at(P.amax, bt, b), 1e-8f, p->q_bits, at(P.codes_cur, bt, b), at(P.qscale_cur, bt, b),
-                                   at(P.dsc, bt, b) + 2, at(P.tc.Yb, bt, b), at(P.tc.Ytb, bt, b), at(res_out, bt, b), st));
+        if (have_lr && fused && amax_valid && lr16_valid) {
+          // quantise Ws - L R in the epilogue of the L R contraction: the product never reaches HBM
+          CB_TRY(lr_quant_b(bt, p, P, m, n, r, Ws, res_out, st));
+        } else {
+          const float* lrp = nullptr;
+          if (have_lr) {
+            if (!lrbuf_valid) CB_TRY(lr_product_b(bt, P, m, n, r, st));
+            lrbuf_valid = true;
+            lrp = P.LRbuf;
+          }
+          for (int b = 0; b < bt.n; ++b) {
+            if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(at(Ws, bt, b), at(lrp, bt, b), numel, at(P.amax, bt, b), st));
+            CB_TRY(quant_form_y_bf16(at(Ws, bt, b), at(lrp, bt, b), at(P.h_eff, bt, b), p->aware ? at(P.sqrt_h, bt, b) : nullptr, m, n,
+                                     at(P.amax, bt, b), 1e-8f, p->q_bits, at(P.codes_cur, bt, b), at(P.qscale_cur, bt, b),
+                                     at(P.dsc, bt, b) + 2, at(P.tc.Yb, bt, b), at(P.tc.Ytb, bt, b), at(res_out, bt, b), st));
+          }
         }
         y_valid = true;
         have_q = true;
@@ -1005,9 +1069,21 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
         warm_valid = true;
         if (P.quant_factors) CB_TRY(lplr_refine_b(bt, p, P, m, n, st));
         have_lr = true;
-        CB_TRY(lr_product_b(bt, P, m, n, r, st));
-        lrbuf_valid = true;
         amax_valid = false;
+        if (fused) {
+          // error of the new iterate and the abs-max of Ws - L R for the next Q update, both in the epilogue of
+          // the L R contraction (alg.py:293-301)
+          CB_TRY(lr_operands_b(bt, P, m, n, r, st));
+          lr16_valid = true;
+          lrbuf_valid = false;
+          CB_TRY(lr_error_b(bt, P, m, n, r, Ws, have_q ? P.codes_cur : nullptr, qcb, p->q_bits, P.qscale_cur, P.h_eff,
+                            P.dsc + 2, P.amax, st));
+          amax_valid = true;
+          num_ready = true;
+        } else {
+          CB_TRY(lr_product_b(bt, P, m, n, r, st));
+          lrbuf_valid = true;
+        }
       }
       if (!num_ready) {
         // right after an LR update this pass also delivers the abs-max the next Q update needs

@@ -719,10 +719,16 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcA
   return CB_OK;
 }
 
-int g_target_ctas = -1;
+thread_local ExecPolicy tl_policy;
+#ifdef CB_MEASURE
 long long* g_timing = nullptr;   // measurement aid, see cb_set_gemm_timing
-int g_staged_epilogue = 1;       // CB_GEMM_STAGED=0 falls back to direct stores (measurement aid)
-int g_kblocks = -1;              // K blocks per TMA instruction for the narrow tiles (CB_GEMM_KBLOCKS: 1 or 2)
+int g_staged_epilogue = 1;       // cb_set_gemm_staged_epilogue(0) falls back to direct stores
+int g_kblocks = 2;               // K blocks per TMA instruction for the narrow tiles (cb_set_gemm_kblocks: 1 or 2)
+#else
+constexpr long long* g_timing = nullptr;
+constexpr int g_staged_epilogue = 1;
+constexpr int g_kblocks = 2;
+#endif
 
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
   return M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && lda % 8 == 0 &&
@@ -743,17 +749,12 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   // (most CTAs) and, if the caller allows it, a K split on top
   const int total_kb = (int)((K + TC_BK - 1) / TC_BK);
   const int64_t mt = (M + TC_BM - 1) / TC_BM;
-  // g_target_ctas: how many CTAs a grid should reach before a fatter N tile / fewer K splits are
+  // tl_policy.target_ctas: how many CTAs a grid should reach before a fatter N tile / fewer K splits are
   // preferred.  Every gemm_tc CTA owns an SM (192 KiB of shared memory), so grids from different
   // streams only overlap when they are small: ~32-CTA grids let four layers' contractions run side by
   // side and move fewer bytes per flop (throughput mode, several layers in flight); ~120-CTA grids
-  // fill the machine for one layer (latency mode, the default).  Set by cb_set_gemm_target_ctas or
-  // the CB_GEMM_MIN_CTAS environment variable.
-  if (g_target_ctas < 0) {
-    const char* e = getenv("CB_GEMM_MIN_CTAS");
-    g_target_ctas = (e != nullptr && atoi(e) > 0) ? atoi(e) : 120;
-  }
-  const int min_ctas = g_target_ctas;
+  // fill the machine for one layer (latency mode, the default).  Part of the call (cb_caldera_params.exec_mode).
+  const int min_ctas = tl_policy.target_ctas;
   int bn = 64;
   if (N >= 192 && mt * ((N + 255) / 256) >= min_ctas) bn = 256;
   else if (N >= 96 && mt * ((N + 127) / 128) >= min_ctas) bn = 128;
@@ -779,14 +780,6 @@ int gemm_tc(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A
   splits = (total_kb + kb_per - 1) / kb_per;
   if (splits_used != nullptr) *splits_used = splits;
   const bool loads_only = (probe_flags & 1) != 0;
-  {
-    static bool read_env = false;
-    if (!read_env) { const char* e = getenv("CB_GEMM_STAGED"); if (e != nullptr && atoi(e) == 0) g_staged_epilogue = 0; read_env = true; }
-  }
-  if (g_kblocks < 0) {
-    const char* e = getenv("CB_GEMM_KBLOCKS");
-    g_kblocks = (e != nullptr && atoi(e) == 1) ? 1 : 2;
-  }
   // two K blocks per TMA instruction where the tile is narrow enough for the stage to stay <= 64 KiB
   const int kbs = (bn <= 128 && K % TC_BK == 0 && g_kblocks >= 2) ? 2 : 1;
   if (kbs > 1 && kb_per % kbs != 0 && splits > 1) {
@@ -986,16 +979,19 @@ extern "C" int cb_packed_linear_f32(const float* x, int64_t T, int64_t n, const 
 // transposed), optional per-column / per-row scaling.  Exported so that the staged epilogue can be tested.
 extern "C" int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
                                        const void* B_bf16, int64_t ldb, void* Cb_bf16, int64_t ldcb, void* Ct_bf16,
-                                       int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
-                                       void* stream) {
+                                       int64_t ldct, const float* colscale, const float* rowscale, int exec_mode,
+                                       int* error_flag, void* stream) {
   if (A_bf16 == nullptr || B_bf16 == nullptr || (Cb_bf16 == nullptr && Ct_bf16 == nullptr)) return CB_ERR_ARG;
+  cb::PolicyScope policy(exec_mode);
   return cb::gemm_tc(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A_bf16), lda,
                      reinterpret_cast<const __nv_bfloat16*>(B_bf16), ldb, nullptr, 0,
                      reinterpret_cast<__nv_bfloat16*>(Cb_bf16), ldcb, reinterpret_cast<__nv_bfloat16*>(Ct_bf16), ldct,
                      colscale, rowscale, 1, error_flag, nullptr, (cudaStream_t)stream, nullptr, 0);
 }
 
+#ifdef CB_MEASURE
 extern "C" void cb_set_gemm_staged_epilogue(int on) { cb::g_staged_epilogue = on != 0 ? 1 : 0; }
+#endif
 
 extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
                                void* Yt_bf16, int64_t ldyt, const float* colscale, void* stream) {
@@ -1004,6 +1000,7 @@ extern "C" int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64
                      reinterpret_cast<__nv_bfloat16*>(Yt_bf16), ldyt, colscale, (cudaStream_t)stream);
 }
 
+#ifdef CB_MEASURE
 // Measurement aid: cycles for n_mma back-to-back 128 x bn x 16 bf16 MMAs on every SM of a `grid`-CTA launch
 // (out: 2 device int64: [0] issue + drain, [1] issue only).
 extern "C" int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream) {
@@ -1025,12 +1022,5 @@ extern "C" int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, vo
 }
 
 extern "C" void cb_set_gemm_timing(void* stamps_dev) { cb::g_timing = reinterpret_cast<long long*>(stamps_dev); }
-extern "C" void cb_set_gemm_target_ctas(int n) { cb::g_target_ctas = n > 0 ? n : 120; }
-
-extern "C" int cb_set_execution_mode(int mode) {
-  if (mode == 0) { cb::g_target_ctas = 120; cb::g_jacobi_single = 0; }        // CB_MODE_LATENCY
-  else if (mode == 1) { cb::g_target_ctas = 32; cb::g_jacobi_single = 1; }    // CB_MODE_THROUGHPUT
-  else return CB_ERR_ARG;
-  return CB_OK;
-}
 extern "C" void cb_set_gemm_kblocks(int n) { cb::g_kblocks = n == 1 ? 1 : 2; }
+#endif  // CB_MEASURE

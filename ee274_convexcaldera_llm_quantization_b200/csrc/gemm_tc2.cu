@@ -12,7 +12,11 @@
 //     CTA loads only half of the B tile; the tensor cores read the other half from the peer's shared memory.  Per
 //     flop this halves the B-operand traffic from L2 compared with the 128 x 256 single-CTA tile of gemm_tc.cu, which
 //     is what bounds a skinny contraction (every m-tile re-reads all of B) once all SMs are busy.
-//   * Persistent: gridDim.x / 2 clusters walk the tile list (batch-major, m fastest) with a fixed stride.  The shared-
+//   * Persistent with a dynamic tile scheduler: warp 3 of the leader CTA hands out tiles (batch-major, m fastest) -- the
+//     first one per cluster statically, the following ones from a global atomic counter -- through a 4-deep ring in
+//     the shared memory of both CTAs (remote store + release.cluster arrive), so a cluster that starts late (because
+//     its SMs were still busy with another stream's Cholesky or element-wise kernel) simply takes fewer tiles instead
+//     of delaying the launch by its whole static share.  Without a counter the assignment is the fixed stride.  The shared-
 //     memory ring (STAGES x {A 16 KiB, B <= 16 KiB}) runs across tile boundaries and tensor memory holds TWO
 //     accumulators (2 x 256 columns), so the epilogue of tile i (tcgen05.ld -> registers -> global) overlaps the main
 //     loop of tile i + 1.
@@ -43,7 +47,9 @@ constexpr int G2_B_BYTES = 128 * G2_BK * 2;            // 16 KiB reserved per st
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_THREADS = 32 * (4 + G2_EPI_WARPS);    // 384
 constexpr int G2_BAR_OFF = G2_STAGES * (G2_A_BYTES + G2_B_BYTES);
-constexpr int G2_SMEM = G2_BAR_OFF + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
+constexpr int G2_SQ = 4;                                   // depth of the tile-id ring
+constexpr int G2_NBAR = 2 * G2_STAGES + 4 + 2 * G2_SQ;     // full/empty ring, tmem full/empty x2, sched full/empty ring
+constexpr int G2_SMEM = G2_BAR_OFF + G2_NBAR * 8 + 16 + 4 * G2_SQ + 1024;
 
 struct Gemm2Args {
   int M, N, K, batch;
@@ -57,6 +63,20 @@ struct Gemm2Args {
   const float* colscale; int64_t sCol;              // per output column, may be null
   const float* rowscale; int64_t sRow;              // per output row, may be null
   int* error_flag; int64_t sFlag;
+  int* tile_counter;             // 2 zeroed ints (next tile, clusters done; the kernel leaves them zero) or null = static
+  // fused epilogues of the outer loop (epi != 0): the product tile never leaves the SM
+  int epi;                       // 0 plain; 1 error + abs-max of W - acc; 2 quantise W - acc (Q update)
+  int code_bytes;                // 1 (int8) or 2 (int16)
+  float lv, eps;                 // quantiser levels 2^(b-1) - 1, scale floor
+  int64_t sE;                    // byte stride between batch items of every pointer below
+  const float* Wsrc; int64_t ldw;     // M x N fp32
+  void* codes; int64_t ldcodes;       // M x N codes: read (epi 1, may be null: Q = 0), written (epi 2)
+  float* qscale;                      // device scalar: read (epi 1), written (epi 2)
+  const float* hvec;                  // N error weights, may be null (all ones)
+  const float* sqrt_h;                // N column weights of Y (epi 2), may be null
+  float* amax;                        // epi 1: out, max |W - acc| (may be null); epi 2: in
+  double* num;                        // += sum_ij h_j E_ij^2
+  __nv_bfloat16* Yb; __nv_bfloat16* Ytb; float* RES;   // epi 2 outputs: (W - Q) sqrt(h) as M x N and N x M bf16, W - Q fp32
 };
 
 // 32 consecutive output columns of one row: scaling, then the fp32 / bf16 / transposed-bf16 stores asked for
@@ -106,6 +126,127 @@ __device__ __forceinline__ void g2_store_chunk(const Gemm2Args& a, int b, int ro
   }
 }
 
+// ---- fused epilogues (alg.py:262 residual, :293-301 error, quantization.py:244-268 quantiser): a thread owns 32
+// consecutive columns of one row of the product tile (v = L R) and streams the matching pieces of W and the codes.
+template <typename code_t>
+__device__ __forceinline__ void load_codes32(const code_t* p, int (&c)[32]) {
+  if (sizeof(code_t) == 1) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c[j] = (int)(int8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+  } else {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const uint4 a = *reinterpret_cast<const uint4*>(p + 8 * q4);
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[8 * q4 + j] = (int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+    }
+  }
+}
+template <typename code_t>
+__device__ __forceinline__ void store_codes32(code_t* p, const int (&c)[32]) {
+  if (sizeof(code_t) == 1) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      w[k] = (uint32_t)(c[4 * k] & 0xFF) | ((uint32_t)(c[4 * k + 1] & 0xFF) << 8) | ((uint32_t)(c[4 * k + 2] & 0xFF) << 16) |
+             ((uint32_t)(c[4 * k + 3] & 0xFF) << 24);
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  } else {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = (uint32_t)(c[8 * q4 + 2 * k] & 0xFFFF) | ((uint32_t)(c[8 * q4 + 2 * k + 1] & 0xFFFF) << 16);
+      *reinterpret_cast<uint4*>(p + 8 * q4) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// epi 1: E = W - Q - L R  ->  part += sum h_j E^2, amx = max |W - L R|   (arithmetic of err_kernel, stages.cu)
+template <typename code_t>
+__device__ __forceinline__ void g2_err_chunk(const Gemm2Args& a, int b, int row, int col0, const float (&v)[32],
+                                             float s, const ScaleRecip& lvr, double& acc, float& amx) {
+  const int64_t off = (int64_t)row * a.ldw + col0;
+  const float* wp = boff(a.Wsrc, a.sE * b) + off;
+  float w[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(wp + j);
+    w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
+  }
+  int c[32];
+  if (a.codes != nullptr) load_codes32<code_t>(boff(reinterpret_cast<const code_t*>(a.codes), a.sE * b) + (int64_t)row * a.ldcodes + col0, c);
+  const float* hp = a.hvec != nullptr ? boff(a.hvec, a.sE * b) + col0 : nullptr;
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float e = w[j];
+    if (a.codes != nullptr) e -= dequant_val(c[j], s, lvr);
+    e -= v[j];
+    part = fmaf((hp != nullptr ? __ldg(hp + j) : 1.f) * e, e, part);
+    amx = fmaxf(amx, fabsf(w[j] - v[j]));
+  }
+  acc += (double)part;
+}
+
+// epi 2: res = W - L R; code = quantise(res); E = res - dequant(code); Y = (W - dequant(code)) sqrt(h)
+// (arithmetic of quant_form_y_bf16_kernel, stages.cu)
+template <typename code_t>
+__device__ __forceinline__ void g2_quant_chunk(const Gemm2Args& a, int b, int row, int col0, const float (&v)[32], float s,
+                                               const ScaleRecip& sr, const ScaleRecip& lvr, double& acc) {
+  const int64_t off = (int64_t)row * a.ldw + col0;
+  const float* wp = boff(a.Wsrc, a.sE * b) + off;
+  float w[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(wp + j);
+    w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
+  }
+  const float* hp = a.hvec != nullptr ? boff(a.hvec, a.sE * b) + col0 : nullptr;
+  const float* sp = a.sqrt_h != nullptr ? boff(a.sqrt_h, a.sE * b) + col0 : nullptr;
+  int c[32];
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float res = w[j] - v[j];
+    c[j] = quant_code(res, sr, a.lv);
+    const float dq = dequant_val(c[j], s, lvr);
+    const float e = res - dq;
+    part = fmaf((hp != nullptr ? __ldg(hp + j) : 1.f) * e, e, part);
+    w[j] -= dq;                                        // W - Q
+  }
+  acc += (double)part;
+  store_codes32<code_t>(boff(reinterpret_cast<code_t*>(a.codes), a.sE * b) + (int64_t)row * a.ldcodes + col0, c);
+  if (a.RES != nullptr) {
+    float* rp = boff(a.RES, a.sE * b) + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rp + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+  }
+  if (sp != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w[j] *= __ldg(sp + j);
+  }
+  __nv_bfloat16* yb = boff(a.Yb, a.sE * b) + off;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(w[j], w[j + 1]), t1 = __floats2bfloat162_rn(w[j + 2], w[j + 3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(w[j + 4], w[j + 5]), t3 = __floats2bfloat162_rn(w[j + 6], w[j + 7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(yb + j) = pk;
+  }
+  __nv_bfloat16* yt = boff(a.Ytb, a.sE * b);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) yt[(int64_t)(col0 + j) * a.M + row] = __float2bfloat16_rn(w[j]);
+}
+
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
@@ -117,8 +258,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * G2_STAGES + 4);
+  auto sched_full_bar = [&](int q) { return bar_base + 8u * (2 * G2_STAGES + 4 + q); };
+  auto sched_empty_bar = [&](int q) { return bar_base + 8u * (2 * G2_STAGES + 4 + G2_SQ + q); };
+  const uint32_t tmem_slot = bar_base + 8u * G2_NBAR;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t sched_tile = tmem_slot + 16u;             // G2_SQ ints: the tile ids handed out by the scheduler
+  volatile int* sched_tile_ptr = reinterpret_cast<volatile int*>(smem_raw + (sched_tile - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -135,6 +280,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * G2_EPI_WARPS); }
+      // consumers of a tile id: 2 producers + 8 epilogue warps per CTA, + the MMA issuer of the leader
+      for (int q = 0; q < G2_SQ; ++q) { mbar_init(sched_full_bar(q), 1); mbar_init(sched_empty_bar(q), 2 * (2 + G2_EPI_WARPS) + 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -145,13 +292,49 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   bool ok = true;
+  // every consumer role walks the same sequence of tile ids: wait for the i-th id, read it, release the ring slot
+  auto next_tile = [&](int i, bool arrive) -> int {
+    const int q = i % G2_SQ;
+    const uint32_t ph = (uint32_t)(i / G2_SQ) & 1u;
+    if (!mbar_wait_cluster(sched_full_bar(q), ph)) { ok = false; return -1; }
+    const int t = sched_tile_ptr[q];
+    if (arrive) mbar_arrive_release_cluster(sched_empty_bar(q), 0);
+    return t;
+  };
+  auto release_tile = [&](int i) { mbar_arrive_release_cluster(sched_empty_bar(i % G2_SQ), 0); };
 
-  if (warp == 0 || warp == 2) {
+  if (warp == 3) {
+    // ---- tile scheduler (leader CTA)
+    if (leader && lane == 0) {
+      int* counter = args.tile_counter;
+      for (int i = 0;; ++i) {
+        const int q = i % G2_SQ;
+        const uint32_t ph = (uint32_t)(i / G2_SQ) & 1u;
+        if (!mbar_wait_cluster(sched_empty_bar(q), ph ^ 1u)) ok = false;
+        int t;
+        if (i == 0) t = cluster_id;
+        else if (counter != nullptr) t = atomicAdd(counter, 1) + n_clusters;
+        else t = cluster_id + i * n_clusters;
+        if (t >= total_tiles || !ok) t = -1;
+        sched_tile_ptr[q] = t;
+        st_shared_cluster_u32(sched_tile + 4u * q, 1, (uint32_t)t);
+        mbar_arrive_release_cluster(sched_full_bar(q), 0);
+        mbar_arrive_release_cluster(sched_full_bar(q), 1);
+        if (t < 0) break;
+      }
+      if (counter != nullptr) {
+        // the last cluster to run out of tiles leaves the counters zeroed for the next launch on this stream
+        if (atomicAdd(counter + 1, 1) == n_clusters - 1) { counter[0] = 0; counter[1] = 0; __threadfence(); }
+      }
+    }
+  } else if (warp == 0 || warp == 2) {
     // ---- TMA producers: warp 0 loads this CTA's 128 rows of A, warp 2 its half of the B tile
     if (lane == 0) {
       const bool is_a = warp == 0;
       uint32_t cnt = 0;
-      for (int t = cluster_id; t < total_tiles && ok; t += n_clusters) {
+      for (int i = 0; ok; ++i) {
+        const int t = next_tile(i, true);
+        if (t < 0) break;
         const int b = t / tiles_per_item, rem = t - b * tiles_per_item;
         const int n_blk = rem / args.tiles_m, m_blk = rem - n_blk * args.tiles_m;
         const int row0 = is_a ? (m_blk * 2 * G2_BM + (int)cta_rank * G2_BM) : (n_blk * args.n_tile + (int)cta_rank * b_rows);
@@ -173,8 +356,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (leader && lane == 0) {
       const uint32_t idesc = make_idesc_bf16(2 * G2_BM, args.n_tile);
       uint32_t cnt = 0;
-      int it = 0;
-      for (int t = cluster_id; t < total_tiles && ok; t += n_clusters, ++it) {
+      for (int it = 0; ok; ++it) {
+        if (next_tile(it, true) < 0) break;
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         if (!mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u)) { ok = false; break; }   // epilogue drained this accumulator
@@ -203,8 +386,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int n_chunks = (args.n_tile + 31) >> 5;
     const int c_split = (n_chunks + 1) >> 1;
     const int c_begin = egrp == 0 ? 0 : c_split, c_end = egrp == 0 ? c_split : n_chunks;
-    int it = 0;
-    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
+    for (int it = 0;; ++it) {
+      const int t = next_tile(it, false);        // every lane reads the id ...
+      __syncwarp();
+      if (lane == 0) release_tile(it);           // ... before the warp gives the ring slot back
+      if (t < 0) break;
       const int b = t / tiles_per_item, rem = t - b * tiles_per_item;
       const int n_blk = rem / args.tiles_m, m_blk = rem - n_blk * args.tiles_m;
       const int acc = it & 1;
@@ -216,14 +402,52 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row = m_blk * 2 * G2_BM + (int)cta_rank * G2_BM + qd * 32 + lane;
       const float* rsp = boff(args.rowscale, args.sRow * b);
       const float rs = (rsp != nullptr && row < args.M) ? rsp[row] : 1.f;
+      if constexpr (EPI == 0) {
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
-        float v[32];
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        g2_store_chunk(args, b, row, n_blk * args.n_tile + c * 32, rs, v);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          g2_store_chunk(args, b, row, n_blk * args.n_tile + c * 32, rs, v);
+        }
+      } else {
+        // fused outer-loop epilogues (host guarantees M % 128 == 0 is not needed: rows are masked; N % 32 == 0)
+        const float lv = args.lv;
+        const ScaleRecip lvr = make_scale_recip(lv);
+        float s_q = 0.f;
+        if constexpr (EPI == 1) s_q = args.codes != nullptr ? boff(args.qscale, args.sE * b)[0] : 0.f;
+        else s_q = fmaxf(boff(args.amax, args.sE * b)[0], args.eps);
+        const ScaleRecip sr = make_scale_recip(s_q);
+        if (EPI == 2 && m_blk == 0 && n_blk == 0 && cta_rank == 0 && warp == 4 && lane == 0)
+          boff(args.qscale, args.sE * b)[0] = s_q;
+        double part = 0.0;
+        float amx = 0.f;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const int col0 = n_blk * args.n_tile + c * 32;
+          if (row < args.M && col0 < args.N) {
+            if constexpr (EPI == 1) {
+              if (args.code_bytes == 1) g2_err_chunk<int8_t>(args, b, row, col0, v, s_q, lvr, part, amx);
+              else g2_err_chunk<int16_t>(args, b, row, col0, v, s_q, lvr, part, amx);
+            } else {
+              if (args.code_bytes == 1) g2_quant_chunk<int8_t>(args, b, row, col0, v, s_q, sr, lvr, part);
+              else g2_quant_chunk<int16_t>(args, b, row, col0, v, s_q, sr, lvr, part);
+            }
+          }
+        }
+        part = warp_sum(part);
+        if (lane == 0 && args.num != nullptr) atomicAdd(boff(args.num, args.sE * b), part);
+        if (EPI == 1 && args.amax != nullptr) {
+          amx = warp_max(amx);
+          if (lane == 0) atomic_max_nonneg(boff(args.amax, args.sE * b), amx);
+        }
       }
       // this warp has read its part of the accumulator: one arrival on the leader's tmem_empty barrier
       tc_fence_before();
@@ -280,16 +504,31 @@ int gemm_tc2(const Gemm2Batch& g, cudaStream_t st) {
   a.Ct = g.Ct; a.ldct = g.ldct; a.sCt = g.sCt;
   a.colscale = g.colscale; a.sCol = g.sCol; a.rowscale = g.rowscale; a.sRow = g.sRow;
   a.error_flag = g.error_flag; a.sFlag = 0;
+  a.tile_counter = g.tile_counter;
+  a.epi = g.epi; a.code_bytes = g.code_bytes; a.lv = g.lv; a.eps = g.eps; a.sE = g.sE;
+  a.Wsrc = g.Wsrc; a.ldw = g.ldw; a.codes = g.codes; a.ldcodes = g.ldcodes; a.qscale = g.qscale; a.hvec = g.hvec;
+  a.sqrt_h = g.sqrt_h; a.amax = g.amax; a.num = g.num; a.Yb = g.Yb; a.Ytb = g.Ytb; a.RES = g.RES;
+  if (a.epi != 0) {
+    // a thread streams whole 32-column chunks of W / codes / Y with 128-bit accesses
+    if (g.N % 32 != 0 || g.ldw % 4 != 0 || g.Wsrc == nullptr || !aligned16(g.Wsrc) || (a.epi == 2 && (g.codes == nullptr ||
+        g.Yb == nullptr || g.Ytb == nullptr || g.amax == nullptr || g.qscale == nullptr || g.M % 2 != 0)) ||
+        (g.codes != nullptr && (g.ldcodes % 16 != 0 || !aligned16(g.codes))) || (a.epi == 1 && g.codes != nullptr && g.qscale == nullptr))
+      return CB_ERR_UNSUPPORTED;
+  }
   CUtensorMap ta, tb;
   CB_TRY(make_tmap_bf16_batched(&ta, g.A, g.M, g.K, g.lda, g.batch, g.sA, G2_BM));
   CB_TRY(make_tmap_bf16_batched(&tb, g.B, g.N, g.K, g.ldb, g.batch, g.sB, a.n_tile / 2));
-  static PerDeviceOnce once;
-  CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel, G2_SMEM, once));
+  static PerDeviceOnce once0, once1, once2;
+  if (a.epi == 0) CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<0>, G2_SMEM, once0));
+  else if (a.epi == 1) CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<1>, G2_SMEM, once1));
+  else CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<2>, G2_SMEM, once2));
   const int64_t total_tiles = (int64_t)a.batch * a.tiles_m * a.tiles_n;
   int clusters = g.max_clusters > 0 ? g.max_clusters : kNumSMs / 2;
   if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
   if (total_tiles < clusters) clusters = (int)total_tiles;
-  gemm_tc2_kernel<<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
+  if (a.epi == 0) gemm_tc2_kernel<0><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
+  else if (a.epi == 1) gemm_tc2_kernel<1><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
+  else gemm_tc2_kernel<2><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
@@ -302,8 +541,8 @@ extern "C" int cb_gemm_bf16_tn_batched(int64_t batch, int64_t M, int64_t N, int6
                                        int64_t stride_b_bytes, float* C, int64_t ldc, int64_t stride_c_bytes, void* Cb_bf16,
                                        int64_t ldcb, int64_t stride_cb_bytes, void* Ct_bf16, int64_t ldct,
                                        int64_t stride_ct_bytes, const float* colscale, int64_t stride_col_bytes,
-                                       const float* rowscale, int64_t stride_row_bytes, int max_clusters, int* error_flag,
-                                       void* stream) {
+                                       const float* rowscale, int64_t stride_row_bytes, int max_clusters, int* tile_counter,
+                                       int* error_flag, void* stream) {
   if (A_bf16 == nullptr || B_bf16 == nullptr || (C == nullptr && Cb_bf16 == nullptr && Ct_bf16 == nullptr)) return CB_ERR_ARG;
   cb::Gemm2Batch g;
   g.batch = batch; g.M = M; g.N = N; g.K = K; g.alpha = alpha;
@@ -313,6 +552,6 @@ extern "C" int cb_gemm_bf16_tn_batched(int64_t batch, int64_t M, int64_t N, int6
   g.Cb = reinterpret_cast<__nv_bfloat16*>(Cb_bf16); g.ldcb = ldcb; g.sCb = stride_cb_bytes;
   g.Ct = reinterpret_cast<__nv_bfloat16*>(Ct_bf16); g.ldct = ldct; g.sCt = stride_ct_bytes;
   g.colscale = colscale; g.sCol = stride_col_bytes; g.rowscale = rowscale; g.sRow = stride_row_bytes;
-  g.max_clusters = max_clusters; g.error_flag = error_flag;
+  g.max_clusters = max_clusters; g.error_flag = error_flag; g.tile_counter = tile_counter;
   return cb::gemm_tc2(g, (cudaStream_t)stream);
 }

@@ -26,10 +26,22 @@ struct SplitWs {
 constexpr size_t kSplitWsBytes = 12u << 20;
 
 
-// execution-mode knobs (cb_set_execution_mode): grid-size target of the tcgen05 contractions and the
-// eigensolver variant; -1 = not yet initialised (environment, then defaults)
-extern int g_target_ctas;
-extern int g_jacobi_single;
+// Execution policy of the single-layer driver: grid-size target of the tcgen05 contractions (gemm_tc.cu) and the
+// eigensolver variant (smalldense.cu).  It is part of the call (cb_caldera_params.exec_mode), never process-wide
+// state: an entry point installs it for its own thread while it enqueues (PolicyScope) and restores it on return.
+struct ExecPolicy {
+  int target_ctas = 120;     // ~120: one layer fills the machine (latency); ~32: several layers' grids side by side
+  int jacobi_single = 0;     // 1: single-CTA eigensolver (3x less SM time), 0: 8-CTA cluster kernel (lower latency)
+};
+extern thread_local ExecPolicy tl_policy;
+struct PolicyScope {
+  ExecPolicy saved;
+  explicit PolicyScope(int exec_mode) : saved(tl_policy) {
+    if (exec_mode == 1) { tl_policy.target_ctas = 32; tl_policy.jacobi_single = 1; }       // CB_MODE_THROUGHPUT
+    else { tl_policy.target_ctas = 120; tl_policy.jacobi_single = 0; }                     // CB_MODE_LATENCY
+  }
+  ~PolicyScope() { tl_policy = saved; }
+};
 
 // sgemm.cu -- C(i,j) = alpha * sum_k A(i,k) B(k,j) [* colscale[j]] (+ C), arbitrary strides
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
@@ -128,6 +140,19 @@ struct Gemm2Batch {
   const float* rowscale = nullptr; int64_t sRow = 0;
   int max_clusters = 0;          // 0 = one cluster per SM pair
   int* error_flag = nullptr;
+  int* tile_counter = nullptr;   // 2 zeroed device ints for the dynamic tile scheduler (left zero by the kernel); null = static
+  // fused epilogues (see gemm_tc2.cu): 1 = weighted error of W - Q - A B^T (+ abs-max of W - A B^T), 2 = Q update
+  int epi = 0, code_bytes = 1;
+  float lv = 1.f, eps = 1e-8f;
+  int64_t sE = 0;
+  const float* Wsrc = nullptr; int64_t ldw = 0;
+  void* codes = nullptr; int64_t ldcodes = 0;
+  float* qscale = nullptr;
+  const float* hvec = nullptr;
+  const float* sqrt_h = nullptr;
+  float* amax = nullptr;
+  double* num = nullptr;
+  __nv_bfloat16* Yb = nullptr; __nv_bfloat16* Ytb = nullptr; float* RES = nullptr;
 };
 bool gemm_tc2_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);
 int gemm_tc2(const Gemm2Batch& g, cudaStream_t st);

@@ -306,7 +306,11 @@ __device__ void tri_inverse(const float* G, int q, float* Linv, __nv_bfloat16* L
 
 constexpr int CHOL_THREADS = 512;   // 128 registers/thread: the 32x32 diagonal factor lives in registers
 
+#ifdef CB_MEASURE
 long long* g_chol_timing = nullptr;   // measurement aid (cb_set_chol_timing): 4 clock64 stamps
+#else
+constexpr long long* g_chol_timing = nullptr;
+#endif
 
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 chol_inv_kernel(float* __restrict__ G_, int q, float* __restrict__ Linv_, __nv_bfloat16* __restrict__ Linv_bf16_,
@@ -730,7 +734,6 @@ jacobi_cluster_kernel(const float* __restrict__ Lc, int q, float* __restrict__ e
 // Rayleigh-Ritz step is second order in the residual coupling, so 3e-5 leaves it exact to fp32.
 constexpr float kJacobiTol = 3e-5f;
 
-int g_jacobi_single = -1;
 
 int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, float* work, int* sweeps,
                           cudaStream_t st, const Bt& bt) {
@@ -738,14 +741,9 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
   if (q > QMAX) return CB_ERR_UNSUPPORTED;
   if (debug_skip() & 2) return CB_OK;
   // The 8-CTA cluster kernel has the lower latency (one layer in flight); the single-CTA kernel spends
-  // ~3x less SM time (many layers in flight).  cb_set_execution_mode / CB_JACOBI_SINGLE=1 select the
-  // latter where it applies.
-  if (g_jacobi_single < 0) {
-    const char* e = getenv("CB_JACOBI_SINGLE");
-    g_jacobi_single = (e != nullptr && atoi(e) == 1) ? 1 : 0;
-  }
+  // ~3x less SM time (many layers in flight).  The caller's execution policy selects (cb_caldera_params.exec_mode).
   if (bt.n > 1 && !(q <= JS_QMAX && q % 4 == 0)) return CB_ERR_UNSUPPORTED;   // batches run the one-CTA-per-layer kernel
-  const bool prefer_single = (g_jacobi_single == 1 || bt.n > 1) && q <= JS_QMAX;
+  const bool prefer_single = (tl_policy.jacobi_single == 1 || bt.n > 1) && q <= JS_QMAX;
   if (!prefer_single && q % 4 == 0 && q >= 64 && aligned16(work) && aligned16(evecs)) {
     // cluster kernel: `work` holds q*q floats of column storage followed by q floats of norms and 2 counters
     float* lam_buf = work + (size_t)q * q;
@@ -915,7 +913,9 @@ int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* sta
 
 }  // namespace cb
 
+#ifdef CB_MEASURE
 extern "C" void cb_set_chol_timing(void* stamps_dev) { cb::g_chol_timing = reinterpret_cast<long long*>(stamps_dev); }
+#endif
 
 extern "C" int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream) {
   return cb::cholesky_inverse(G, (int)q, Linv, status, (cudaStream_t)stream);

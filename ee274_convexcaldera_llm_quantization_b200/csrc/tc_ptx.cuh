@@ -150,6 +150,41 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       ::"r"(bar), "r"(cta) : "memory");
 }
 
+// cluster-scope variants for barriers that order plain shared-memory data written by another CTA of the cluster
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) return false;
+  }
+  return true;
+}
+// release.cluster arrive on the barrier at this offset in CTA `cta` (may be the executing CTA itself)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+// 32-bit store into the shared memory of CTA `cta` of the cluster at the same offset
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t addr, uint32_t cta, uint32_t value) {
+  asm volatile(
+      "{\n\t.reg .b32 remAddr32;\n\t"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+      "st.shared::cluster.u32 [remAddr32], %2;\n\t}"
+      ::"r"(addr), "r"(cta), "r"(value) : "memory");
+}
+
 // ---------------------------------------------------------------- host: tensor-map encoder entry point
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

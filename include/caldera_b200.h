@@ -153,10 +153,6 @@ int cb_lplr_iter(const float* res, int64_t m, int64_t n, const float* h, int h_k
  * retried on G + ridge*mean(diag)*I with ridge = 1e-6, 1e-4, 1e-2 and *status gets the
  * number of retries (device int, may be NULL). */
 int cb_cholesky_inverse_f32(float* G, int64_t q, float* Linv, int* status, void* stream);
-/* Measurement aid: when non-NULL the Cholesky kernel writes 4 clock64 stamps (start, factor done, diagonal
- * block inverses done, inverse done; then 5 per panel for the first 3 panels: start, block loaded, block
- * factored, panel solved, trailing update done) to this device buffer of 24 int64.  Process-wide; NULL = off. */
-void cb_set_chol_timing(void* stamps_dev);
 /* Eigen-decomposition of the SPD matrix G = Lc Lc^T from its Cholesky factor by one-sided
  * Jacobi on Lc's columns.  evals[q] descending, evecs row k = k-th eigenvector.
  * work: q*q + q + 8 floats of scratch (column storage, norms, sweep counters). */
@@ -192,26 +188,27 @@ int cb_gemm_bf16_tn(int64_t M, int64_t N, int64_t K, float alpha, const void* A_
 /* The same contraction with the bf16 epilogues the layer driver uses: Cb (M x N row-major bf16, ldcb) and/or
  * Ct (N x M bf16, the transpose, ldct), either may be NULL; optional per-column / per-row fp32 scaling
  * (NULL = none).  When the outputs are vector-aligned (N % 8 == 0, ldcb % 8 == 0; M % 4 == 0, ldct % 4 == 0)
- * the tile is staged through shared memory and written as whole rows; cb_set_gemm_staged_epilogue(0)
- * forces the direct-store epilogue (same results).  Exported for validation. */
+ * the tile is staged through shared memory and written as whole rows.  exec_mode (CB_MODE_*): the grid policy of
+ * the call, as in cb_caldera_params.  Exported for validation. */
 int cb_gemm_bf16_tn_bf16out(int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
                             const void* B_bf16, int64_t ldb, void* Cb_bf16, int64_t ldcb, void* Ct_bf16,
-                            int64_t ldct, const float* colscale, const float* rowscale, int* error_flag,
+                            int64_t ldct, const float* colscale, const float* rowscale, int exec_mode, int* error_flag,
                             void* stream);
-void cb_set_gemm_staged_epilogue(int on);
 /* The batched, persistent CTA-pair form of the same contraction (csrc/gemm_tc2.cu): for b < batch,
  *   C[b] (M x N) = alpha * A[b] (M x K) * B[b] (N x K)^T  [* rowscale[b][i] * colscale[b][j]]
  * with `tcgen05.mma.cta_group::2` on 256 x N_TILE tiles (N_TILE = min(256, N rounded up to 16)), two accumulators
  * in tensor memory so that the epilogue of a tile overlaps the main loop of the next, and the batch as a third
  * tensor-map dimension.  stride_*_bytes: distance between two batch items of each array (multiples of 16 for A and
  * B).  Any subset of C (fp32), Cb (bf16 row-major), Ct (bf16, N x M) may be given.  max_clusters <= 0: one cluster
- * per SM pair.  This is what the batched layer driver runs; exported for validation. */
+ * per SM pair.  tile_counter: two zeroed device ints for the dynamic tile scheduler (the kernel leaves them zero, so
+ * launches that follow each other on one stream can share them), or NULL for a fixed tile -> cluster assignment; the
+ * results do not depend on it.  This is what the batched layer driver runs; exported for validation. */
 int cb_gemm_bf16_tn_batched(int64_t batch, int64_t M, int64_t N, int64_t K, float alpha, const void* A_bf16, int64_t lda,
                             int64_t stride_a_bytes, const void* B_bf16, int64_t ldb, int64_t stride_b_bytes, float* C,
                             int64_t ldc, int64_t stride_c_bytes, void* Cb_bf16, int64_t ldcb, int64_t stride_cb_bytes,
                             void* Ct_bf16, int64_t ldct, int64_t stride_ct_bytes, const float* colscale,
                             int64_t stride_col_bytes, const float* rowscale, int64_t stride_row_bytes, int max_clusters,
-                            int* error_flag, void* stream);
+                            int* tile_counter, int* error_flag, void* stream);
 /* ---- consumer of the packed decomposition (the reference reconstructs a dense matrix,
  * main.py:197 / README.md:182 `W_hat = Q + L @ R`, and multiplies with that) ----
  * y[T, m] = global_scale * x[T, n] * (Q + L R)^T with Q = (codes / levels) * q_scale read from its packed
@@ -242,33 +239,17 @@ int cb_hessian_accumulate_f32(const float* X, int64_t T, int64_t n, float* H, fl
 size_t cb_hadamard_workspace_bytes(int64_t prows, int64_t pcols);
 int cb_hadamard_transform_f32(const float* W, int64_t rows, int64_t cols, float* out, int64_t prows, int64_t pcols,
                               void* ws, size_t ws_bytes, void* stream);
-/* How one layer uses the machine.  Process-wide; choose before the first layer (captured CUDA graphs
- * keep the mode they were captured in).  Results are bitwise reproducible within a mode and agree to
- * rounding level between modes (different K-split counts and eigensolver sweep order).
- *   CB_MODE_LATENCY (default): one layer at a time should finish as early as possible -- contractions
- *     spread over ~all SMs, the 8-CTA cluster eigensolver.
- *   CB_MODE_THROUGHPUT: many independent layers are in flight on different streams (the model-level
- *     job) -- contractions use ~32-CTA grids with the widest tiles (3x less SM time and fabric traffic
- *     per flop, and four of them fit side by side), the single-CTA eigensolver (3x less SM time). */
+/* How one layer uses the machine: the `exec_mode` field of cb_caldera_params (part of the call, never process-wide
+ * state).  Results are bitwise reproducible within a mode and agree to rounding level between modes (different
+ * K-split counts and eigensolver sweep order).
+ *   CB_MODE_LATENCY (0): one layer at a time should finish as early as possible -- contractions spread over ~all
+ *     SMs, the 8-CTA cluster eigensolver.
+ *   CB_MODE_THROUGHPUT (1): many independent layers are in flight on different streams -- contractions use ~32-CTA
+ *     grids with the widest tiles (3x less SM time and fabric traffic per flop, four of them fit side by side), the
+ *     single-CTA eigensolver (3x less SM time).
+ * The batched driver (cb_caldera_batch) has one policy and ignores the field. */
 #define CB_MODE_LATENCY 0
 #define CB_MODE_THROUGHPUT 1
-int cb_set_execution_mode(int mode);
-/* Grid-size policy of the tcgen05 contractions: ~120 (default) fills the machine for a single layer
- * (lowest latency); ~32 keeps grids small so that the contractions of several layers in flight on
- * different streams overlap (highest throughput).  Process-wide. */
-void cb_set_gemm_target_ctas(int n);
-/* 64-wide K blocks fetched per TMA instruction in the narrow-tile contractions (1 or 2, default 2).
- * Results do not depend on it.  Process-wide. */
-void cb_set_gemm_kblocks(int n);
-/* Measurement aid for bench.py / scripts: cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16,
- * bf16, both operands resident in shared memory, no TMA, no per-stage barriers) take on an SM, on a
- * grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */
-/* Measurement aid: when non-NULL, CTA (0,0,0) of every tcgen05 contraction writes clock64 stamps to this
- * device buffer of 12 int64 ([0..7]: entry, prologue done, last load issued, first stage landed, last
- * stage landed, accumulator complete, epilogue stores issued, exit; [8..9]: staged epilogue -- tile in
- * shared memory, barrier passed).  Process-wide; NULL turns it off. */
-void cb_set_gemm_timing(void* stamps_dev);
-int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream);
 /* fp32 (rows x cols, ldx) -> bf16 copy Y (ldy) and/or transposed copy Yt (cols x rows, ldyt),
  * optionally scaling column c by colscale[c] first. */
 int cb_convert_bf16(const float* X, int64_t rows, int64_t cols, int64_t ldx, void* Y_bf16, int64_t ldy,
@@ -299,6 +280,7 @@ typedef struct cb_caldera_params {
   int32_t warm_start;       /* reuse the previous outer iteration's basis */
   int32_t use_tensor_cores; /* 1: bf16 tcgen05 contractions where the shape allows (dims % 8 == 0,
                                m, n >= 256); 0: fp32 SIMT contractions everywhere        */
+  int32_t exec_mode;        /* CB_MODE_LATENCY (0) or CB_MODE_THROUGHPUT (1): grid policy of this call     */
   uint64_t seed;
 } cb_caldera_params;
 
@@ -380,6 +362,27 @@ int cb_quantize_residual_f32(const float* R, const float* base, int64_t rows, in
 /* out = X scaled along rows (axis 0) or columns (axis 1) by v: mode 0 multiply, 1 divide. */
 int cb_scale_f32(const float* X, int64_t rows, int64_t cols, const float* v, int axis, int mode, float* out,
                  void* stream);
+
+/* ------------------------------------------------------------------------- measurement aids
+ * Compiled only into libcaldera_b200_measure.so (`python -m ee274_convexcaldera_llm_quantization_b200.build --measure`,
+ * -DCB_MEASURE) for scripts/probe_*.py; the release library exports none of them and has no process-wide setter.  That
+ * build also honours CB_DEBUG_SKIP (drops whole kernel classes for knock-out timing; results are then garbage). */
+#ifdef CB_MEASURE
+/* 64-wide K blocks fetched per TMA instruction in the narrow-tile contractions (1 or 2, default 2). */
+void cb_set_gemm_kblocks(int n);
+/* 0: direct-store epilogue instead of the shared-memory staged one (same results). */
+void cb_set_gemm_staged_epilogue(int on);
+/* When non-NULL, CTA (0,0,0) of every tcgen05 contraction writes clock64 stamps to this device buffer of 12 int64
+ * ([0..7]: entry, prologue done, last load issued, first stage landed, last stage landed, accumulator complete,
+ * epilogue stores issued, exit; [8..9]: staged epilogue -- tile in shared memory, barrier passed). */
+void cb_set_gemm_timing(void* stamps_dev);
+/* When non-NULL the Cholesky kernel writes clock64 stamps (start, factor done, diagonal block inverses done, inverse
+ * done; then 5 per panel for the first 3 panels) to this device buffer of 24 int64. */
+void cb_set_chol_timing(void* stamps_dev);
+/* Cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16, bf16, operands resident in shared memory) take on an SM,
+ * on a grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */
+int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream);
+#endif
 
 #ifdef __cplusplus
 }

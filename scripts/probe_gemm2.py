@@ -16,12 +16,13 @@ for batch in (1, 4, 16, 32, 37):
     Cb = torch.empty(batch, M, N, device=dev, dtype=torch.bfloat16)
     Ct = torch.empty(batch, N, M, device=dev, dtype=torch.bfloat16)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
     k = [0]
     def run(mc=0):
         A = As[k[0] % nrot]; k[0] += 1
         st = lib.cb_gemm_bf16_tn_batched(batch, M, N, K, 1.0, _lib.ptr(A), K, A.stride(0) * 2, _lib.ptr(B), K, B.stride(0) * 2,
                                          None, 0, 0, _lib.ptr(Cb), N, Cb.stride(0) * 2, _lib.ptr(Ct), M, Ct.stride(0) * 2,
-                                         None, 0, None, 0, mc, _lib.ptr(flag), _lib.stream_ptr())
+                                         None, 0, None, 0, mc, _lib.ptr(counter), _lib.ptr(flag), _lib.stream_ptr())
         assert st == 0, st
     for mc in ((0,) if batch != 32 else (0, 64, 32)):
         for _ in range(3): run(mc)

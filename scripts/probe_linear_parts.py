@@ -1,3 +1,6 @@
+# Phase stamps of the packed-linear consumer kernel.  Needs the measurement build of the library:
+#   python -m ee274_convexcaldera_llm_quantization_b200.build --measure
+#   CB_LIBRARY=libcaldera_b200_measure.so python scripts/probe_linear_parts.py
 import sys; sys.path.insert(0, "/root/repo")
 import torch
 from ee274_convexcaldera_llm_quantization_b200 import _lib

@@ -1,3 +1,6 @@
+# Raw tcgen05.mma issue rate.  Needs the measurement build of the library:
+#   python -m ee274_convexcaldera_llm_quantization_b200.build --measure
+#   CB_LIBRARY=libcaldera_b200_measure.so python scripts/probe_mma_rate.py
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

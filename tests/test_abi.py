@@ -19,10 +19,11 @@ def lib():
     return _lib.load()
 
 
-def declared_symbols():
+def declared_symbols(measure=False):
     text = open(os.path.join(ROOT, "include", "caldera_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", text)))
+    release, _, aids = text.partition("#ifdef CB_MEASURE")
+    return sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", aids if measure else release)))
 
 
 def test_header_symbols_exported(lib):
@@ -33,6 +34,22 @@ def test_header_symbols_exported(lib):
         assert hasattr(raw, n), f"{n} declared in include/caldera_b200.h but not exported"
     # and the ctypes table binds exactly the declared set
     assert sorted(_lib.exported_symbols()) == names
+
+
+def test_release_library_has_no_process_wide_state(lib):
+    """re-entrant, no globals.  The execution policy is a field of cb_caldera_params; the measurement
+    aids (timing stamps, probes, knock-out switch) are declared under CB_MEASURE and compiled only into
+    libcaldera_b200_measure.so."""
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    aids = declared_symbols(measure=True)
+    assert "cb_set_gemm_timing" in aids and "cb_probe_mma_rate" in aids
+    for n in aids + ["cb_set_execution_mode", "cb_set_gemm_target_ctas"]:
+        assert not hasattr(raw, n), f"{n} must not be exported by the release library"
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("cb_")]
+    assert not [n for n in exported if n.startswith("cb_set_") or n.startswith("cb_probe_")], exported
+    assert "exec_mode" in [f for f, _ in _lib.cb_caldera_params._fields_]
 
 
 def test_version_and_status_strings(lib):

@@ -181,7 +181,7 @@ def test_golden_whole_pipeline_fallback_branch(gold):
             ci, cg = np.rint(d.R_star.cpu().numpy() / d.group_info["delta"]), np.rint(Rg / c["delta"])
             assert np.abs(ci - cg).max() <= 1 and np.mean(ci != cg) <= 0.02, (c, np.mean(ci != cg))
         assert torch.equal(d.W_compressed, d.L_star + d.R_star)
-        np.testing.assert_allclose(d.duality_gap, c["duality_gap"], rtol=2e-2, atol=1e-9)
+        np.testing.assert_allclose(d.duality_gap, c["duality_gap"], rtol=2e-2, atol=1e-5)
         Lf, Rf = z[f"e2e_{k}_L"], z[f"e2e_{k}_R_lr"]
         L, R = d.group_info["L"], d.group_info["R_lr"]
         assert tuple(L.shape) == Lf.shape and tuple(R.shape) == Rf.shape
@@ -203,3 +203,31 @@ def test_gpu_solution_satisfies_kkt(mu, tau):
     Hp, lam_max, kappa, c = co.calibrate(W, h)
     rl, rr = co.kkt_residuals(W, d.L_star.cpu().numpy(), d.group_info["R_continuous"].cpu().numpy(), Hp, lam_max, kappa, c, prm)
     assert rl <= 2e-3 and rr <= 2e-3, (rl, rr)
+
+
+def test_large_shape_satisfies_kkt_and_structure():
+    """Config 5 at a size where the whole matrix can still be checked on the host (2048 x 4096, penalty form,
+    tensor-core path): the returned point is a fixed point of an exact float64 proximal-gradient step, the low-rank
+    part has the planted rank, and the residual lives on the reference's grid."""
+    m, n, k = 2048, 4096, 48
+    g = torch.Generator().manual_seed(11)
+    U = torch.linalg.qr(torch.randn(m, k, generator=g))[0]
+    V = torch.linalg.qr(torch.randn(n, k, generator=g))[0]
+    s = 24.0 * torch.arange(1, k + 1, dtype=torch.float32) ** -0.3        # 24 ... 7.5
+    W = 0.02 * torch.randn(m, n, generator=g) + (U * s) @ V.T
+    h = 0.5 + torch.rand(n, generator=g)
+    # a direction of size sigma moves from R into L once 2 lambda sigma / kappa > mu (kappa = ||W||_F): put that
+    # threshold between the noise (largest singular value ~0.02 (sqrt(m) + sqrt(n)) = 2.2) and the planted part
+    kappa = float(W.norm())
+    kw = dict(mu=1.0, lambda_reg=1.0 * kappa / (2.0 * 3.0), B_tot=4.0, solver_tol=1e-7)
+    d = convex_caldera(W, h, params=ConvexCalderaParams(**kw), device=DEV, rank_cap=96, max_iters=400, check_every=20)
+    assert d.solver_status == "optimal" and not d.group_info["rank_capped"]
+    assert 8 <= d.effective_rank <= k                           # the planted directions above the threshold, no noise
+    prm = co.ConvexOracleParams(**kw)
+    Hp, lam_max, kappa, c = co.calibrate(W.numpy(), h.numpy())
+    rl, rr = co.kkt_residuals(W.numpy(), d.L_star.cpu().numpy(), d.group_info["R_continuous"].cpu().numpy(), Hp, lam_max,
+                              kappa, c, prm)
+    assert rl <= 2e-2 and rr <= 2e-3, (rl, rr)                  # bf16 contractions inside the thresholding
+    codes = d.R_star / d.group_info["delta"]
+    assert float((codes - codes.round()).abs().max()) < 1e-3
+    assert torch.equal(d.W_compressed, d.L_star + d.R_star)

@@ -67,8 +67,11 @@ def test_gemm_tc_split_without_workspace_is_an_error():
 @pytest.mark.parametrize("M,N,K,splitk", [(256, 4096, 4096, 1), (224, 224, 4096, 0), (4096, 128, 4096, 0), (128, 512, 192, 1),
                                            (256, 1024, 4096 + 64, 3)])
 def test_gemm_tc_kblocks_per_copy_do_not_change_results(M, N, K, splitk):
-    """One or two 64-wide K blocks per TMA instruction (3-D tensor map): same bits."""
+    """One or two 64-wide K blocks per TMA instruction (3-D tensor map): same bits.  (Needs the measurement build,
+    CB_LIBRARY=libcaldera_b200_measure.so: the release library has no such switch.)"""
     lib = _lib.load()
+    if not hasattr(lib, "cb_set_gemm_kblocks"):
+        pytest.skip("measurement aids are not compiled into the release library")
     try:
         lib.cb_set_gemm_kblocks(1)
         _, C1 = _run(M, N, K, splitk, return_C=True)
@@ -79,12 +82,13 @@ def test_gemm_tc_kblocks_per_copy_do_not_change_results(M, N, K, splitk):
     assert torch.equal(C1, C2)
 
 
-@pytest.mark.parametrize("M,N,K,ctas", [(224, 4096, 4096, 120), (224, 4096, 4096, 32), (4096, 224, 224, 120),
-                                         (224, 1024, 256, 64), (100, 72, 200, 120), (256, 520, 128, 32)])
+@pytest.mark.parametrize("M,N,K,mode", [(224, 4096, 4096, 0), (224, 4096, 4096, 1), (4096, 224, 224, 0),
+                                         (224, 1024, 256, 1), (100, 72, 200, 0), (256, 520, 128, 1)])
 @pytest.mark.parametrize("outs", ["both", "rowmajor", "transposed"])
-def test_gemm_tc_bf16_epilogues(M, N, K, ctas, outs):
-    """bf16 row-major / transposed outputs with scaling: shared-memory staged epilogue == direct stores ==
-    torch, for every tile width (grid policy) and for shapes that cannot be staged (ragged N / M)."""
+def test_gemm_tc_bf16_epilogues(M, N, K, mode, outs):
+    """bf16 row-major / transposed outputs with scaling against torch, for both grid policies (exec_mode of the call:
+    wide tiles on ~32 CTAs or narrow tiles over the machine) and for shapes that cannot be staged (ragged N / M);
+    with the measurement build also: shared-memory staged epilogue == direct stores, bit for bit."""
     lib = _lib.load()
     g = torch.Generator(device=DEV).manual_seed(M + N + K)
     Kp = (K + 7) // 8 * 8
@@ -97,20 +101,21 @@ def test_gemm_tc_bf16_epilogues(M, N, K, ctas, outs):
     ldcb, ldct = (N + 7) // 8 * 8, (M + 7) // 8 * 8
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
     res = []
+    have_aids = hasattr(lib, "cb_set_gemm_staged_epilogue")
     try:
-        lib.cb_set_gemm_target_ctas(ctas)
-        for staged in (1, 0):
-            lib.cb_set_gemm_staged_epilogue(staged)
+        for staged in ((1, 0) if have_aids else (1,)):
+            if have_aids:
+                lib.cb_set_gemm_staged_epilogue(staged)
             Cb = torch.full((M, ldcb), 7.0, device=DEV, dtype=torch.bfloat16)
             Ct = torch.full((N, ldct), 7.0, device=DEV, dtype=torch.bfloat16)
             _lib.check(lib.cb_gemm_bf16_tn_bf16out(M, N, K, 0.5, _lib.ptr(A), Kp, _lib.ptr(B), Kp,
                                                    _lib.ptr(Cb) if outs != "transposed" else None, ldcb,
                                                    _lib.ptr(Ct) if outs != "rowmajor" else None, ldct,
-                                                   _lib.ptr(cs), _lib.ptr(rs), _lib.ptr(flag), _lib.stream_ptr()), "gemm")
+                                                   _lib.ptr(cs), _lib.ptr(rs), mode, _lib.ptr(flag), _lib.stream_ptr()), "gemm")
             res.append((Cb, Ct))
     finally:
-        lib.cb_set_gemm_staged_epilogue(1)
-        lib.cb_set_gemm_target_ctas(120)
+        if have_aids:
+            lib.cb_set_gemm_staged_epilogue(1)
     torch.cuda.synchronize()
     assert int(flag.item()) == 0
     ref = (0.5 * (A[:, :K].double() @ B[:, :K].double().T) * rs[:, None].double() * cs[None, :].double())
@@ -121,7 +126,8 @@ def test_gemm_tc_bf16_epilogues(M, N, K, ctas, outs):
         if outs != "rowmajor":
             assert float((Ct[:, :M].double() - ref.T).abs().max() / ref.abs().max()) < 6e-3
             assert bool((Ct[:, M:] == 7.0).all())
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    if have_aids:
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
 
 
 def test_gemm_tc_alpha_and_ld():

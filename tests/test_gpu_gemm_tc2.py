@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run(batch, M, N, K, max_clusters=0, outs=("C", "Cb", "Ct"), scales=False, alpha=1.0, pad=0):
+def _run(batch, M, N, K, max_clusters=0, outs=("C", "Cb", "Ct"), scales=False, alpha=1.0, pad=0, dynamic=True):
     lib = _lib.load()
     g = torch.Generator(device=DEV).manual_seed(batch + 3 * M + 5 * N + 7 * K + max_clusters)
     lda = (K + 7) // 8 * 8 + pad
@@ -24,13 +24,17 @@ def _run(batch, M, N, K, max_clusters=0, outs=("C", "Cb", "Ct"), scales=False, a
     cs = (0.5 + torch.rand(batch, N, generator=g, device=DEV)) if scales else None
     rs = (0.5 + torch.rand(batch, M, generator=g, device=DEV)) if scales else None
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV) if dynamic else None
     sb = lambda t: 0 if t is None else t.stride(0) * t.element_size()  # noqa: E731
     st = lib.cb_gemm_bf16_tn_batched(batch, M, N, K, alpha, _lib.ptr(A), lda, sb(A), _lib.ptr(B), lda, sb(B),
                                      _lib.ptr(C), N, sb(C), _lib.ptr(Cb), N, sb(Cb), _lib.ptr(Ct), M, sb(Ct),
-                                     _lib.ptr(cs), sb(cs), _lib.ptr(rs), sb(rs), max_clusters, _lib.ptr(flag), _lib.stream_ptr())
+                                     _lib.ptr(cs), sb(cs), _lib.ptr(rs), sb(rs), max_clusters, _lib.ptr(counter), _lib.ptr(flag),
+                                     _lib.stream_ptr())
     _lib.check(st, "gemm_bf16_tn_batched")
     torch.cuda.synchronize()
     assert int(flag.item()) == 0, "pipeline watchdog fired"
+    if counter is not None:
+        assert counter.tolist() == [0, 0], "the dynamic tile scheduler must leave its counters zeroed"
     ref = alpha * torch.bmm(A[:, :, :K].double(), B[:, :, :K].double().transpose(1, 2))
     if scales:
         ref = ref * rs.double()[:, :, None] * cs.double()[:, None, :]
@@ -62,6 +66,7 @@ def test_gemm_tc2_many_tiles_per_cluster(max_clusters):
     """Few clusters, many tiles: both TMEM accumulators, their full/empty barriers and many laps of the smem ring."""
     _check(_run(3, 1280, 224, 640, max_clusters=max_clusters))
     _check(_run(2, 768, 600, 192, max_clusters=max_clusters))
+    _check(_run(3, 1280, 224, 640, max_clusters=max_clusters, dynamic=False))     # fixed tile -> cluster assignment
 
 
 def test_gemm_tc2_scales_alpha_and_output_subsets():
@@ -77,13 +82,15 @@ def test_gemm_tc2_is_bitwise_reproducible():
     A = torch.randn(4, 1024, 512, generator=g, device=DEV).bfloat16()
     B = torch.randn(4, 224, 512, generator=g, device=DEV).bfloat16()
     outs = []
-    for mc in (0, 3, 0):
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    for mc, dyn in ((0, True), (3, True), (0, False), (5, True)):
         C = torch.empty(4, 1024, 224, device=DEV)
         flag = torch.zeros(1, dtype=torch.int32, device=DEV)
         _lib.check(lib.cb_gemm_bf16_tn_batched(4, 1024, 224, 512, 1.0, _lib.ptr(A), 512, A.stride(0) * 2, _lib.ptr(B), 512,
                                                B.stride(0) * 2, _lib.ptr(C), 224, C.stride(0) * 4, None, 0, 0, None, 0, 0,
-                                               None, 0, None, 0, mc, _lib.ptr(flag), _lib.stream_ptr()), "g2")
+                                               None, 0, None, 0, mc, _lib.ptr(counter) if dyn else None, _lib.ptr(flag),
+                                               _lib.stream_ptr()), "g2")
         torch.cuda.synchronize()
         assert int(flag.item()) == 0
         outs.append(C)
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])    # no dependence on the tile -> cluster map
+    assert all(torch.equal(outs[0], o) for o in outs[1:])    # no dependence on the tile -> cluster map
