@@ -473,6 +473,19 @@ def run_ours(args):
         for hd in pending:
             last = hd.result()
         return last
+    # context for the e2e number: what the host link delivers to this GPU for one pinned 256 MiB buffer
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(4):
+        probe_d.copy_(probe_h, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * probe_h.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del probe_h, probe_d
     e2e_steps = max(1, args.steps)
     run_e2e(0, max(1, min(args.warmup, 2)) * batch)       # every slot captures its graph
     barrier()
@@ -563,7 +576,10 @@ def run_ours(args):
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps},
+                        "steps": e2e_steps, "host_link_h2d_gbs_measured": h2d_gbs,
+                        "h2d_gbs_used": e2e_value / world * (M * N * 4 + N * 4) / 1e9,
+                        "note": "fp32 W crosses the host link once per layer (67 MB): e2e per GPU is bounded by "
+                                "host_link_h2d_gbs_measured / 0.0671 matrices/s"},
                 "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "clocks": clocks,
                 "errors_last_layer": [round(e, 6) for e in errs],
                 "e2e_errors_last_layer": {k: [round(e, 6) for e in v] for k, v in last_dec.errors.items()},

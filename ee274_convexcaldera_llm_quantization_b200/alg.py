@@ -277,7 +277,7 @@ def caldera_async(
         return get_engine(dev, slots, batch).submit(p, Wsrc, h_kind, Hd, seed, finish,
                                                     want_packed=return_packed or consume is not None,
                                                     want_w_scaled=want_w and scale_W, consume=consume_all,
-                                                    batch_hint=batch_hint)
+                                                    batch_hint=batch_hint, want_dense=return_dense)
 
 
 def caldera(

@@ -143,6 +143,13 @@ __device__ __forceinline__ void quant_code4(const float4& v, const ScaleRecip& r
     c2 = quant_code(v.z, r.s, lv); c3 = quant_code(v.w, r.s, lv);
   }
 }
+// The ternary ("2-bit", levels = 1) code without any division: rint(fmul(fdiv(x, s), 1)) is +1 exactly when the correctly
+// rounded quotient exceeds 0.5 (a tie at 0.5 rounds to the even 0), i.e. when x / s > 0.5 + 2^-25 in real arithmetic;
+// s / 2 is exact in fp32 and the next fp32 value above it is s / 2 + ulp(s / 2) >= s / 2 (1 + 2^-23) > s (0.5 + 2^-25),
+// so for an fp32 x this is the same as x > s / 2.  Symmetric for -1.  Valid for |x| <= s and a normal s / 2.
+__device__ __forceinline__ bool ternary_ok(float s) { return s > 1e-30f && s < 1e30f; }
+__device__ __forceinline__ int ternary_code(float x, float half_s) { return (int)(x > half_s) - (int)(x < -half_s); }
+
 // quantization.py:105, 295
 __device__ __forceinline__ float dequant_val(int code, float s, float lv) {
   return __fmul_rn(__fdiv_rn((float)code, lv), s);

@@ -535,9 +535,10 @@ static int lplr_refine(const cb_caldera_params* p, const LayerPlan& P, int64_t m
 // skinny contraction goes to M and the sketch width q (224) becomes the instruction's N.
 static int g2(const Bt& bt, int64_t M, int64_t N, int64_t K, const bf16* A, int64_t lda, const bf16* B, int64_t ldb,
               float* C, int64_t ldc, bf16* Cb, int64_t ldcb, bf16* Ct, int64_t ldct, const float* colscale, int* wd,
-              cudaStream_t st, int* tile_counter = nullptr) {
+              cudaStream_t st, int* tile_counter = nullptr, bf16* Cs = nullptr, int split_mode = 0) {
   Gemm2Batch g;
   g.tile_counter = tile_counter;
+  g.Cs = Cs; g.sCs = bt.stride; g.split_mode = split_mode;
   g.batch = bt.n; g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = lda; g.sA = bt.stride; g.B = B; g.ldb = ldb; g.sB = bt.stride;
   g.C = C; g.ldc = ldc; g.sC = bt.stride; g.Cb = Cb; g.ldcb = ldcb; g.sCb = bt.stride; g.Ct = Ct; g.ldct = ldct; g.sCt = bt.stride;
@@ -551,7 +552,10 @@ static int orthonormalize_b(const Bt& bt, const bf16* Xt, const bf16* X, int64_t
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
   CB_TRY(g2(bt, q, q, N, Xt, N, Xt, N, b.G, q, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter));              // G = X^T X
   CB_TRY(cholesky_inverse(b.G, (int)q, b.Linv, b.status, st, b.Linvb, bt));
-  return g2(bt, N, q, q, X, q, b.Linvb, q, nullptr, 0, Xo, q, Xot, N, nullptr, wd, st, b.tile_counter);                // Xo = X Linv^T
+  // Xot[q, N] = Linv[q, K = q] * X[N, K = q]^T with the sketch width on M: the orientation every consumer inside the
+  // power loop needs (Xot) is then the row-major output (whole 64-byte pieces per thread); the transposed one (Xo,
+  // 2-byte stores) is only written when a caller asks for it.  K is tiny here, so the epilogue is the kernel.
+  return g2(bt, q, N, q, b.Linvb, q, X, q, nullptr, 0, Xot, N, Xo, q, nullptr, wd, st, b.tile_counter);
 }
 
 static int copy_b(const Bt& bt, void* dst, const void* src, size_t bytes, cudaStream_t st) {
@@ -560,21 +564,25 @@ static int copy_b(const Bt& bt, void* dst, const void* src, size_t bytes, cudaSt
   return copy_if_multi(nullptr, c, st, bt);
 }
 
+// Lsplit / Rtsplit (optional, aware only): the split-bf16 operands of the L R contraction, written by the epilogues of
+// the two contractions that produce L and R instead of by a conversion pass of their own
 static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t q, int niter, uint64_t seed, int aware,
-                          const float* inv_sqrt_h, bool warm_valid, float* L, float* R, const LowrankTcBufs& b, cudaStream_t st) {
+                          const float* inv_sqrt_h, bool warm_valid, float* L, float* R, const LowrankTcBufs& b, cudaStream_t st,
+                          bf16* Lsplit = nullptr, bf16* Rtsplit = nullptr) {
   int* wd = b.status != nullptr ? b.status + 2 : nullptr;
   if (!warm_valid) {
     dim3 grid((unsigned)grid_for(q * n, 256 * 4, 1), (unsigned)bt.n);
     randn_bf16_kernel<<<grid, 256, 0, st>>>(b.Ptb, q * n, seed, b.seed_dev, bt.stride);
     CB_CHECK_LAUNCH();
     CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Ptb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st, b.tile_counter));        // Z = Y P
-    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, niter == 0 ? b.Zob : nullptr, b, st));
   }
   for (int it = 0; it < niter; ++it) {
     CB_TRY(g2(bt, n, q, m, b.Ytb, m, b.Zotb, m, nullptr, 0, b.Pb, q, b.Ptb, n, nullptr, wd, st, b.tile_counter));      // P = Y^T Zo
     CB_TRY(orthonormalize_b(bt, b.Ptb, b.Pb, n, q, b.Potb, nullptr, b, st));
     CB_TRY(g2(bt, m, q, n, b.Yb, n, b.Potb, n, nullptr, 0, b.Zb, q, b.Ztb, m, nullptr, wd, st, b.tile_counter));       // Z = Y Po
-    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, b.Zob, b, st));
+    // (the m x q orientation of the basis is only consumed after the loop)
+    CB_TRY(orthonormalize_b(bt, b.Ztb, b.Zb, m, q, b.Zotb, it == niter - 1 ? b.Zob : nullptr, b, st));
   }
   // CholeskyQR2 on the (bf16-rounded) basis itself
   {
@@ -591,8 +599,9 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
   CB_TRY(jacobi_eigh_from_chol(b.G, (int)q, b.evals, b.V, b.work, b.status != nullptr ? b.status + 1 : nullptr, st, bt));
   CB_TRY(to_bf16(b.V, q, q, q, b.Vb, q, nullptr, 0, nullptr, st, bt));
   // L[m, r] = Zo V_r^T ;  R[r, n] = V_r B (column-scaled by 1 / sqrt(h))
-  CB_TRY(g2(bt, m, r, q, b.Zob, q, b.Vb, q, L, r, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter));
-  CB_TRY(g2(bt, r, n, q, b.Vb, q, b.Btb, q, R, n, nullptr, 0, nullptr, 0, aware ? inv_sqrt_h : nullptr, wd, st, b.tile_counter));
+  CB_TRY(g2(bt, m, r, q, b.Zob, q, b.Vb, q, L, r, nullptr, 0, nullptr, 0, nullptr, wd, st, b.tile_counter, aware ? Lsplit : nullptr, 1));
+  CB_TRY(g2(bt, r, n, q, b.Vb, q, b.Btb, q, R, n, nullptr, 0, nullptr, 0, aware ? inv_sqrt_h : nullptr, wd, st, b.tile_counter,
+            aware ? Rtsplit : nullptr, 2));
   if (!aware) {
     for (int k = 0; k < bt.n; ++k) {
       CB_TRY(scale_cols(at(L, bt, k), m, r, at(b.evals, bt, k), 2, at(L, bt, k), st));
@@ -607,60 +616,18 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
   return copy_if_multi(nullptr, c, st, bt);
 }
 
-static int lr_product_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
-  dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
-  split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
-  CB_CHECK_LAUNCH();
-  split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
-  CB_CHECK_LAUNCH();
-  return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st, P.tc.tile_counter);
-}
-
-// The split-bf16 operands of L R ([Lh | Lh | Ll] and [Rh^T | Rl^T | Rh^T], K = 3r) for the fused contractions below
-static int lr_operands_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st) {
-  dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
-  split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
-  CB_CHECK_LAUNCH();
-  split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
-  CB_CHECK_LAUNCH();
-  return CB_OK;
-}
-
-static Gemm2Batch lr_gemm_desc(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r) {
-  Gemm2Batch g;
-  g.batch = bt.n; g.M = m; g.N = n; g.K = 3 * r;
-  g.A = P.Lb16; g.lda = 3 * r; g.sA = bt.stride; g.B = P.Rtb16; g.ldb = 3 * r; g.sB = bt.stride;
-  g.error_flag = P.flags + 4; g.sE = bt.stride; g.tile_counter = P.tc.tile_counter;
-  return g;
-}
-
-// num += sum_ij hvec_j (Wsrc - Q - L R)_ij^2 and (optionally) amax = max |Wsrc - L R| with L R computed tile by tile in
-// tensor memory and consumed in the contraction's epilogue: the m x n product never exists in HBM (alg.py:293-301,
-// and :182 for the LPLR inner error with Wsrc = residual, no codes)
-static int lr_error_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, const float* Wsrc, void* codes,
-                      int cbytes, int bits, float* qscale, const float* hvec, double* num, float* amax, cudaStream_t st) {
-  Gemm2Batch g = lr_gemm_desc(bt, P, m, n, r);
-  g.epi = 1; g.code_bytes = cbytes; g.lv = (float)((1 << (bits - 1)) - 1);
-  g.Wsrc = Wsrc; g.ldw = n; g.codes = codes; g.ldcodes = n; g.qscale = qscale; g.hvec = hvec; g.num = num; g.amax = amax;
-  if (amax != nullptr) {
-    CopySegments z;
-    z.add(amax, nullptr, sizeof(float));
-    CB_TRY(copy_if_multi(nullptr, z, st, bt));
+// LRbuf = L R for the whole batch (split-bf16 operands, K = 3r, see lr_product_raw).  operands_ready: P.Lb16 / P.Rtb16
+// already hold the split operands of the current L, R (written by the epilogues of the contractions that produced them).
+static int lr_product_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st,
+                        bool operands_ready = false) {
+  if (!operands_ready) {
+    dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
+    split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
+    CB_CHECK_LAUNCH();
+    split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
+    CB_CHECK_LAUNCH();
   }
-  return gemm_tc2(g, st);
-}
-
-// The Q update (maybe_update_Q, alg.py:253-283) as the epilogue of the same contraction: quantise Ws - L R with the
-// abs-max already known, write the codes, the bf16 operands of the next rank-r step (and the fp32 residual for the
-// LPLR loop) and accumulate the weighted error of the new iterate.
-static int lr_quant_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan& P, int64_t m, int64_t n, int64_t r,
-                      const float* Ws, float* res_out, cudaStream_t st) {
-  Gemm2Batch g = lr_gemm_desc(bt, P, m, n, r);
-  g.epi = 2; g.code_bytes = code_bytes(p->q_bits); g.lv = (float)((1 << (p->q_bits - 1)) - 1); g.eps = 1e-8f;
-  g.Wsrc = Ws; g.ldw = n; g.codes = P.codes_cur; g.ldcodes = n; g.qscale = P.qscale_cur; g.hvec = P.h_eff;
-  g.sqrt_h = p->aware ? P.sqrt_h : nullptr; g.amax = P.amax; g.num = P.dsc + 2;
-  g.Yb = P.tc.Yb; g.Ytb = P.tc.Ytb; g.RES = res_out;
-  return gemm_tc2(g, st);
+  return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st, P.tc.tile_counter);
 }
 
 // lplr_step_tc for a batch: contractions batched, the fp32 r x r solves and the whole-tensor quantiser per layer
@@ -692,11 +659,7 @@ static int lplr_step_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan
     CB_TRY(sgemm(r, n, r, 1.f, at(P.Ginv, bt, k), r, 1, at(P.Br, bt, k), n, 1, at(P.Rtmp, bt, k), n, 1, false, nullptr, st));
     CB_TRY(quantize_whole(at(P.Rtmp, bt, k), r, n, p->r_bits, at(P.Rcodes_cur, bt, k), at(P.Rscale_cur, bt, k), at(P.Rcur, bt, k), st));
   }
-  // ---- inner error (alg.py:182), fused into the L R contraction when the shape allows
-  if (n % 32 == 0) {
-    CB_TRY(lr_operands_b(bt, P, m, n, r, st));
-    return lr_error_b(bt, P, m, n, r, res, nullptr, 1, 8, nullptr, P.w_inner, P.dsc + 3, nullptr, st);
-  }
+  // ---- inner error (alg.py:182)
   CB_TRY(lr_product_b(bt, P, m, n, r, st));
   for (int k = 0; k < bt.n; ++k)
     CB_TRY(err_accum(at(res, bt, k), nullptr, 8, nullptr, at(P.LRbuf, bt, k), at(P.w_inner, bt, k), m, n, at(P.dsc, bt, k) + 3, st));
@@ -965,7 +928,8 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
   if (!batch_supported(p, m, n, h_kind)) return CB_ERR_UNSUPPORTED;
   if (W == nullptr || out == nullptr || ws == nullptr) return CB_ERR_ARG;
   if (h_kind == CB_H_DIAG && h == nullptr) return CB_ERR_ARG;
-  if (out->Q == nullptr || out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr ||
+  // out->Q (the dense fp32 Q) is optional here: callers that consume the packed codes do not need it
+  if (out->L == nullptr || out->R == nullptr || out->errors == nullptr || out->scalars == nullptr ||
       out->Q_idxs == nullptr || out->Q_scale == nullptr)
     return CB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -999,6 +963,7 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
     z2.add(P.Lcur, nullptr, sizeof(float) * m * r);
     z2.add(P.Rcur, nullptr, sizeof(float) * r * n);
     z2.add(P.tc.tile_counter, nullptr, sizeof(int) * 4);
+    z2.add(P.amax, nullptr, sizeof(float) * 4);
     if (P.quant_factors) {
       z2.add(P.Lcodes_out, nullptr, (size_t)m * r * lcb);
       z2.add(out->R_idxs, nullptr, (size_t)r * n * rcb);
@@ -1011,8 +976,9 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
   CB_TRY(finalize_global_scale(P.dsc + 0, numel, p->global_scale_in, scale_w, P.scalars, st, bt));
   CB_TRY(prep_hessian_diag(h_kind == CB_H_DIAG ? h : nullptr, n, p->sigma_reg, p->aware, P.h_eff, P.sqrt_h, P.inv_sqrt_h,
                            P.w_inner, nullptr, st, bt));
-  for (int b = 0; b < bt.n; ++b)
-    CB_TRY(scale_and_den(at(W, bt, b), at(P.Ws, bt, b), m, n, at(P.scalars, bt, b), at(P.h_eff, bt, b), at(P.dsc, bt, b) + 1, st));
+  for (int b = 0; b < bt.n; ++b)   // also delivers max |W / gs|, the abs-max of a first Q update (its residual is W / gs)
+    CB_TRY(scale_and_den(at(W, bt, b), at(P.Ws, bt, b), m, n, at(P.scalars, bt, b), at(P.h_eff, bt, b), at(P.dsc, bt, b) + 1, st,
+                         at(P.amax, bt, b)));
   const float* Ws = scale_w ? P.Ws : W;
   if (out->W_scaled != nullptr) CB_TRY(copy_b(bt, out->W_scaled, Ws, sizeof(float) * numel, st));
 
@@ -1020,9 +986,8 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
   const int niter_warm = p->power_iters_warm >= 0 ? p->power_iters_warm
                                                   : (p->power_iters >= 0 ? p->power_iters : (p->rand_svd ? 2 : 3));
   bool have_q = false, have_lr = false, lrbuf_valid = false, warm_valid = false, basis_saw_q = false;
-  bool y_valid = false, amax_valid = false;
-  bool lr16_valid = false;                 // P.Lb16 / P.Rtb16 hold the split-bf16 operands of the current L, R
-  const bool fused = n % 32 == 0 && m % 2 == 0;   // fused L R epilogues (whole 32-column chunks per thread)
+  bool y_valid = false;
+  bool amax_valid = true;                  // P.amax holds max |Ws - L R| of the current L, R (L = R = 0 so far: max |Ws|)
   bool updated[8] = {false, false, false, false, false, false, false, false};
   float* res_out = P.quant_factors ? (p->aware ? P.RES : P.Y) : nullptr;   // fp32 residual W - Q for the LPLR loop
   int step = 0;
@@ -1032,10 +997,7 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
       bool num_ready = false;
       if (which == 0) {
         // ---- Q update (maybe_update_Q, alg.py:253-283) fused with the bf16 operand builder of the next rank-r step
-        if (have_lr && fused && amax_valid && lr16_valid) {
-          // quantise Ws - L R in the epilogue of the L R contraction: the product never reaches HBM
-          CB_TRY(lr_quant_b(bt, p, P, m, n, r, Ws, res_out, st));
-        } else {
+        {
           const float* lrp = nullptr;
           if (have_lr) {
             if (!lrbuf_valid) CB_TRY(lr_product_b(bt, P, m, n, r, st));
@@ -1043,7 +1005,7 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
             lrp = P.LRbuf;
           }
           for (int b = 0; b < bt.n; ++b) {
-            if (!(amax_valid && lrp != nullptr)) CB_TRY(resid_absmax(at(Ws, bt, b), at(lrp, bt, b), numel, at(P.amax, bt, b), st));
+            if (!amax_valid) CB_TRY(resid_absmax(at(Ws, bt, b), at(lrp, bt, b), numel, at(P.amax, bt, b), st));
             CB_TRY(quant_form_y_bf16(at(Ws, bt, b), at(lrp, bt, b), at(P.h_eff, bt, b), p->aware ? at(P.sqrt_h, bt, b) : nullptr, m, n,
                                      at(P.amax, bt, b), 1e-8f, p->q_bits, at(P.codes_cur, bt, b), at(P.qscale_cur, bt, b),
                                      at(P.dsc, bt, b) + 2, at(P.tc.Yb, bt, b), at(P.tc.Ytb, bt, b), at(res_out, bt, b), st));
@@ -1064,26 +1026,18 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
         }
         const int niter = (warm_valid && p->warm_start && basis_saw_q) ? niter_warm : niter_cold;
         basis_saw_q = have_q;
+        // 16-bit factors: L and R leave the rank-r step as they are, so their split-bf16 operands come out of the
+        // epilogues that produce them
+        const bool split_in_epilogue = p->aware && !P.quant_factors;
         CB_TRY(lowrank_core_b(bt, m, n, r, P.q, niter, p->seed + 0x9E37ull * (uint64_t)step, p->aware, P.inv_sqrt_h,
-                              warm_valid && p->warm_start, P.Lcur, P.Rcur, P.tc, st));
+                              warm_valid && p->warm_start, P.Lcur, P.Rcur, P.tc, st, split_in_epilogue ? P.Lb16 : nullptr,
+                              split_in_epilogue ? P.Rtb16 : nullptr));
         warm_valid = true;
         if (P.quant_factors) CB_TRY(lplr_refine_b(bt, p, P, m, n, st));
         have_lr = true;
         amax_valid = false;
-        if (fused) {
-          // error of the new iterate and the abs-max of Ws - L R for the next Q update, both in the epilogue of
-          // the L R contraction (alg.py:293-301)
-          CB_TRY(lr_operands_b(bt, P, m, n, r, st));
-          lr16_valid = true;
-          lrbuf_valid = false;
-          CB_TRY(lr_error_b(bt, P, m, n, r, Ws, have_q ? P.codes_cur : nullptr, qcb, p->q_bits, P.qscale_cur, P.h_eff,
-                            P.dsc + 2, P.amax, st));
-          amax_valid = true;
-          num_ready = true;
-        } else {
-          CB_TRY(lr_product_b(bt, P, m, n, r, st));
-          lrbuf_valid = true;
-        }
+        CB_TRY(lr_product_b(bt, P, m, n, r, st, split_in_epilogue));
+        lrbuf_valid = true;
       }
       if (!num_ready) {
         // right after an LR update this pass also delivers the abs-max the next Q update needs
@@ -1123,7 +1077,8 @@ extern "C" int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t s
   }
   // ---- materialise the best iterate
   for (int b = 0; b < bt.n; ++b) {
-    CB_TRY(cb_dequantize_f32(at(out->Q_idxs, bt, b), nullptr, at(out->Q_scale, bt, b), numel, p->q_bits, 0, at(out->Q, bt, b), stream));
+    if (out->Q != nullptr)
+      CB_TRY(cb_dequantize_f32(at(out->Q_idxs, bt, b), nullptr, at(out->Q_scale, bt, b), numel, p->q_bits, 0, at(out->Q, bt, b), stream));
     if (out->Q_packed != nullptr) CB_TRY(cb_pack_codes(at(out->Q_idxs, bt, b), numel, p->q_bits, at(out->Q_packed, bt, b), stream));
     if (P.quant_factors) {
       CB_TRY(transpose_codes(at(P.Lcodes_out, bt, b), m, r, lcb, at(out->L_idxs, bt, b), st));

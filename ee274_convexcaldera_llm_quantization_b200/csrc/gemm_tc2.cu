@@ -41,13 +41,13 @@ namespace cb {
 
 constexpr int G2_BM = 128;                 // rows per CTA (256 per cluster)
 constexpr int G2_BK = 64;
-constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KiB
 constexpr int G2_B_BYTES = 128 * G2_BK * 2;            // 16 KiB reserved per stage (N_TILE / 2 <= 128 rows used)
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_THREADS = 32 * (4 + G2_EPI_WARPS);    // 384
-constexpr int G2_BAR_OFF = G2_STAGES * (G2_A_BYTES + G2_B_BYTES);
 constexpr int G2_SQ = 4;                                   // depth of the tile-id ring
+constexpr int G2_STAGES = 6;
+constexpr int G2_BAR_OFF = G2_STAGES * (G2_A_BYTES + G2_B_BYTES);
 constexpr int G2_NBAR = 2 * G2_STAGES + 4 + 2 * G2_SQ;     // full/empty ring, tmem full/empty x2, sched full/empty ring
 constexpr int G2_SMEM = G2_BAR_OFF + G2_NBAR * 8 + 16 + 4 * G2_SQ + 1024;
 
@@ -60,23 +60,14 @@ struct Gemm2Args {
   float* C; int64_t ldc; int64_t sC;
   __nv_bfloat16* Cb; int64_t ldcb; int64_t sCb;     // row-major bf16
   __nv_bfloat16* Ct; int64_t ldct; int64_t sCt;     // transposed (N x M) bf16
+  // optional split-bf16 copy of C for a later K = 3 N' contraction ([hi | hi | lo] x [hi | lo | hi]^T ~ fp32 product):
+  // split_mode 1: row i of Cs (M x 3N) = [hi(C[i,:]) | hi(C[i,:]) | lo(C[i,:])]
+  // split_mode 2: row j of Cs (N x 3M) = [hi(C[:,j]) | lo(C[:,j]) | hi(C[:,j])]   (transposed)
+  __nv_bfloat16* Cs; int64_t sCs; int split_mode;
   const float* colscale; int64_t sCol;              // per output column, may be null
   const float* rowscale; int64_t sRow;              // per output row, may be null
   int* error_flag; int64_t sFlag;
   int* tile_counter;             // 2 zeroed ints (next tile, clusters done; the kernel leaves them zero) or null = static
-  // fused epilogues of the outer loop (epi != 0): the product tile never leaves the SM
-  int epi;                       // 0 plain; 1 error + abs-max of W - acc; 2 quantise W - acc (Q update)
-  int code_bytes;                // 1 (int8) or 2 (int16)
-  float lv, eps;                 // quantiser levels 2^(b-1) - 1, scale floor
-  int64_t sE;                    // byte stride between batch items of every pointer below
-  const float* Wsrc; int64_t ldw;     // M x N fp32
-  void* codes; int64_t ldcodes;       // M x N codes: read (epi 1, may be null: Q = 0), written (epi 2)
-  float* qscale;                      // device scalar: read (epi 1), written (epi 2)
-  const float* hvec;                  // N error weights, may be null (all ones)
-  const float* sqrt_h;                // N column weights of Y (epi 2), may be null
-  float* amax;                        // epi 1: out, max |W - acc| (may be null); epi 2: in
-  double* num;                        // += sum_ij h_j E_ij^2
-  __nv_bfloat16* Yb; __nv_bfloat16* Ytb; float* RES;   // epi 2 outputs: (W - Q) sqrt(h) as M x N and N x M bf16, W - Q fp32
 };
 
 // 32 consecutive output columns of one row: scaling, then the fp32 / bf16 / transposed-bf16 stores asked for
@@ -124,129 +115,51 @@ __device__ __forceinline__ void g2_store_chunk(const Gemm2Args& a, int b, int ro
     for (int j = 0; j < 32; ++j)
       if (col0 + j < a.N) p[(int64_t)(col0 + j) * a.ldct + row] = __float2bfloat16_rn(v[j]);
   }
-}
-
-// ---- fused epilogues (alg.py:262 residual, :293-301 error, quantization.py:244-268 quantiser): a thread owns 32
-// consecutive columns of one row of the product tile (v = L R) and streams the matching pieces of W and the codes.
-template <typename code_t>
-__device__ __forceinline__ void load_codes32(const code_t* p, int (&c)[32]) {
-  if (sizeof(code_t) == 1) {
-    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (a.Cs != nullptr) {
+    __nv_bfloat16* p = boff(a.Cs, a.sCs * b);
+    if (a.split_mode == 1) {
+      __nv_bfloat16* q = p + (int64_t)row * 3 * a.N + col0;
+      if (full && a.N % 8 == 0 && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0)) {
+        // 32 consecutive columns of one row: three 64-byte pieces (hi, hi, lo), 128-bit stores
 #pragma unroll
-    for (int j = 0; j < 32; ++j) c[j] = (int)(int8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-  } else {
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t h[4], l[4];
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const uint4 a = *reinterpret_cast<const uint4*>(p + 8 * q4);
-      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[j + 2 * k]), h1 = __float2bfloat16_rn(v[j + 2 * k + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[j + 2 * k] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[j + 2 * k + 1] - __bfloat162float(h1));
+            h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(q + j) = hv;
+          *reinterpret_cast<uint4*>(q + a.N + j) = hv;
+          *reinterpret_cast<uint4*>(q + 2 * a.N + j) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      } else {
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < a.N) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+            q[j] = hi; q[a.N + j] = hi; q[2 * a.N + j] = lo;
+          }
+        }
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c[8 * q4 + j] = (int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < a.N) {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+          __nv_bfloat16* q = p + (int64_t)(col0 + j) * 3 * a.M + row;
+          q[0] = hi; q[a.M] = lo; q[2 * a.M] = hi;
+        }
+      }
     }
   }
 }
-template <typename code_t>
-__device__ __forceinline__ void store_codes32(code_t* p, const int (&c)[32]) {
-  if (sizeof(code_t) == 1) {
-    uint32_t w[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      w[k] = (uint32_t)(c[4 * k] & 0xFF) | ((uint32_t)(c[4 * k + 1] & 0xFF) << 8) | ((uint32_t)(c[4 * k + 2] & 0xFF) << 16) |
-             ((uint32_t)(c[4 * k + 3] & 0xFF) << 24);
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(p + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-  } else {
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        w[k] = (uint32_t)(c[8 * q4 + 2 * k] & 0xFFFF) | ((uint32_t)(c[8 * q4 + 2 * k + 1] & 0xFFFF) << 16);
-      *reinterpret_cast<uint4*>(p + 8 * q4) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-}
 
-// epi 1: E = W - Q - L R  ->  part += sum h_j E^2, amx = max |W - L R|   (arithmetic of err_kernel, stages.cu)
-template <typename code_t>
-__device__ __forceinline__ void g2_err_chunk(const Gemm2Args& a, int b, int row, int col0, const float (&v)[32],
-                                             float s, const ScaleRecip& lvr, double& acc, float& amx) {
-  const int64_t off = (int64_t)row * a.ldw + col0;
-  const float* wp = boff(a.Wsrc, a.sE * b) + off;
-  float w[32];
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(wp + j);
-    w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
-  }
-  int c[32];
-  if (a.codes != nullptr) load_codes32<code_t>(boff(reinterpret_cast<const code_t*>(a.codes), a.sE * b) + (int64_t)row * a.ldcodes + col0, c);
-  const float* hp = a.hvec != nullptr ? boff(a.hvec, a.sE * b) + col0 : nullptr;
-  float part = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float e = w[j];
-    if (a.codes != nullptr) e -= dequant_val(c[j], s, lvr);
-    e -= v[j];
-    part = fmaf((hp != nullptr ? __ldg(hp + j) : 1.f) * e, e, part);
-    amx = fmaxf(amx, fabsf(w[j] - v[j]));
-  }
-  acc += (double)part;
-}
-
-// epi 2: res = W - L R; code = quantise(res); E = res - dequant(code); Y = (W - dequant(code)) sqrt(h)
-// (arithmetic of quant_form_y_bf16_kernel, stages.cu)
-template <typename code_t>
-__device__ __forceinline__ void g2_quant_chunk(const Gemm2Args& a, int b, int row, int col0, const float (&v)[32], float s,
-                                               const ScaleRecip& sr, const ScaleRecip& lvr, double& acc) {
-  const int64_t off = (int64_t)row * a.ldw + col0;
-  const float* wp = boff(a.Wsrc, a.sE * b) + off;
-  float w[32];
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(wp + j);
-    w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
-  }
-  const float* hp = a.hvec != nullptr ? boff(a.hvec, a.sE * b) + col0 : nullptr;
-  const float* sp = a.sqrt_h != nullptr ? boff(a.sqrt_h, a.sE * b) + col0 : nullptr;
-  int c[32];
-  float part = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float res = w[j] - v[j];
-    c[j] = quant_code(res, sr, a.lv);
-    const float dq = dequant_val(c[j], s, lvr);
-    const float e = res - dq;
-    part = fmaf((hp != nullptr ? __ldg(hp + j) : 1.f) * e, e, part);
-    w[j] -= dq;                                        // W - Q
-  }
-  acc += (double)part;
-  store_codes32<code_t>(boff(reinterpret_cast<code_t*>(a.codes), a.sE * b) + (int64_t)row * a.ldcodes + col0, c);
-  if (a.RES != nullptr) {
-    float* rp = boff(a.RES, a.sE * b) + off;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(rp + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
-  }
-  if (sp != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) w[j] *= __ldg(sp + j);
-  }
-  __nv_bfloat16* yb = boff(a.Yb, a.sE * b) + off;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 pk;
-    __nv_bfloat162 t0 = __floats2bfloat162_rn(w[j], w[j + 1]), t1 = __floats2bfloat162_rn(w[j + 2], w[j + 3]);
-    __nv_bfloat162 t2 = __floats2bfloat162_rn(w[j + 4], w[j + 5]), t3 = __floats2bfloat162_rn(w[j + 6], w[j + 7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-    *reinterpret_cast<uint4*>(yb + j) = pk;
-  }
-  __nv_bfloat16* yt = boff(a.Ytb, a.sE * b);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) yt[(int64_t)(col0 + j) * a.M + row] = __float2bfloat16_rn(w[j]);
-}
-
-template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
@@ -402,52 +315,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row = m_blk * 2 * G2_BM + (int)cta_rank * G2_BM + qd * 32 + lane;
       const float* rsp = boff(args.rowscale, args.sRow * b);
       const float rs = (rsp != nullptr && row < args.M) ? rsp[row] : 1.f;
-      if constexpr (EPI == 0) {
 #pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
-          float v[32];
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          g2_store_chunk(args, b, row, n_blk * args.n_tile + c * 32, rs, v);
-        }
-      } else {
-        // fused outer-loop epilogues (host guarantees M % 128 == 0 is not needed: rows are masked; N % 32 == 0)
-        const float lv = args.lv;
-        const ScaleRecip lvr = make_scale_recip(lv);
-        float s_q = 0.f;
-        if constexpr (EPI == 1) s_q = args.codes != nullptr ? boff(args.qscale, args.sE * b)[0] : 0.f;
-        else s_q = fmaxf(boff(args.amax, args.sE * b)[0], args.eps);
-        const ScaleRecip sr = make_scale_recip(s_q);
-        if (EPI == 2 && m_blk == 0 && n_blk == 0 && cta_rank == 0 && warp == 4 && lane == 0)
-          boff(args.qscale, args.sE * b)[0] = s_q;
-        double part = 0.0;
-        float amx = 0.f;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * 256 + c * 32), r);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const int col0 = n_blk * args.n_tile + c * 32;
-          if (row < args.M && col0 < args.N) {
-            if constexpr (EPI == 1) {
-              if (args.code_bytes == 1) g2_err_chunk<int8_t>(args, b, row, col0, v, s_q, lvr, part, amx);
-              else g2_err_chunk<int16_t>(args, b, row, col0, v, s_q, lvr, part, amx);
-            } else {
-              if (args.code_bytes == 1) g2_quant_chunk<int8_t>(args, b, row, col0, v, s_q, sr, lvr, part);
-              else g2_quant_chunk<int16_t>(args, b, row, col0, v, s_q, sr, lvr, part);
-            }
-          }
-        }
-        part = warp_sum(part);
-        if (lane == 0 && args.num != nullptr) atomicAdd(boff(args.num, args.sE * b), part);
-        if (EPI == 1 && args.amax != nullptr) {
-          amx = warp_max(amx);
-          if (lane == 0) atomic_max_nonneg(boff(args.amax, args.sE * b), amx);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        g2_store_chunk(args, b, row, n_blk * args.n_tile + c * 32, rs, v);
       }
       // this warp has read its part of the accumulator: one arrival on the leader's tmem_empty barrier
       tc_fence_before();
@@ -503,32 +378,19 @@ int gemm_tc2(const Gemm2Batch& g, cudaStream_t st) {
   a.Cb = g.Cb; a.ldcb = g.ldcb; a.sCb = g.sCb;
   a.Ct = g.Ct; a.ldct = g.ldct; a.sCt = g.sCt;
   a.colscale = g.colscale; a.sCol = g.sCol; a.rowscale = g.rowscale; a.sRow = g.sRow;
+  a.Cs = g.Cs; a.sCs = g.sCs; a.split_mode = g.split_mode;
   a.error_flag = g.error_flag; a.sFlag = 0;
   a.tile_counter = g.tile_counter;
-  a.epi = g.epi; a.code_bytes = g.code_bytes; a.lv = g.lv; a.eps = g.eps; a.sE = g.sE;
-  a.Wsrc = g.Wsrc; a.ldw = g.ldw; a.codes = g.codes; a.ldcodes = g.ldcodes; a.qscale = g.qscale; a.hvec = g.hvec;
-  a.sqrt_h = g.sqrt_h; a.amax = g.amax; a.num = g.num; a.Yb = g.Yb; a.Ytb = g.Ytb; a.RES = g.RES;
-  if (a.epi != 0) {
-    // a thread streams whole 32-column chunks of W / codes / Y with 128-bit accesses
-    if (g.N % 32 != 0 || g.ldw % 4 != 0 || g.Wsrc == nullptr || !aligned16(g.Wsrc) || (a.epi == 2 && (g.codes == nullptr ||
-        g.Yb == nullptr || g.Ytb == nullptr || g.amax == nullptr || g.qscale == nullptr || g.M % 2 != 0)) ||
-        (g.codes != nullptr && (g.ldcodes % 16 != 0 || !aligned16(g.codes))) || (a.epi == 1 && g.codes != nullptr && g.qscale == nullptr))
-      return CB_ERR_UNSUPPORTED;
-  }
   CUtensorMap ta, tb;
   CB_TRY(make_tmap_bf16_batched(&ta, g.A, g.M, g.K, g.lda, g.batch, g.sA, G2_BM));
   CB_TRY(make_tmap_bf16_batched(&tb, g.B, g.N, g.K, g.ldb, g.batch, g.sB, a.n_tile / 2));
-  static PerDeviceOnce once0, once1, once2;
-  if (a.epi == 0) CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<0>, G2_SMEM, once0));
-  else if (a.epi == 1) CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<1>, G2_SMEM, once1));
-  else CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel<2>, G2_SMEM, once2));
+  static PerDeviceOnce once;
+  CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel, G2_SMEM, once));
   const int64_t total_tiles = (int64_t)a.batch * a.tiles_m * a.tiles_n;
   int clusters = g.max_clusters > 0 ? g.max_clusters : kNumSMs / 2;
   if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
   if (total_tiles < clusters) clusters = (int)total_tiles;
-  if (a.epi == 0) gemm_tc2_kernel<0><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
-  else if (a.epi == 1) gemm_tc2_kernel<1><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
-  else gemm_tc2_kernel<2><<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
+  gemm_tc2_kernel<<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -70,8 +70,9 @@ struct HessianVecs {
 int sumsq(const float* x, int64_t numel, double* out, cudaStream_t st);
 int finalize_global_scale(const double* sumsq, int64_t numel, float gs_in, int scale_w, float* scalars,
                           cudaStream_t st, const Bt& bt = Bt());
+// amax (optional, zeroed by the caller): receives max |W / gs|, the abs-max the first Q update needs
 int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h,
-                  double* den, cudaStream_t st);
+                  double* den, cudaStream_t st, float* amax = nullptr);
 int prep_hessian_diag(const float* h_in, int64_t n, float sigma_reg, int aware, float* h_eff, float* sqrt_h,
                       float* inv_sqrt_h, float* w_inner, float* scratch, cudaStream_t st, const Bt& bt = Bt());
 int resid_absmax(const float* Ws, const float* LR, int64_t numel, float* amax, cudaStream_t st);
@@ -138,21 +139,10 @@ struct Gemm2Batch {
   __nv_bfloat16* Ct = nullptr; int64_t ldct = 0, sCt = 0;
   const float* colscale = nullptr; int64_t sCol = 0;
   const float* rowscale = nullptr; int64_t sRow = 0;
+  __nv_bfloat16* Cs = nullptr; int64_t sCs = 0; int split_mode = 0;   // split-bf16 copy of C, see gemm_tc2.cu
   int max_clusters = 0;          // 0 = one cluster per SM pair
   int* error_flag = nullptr;
   int* tile_counter = nullptr;   // 2 zeroed device ints for the dynamic tile scheduler (left zero by the kernel); null = static
-  // fused epilogues (see gemm_tc2.cu): 1 = weighted error of W - Q - A B^T (+ abs-max of W - A B^T), 2 = Q update
-  int epi = 0, code_bytes = 1;
-  float lv = 1.f, eps = 1e-8f;
-  int64_t sE = 0;
-  const float* Wsrc = nullptr; int64_t ldw = 0;
-  void* codes = nullptr; int64_t ldcodes = 0;
-  float* qscale = nullptr;
-  const float* hvec = nullptr;
-  const float* sqrt_h = nullptr;
-  float* amax = nullptr;
-  double* num = nullptr;
-  __nv_bfloat16* Yb = nullptr; __nv_bfloat16* Ytb = nullptr; float* RES = nullptr;
 };
 bool gemm_tc2_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb);
 int gemm_tc2(const Gemm2Batch& g, cudaStream_t st);

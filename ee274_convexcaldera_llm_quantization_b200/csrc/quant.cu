@@ -80,7 +80,11 @@ quant_fast_kernel(const float* __restrict__ x, int64_t numel, float eps,
       }
       const float s = sr.s;
       int c[8];
-      if (sr.exact) {
+      if (BITS == 2 && ternary_ok(s)) {     // two compares per element instead of an exact division (common.cuh)
+        const float hs = 0.5f * s;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] = ternary_code(v[j].v[e], hs);
+      } else if (sr.exact) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) c[e] = __float2int_rn(__fmul_rn(div_by_scale_exact(v[j].v[e], sr), lv));
       } else {   // uniform over the lanes that share the scale, rare

@@ -106,10 +106,13 @@ __global__ void finalize_gs_kernel(const double* sumsq, int64_t numel, float gs_
 template <int VEC>
 __global__ void __launch_bounds__(256)
 scale_den_kernel(const float* __restrict__ W, float* __restrict__ Ws, int64_t numel, int64_t n,
-                 const float* __restrict__ gs_ptr, const float* __restrict__ h, double* __restrict__ den) {
+                 const float* __restrict__ gs_ptr, const float* __restrict__ h, double* __restrict__ den,
+                 float* __restrict__ amax) {
   __shared__ double red[32];
+  __shared__ float redf[32];
   const ScaleRecip gs = make_scale_recip(gs_ptr[0]);
   double acc = 0.0;
+  float amx = 0.f;      // max |W / gs|: the abs-max of the first Q update (its residual is W / gs itself)
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
     const int64_t i = ch__ * VEC;
     const int64_t j = CB_CHUNK_COL(VEC, n);
@@ -121,12 +124,17 @@ scale_den_kernel(const float* __restrict__ W, float* __restrict__ Ws, int64_t nu
     for (int k = 0; k < VEC; ++k) {
       w.v[k] = div_by_scale(w.v[k], gs);  // alg.py:42, true (correctly rounded) division
       part = fmaf((h != nullptr ? hv.v[k] : 1.f) * w.v[k], w.v[k], part);
+      amx = fmaxf(amx, fabsf(w.v[k]));
     }
     if (Ws != nullptr) w.store(Ws + i);
     acc += (double)part;
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(den, acc);
+  if (amax != nullptr) {
+    amx = block_max(amx, redf);
+    if (threadIdx.x == 0) atomic_max_nonneg(amax, amx);
+  }
 }
 
 // ---------------------------------------------------------------- diagonal Hessian prep
@@ -212,6 +220,8 @@ quant_err_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, con
   __shared__ double red[32];
   const float s = fmaxf(amax[0], eps);
   const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
+  const bool tern = lv == 1.f && ternary_ok(s);      // 2-bit grid: exact codes from two compares (common.cuh)
+  const float hs = 0.5f * s;
   if (blockIdx.x == 0 && threadIdx.x == 0) qscale[0] = s;
   double acc = 0.0;
   CB_GRID_STRIDE_CHUNKS(VEC, numel) {
@@ -226,7 +236,7 @@ quant_err_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, con
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float res = LR != nullptr ? w.v[k] - p.v[k] : w.v[k];
-      c[k] = quant_code(res, sr, lv);
+      c[k] = tern ? ternary_code(res, hs) : quant_code(res, sr, lv);
       const float e = res - dequant_val(c[k], s, lvr);
       part = fmaf((h != nullptr ? hv.v[k] : 1.f) * e, e, part);
     }
@@ -369,6 +379,8 @@ quant_form_y_bf16_kernel(const float* __restrict__ Ws, const float* __restrict__
   __shared__ double red[32];
   const float s = fmaxf(amax[0], eps);
   const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
+  const bool tern = lv == 1.f && ternary_ok(s);      // 2-bit grid: exact codes from two compares (common.cuh)
+  const float hs = 0.5f * s;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) qscale[0] = s;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int col = blockIdx.x * 64 + 4 * tx;
@@ -389,7 +401,7 @@ quant_form_y_bf16_kernel(const float* __restrict__ Ws, const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float res = LR != nullptr ? w.v[j] - p.v[j] : w.v[j];
-        c[j] = quant_code(res, sr, lv);
+        c[j] = tern ? ternary_code(res, hs) : quant_code(res, sr, lv);
         const float dq = dequant_val(c[j], s, lvr);
         const float e = res - dq;
         part = fmaf((h_err != nullptr ? he.v[j] : 1.f) * e, e, part);
@@ -777,12 +789,13 @@ int finalize_global_scale(const double* ss, int64_t numel, float gs_in, int scal
   CB_CHECK_LAUNCH();
   return CB_OK;
 }
-int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h, double* den, cudaStream_t st) {
+int scale_and_den(const float* W, float* Ws, int64_t m, int64_t n, const float* gs, const float* h, double* den, cudaStream_t st,
+                  float* amax) {
   const int64_t numel = m * n;
   if (can_vec4(n, {W, Ws, h}))
-    scale_den_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den);
+    scale_den_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den, amax);
   else
-    scale_den_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den);
+    scale_den_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Ws, numel, n, gs, h, den, amax);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -131,18 +131,21 @@ class LayerEngine:
             for slot in self.slots:
                 self._arena(slot, min(nbytes, self._slot_bytes()))
 
-    def batch_for(self, p, m: int, n: int, h_kind: int, want_packed: bool, want_w_scaled: bool, hint: Optional[int]) -> int:
+    def batch_for(self, p, m: int, n: int, h_kind: int, want_packed: bool, want_w_scaled: bool, hint: Optional[int],
+                  want_dense: bool = True) -> int:
         """Layers per graph replay for this configuration: 0 = not batchable (single-layer graph)."""
         lib = _lib.load()
         if self.batch <= 1 or not lib.cb_caldera_batch_supported(C.byref(p), m, n, h_kind):
             return 0
         b = self.batch if not hint else max(1, min(self.batch, int(hint)))
-        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled)
+        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled, want_dense)
         return max(1, min(b, self._slot_bytes() // stride))
 
-    def _group_for(self, p, m, n, h_kind, want_packed, want_w_scaled, hint) -> _Group:
-        nb = self.batch_for(p, m, n, h_kind, want_packed, want_w_scaled, hint)
-        key = (_params_signature(p), m, n, h_kind, want_packed, want_w_scaled, _lib.execution_mode(), nb)
+    def _group_for(self, p, m, n, h_kind, want_packed, want_w_scaled, hint, want_dense=True) -> _Group:
+        nb = self.batch_for(p, m, n, h_kind, want_packed, want_w_scaled, hint, want_dense)
+        if nb == 0:
+            want_dense = True                 # the single-layer driver always materialises Q
+        key = (_params_signature(p), m, n, h_kind, want_packed, want_w_scaled, want_dense, nb)
         g = self.filling.get(key)
         if g is not None:
             return g
@@ -152,9 +155,9 @@ class LayerEngine:
             if run is None:
                 with torch.cuda.stream(slot.stream):
                     if nb > 0:
-                        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled)
+                        stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled, want_dense)
                         run = BatchRunner(p, m, n, h_kind, nb, self.device, want_packed=want_packed, want_w_scaled=want_w_scaled,
-                                          slab=self._arena(slot, max(stride * nb, slot.arena.numel() if slot.arena is not None else 0)))
+                                          want_dense=want_dense, slab=self._arena(slot, max(stride * nb, slot.arena.numel() if slot.arena is not None else 0)))
                     else:
                         need = workspace_bytes(p, m, n, h_kind)
                         run = CalderaLayerRunner(p, m, n, h_kind, self.device, want_packed=want_packed, want_w_scaled=want_w_scaled,
@@ -176,7 +179,7 @@ class LayerEngine:
     # ------------------------------------------------------------------ submission
     def submit(self, p, W: torch.Tensor, h_kind: int, H: Optional[torch.Tensor], seed: int, finish: Callable,
                want_packed: bool = True, want_w_scaled: bool = False,
-               consume: Optional[Callable] = None, batch_hint: Optional[int] = None) -> LayerHandle:
+               consume: Optional[Callable] = None, batch_hint: Optional[int] = None, want_dense: bool = True) -> LayerHandle:
         """Stages one layer and returns immediately.  W / H: device tensors or pinned host tensors.  `consume(view,
         kept)` runs right after the layer's graph replay was enqueued, with the slot's stream current, and must only
         enqueue device work (copies of view.Q_packed, view.L, ... to where they are going); tensors it stores in
@@ -185,7 +188,7 @@ class LayerEngine:
         to submit (bounds the batch size so that a short job does not run a mostly empty batch)."""
         m, n = int(W.shape[0]), int(W.shape[1])
         with self.lock, torch.cuda.device(self.device):
-            g = self._group_for(p, m, n, h_kind, want_packed, want_w_scaled, batch_hint)
+            g = self._group_for(p, m, n, h_kind, want_packed, want_w_scaled, batch_hint, want_dense)
             idx = len(g.handles)
             handle = LayerHandle(g, idx, finish, consume, seed)
             caller = torch.cuda.current_stream()

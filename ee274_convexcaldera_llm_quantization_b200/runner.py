@@ -152,7 +152,8 @@ class BatchRunner:
     in flight at the same time)."""
 
     def __init__(self, c_params: "_lib.cb_caldera_params", m: int, n: int, h_kind: int, batch: int, device: torch.device,
-                 want_packed: bool = True, want_w_scaled: bool = False, slab: Optional[torch.Tensor] = None):
+                 want_packed: bool = True, want_w_scaled: bool = False, slab: Optional[torch.Tensor] = None,
+                 want_dense: bool = True):
         self.lib = _lib.load()
         self.p = c_params
         p = c_params
@@ -162,7 +163,7 @@ class BatchRunner:
         self.nsteps = p.iters * p.n_order
         self.nerr_pad = (self.nsteps + 3) // 4 * 4
         self.nsmall = self.nerr_pad + 8 + 12
-        self.off, self.stride, self.ws_bytes = self._layout(p, m, n, h_kind, want_packed, want_w_scaled)
+        self.off, self.stride, self.ws_bytes = self._layout(p, m, n, h_kind, want_packed, want_w_scaled, want_dense)
         total = self.stride * self.batch
         with torch.cuda.device(device):
             if slab is not None and slab.numel() >= total and slab.device == device:
@@ -209,7 +210,7 @@ class BatchRunner:
         self.seeds_host = torch.zeros(self.batch, dtype=torch.int64).pin_memory()
 
     @staticmethod
-    def _layout(p, m, n, h_kind, want_packed, want_w_scaled):
+    def _layout(p, m, n, h_kind, want_packed, want_w_scaled, want_dense=True):
         """Byte offsets of one layer's buffers inside its slab: ({name: (offset, nbytes)}, stride, workspace bytes)."""
         lib = _lib.load()
         r = int(p.rank)
@@ -218,7 +219,7 @@ class BatchRunner:
         cb = lambda b: 1 if b <= 8 else 2  # noqa: E731
         ws_bytes = int(lib.cb_caldera_layer_workspace_bytes(C.byref(p), m, n, h_kind)) or 256
         fields = [("W_in", 4 * m * n), ("h_in", 4 * n if h_kind == _lib.CB_H_DIAG else 0), ("small", 4 * nsmall),
-                  ("seed", 8), ("Q", 4 * m * n), ("L", 4 * m * r), ("R", 4 * r * n), ("Q_idxs", m * n * cb(p.q_bits)),
+                  ("seed", 8), ("Q", 4 * m * n if want_dense else 0), ("L", 4 * m * r), ("R", 4 * r * n), ("Q_idxs", m * n * cb(p.q_bits)),
                   ("Q_packed", int(lib.cb_packed_bytes(m * n, p.q_bits)) if want_packed else 0),
                   ("L_idxs", r * m * cb(p.l_bits) if quant_factors else 0),
                   ("R_idxs", r * n * cb(p.r_bits) if quant_factors else 0),
@@ -233,8 +234,8 @@ class BatchRunner:
         return off, o, ws_bytes
 
     @staticmethod
-    def slab_stride(p, m, n, h_kind, want_packed=True, want_w_scaled=False) -> int:
-        return BatchRunner._layout(p, m, n, h_kind, want_packed, want_w_scaled)[1]
+    def slab_stride(p, m, n, h_kind, want_packed=True, want_w_scaled=False, want_dense=True) -> int:
+        return BatchRunner._layout(p, m, n, h_kind, want_packed, want_w_scaled, want_dense)[1]
 
     def _ptr(self, name):
         return C.c_void_p(self.slab.data_ptr() + self.off[name][0]) if name in self.off else None
