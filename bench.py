@@ -266,6 +266,23 @@ def roofline_probes(dev, peaks, nbatch):
                                     "unit": "GB/s", "frac": bytes_q / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
                                     "seconds": t, "algorithmic_bytes": bytes_q}
 
+    # (a') the same kernel on a 4x larger tensor (8192 x 8192): at 4096 x 4096 a launch lasts ~17 us, of which the ramp
+    #      up and the tail are a fixed ~3-4 us; this entry shows the rate the kernel streams at once that is amortised
+    big = [0.02 * torch.randn(2 * M, 2 * N, device=dev) for _ in range(2)]
+    packed_b = torch.empty(numel, dtype=torch.uint8, device=dev)
+    scales_b = torch.empty(numel // 16, device=dev)
+
+    def quant_big():
+        x = big[k[0] % 2]
+        k[0] += 1
+        lib.cb_quantize_f32(_lib.ptr(x), 2 * M, 2 * N, 2 * N, 1, 2, 64, 1e-8, None, _lib.ptr(packed_b), _lib.ptr(scales_b), None,
+                            _lib.stream_ptr())
+    t = time_kernel(quant_big)
+    out["quantize_pack_b2_bs64_8192x8192"] = {"bound": "hbm", "achieved": 4 * bytes_q / t / 1e9, "peak": peaks["hbm_gbs"],
+                                              "unit": "GB/s", "frac": 4 * bytes_q / t / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                              "seconds": t, "algorithmic_bytes": 4 * bytes_q}
+    del big, packed_b, scales_b
+
     # (b) whole-tensor quantise + pack (the form caldera() itself uses, alg.py:247): two passes
     def quant_whole():
         x = xs[k[0] % 3]
@@ -463,12 +480,17 @@ def run_ours(args):
         return caldera_async(qp, W, h, device=dev, use_tqdm=False, W_copy="none", seed=1000 + rank, return_dense=False,
                              return_packed=False, consume=to_host, slots=nslots, batch=nbatch)
 
+    e2e_marks = []
+
     def run_e2e(first, count):
         pending, last = [], None
+        del e2e_marks[:]
         for i in range(count):
             pending.append(submit_e2e(first + i))
             if len(pending) > nstreams:                  # harvest a layer submitted a whole batch ago
                 last = pending.pop(0).result()
+            if (i + 1) % nstreams == 0:
+                e2e_marks.append(time.perf_counter())    # submit-side clock, one mark per step
         engine.flush()
         for hd in pending:
             last = hd.result()
@@ -493,7 +515,10 @@ def run_ours(args):
     last_dec = run_e2e(args.warmup * batch, e2e_steps * batch)
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
+    e2e_step_secs = [round(b - a, 4) for a, b in zip([t0] + e2e_marks[:-1], e2e_marks)]
     barrier()
+    e2e_errors = {k: [round(e, 6) for e in v] for k, v in last_dec.errors.items()}
+    del last_dec                                  # its factors are views of a slot's arena
 
     tmax = torch.tensor([secs, e2e_secs], dtype=torch.float64, device=dev)
     if world > 1:
@@ -523,11 +548,16 @@ def run_ours(args):
     # ---- second half of the metric: the full Llama-2-7B-shape job (config 4), L/R 16-bit and 4-bit
     full7b = None
     if not args.no_model:
+        import gc
         release_engines()
+        del out_hosts, engine
+        gc.collect()
         torch.cuda.empty_cache()
+        sys.stderr.write(f"[bench] before the model-level job: {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB allocated, "
+                         f"{torch.cuda.mem_get_info(dev)[0] / 2**30:.1f} GiB free\n")
         names, shapes = mj.llama_shapes(args.model_blocks)
         full7b = {"layers": len(names), "params": sum(m * n for m, n in shapes), "rank": RANK, "iters": ITERS,
-                  "streams": args.model_streams, "inputs": "generated on the owning GPU before the clock (SURVEY 8e)",
+                  "streams": args.model_streams, "slots": args.model_slots, "inputs": "generated on the owning GPU before the clock (SURVEY 8e)",
                   "timed": "barrier -> all layers decomposed -> packed blobs gathered on rank 0 -> device synchronised; "
                            "max over ranks; second pass (the first one captures the CUDA graphs)"}
         shards = sch.shard_layout(params_for(16), shapes, world)[0]
@@ -537,8 +567,8 @@ def run_ours(args):
             prm = params_for(lbits)
             res = None
             for attempt in range(2):
-                res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams, slots=nslots,
-                                       barrier=barrier)
+                res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams,
+                                       slots=args.model_slots, barrier=barrier)
                 tt = torch.tensor([res["decompose_s"], res["gather_s"], res["wall_s"]], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -547,7 +577,8 @@ def run_ours(args):
                     res = None
             key = f"lr{lbits}"
             full7b[key] = {"wall_s": float(tt[2]), "decompose_s": float(tt[0]), "gather_s": float(tt[1]),
-                           "gathered_bytes": int(res["gathered_bytes"]), "first_pass_wall_s_incl_graph_capture": first_pass}
+                           "gathered_bytes": int(res["gathered_bytes"]), "first_pass_wall_s_incl_graph_capture": first_pass,
+                           "graphs_captured_in_timed_pass": int(res["graphs_captured"])}
             if rank == 0:
                 parts = sch.split_gathered(res["arena"], res["shards"], res["sizes"])
                 first = sch.unpack_decomposition(parts[0])
@@ -576,18 +607,18 @@ def run_ours(args):
                            "parallelism": f"layer-sharded x{world}, no data-path collective",
                            "sketch_width": 224, "power_iters": "12 cold + 3 per warm-started step", "peaks": peaks["source"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "host_link_h2d_gbs_measured": h2d_gbs,
+                        "steps": e2e_steps, "submit_side_step_seconds": e2e_step_secs, "host_link_h2d_gbs_measured": h2d_gbs,
                         "h2d_gbs_used": e2e_value / world * (M * N * 4 + N * 4) / 1e9,
                         "note": "fp32 W crosses the host link once per layer (67 MB): e2e per GPU is bounded by "
                                 "host_link_h2d_gbs_measured / 0.0671 matrices/s"},
                 "gpu_launches": int(launches) * world, "gpu_launches_per_rank": int(launches), "clocks": clocks,
                 "errors_last_layer": [round(e, 6) for e in errs],
-                "e2e_errors_last_layer": {k: [round(e, 6) for e in v] for k, v in last_dec.errors.items()},
+                "e2e_errors_last_layer": e2e_errors,
                 "parity": parity_rep}
         if full7b is not None:
             line["full_7b_wall_s"] = {k: v["wall_s"] for k, v in full7b.items() if isinstance(v, dict)}
             line["full_7b"] = full7b
-        if world == 1:
+        if True:                                   # rank 0, every N: the dominant kernel timed alone on this GPU
             probes = roofline_probes(dev, peaks, nbatch)
             dominant = os.environ.get("CB_DOMINANT", "sketch_gemm_tcgen05")
             tpath = os.path.join(ROOT, "profiles", "traffic.json")      # ncu --set full, DRAM bytes per launch
@@ -599,12 +630,12 @@ def run_ours(args):
             line["roofline"] = {k: probes[dominant][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             line["roofline"]["kernel"] = dominant
             line["roofline_all"] = probes
-            if not args.no_cpu:
+            if world == 1 and not args.no_cpu:
                 cores = host_threads()
                 pin_host_threads(cores)
                 dt, kind, desc = cpu_sample()
                 line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
-            if not args.no_ref_cuda and reference_available():
+            if world == 1 and not args.no_ref_cuda and reference_available():
                 # informational: what a user of the reference gets today on this GPU (torch / cuBLAS / cuSOLVER)
                 try:
                     reference_layer(str(dev), 512, 512, 16, 1)
@@ -631,7 +662,8 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
     ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
     ap.add_argument("--model-streams", type=int, default=48, help="layers in flight per GPU in the model-level job")
-    ap.add_argument("--slots", type=int, default=3, help="graph replays in flight per GPU")
+    ap.add_argument("--slots", type=int, default=6, help="graph replays in flight per GPU")
+    ap.add_argument("--model-slots", type=int, default=3, help="graph replays in flight per GPU in the model-level job")
     ap.add_argument("--batch", type=int, default=16, help="same-shape layers advancing in lock step per graph replay")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="execution mode written into cb_caldera_params.exec_mode (single-layer driver only)")

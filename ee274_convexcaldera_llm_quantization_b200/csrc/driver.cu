@@ -425,13 +425,43 @@ split3_kernel(const float* __restrict__ X_, int64_t rows, int64_t cols, int tran
   }
 }
 
+// transpose == 1 form of split3_kernel through a 32 x 32 shared-memory tile: reads run along a row of X, writes along
+// the inner index of an output row (blockIdx.z = layer of a batch).
+__global__ void __launch_bounds__(256)
+split3_t_kernel(const float* __restrict__ X_, int rows, int cols, int second_is_lo, bf16* __restrict__ out_, int64_t bstride) {
+  __shared__ float tile[32][33];
+  const float* __restrict__ X = boff(X_, bstride * blockIdx.z);
+  bf16* __restrict__ out = boff(out_, bstride * blockIdx.z);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + ty + 8 * k, j = j0 + tx;
+    tile[ty + 8 * k][tx] = (i < rows && j < cols) ? X[(int64_t)i * cols + j] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = j0 + ty + 8 * k, i = i0 + tx;
+    if (i < rows && j < cols) {
+      const float v = tile[tx][ty + 8 * k];
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      bf16* o = out + (int64_t)j * 3 * rows + i;
+      o[0] = hi;
+      o[rows] = second_is_lo ? lo : hi;
+      o[2 * (int64_t)rows] = second_is_lo ? hi : lo;
+    }
+  }
+}
+
 static int lr_product_raw(bool use_tc, const float* Lcur, const float* Rcur, int64_t m, int64_t n, int64_t r,
                           float* LRbuf, bf16* Lb16, bf16* Rtb16, int* watchdog, cudaStream_t st) {
   if (use_tc) {
     // A' = [Lh | Lh | Ll] (m x 3r),  B' = [Rh^T | Rl^T | Rh^T] (n x 3r)
     split3_kernel<<<grid_for(m * r, 256 * 4, 4), 256, 0, st>>>(Lcur, m, r, 0, 0, Lb16);
     CB_CHECK_LAUNCH();
-    split3_kernel<<<grid_for(r * n, 256 * 4, 4), 256, 0, st>>>(Rcur, r, n, 1, 1, Rtb16);
+    split3_t_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((r + 31) / 32), 1), 256, 0, st>>>(Rcur, (int)r, (int)n, 1, Rtb16, 0);
     CB_CHECK_LAUNCH();
     return gemm_tc(m, n, 3 * r, 1.f, Lb16, 3 * r, Rtb16, 3 * r, LRbuf, n, nullptr, 0, nullptr, 0, nullptr, nullptr, 1,
                    watchdog, nullptr, st);
@@ -621,10 +651,11 @@ static int lowrank_core_b(const Bt& bt, int64_t m, int64_t n, int64_t r, int64_t
 static int lr_product_b(const Bt& bt, const LayerPlan& P, int64_t m, int64_t n, int64_t r, cudaStream_t st,
                         bool operands_ready = false) {
   if (!operands_ready) {
-    dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n), g2_((unsigned)grid_for(r * n, 256 * 4, 1), (unsigned)bt.n);
+    dim3 g1((unsigned)grid_for(m * r, 256 * 4, 1), (unsigned)bt.n);
     split3_kernel<<<g1, 256, 0, st>>>(P.Lcur, m, r, 0, 0, P.Lb16, bt.stride);
     CB_CHECK_LAUNCH();
-    split3_kernel<<<g2_, 256, 0, st>>>(P.Rcur, r, n, 1, 1, P.Rtb16, bt.stride);
+    dim3 gt((unsigned)((n + 31) / 32), (unsigned)((r + 31) / 32), (unsigned)bt.n);
+    split3_t_kernel<<<gt, 256, 0, st>>>(P.Rcur, (int)r, (int)n, 1, P.Rtb16, bt.stride);
     CB_CHECK_LAUNCH();
   }
   return g2(bt, m, n, 3 * r, P.Lb16, 3 * r, P.Rtb16, 3 * r, P.LRbuf, n, nullptr, 0, nullptr, 0, nullptr, P.flags + 4, st, P.tc.tile_counter);
@@ -637,28 +668,22 @@ static int lplr_step_b(const Bt& bt, const cb_caldera_params* p, const LayerPlan
   int* wd = P.flags + 4;
   auto spd = [&](cudaStream_t s_) -> int {
     CB_TRY(cholesky_inverse(P.Gs, (int)r, P.Linv, P.flags + 2, s_, nullptr, bt));
-    for (int k = 0; k < bt.n; ++k)
-      CB_TRY(sgemm(r, r, r, 1.f, at(P.Linv, bt, k), 1, r, at(P.Linv, bt, k), r, 1, at(P.Ginv, bt, k), r, 1, false, nullptr, s_));
-    return CB_OK;
+    return sgemm(r, r, r, 1.f, P.Linv, 1, r, P.Linv, r, 1, P.Ginv, r, 1, false, nullptr, s_, nullptr, bt);   // G^-1 = Linv^T Linv
   };
   // ---- L update (alg.py:163 / :167)
   CB_TRY(to_bf16(P.Rcur, r, n, n, P.Rsb16, n, nullptr, 0, p->aware ? P.sqrt_h : nullptr, st, bt));
   CB_TRY(g2(bt, r, r, n, P.Rsb16, n, P.Rsb16, n, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(g2(bt, m, r, n, P.tc.Yb, n, P.Rsb16, n, P.Bl, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(spd(st));
-  for (int k = 0; k < bt.n; ++k) {
-    CB_TRY(sgemm(m, r, r, 1.f, at(P.Bl, bt, k), r, 1, at(P.Ginv, bt, k), r, 1, at(P.Ltmp, bt, k), r, 1, false, nullptr, st));
-    CB_TRY(quantize_whole(at(P.Ltmp, bt, k), m, r, p->l_bits, at(P.Lcodes_cur, bt, k), at(P.Lscale_cur, bt, k), at(P.Lcur, bt, k), st));
-  }
+  CB_TRY(sgemm(m, r, r, 1.f, P.Bl, r, 1, P.Ginv, r, 1, P.Ltmp, r, 1, false, nullptr, st, nullptr, bt));
+  CB_TRY(quantize_whole_batched(P.Ltmp, m * r, p->l_bits, P.Lcodes_cur, P.Lscale_cur, P.Lcur, P.amax + 1, st, bt));  // alg.py:171-172
   // ---- R update (alg.py:175)
   CB_TRY(to_bf16(P.Lcur, m, r, r, nullptr, 0, P.Ltb16, m, nullptr, st, bt));
   CB_TRY(g2(bt, r, r, m, P.Ltb16, m, P.Ltb16, m, P.Gs, r, nullptr, 0, nullptr, 0, nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(g2(bt, r, n, m, P.Ltb16, m, P.tc.Ytb, m, P.Br, n, nullptr, 0, nullptr, 0, p->aware ? P.inv_sqrt_h : nullptr, wd, st, P.tc.tile_counter));
   CB_TRY(spd(st));
-  for (int k = 0; k < bt.n; ++k) {
-    CB_TRY(sgemm(r, n, r, 1.f, at(P.Ginv, bt, k), r, 1, at(P.Br, bt, k), n, 1, at(P.Rtmp, bt, k), n, 1, false, nullptr, st));
-    CB_TRY(quantize_whole(at(P.Rtmp, bt, k), r, n, p->r_bits, at(P.Rcodes_cur, bt, k), at(P.Rscale_cur, bt, k), at(P.Rcur, bt, k), st));
-  }
+  CB_TRY(sgemm(r, n, r, 1.f, P.Ginv, r, 1, P.Br, n, 1, P.Rtmp, n, 1, false, nullptr, st, nullptr, bt));
+  CB_TRY(quantize_whole_batched(P.Rtmp, r * n, p->r_bits, P.Rcodes_cur, P.Rscale_cur, P.Rcur, P.amax + 2, st, bt));  // alg.py:179-180
   // ---- inner error (alg.py:182)
   CB_TRY(lr_product_b(bt, P, m, n, r, st));
   for (int k = 0; k < bt.n; ++k)

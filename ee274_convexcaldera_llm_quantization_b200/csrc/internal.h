@@ -46,7 +46,7 @@ struct PolicyScope {
 // sgemm.cu -- C(i,j) = alpha * sum_k A(i,k) B(k,j) [* colscale[j]] (+ C), arbitrary strides
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
           const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
-          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw = nullptr);
+          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw = nullptr, const Bt& bt = Bt());
 
 // smalldense.cu
 int cholesky_inverse(float* G, int q, float* Linv, int* status, cudaStream_t st,
@@ -113,6 +113,10 @@ int form_y_bf16(const float* Ws, const void* codes, int bits, const float* qscal
 int quant_form_y_bf16(const float* Ws, const float* LR, const float* h_err, const float* sqrt_h, int64_t m, int64_t n,
                       const float* amax, float eps, int bits, void* codes, float* qscale, double* num,
                       __nv_bfloat16* Yb, __nv_bfloat16* Ytb, float* RES, cudaStream_t st);
+// whole-tensor quantise + dequantise (quantize_matrix, alg.py:245-250) of one contiguous fp32 tensor per layer of a
+// batch: codes (int8 / int16), the clamped scale, the dequantised values.  amax_scratch: one float per layer.
+int quantize_whole_batched(const float* x, int64_t numel, int bits, void* codes, float* scale_out, float* deq,
+                           float* amax_scratch, cudaStream_t st, const Bt& bt);
 int cvx_point(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, const float* h,
               int64_t m, int64_t n, float beta, float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st);
 int cvx_shrink(const float* sigma2, int r, float thresh, float tau_star, int constrained, const double* vr_sumsq,

@@ -19,14 +19,18 @@ sgemm_kernel(int M, int N, int K, float alpha,
              const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
              float* __restrict__ C, int64_t c_rs, int64_t c_cs,
              const float* __restrict__ colscale, int klen, int mode /*0 store, 1 accumulate*/,
-             float* __restrict__ split_ws) {
+             float* __restrict__ split_ws, int64_t bstride /* > 0: blockIdx.z is a batch index, no K split */) {
+  if (bstride > 0) {
+    const int64_t bo = bstride * blockIdx.z;
+    A = boff(A, bo); B = boff(B, bo); C = boff(C, bo); colscale = boff(colscale, bo);
+  }
   constexpr int TM = 16 * MT, TN = 16 * MT, TK = 16;
   constexpr int H = MT / 4;
   __shared__ __align__(16) float As[TK][TM + 4];
   __shared__ __align__(16) float Bs[TK][TN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int bm = blockIdx.y * TM, bn = blockIdx.x * TN;
-  const int k0 = blockIdx.z * klen;
+  const int k0 = bstride > 0 ? 0 : blockIdx.z * klen;
   const int k1 = min(K, k0 + klen);
   float acc[MT][MT];
 #pragma unroll
@@ -70,7 +74,7 @@ sgemm_kernel(int M, int N, int K, float alpha,
     __syncthreads();
   }
 
-  if (gridDim.z > 1) {
+  if (bstride == 0 && gridDim.z > 1) {
     // split-K: park the raw register tile ([tile][slice][thread][MT*MT]); sgemm_splitk_reduce_kernel
     // follows on the same stream
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
@@ -148,7 +152,8 @@ __global__ void fill_strided_kernel(float* C, int M, int N, int64_t c_rs, int64_
 
 int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t a_rs, int64_t a_cs,
           const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs, int64_t c_cs,
-          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw) {
+          bool accumulate, const float* colscale, cudaStream_t st, const SplitWs* sw, const Bt& bt) {
+  if (bt.n > 1) sw = nullptr;        // a batch runs unsplit: blockIdx.z carries the batch index
   if (M < 0 || N < 0 || K < 0 || (M > 0 && N > 0 && (C == nullptr)) ||
       (K > 0 && M > 0 && N > 0 && (A == nullptr || B == nullptr)))
     return CB_ERR_ARG;
@@ -178,12 +183,13 @@ int sgemm(int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t 
   splitk = (int)((K + klen - 1) / klen);
   const int mode = accumulate ? 1 : 0;
   float* split_ws = splitk > 1 ? sw->buf : nullptr;
-  dim3 grid((unsigned)((N + T - 1) / T), (unsigned)((M + T - 1) / T), (unsigned)splitk);
+  dim3 grid((unsigned)((N + T - 1) / T), (unsigned)((M + T - 1) / T), (unsigned)(bt.n > 1 ? bt.n : splitk));
+  const int64_t bstride = bt.n > 1 ? bt.stride : 0;
   const bool akc = (a_cs == 1), bnc = (b_cs == 1);
 #define CB_SGEMM_LAUNCH(MT, AK, BN)                                                                     \
   sgemm_kernel<MT, AK, BN><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, a_rs, a_cs, B, b_rs, \
                                                  b_cs, C, c_rs, c_cs, colscale, klen, mode, \
-                                                 split_ws)
+                                                 split_ws, bstride)
   if (big) {
     if (akc && bnc) CB_SGEMM_LAUNCH(8, true, true);
     else if (akc) CB_SGEMM_LAUNCH(8, true, false);

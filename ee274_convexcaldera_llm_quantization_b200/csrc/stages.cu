@@ -992,6 +992,52 @@ int quant_form_y_bf16(const float* Ws, const float* LR, const float* h_err, cons
   return CB_OK;
 }
 
+// ---------------------------------------------------------------- batched whole-tensor quantiser (LPLR factors)
+__global__ void __launch_bounds__(256) absmax_b_kernel(const float* __restrict__ x_, int64_t numel, float* __restrict__ out_, int64_t bstride) {
+  __shared__ float red[32];
+  const float* __restrict__ x = boff(x_, bstride * blockIdx.y);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float a = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) a = fmaxf(a, fabsf(x[i]));
+  a = block_max(a, red);
+  if (threadIdx.x == 0) atomic_max_nonneg(boff(out_, bstride * blockIdx.y), a);
+}
+template <typename code_t>
+__global__ void __launch_bounds__(256)
+quant_whole_b_kernel(const float* __restrict__ x_, int64_t numel, const float* __restrict__ amax_, float eps, float lv,
+                     code_t* __restrict__ codes_, float* __restrict__ scale_out_, float* __restrict__ deq_, int64_t bstride) {
+  const int64_t bo = bstride * blockIdx.y;
+  const float* __restrict__ x = boff(x_, bo);
+  code_t* __restrict__ codes = boff(codes_, bo);
+  float* __restrict__ deq = boff(deq_, bo);
+  const float s = fmaxf(boff(amax_, bo)[0], eps);                 // quantization.py:262-265
+  const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
+  if (blockIdx.x == 0 && threadIdx.x == 0) boff(scale_out_, bo)[0] = s;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const int c = quant_code(x[i], sr, lv);
+    codes[i] = (code_t)c;
+    if (deq != nullptr) deq[i] = dequant_val(c, s, lvr);
+  }
+}
+
+int quantize_whole_batched(const float* x, int64_t numel, int bits, void* codes, float* scale_out, float* deq,
+                           float* amax_scratch, cudaStream_t st, const Bt& bt) {
+  CopySegments z;
+  z.add(amax_scratch, nullptr, sizeof(float));
+  CB_TRY(copy_if_multi(nullptr, z, st, bt));
+  dim3 grid((unsigned)grid_for(numel, 256 * 4, 1), (unsigned)bt.n);
+  absmax_b_kernel<<<grid, 256, 0, st>>>(x, numel, amax_scratch, bt.stride);
+  CB_CHECK_LAUNCH();
+  const float lv = (float)((1 << (bits - 1)) - 1);
+  if (bits <= 8)
+    quant_whole_b_kernel<int8_t><<<grid, 256, 0, st>>>(x, numel, amax_scratch, 1e-8f, lv, reinterpret_cast<int8_t*>(codes), scale_out, deq, bt.stride);
+  else
+    quant_whole_b_kernel<int16_t><<<grid, 256, 0, st>>>(x, numel, amax_scratch, 1e-8f, lv, reinterpret_cast<int16_t*>(codes), scale_out, deq, bt.stride);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+
 // ---------------------------------------------------------------- Hadamard pre-rotation
 // Normalised Walsh-Hadamard transform (Sylvester ordering, like scipy.linalg.hadamard / sqrt(P)) of every
 // row of a matrix: one CTA per row, the row lives in shared memory for the log2(P) butterfly stages.  Rows

@@ -16,6 +16,13 @@ by the host's core count.  The engine decouples the two:
   LayerHandle.result()  launches the handle's batch if it is still filling, waits for its event and builds the
              CalderaDecomposition.
 
+Graph launches go through one launcher thread per slot: cudaGraphLaunch of a several-hundred-node graph blocks the
+calling thread for tens of milliseconds whenever the device's queues are deep (measured: 2-10 ms typically, up to
+100 ms, scripts/probe_e2e_trace.py), and a submitting thread that is stuck there cannot stage the next batch's
+input copies -- the host link then idles and the end-to-end rate drops by up to 2x.  The caller's thread only stages
+inputs and hands full batches over; the slot's launcher replays, runs the `consume` hooks and records the slot's
+event (one thread per slot, so that a launch that blocks does not hold up the launches of the other slots).
+
 Slots own a stream and one device arena that the graphs of every shape captured in that slot share (they are never in
 flight together), so device memory is slots x (largest batch footprint) whatever the number of distinct shapes; the
 arena is bounded by `CB_ENGINE_MAX_BYTES` (default 60 % of the device memory free at creation) through the batch size.
@@ -24,6 +31,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import queue
 import threading
 from typing import Callable, Dict, List, Optional
 
@@ -53,7 +61,7 @@ class LayerHandle:
 
     def done(self) -> bool:
         g = self._group
-        return g.host is not None or (g.launched and g.slot.event.query())
+        return g.host is not None or (g.launched and g.issued.is_set() and g.error is None and g.slot.event.query())
 
     def result(self):
         if not self._done:
@@ -65,13 +73,23 @@ class LayerHandle:
         return self._value
 
 
+class _ViewMeta:
+    """What is left of a layer's view once its group was collected: the layout of its host record."""
+    __slots__ = ("nsteps", "nerr_pad")
+
+    def __init__(self, nsteps: int, nerr_pad: int):
+        self.nsteps, self.nerr_pad = nsteps, nerr_pad
+
+
 class _Group:
     """The layers sharing one graph replay in one slot (a full or partial batch, or a single layer)."""
 
     def __init__(self, engine, slot, runner, views, key):
         self.engine, self.slot, self.runner, self.views, self.key = engine, slot, runner, views, key
         self.handles: List[LayerHandle] = []
-        self.launched = False
+        self.launched = False                    # handed to the launcher thread
+        self.issued = threading.Event()          # the launcher has enqueued everything on the slot's stream
+        self.error: Optional[BaseException] = None
         self.host = None
 
 
@@ -84,6 +102,8 @@ class _Slot:
         self.runners: Dict[tuple, object] = {}
         self.host_small: Optional[torch.Tensor] = None
         self.group: Optional[_Group] = None
+        self.work: "queue.SimpleQueue[Optional[_Group]]" = queue.SimpleQueue()
+        self.launcher: Optional[threading.Thread] = None
 
 
 class LayerEngine:
@@ -100,13 +120,13 @@ class LayerEngine:
         self.free = list(reversed(self.slots))       # pop() hands out slot 0 first
         self.inflight: List[_Slot] = []              # launched, in launch order
         self.filling: Dict[tuple, _Group] = {}       # key -> group still collecting layers
-        self.kernels_replayed = 0
+        self.captures = 0                            # graphs captured so far (a warm job captures none)
 
     # ------------------------------------------------------------------ slots
     def _slot_bytes(self) -> int:
         return self.max_bytes // len(self.slots)
 
-    def _acquire(self) -> _Slot:
+    def _acquire(self, key=None) -> _Slot:
         if not self.free:
             if self.inflight:
                 self._collect(self.inflight[0].group)           # blocks until the oldest group in flight is done
@@ -115,6 +135,8 @@ class LayerEngine:
                 g = max(self.filling.values(), key=lambda g_: len(g_.handles))
                 self._launch(g)
                 self._collect(g)
+        # plain LIFO (slot 0 first on an idle engine, see _collect): a job that is repeated on an idle engine is dealt
+        # the same slot sequence again and therefore meets the graphs its first pass captured
         return self.free.pop()
 
     def _arena(self, slot: _Slot, nbytes: int) -> torch.Tensor:
@@ -149,10 +171,11 @@ class LayerEngine:
         g = self.filling.get(key)
         if g is not None:
             return g
-        slot = self._acquire()
+        slot = self._acquire(key)
         try:
             run = slot.runners.get(key)
             if run is None:
+                self.captures += 1
                 with torch.cuda.stream(slot.stream):
                     if nb > 0:
                         stride = BatchRunner.slab_stride(p, m, n, h_kind, want_packed, want_w_scaled, want_dense)
@@ -206,8 +229,33 @@ class LayerEngine:
             return handle
 
     def _launch(self, g: _Group) -> None:
+        """Hands a group to the launcher thread (idempotent).  Called with the engine lock held."""
         if g.launched:
             return
+        g.launched = True
+        self.filling.pop(g.key, None)
+        self.inflight.append(g.slot)
+        slot = g.slot
+        if slot.launcher is None or not slot.launcher.is_alive():
+            slot.launcher = threading.Thread(target=self._launcher_loop, args=(slot,), daemon=True,
+                                             name=f"caldera-launcher-{self.device.index}-{slot.index}")
+            slot.launcher.start()
+        slot.work.put(g)
+
+    def _launcher_loop(self, slot: "_Slot") -> None:
+        # never takes the engine lock: a group in the queue is owned by this thread until `issued` is set
+        while True:
+            g = slot.work.get()
+            if g is None:
+                return
+            try:
+                self._issue(g)
+            except BaseException as exc:      # noqa: BLE001  (re-raised in the caller's thread by _collect)
+                g.error = exc
+            finally:
+                g.issued.set()
+
+    def _issue(self, g: _Group) -> None:
         slot = g.slot
         with torch.cuda.device(self.device), torch.cuda.stream(slot.stream):
             seeds = [h._seed for h in g.handles]
@@ -217,7 +265,6 @@ class LayerEngine:
                 g.runner.seed_dev.fill_(int(seeds[0]))
                 g.runner.graph.replay()
                 g.runner.lib.cb_note_launches(g.runner.graph_kernels)
-            self.kernels_replayed += g.runner.graph_kernels
             for h in g.handles:
                 if h._consume is not None:
                     h._consume(g.views[h._index], h.kept)
@@ -228,9 +275,6 @@ class LayerEngine:
             else:
                 dst[0].copy_(g.runner.small, non_blocking=True)
             slot.event.record(slot.stream)
-        g.launched = True
-        self.filling.pop(g.key, None)
-        self.inflight.append(slot)
 
     def _collect(self, g: _Group) -> None:
         """Waits for a group and frees its slot (idempotent)."""
@@ -239,13 +283,24 @@ class LayerEngine:
                 return
             self._launch(g)
             slot = g.slot
-            slot.event.synchronize()
+            g.issued.wait()
+            if g.error is None:
+                slot.event.synchronize()
             nsmall = g.views[0].small.numel()
             g.host = slot.host_small[:len(g.views) * nsmall].view(len(g.views), nsmall).clone()
+            # a finished group must not keep the slot's arena alive (the caller may hold its handles for a long time):
+            # `finish` only needs the record layout
+            g.views = [_ViewMeta(v.nsteps, v.nerr_pad) for v in g.views]
+            g.runner = None
             slot.group = None
             if slot in self.inflight:
                 self.inflight.remove(slot)
             self.free.append(slot)
+            if len(self.free) == len(self.slots):
+                # idle: hand the slots out in the same order as a fresh engine, so that a repeated job meets its graphs
+                self.free.sort(key=lambda s_: -s_.index)
+            if g.error is not None:
+                raise g.error
 
     def flush(self) -> None:
         """Launches every partially filled batch."""
@@ -267,6 +322,11 @@ class LayerEngine:
             for slot in self.slots:
                 slot.runners.clear()
                 slot.arena = None
+            for slot in self.slots:
+                if slot.launcher is not None:
+                    slot.work.put(None)                  # restarted by the slot's next launch
+                    slot.launcher.join(timeout=10.0)
+                    slot.launcher = None
 
 
 _ENGINES: Dict[int, LayerEngine] = {}

@@ -52,6 +52,8 @@ def run_model_job(params, names, shapes, store, rank: int, world: int, dev: torc
         torch.cuda.synchronize(dev)
         if barrier is not None:
             barrier()
+        from .engine import get_engine
+        captured = get_engine(dev, slots, max(1, streams // max(1, slots))).captures
         t0 = time.perf_counter()
         shard = sch.decompose_layers(layers, shapes, params, rank, world, device=dev, streams=streams, slots=slots,
                                      factor_dtype=factor_dtype, arena=arena)
@@ -62,4 +64,5 @@ def run_model_job(params, names, shapes, store, rank: int, world: int, dev: torc
             torch.cuda.synchronize(dev)
         t2 = time.perf_counter()
     return {"decompose_s": t1 - t0, "gather_s": t2 - t1, "wall_s": t2 - t0, "gathered_bytes": total, "arena": big,
+            "graphs_captured": get_engine(dev).captures - captured,
             "shard": shard, "shards": shards, "sizes": sizes}

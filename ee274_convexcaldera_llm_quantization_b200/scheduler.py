@@ -313,6 +313,16 @@ def decompose_layers(layers: Sequence[Tuple[str, Callable[[], Tuple[torch.Tensor
         _lib.set_execution_mode(previous_mode)
 
 
+def batch_plan(count: int, batch: int) -> List[int]:
+    """Sizes of the groups `count` same-shape layers run in when at most `batch` advance together: as few groups as
+    possible, sizes differing by at most one."""
+    if count <= 0:
+        return []
+    k = -(-count // max(1, batch))
+    base, rem = divmod(count, k)
+    return [base + 1] * rem + [base] * (k - rem)
+
+
 def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, streams, factor_dtype, arena, slots,
                       caldera_kwargs):
     from .alg import caldera_async
@@ -326,9 +336,18 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
     slots = max(1, int(slots))
     batch = max(1, int(streams) // slots)
     engine = get_engine(dev, slots, batch)
-    per_shape = {}
-    for i in mine:
-        per_shape[tuple(shapes[i])] = per_shape.get(tuple(shapes[i]), 0) + 1
+    # a captured batch always advances all of its layers, so a shape's layers are split into equal groups up front
+    # (17 layers at batch 16 -> 9 + 8) instead of ending in a mostly empty batch
+    per_shape, group_of = {}, {}
+    for i in order:
+        per_shape.setdefault(tuple(shapes[i]), []).append(i)
+    for members in per_shape.values():
+        sizes_ = batch_plan(len(members), batch)
+        pos = 0
+        for sz in sizes_:
+            for i in members[pos:pos + sz]:
+                group_of[i] = sz
+            pos += sz
     t_start = time.perf_counter()
     with torch.cuda.device(dev):
         offsets, off = {}, 0
@@ -363,9 +382,8 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
                         else:
                             dst.copy_(src.reshape(-1).view(torch.uint8))
                 kw.update(return_dense=False, return_packed=False, consume=consume)
-            # a shape with fewer layers than a batch runs a batch of exactly that many
             handles[i] = caldera_async(params, W, H, device=dev, use_tqdm=False, slots=slots, batch=batch,
-                                       batch_hint=per_shape[tuple(shapes[i])], **kw)
+                                       batch_hint=group_of[i], **kw)
         engine.flush()
         t_submit = time.perf_counter()
         results, records = {}, {}
@@ -397,7 +415,8 @@ def _decompose_layers(layers, shapes, params, rank, world_size, device, pack, st
     if os.environ.get("CB_SCHEDULER_TIMES"):
         import sys
         sys.stderr.write(f"[decompose_layers] rank {rank}: {len(mine)} layers, submit {t_submit - t_start:.3f} s, "
-                         f"total {time.perf_counter() - t_start:.3f} s\n")
+                         f"total {time.perf_counter() - t_start:.3f} s, graphs captured so far {engine.captures}, "
+                         f"groups { {k: batch_plan(len(v), batch) for k, v in per_shape.items()} }\n")
     if pack:
         return ShardResult(mine, arena, [results[i] for i in mine], records)
     return mine, [results[i] for i in mine]

@@ -152,3 +152,17 @@ def test_blob_layout_and_fixed_header():
     # a very long error trajectory is truncated rather than overflowing the fixed header
     long_meta = {"name": "y", "errors": {"Q": [0.123456789] * 400, "LR": [0.5] * 400}, "sections": []}
     assert len(sch._header_bytes(long_meta)) == sch.HEADER_BYTES
+
+
+def test_batch_plan_splits_evenly():
+    from ee274_convexcaldera_llm_quantization_b200.scheduler import batch_plan
+    assert batch_plan(0, 16) == []
+    assert batch_plan(16, 16) == [16]
+    assert batch_plan(17, 16) == [9, 8]
+    assert batch_plan(4, 16) == [4]
+    assert batch_plan(64, 16) == [16] * 4
+    for count in range(1, 70):
+        for batch in (1, 3, 16):
+            plan = batch_plan(count, batch)
+            assert sum(plan) == count and max(plan) <= batch and max(plan) - min(plan) <= 1
+            assert len(plan) == -(-count // batch)
