@@ -17,9 +17,15 @@ The step functions are also exported under the reference's names (`compute_hessi
 `round_bit_allocations`, `low_rank_factorization`, `quantize_residual`, `compute_certificates`) and run on
 the GPU; they take torch tensors (any device) or numpy arrays.
 
-Scope of this build: identity or diagonal Hessians (a dense matrix whose off-diagonal entries
-are all zero is accepted); a genuinely dense H or `calibration_data` raises
-NotImplementedError.  There is no CPU fallback.
+Hessians: identity, diagonal (a dense matrix whose off-diagonal entries are all zero is routed there) and dense
+symmetric positive semi-definite matrices, including the Gram matrix X^T X of `calibration_data` (:103-108).  The
+dense path never forms H^(1/2) or an eigendecomposition (:111-117): the solver only needs products with H
+(`cb_convex_prox_iters_dense`), the eigenvalue clamp at 1e-8 (:113) becomes a diagonal shift by
+max(0, 1e-8 - lambda_min) and the step size comes from lambda_max, both from a Lanczos run on the GPU
+(`cb_convex_dense_prepare`).  An indefinite H (lambda_min < -1e-4 lambda_max), whose negative eigenvalues the
+reference would clamp away, raises NotImplementedError; so does the stand-alone
+`compute_hessian_and_sensitivities` for a dense H (it would have to return the dense square root).  There is no
+CPU fallback.
 """
 from __future__ import annotations
 
@@ -107,17 +113,43 @@ def compute_hessian_and_sensitivities(W, H=None, calibration_data=None, device: 
         Wd = _as_device_f32(W, dev)
         n = int(Wd.shape[1])
         if H is None and calibration_data is not None:
-            raise NotImplementedError("convex_caldera: Hessians from calibration_data (dense X^T X) are not built "
-                                      "in the B200 path yet; pass the diagonal of H")
+            H = _gram_matrix(lib, calibration_data, n, dev)
         h_kind, Hd = _classify_hessian(None if H is None else _as_device_f32(H, dev), n, dev)
         if h_kind == _lib.CB_H_DENSE:
-            raise NotImplementedError("convex_caldera: dense (non-diagonal) Hessians are not built in the B200 path yet")
+            raise NotImplementedError("compute_hessian_and_sensitivities: the dense square root of a non-diagonal Hessian "
+                                      "is not formed on the B200 path (convex_caldera() itself accepts dense Hessians: "
+                                      "its solver only needs products with H)")
         hdiag = torch.ones(n, dtype=torch.float32, device=dev) if Hd is None else Hd.clamp_min(1e-8)   # :113
         s1, s2, _ = _sum_stats(lib, Wd)
         numel = Wd.numel()
         kappa = math.sqrt(s2)                                       # torch.norm(W, 'fro') (:120)
         c = 0.1 * (s2 - s1 * s1 / numel) / max(numel - 1, 1)        # torch.var(W) * 0.1, unbiased (:123)
         return torch.diag(hdiag.sqrt()), kappa, c
+
+
+def _gram_matrix(lib, X, n: int, dev: torch.device) -> torch.Tensor:
+    """H = X^T X of calibration activations X (samples x n), convex_caldera.py:108, as one fp32 contraction."""
+    Xd = _as_device_f32(X, dev)
+    if Xd.dim() != 2 or int(Xd.shape[1]) != n:
+        raise ValueError(f"calibration_data must be (samples, {n}), got {tuple(Xd.shape)}")
+    N = int(Xd.shape[0])
+    H = torch.empty((n, n), dtype=torch.float32, device=dev)
+    _lib.check(lib.cb_sgemm_strided(n, n, N, 1.0, _lib.ptr(Xd), 1, n, _lib.ptr(Xd), n, 1, _lib.ptr(H), n, 1, 0,
+                                    _lib.stream_ptr()), "sgemm")
+    return H
+
+
+def _prepare_dense_hessian(lib, H: torch.Tensor, n: int, dev: torch.device):
+    """(Hs, lambda_min, lambda_max): Hs = (H + H^T)/2 (:111) + max(0, 1e-8 - lambda_min) I (the clamp of :113 as a
+    shift), extreme eigenvalues by Lanczos on the GPU.  lambda_min is that of the symmetrised input."""
+    Hs = torch.empty((n, n), dtype=torch.float32, device=dev)
+    stats = torch.zeros(3, dtype=torch.float32, device=dev)
+    nbytes = lib.cb_min_eig_shift_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.cb_convex_dense_prepare(_lib.ptr(H), n, 1e-8, _lib.ptr(Hs), _lib.ptr(stats), _lib.ptr(ws), nbytes,
+                                           _lib.stream_ptr()), "convex_dense_prepare")
+    shift, lam_min, lam_max = stats.tolist()
+    return Hs, lam_min, lam_max + shift
 
 
 def _truncated_svd(lib, A: torch.Tensor, r: int, q: int, power_iters: int, seed: int):
@@ -250,16 +282,21 @@ def convex_caldera(
         Wd = W.to(dev, torch.float32).contiguous()
         # ---- Step 1: calibration (convex_caldera.py:85-125)
         if H is None and calibration_data is not None:
-            raise NotImplementedError("convex_caldera: Hessians from calibration_data (dense X^T X) are not built "
-                                      "in the B200 path yet; pass the diagonal of H")
+            H = _gram_matrix(lib, calibration_data, n, dev)              # H = X^T X (:108)
         h_kind, Hd = _classify_hessian(H, n, dev)
-        if h_kind == _lib.CB_H_DENSE:
-            raise NotImplementedError("convex_caldera: dense (non-diagonal) Hessians are not built in the B200 path yet")
         h = None
         lam_max = 1.0
+        dense = h_kind == _lib.CB_H_DENSE
         if h_kind == _lib.CB_H_DIAG:
             h = Hd.clamp_min(1e-8).contiguous()          # eigvals = clamp(eigvals, min=1e-8) (:113)
             lam_max = float(h.max().item())
+        elif dense:
+            h, lam_min, lam_max = _prepare_dense_hessian(lib, Hd, n, dev)
+            if lam_min < -1e-4 * lam_max:
+                raise NotImplementedError(f"convex_caldera: indefinite Hessian (lambda_min {lam_min:.3e}, lambda_max "
+                                          f"{lam_max:.3e}); the reference clamps negative eigenvalues (:113), which "
+                                          "needs an eigendecomposition that the B200 path does not form")
+            lam_max *= 1.02                              # Ritz values approach lambda_max from below
         s1, s2, _ = _sum_stats(lib, Wd)
         numel = m * n
         kappa = math.sqrt(s2)                             # torch.norm(W, 'fro') (:120)
@@ -308,7 +345,8 @@ def convex_caldera(
             prev_obj, obj, status, done, warm = float("inf"), float("inf"), "max_iters", 0, 0
             while done < max_iters:
                 step = min(check_every, max_iters - done)
-                st = lib.cb_convex_prox_iters(_lib.ptr(Wd), _lib.ptr(h), m, n, mu, tau, float(params.lambda_reg),
+                prox = lib.cb_convex_prox_iters_dense if dense else lib.cb_convex_prox_iters
+                st = prox(_lib.ptr(Wd), _lib.ptr(h), m, n, mu, tau, float(params.lambda_reg),
                                               kappa, q0, step_t, r, q, int(power_iters), int(seed) + done, warm,
                                               int(use_tensor_cores), step, C.byref(theta), _lib.ptr(L), _lib.ptr(Lp),
                                               _lib.ptr(R), _lib.ptr(Rp), _lib.ptr(Lf), _lib.ptr(Rf), _lib.ptr(svals),

@@ -1369,12 +1369,16 @@ extern "C" size_t cb_convex_prox_workspace_bytes(int64_t m, int64_t n, int64_t r
   return a.off + 256;
 }
 
-extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, int64_t n, float mu, float tau_star,
-                                    float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
-                                    int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
-                                    int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
-                                    float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
-                                    void* stream) {
+// h: diagonal of the Hessian (nullptr = identity) or, with `dense`, the symmetric n x n matrix itself.  For a dense
+// Hessian the gradient (W - Y_L - Y_R) H is one fp32 contraction per iteration and the smooth term of the objective
+// (one more contraction) is evaluated for the last iterate of the call only -- the caller reads it back once per call.
+static int convex_prox_iters(const float* W, const float* h, bool dense, int64_t m, int64_t n, float mu, float tau_star,
+                             float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                             int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                             int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                             float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                             void* stream) {
+  if (dense && h == nullptr) return CB_ERR_ARG;
   if (W == nullptr || L == nullptr || Lp == nullptr || R == nullptr || Rp == nullptr || Lf == nullptr ||
       Rf == nullptr || svals == nullptr || scalars == nullptr || theta_io == nullptr || ws == nullptr)
     return CB_ERR_ARG;
@@ -1397,7 +1401,13 @@ extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, i
     const float beta = (float)((theta - 1.0) / theta_next);
     theta = theta_next;
     CB_CUDA(cudaMemsetAsync(scalars + 3, 0, sizeof(double) * 2, st));        // smooth term, ||V_R||^2
-    CB_TRY(cvx_point(W, Lc, Lprev, Rc, Rprev, h, m, n, beta, step_t, P.VL, P.VR, scalars + 4, st));
+    if (dense) {
+      CB_TRY(cvx_resid(W, Lc, Lprev, Rc, Rprev, m, n, beta, P.VR, st));
+      CB_TRY(sgemm(m, n, n, 1.f, P.VR, n, 1, h, n, 1, P.VL, n, 1, false, nullptr, st));
+      CB_TRY(cvx_point_dense(Lc, Lprev, Rc, Rprev, m, n, beta, step_t, P.VL, P.VR, scalars + 4, st));
+    } else {
+      CB_TRY(cvx_point(W, Lc, Lprev, Rc, Rprev, h, m, n, beta, step_t, P.VL, P.VR, scalars + 4, st));
+    }
     // singular-value thresholding of V_L: top-r factors U sqrt(S), sqrt(S) V^T and S^2
     const float* sig2;
     if (P.use_tc) {
@@ -1416,7 +1426,17 @@ extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, i
     CB_TRY(scale_cols(Lf, m, r, svals + r, 0, P.Lw, st));
     // the new L overwrites the buffer of the iterate before last, then roles rotate
     CB_TRY(lr_product_raw(P.use_tc, P.Lw, Rf, m, n, r, Lprev, P.Lb16, P.Rtb16, P.flags + 2, st));
-    CB_TRY(cvx_finish(W, Lprev, P.VR, h, m, n, scalars, Rprev, scalars + 3, st));
+    if (dense) {
+      const bool last = it == n_iters - 1;
+      CB_TRY(cvx_finish_dense(W, Lprev, P.VR, m, n, scalars, Rprev, last ? P.VL : nullptr, st));
+      if (last) {                       // smooth term 1/2 sum (E H) (.) E of the iterate the caller will read
+        CB_TRY(sgemm(m, n, n, 1.f, P.VL, n, 1, h, n, 1, P.VR, n, 1, false, nullptr, st));
+        CB_TRY(dot_accum(P.VR, P.VL, m * n, scalars + 3, st));
+        CB_TRY(scale_double(scalars + 3, 0.5, st));
+      }
+    } else {
+      CB_TRY(cvx_finish(W, Lprev, P.VR, h, m, n, scalars, Rprev, scalars + 3, st));
+    }
     float* tmp = Lc; Lc = Lprev; Lprev = tmp;
     tmp = Rc; Rc = Rprev; Rprev = tmp;
   }
@@ -1431,6 +1451,28 @@ extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, i
   }
   *theta_io = theta;
   return CB_OK;
+}
+
+extern "C" int cb_convex_prox_iters(const float* W, const float* h, int64_t m, int64_t n, float mu, float tau_star,
+                                    float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                                    int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                                    int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                                    float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  return convex_prox_iters(W, h, false, m, n, mu, tau_star, lambda_reg, kappa, q0, step_t, rank_cap, q_width, power_iters,
+                           seed, warm, use_tensor_cores, n_iters, theta_io, L, Lp, R, Rp, Lf, Rf, svals, scalars, ws,
+                           ws_bytes, stream);
+}
+
+extern "C" int cb_convex_prox_iters_dense(const float* W, const float* Hs, int64_t m, int64_t n, float mu, float tau_star,
+                                          float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                                          int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                                          int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                                          float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                                          void* stream) {
+  return convex_prox_iters(W, Hs, true, m, n, mu, tau_star, lambda_reg, kappa, q0, step_t, rank_cap, q_width, power_iters,
+                           seed, warm, use_tensor_cores, n_iters, theta_io, L, Lp, R, Rp, Lf, Rf, svals, scalars, ws,
+                           ws_bytes, stream);
 }
 
 extern "C" int cb_scale_f32(const float* X, int64_t rows, int64_t cols, const float* v, int axis, int mode, float* out,

@@ -55,9 +55,10 @@ int jacobi_eigh_from_chol(const float* Lc, int q, float* evals, float* evecs, fl
                           cudaStream_t st, const Bt& bt = Bt());
 
 // Hs (n x n symmetric, in place) += max(0, sigma_reg - lambda_min(Hs)) I with lambda_min from a Lanczos run
-// (alg.py:57-64); work: min_eig_shift_workspace_floats(n) floats; stats (optional): shift, lambda_min
+// (alg.py:57-64); work: min_eig_shift_workspace_floats(n) floats; stats (optional, nstats <= 3 floats): shift,
+// lambda_min, lambda_max (the extreme Ritz values of the same run)
 size_t min_eig_shift_workspace_floats(int64_t n);
-int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st);
+int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st, int nstats = 2);
 
 // stages.cu -- fused element-wise stages of the outer loop (all asynchronous on `st`)
 struct HessianVecs {
@@ -119,6 +120,14 @@ int quantize_whole_batched(const float* x, int64_t numel, int bits, void* codes,
                            float* amax_scratch, cudaStream_t st, const Bt& bt);
 int cvx_point(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, const float* h,
               int64_t m, int64_t n, float beta, float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st);
+// dense-Hessian variants: the step is split around the contraction G = (W - Y_L - Y_R) H
+int cvx_resid(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, int64_t m, int64_t n,
+              float beta, float* D, cudaStream_t st);
+int cvx_point_dense(const float* L, const float* Lp, const float* R, const float* Rp, int64_t m, int64_t n, float beta,
+                    float t, float* VL /* in: G, out: V_L */, float* VR, double* vr_sumsq, cudaStream_t st);
+int cvx_finish_dense(const float* W, const float* Lnew, const float* VR, int64_t m, int64_t n, const double* sc,
+                     float* Rnew, float* E /* optional: W - L_new - R_new */, cudaStream_t st);
+int scale_double(double* x, double f, cudaStream_t st);
 int cvx_shrink(const float* sigma2, int r, float thresh, float tau_star, int constrained, const double* vr_sumsq,
                float t_lambda, float kappa, float q0, float* colw, float* s_out, double* sc, cudaStream_t st);
 int cvx_finish(const float* W, const float* Lnew, const float* VR, const float* h, int64_t m, int64_t n, const double* sc,

@@ -845,7 +845,7 @@ lanczos_step_kernel(float* __restrict__ V, float* __restrict__ y, float* __restr
 
 // smallest eigenvalue of the k x k tridiagonal matrix (alpha, beta) by bisection on the Sturm count; one thread
 __global__ void lanczos_finish_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const int* __restrict__ kdone,
-                                      int kmax, float sigma_reg, float* __restrict__ out /* [0] shift, [1] lambda_min */) {
+                                      int kmax, float sigma_reg, float* __restrict__ out /* [0] shift, [1] lambda_min, [2] lambda_max */) {
   const int k = kdone[0] != 0 ? kdone[0] : kmax;
   double lo = 1e300, hi = -1e300;
   for (int i = 0; i < k; ++i) {
@@ -872,6 +872,17 @@ __global__ void lanczos_finish_kernel(const float* __restrict__ alpha, const flo
   const float lam = (float)(0.5 * (lo + hi));
   out[1] = lam;
   out[0] = lam < sigma_reg ? sigma_reg - lam : 0.f;      // alg.py:59-63
+  // largest Ritz value (step size of the dense-Hessian proximal-gradient loop)
+  double lo2 = lo, hi2 = -1e300;
+  for (int i = 0; i < k; ++i) {
+    const double off = (i > 0 ? fabs((double)beta[i - 1]) : 0.0) + (i + 1 < k ? fabs((double)beta[i]) : 0.0);
+    hi2 = fmax(hi2, (double)alpha[i] + off);
+  }
+  for (int it = 0; it < 200 && hi2 - lo2 > 1e-14 * fmax(fabs(lo2), fabs(hi2)) + 1e-300; ++it) {
+    const double mid = 0.5 * (lo2 + hi2);
+    if (count_below(mid) >= k) hi2 = mid; else lo2 = mid;
+  }
+  out[2] = (float)(0.5 * (lo2 + hi2));
 }
 
 __global__ void __launch_bounds__(256) add_diag_kernel(float* __restrict__ A, int n, const float* __restrict__ shift) {
@@ -886,7 +897,7 @@ size_t min_eig_shift_workspace_floats(int64_t n) {
 }
 
 // Hs (n x n symmetric, in place) += max(0, sigma_reg - lambda_min(Hs)) I; stats (optional, 2 floats): shift, lambda_min
-int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st) {
+int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* stats, cudaStream_t st, int nstats) {
   if (Hs == nullptr || work == nullptr || n <= 0) return CB_ERR_ARG;
   const int k = (int)(n < kLanczosMax ? n : kLanczosMax);
   float* V = work;
@@ -907,7 +918,8 @@ int min_eig_shift(float* Hs, int64_t n, float sigma_reg, float* work, float* sta
   CB_CHECK_LAUNCH();
   add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Hs, (int)n, out);
   CB_CHECK_LAUNCH();
-  if (stats != nullptr) CB_CUDA(cudaMemcpyAsync(stats, out, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (stats != nullptr && nstats > 0)
+    CB_CUDA(cudaMemcpyAsync(stats, out, (size_t)(nstats < 3 ? nstats : 3) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return CB_OK;
 }
 
@@ -928,6 +940,14 @@ extern "C" int cb_min_eig_shift_f32(float* H, int64_t n, float sigma_reg, float*
   if (H == nullptr || ws == nullptr || n <= 0) return CB_ERR_ARG;
   if (ws_bytes < cb_min_eig_shift_workspace_bytes(n)) return CB_ERR_WORKSPACE;
   return cb::min_eig_shift(H, n, sigma_reg, reinterpret_cast<float*>(ws), stats, (cudaStream_t)stream);
+}
+
+extern "C" int cb_convex_dense_prepare(const float* H, int64_t n, float floor, float* Hs, float* stats3, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  if (H == nullptr || Hs == nullptr || stats3 == nullptr || ws == nullptr || n <= 0) return CB_ERR_ARG;
+  if (ws_bytes < cb_min_eig_shift_workspace_bytes(n)) return CB_ERR_WORKSPACE;
+  CB_TRY(cb::symmetrize(H, n, Hs, (cudaStream_t)stream));
+  return cb::min_eig_shift(Hs, n, floor, reinterpret_cast<float*>(ws), stats3, (cudaStream_t)stream, 3);
 }
 
 extern "C" int cb_jacobi_eigh_from_chol_f32(const float* Lc, int64_t q, float* evals, float* evecs, float* work,

@@ -611,6 +611,77 @@ cvx_finish_kernel(const float* __restrict__ W, const float* __restrict__ Lnew, c
   if (threadIdx.x == 0) atomicAdd(smooth, 0.5 * acc);
 }
 
+// Dense Hessian: the gradient (W - Y_L - Y_R) H is a contraction, so the step is split around it.
+// Part 1: D = W - Y_L - Y_R at the extrapolated point Y = X + beta (X - X_prev).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_resid_kernel(const float* __restrict__ W, const float* __restrict__ L, const float* __restrict__ Lp,
+                 const float* __restrict__ R, const float* __restrict__ Rp, int64_t numel, float beta,
+                 float* __restrict__ D) {
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> w, l, lp, r, rp, d;
+    w.load_stream(W + i); l.load(L + i); lp.load(Lp + i); r.load(R + i); rp.load(Rp + i);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float yl = l.v[k] + beta * (l.v[k] - lp.v[k]);
+      const float yr = r.v[k] + beta * (r.v[k] - rp.v[k]);
+      d.v[k] = w.v[k] - yl - yr;
+    }
+    d.store(D + i);
+  }
+}
+// Part 2: VL holds G = D H on entry; V_L = Y_L + t G (in place), V_R = Y_R + t G, sum V_R^2.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_point_dense_kernel(const float* __restrict__ L, const float* __restrict__ Lp, const float* __restrict__ R,
+                       const float* __restrict__ Rp, int64_t numel, float beta, float t, float* __restrict__ VL,
+                       float* __restrict__ VR, double* __restrict__ vr_sumsq) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> l, lp, r, rp, g, vl, vr;
+    l.load(L + i); lp.load_stream(Lp + i); r.load(R + i); rp.load_stream(Rp + i); g.load(VL + i);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float yl = l.v[k] + beta * (l.v[k] - lp.v[k]);
+      const float yr = r.v[k] + beta * (r.v[k] - rp.v[k]);
+      vl.v[k] = fmaf(t, g.v[k], yl);
+      vr.v[k] = fmaf(t, g.v[k], yr);
+      part = fmaf(vr.v[k], vr.v[k], part);
+    }
+    vl.store(VL + i);
+    vr.store(VR + i);
+    acc += (double)part;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(vr_sumsq, acc);
+}
+// R_new = alpha V_R and (optionally) E = W - L_new - R_new for the smooth term 1/2 sum (E H) (.) E
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cvx_finish_dense_kernel(const float* __restrict__ W, const float* __restrict__ Lnew, const float* __restrict__ VR,
+                        int64_t numel, const double* __restrict__ sc, float* __restrict__ Rnew, float* __restrict__ E) {
+  const float alpha = (float)sc[1];
+  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
+    const int64_t i = ch__ * VEC;
+    FVec<VEC> w, l, v, e;
+    v.load_stream(VR + i);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v.v[k] *= alpha;
+    v.store(Rnew + i);
+    if (E != nullptr) {
+      w.load_stream(W + i); l.load(Lnew + i);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) e.v[k] = w.v[k] - l.v[k] - v.v[k];
+      e.store(E + i);
+    }
+  }
+}
+__global__ void scale_double_kernel(double* x, double f) { x[0] *= f; }
+
 // quantize_residual (convex_caldera.py:342-373): delta = 2 t / (2^b - 1) (t / 2^15 for b = 16),
 // R_int = clamp(rint(R / delta), +-(2^(b-1) - 1)); out = base + delta * R_int
 template <int VEC>
@@ -940,6 +1011,41 @@ int cvx_point(const float* W, const float* L, const float* Lp, const float* R, c
     cvx_point_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, L, Lp, R, Rp, h, numel, n, beta, t, VL, VR, vr_sumsq);
   else
     cvx_point_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, L, Lp, R, Rp, h, numel, n, beta, t, VL, VR, vr_sumsq);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int cvx_resid(const float* W, const float* L, const float* Lp, const float* R, const float* Rp, int64_t m, int64_t n,
+              float beta, float* D, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {W, L, Lp, R, Rp, D}))
+    cvx_resid_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, L, Lp, R, Rp, numel, beta, D);
+  else
+    cvx_resid_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, L, Lp, R, Rp, numel, beta, D);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int cvx_point_dense(const float* L, const float* Lp, const float* R, const float* Rp, int64_t m, int64_t n, float beta,
+                    float t, float* VL, float* VR, double* vr_sumsq, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {L, Lp, R, Rp, VL, VR}))
+    cvx_point_dense_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(L, Lp, R, Rp, numel, beta, t, VL, VR, vr_sumsq);
+  else
+    cvx_point_dense_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(L, Lp, R, Rp, numel, beta, t, VL, VR, vr_sumsq);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int cvx_finish_dense(const float* W, const float* Lnew, const float* VR, int64_t m, int64_t n, const double* sc,
+                     float* Rnew, float* E, cudaStream_t st) {
+  const int64_t numel = m * n;
+  if (can_vec4(n, {W, Lnew, VR, Rnew, E}))
+    cvx_finish_dense_kernel<4><<<grid_for(numel / 4, 256 * 2, 8), 256, 0, st>>>(W, Lnew, VR, numel, sc, Rnew, E);
+  else
+    cvx_finish_dense_kernel<1><<<grid_for(numel, 256 * 4, 8), 256, 0, st>>>(W, Lnew, VR, numel, sc, Rnew, E);
+  CB_CHECK_LAUNCH();
+  return CB_OK;
+}
+int scale_double(double* x, double f, cudaStream_t st) {
+  scale_double_kernel<<<1, 1, 0, st>>>(x, f);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

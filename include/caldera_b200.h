@@ -352,6 +352,23 @@ int cb_convex_prox_iters(const float* W, const float* h, int64_t m, int64_t n, f
 size_t cb_convex_prox_workspace_bytes(int64_t m, int64_t n, int64_t rank_cap, int64_t q_width,
                                       int use_tensor_cores);
 
+/* Dense (non-diagonal) Hessians, e.g. the Gram matrix X^T X of calibration data (convex_caldera.py:103-117).
+ * cb_convex_dense_prepare: Hs = (H + H^T) / 2 (:111) shifted by max(0, floor - lambda_min) on its diagonal (the
+ * reference clamps the eigenvalues at 1e-8, :113; for a positive semi-definite H the two differ by at most `floor`
+ * on every eigenvalue); stats3 (device floats) = {shift, lambda_min, lambda_max}, the extreme eigenvalues from a
+ * Lanczos run (<= 96 steps, full reorthogonalisation).  ws: cb_min_eig_shift_workspace_bytes(n).
+ * cb_convex_prox_iters_dense: cb_convex_prox_iters with the smooth term 1/2 ||(W-L-R) Hs^(1/2)||_F^2 for the dense
+ * symmetric Hs; no square root is formed: the gradient is (L+R-W) Hs (one fp32 contraction per iteration) and
+ * scalars[3] (1/2 sum (E Hs) (.) E) is evaluated for the last iterate of the call.  step_t <= 1 / (2 lambda_max). */
+int cb_convex_dense_prepare(const float* H, int64_t n, float floor, float* Hs, float* stats3, void* ws, size_t ws_bytes,
+                            void* stream);
+int cb_convex_prox_iters_dense(const float* W, const float* Hs, int64_t m, int64_t n, float mu, float tau_star,
+                               float lambda_reg, float kappa, float q0, float step_t, int64_t rank_cap,
+                               int64_t q_width, int power_iters, uint64_t seed, int warm, int use_tensor_cores,
+                               int n_iters, double* theta_io, float* L, float* Lp, float* R, float* Rp,
+                               float* Lf, float* Rf, float* svals, double* scalars, void* ws, size_t ws_bytes,
+                               void* stream);
+
 /* quantize_residual (convex_caldera.py:342-373): delta = 2 max|R| / (2^bits - 1) (max|R| / 2^15 for
  * bits == 16), R_int = clamp(rint(R / delta), +-(2^(bits-1) - 1)), Rq = delta * R_int and, when
  * base/Wc are given, Wc = base + Rq (the reconstruction L* + delta R_int, :484-485).

@@ -7,6 +7,7 @@ import torch
 
 from oracle import convex_oracle as co
 from src.convex_caldera.decomposition.convex_caldera import ConvexCalderaParams, convex_caldera
+from ee274_convexcaldera_llm_quantization_b200 import convex_caldera as cc
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -82,8 +83,10 @@ def test_error_conventions():
     W = torch.randn(32, 32)
     with pytest.raises(ValueError):
         convex_caldera(W, params=ConvexCalderaParams(B_tot=1.0, b_min=2.0), device=DEV)
+    with pytest.raises(ValueError):
+        convex_caldera(W, calibration_data=torch.randn(100, 31), device=DEV)        # wrong feature count
     with pytest.raises(NotImplementedError):
-        convex_caldera(W, calibration_data=torch.randn(100, 32), device=DEV)
+        cc.compute_hessian_and_sensitivities(W, calibration_data=torch.randn(100, 32), device=DEV)   # dense H^(1/2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         convex_caldera(W, device="cpu")
 
@@ -231,3 +234,96 @@ def test_large_shape_satisfies_kkt_and_structure():
     codes = d.R_star / d.group_info["delta"]
     assert float((codes - codes.round()).abs().max()) < 1e-3
     assert torch.equal(d.W_compressed, d.L_star + d.R_star)
+
+
+def _correlated_activations(rng, samples, n, rank):
+    """Calibration activations with a strongly non-diagonal Gram matrix (a few shared directions plus noise)."""
+    basis = rng.standard_normal((rank, n))
+    return (rng.standard_normal((samples, rank)) @ basis / np.sqrt(rank) + 0.3 * rng.standard_normal((samples, n))).astype(np.float32)
+
+
+@pytest.mark.parametrize("mu,tau,lam", [(0.05, None, 0.5), (None, 0.4, 0.01)])
+def test_dense_hessian_solution_satisfies_kkt(mu, tau, lam):
+    """SURVEY 8 row C1/C2 with a dense Hessian (convex_caldera.py:103-117): the solver only uses products with H; its
+    answer must be a fixed point of an exact float64 proximal-gradient step of the program with that dense H."""
+    rng = np.random.default_rng(9)
+    m, n = 72, 96
+    W = (0.02 * rng.standard_normal((m, n))).astype(np.float32)
+    X = _correlated_activations(rng, 400, n, 6)
+    H = (X.T.astype(np.float64) @ X.astype(np.float64) / 400).astype(np.float32)
+    assert np.abs(H - np.diag(np.diag(H))).max() > 0.2 * np.abs(np.diag(H)).max()        # genuinely dense
+    kw = dict(mu=mu, tau_star=tau, lambda_reg=lam, solver_tol=1e-10)     # (lambda_reg: a rank-6 L* in the penalty form)
+    d = convex_caldera(torch.from_numpy(W), torch.from_numpy(H), params=ConvexCalderaParams(**kw), device=DEV,
+                       rank_cap=72, sketch_width=72, power_iters=3, max_iters=6000, check_every=50, use_tensor_cores=False)
+    prm = co.ConvexOracleParams(**kw)
+    Hp, lam_max, kappa, c = co.calibrate(W, H)
+    L, R = d.L_star.cpu().numpy(), d.group_info["R_continuous"].cpu().numpy()
+    rl, rr = co.kkt_residuals(W, L, R, Hp, lam_max, kappa, c, prm)
+    assert rl <= 3e-3 and rr <= 3e-3, (rl, rr)
+    # the objective it reports is the program's objective at that point
+    nuc = float(np.linalg.svd(L.astype(np.float64), compute_uv=False).sum())
+    q0 = c * np.exp(-prm.k * min(prm.b_max, prm.B_tot))
+    obj = co.objective(W.astype(np.float64), L.astype(np.float64), R.astype(np.float64), Hp, mu if mu is not None else 0.0,
+                       tau, prm.lambda_reg, kappa, q0, nuc)
+    np.testing.assert_allclose(d.objective_value, obj, rtol=2e-4)
+    # and the oracle's own solve of the same program lands on the same objective
+    Lo, Ro, _, obj_o, _, (_, so, _), _ = co.solve_prox(W, Hp, lam_max, kappa, c, co.ConvexOracleParams(max_iters=6000, **kw))
+    np.testing.assert_allclose(d.objective_value, obj_o, rtol=1e-3)
+    assert d.effective_rank == int((so > so[0] * 1e-6).sum()) > 0
+
+
+def test_calibration_data_equals_its_gram_matrix():
+    """convex_caldera.py:103-108: H = X^T X when only calibration data is given."""
+    rng = np.random.default_rng(10)
+    m, n = 64, 128
+    W = torch.from_numpy((0.02 * rng.standard_normal((m, n))).astype(np.float32))
+    X = torch.from_numpy(_correlated_activations(rng, 256, n, 4) / 16.0)
+    kw = dict(mu=0.05, solver_tol=1e-9)
+    args = dict(device=DEV, rank_cap=64, sketch_width=64, power_iters=3, max_iters=2000, check_every=50, use_tensor_cores=False)
+    a = convex_caldera(W, None, calibration_data=X, params=ConvexCalderaParams(**kw), **args)
+    H = (X.double().T @ X.double()).float()
+    b = convex_caldera(W, H, params=ConvexCalderaParams(**kw), **args)
+    np.testing.assert_allclose(a.objective_value, b.objective_value, rtol=1e-5)
+    assert float((a.L_star - b.L_star).abs().max()) <= 1e-4 * float(b.L_star.abs().max()) + 1e-7
+    assert a.effective_rank == b.effective_rank
+
+
+def test_dense_hessian_with_zero_off_diagonal_takes_the_diagonal_path():
+    rng = np.random.default_rng(12)
+    W = torch.from_numpy((0.02 * rng.standard_normal((64, 96))).astype(np.float32))
+    h = torch.from_numpy((0.5 + rng.random(96)).astype(np.float32))
+    kw = dict(mu=0.05, solver_tol=1e-8)
+    args = dict(device=DEV, rank_cap=64, sketch_width=64, power_iters=3, max_iters=600, check_every=50, use_tensor_cores=False)
+    a = convex_caldera(W, h, params=ConvexCalderaParams(**kw), **args)
+    b = convex_caldera(W, torch.diag(h), params=ConvexCalderaParams(**kw), **args)
+    assert torch.equal(a.L_star, b.L_star) and a.objective_value == b.objective_value
+
+
+def test_indefinite_hessian_is_rejected():
+    rng = np.random.default_rng(13)
+    W = torch.from_numpy((0.02 * rng.standard_normal((32, 64))).astype(np.float32))
+    A = rng.standard_normal((64, 64))
+    H = torch.from_numpy(((A + A.T) / 2).astype(np.float32))              # eigenvalues of both signs
+    with pytest.raises(NotImplementedError):
+        convex_caldera(W, H, params=ConvexCalderaParams(), device=DEV)
+
+
+def test_dense_hessian_large_shape_tensor_core_thresholding():
+    """Dense-Hessian solve at 1024 x 2048 with the tcgen05 thresholding path: KKT fixed point in float64."""
+    m, n, k = 1024, 2048, 24
+    g = torch.Generator().manual_seed(21)
+    U = torch.linalg.qr(torch.randn(m, k, generator=g))[0]
+    V = torch.linalg.qr(torch.randn(n, k, generator=g))[0]
+    s = 16.0 * torch.arange(1, k + 1, dtype=torch.float32) ** -0.3
+    W = 0.02 * torch.randn(m, n, generator=g) + (U * s) @ V.T
+    B = torch.randn(4, n, generator=g)
+    H = torch.eye(n) + (0.03 ** 2) * (B.T @ B)              # dense, eigenvalues 1 ... ~2.9
+    kappa = float(W.norm())
+    kw = dict(mu=1.0, lambda_reg=1.0 * kappa / (2.0 * 2.0), B_tot=4.0, solver_tol=1e-7)
+    d = convex_caldera(W, H, params=ConvexCalderaParams(**kw), device=DEV, rank_cap=64, max_iters=1500, check_every=25)
+    prm = co.ConvexOracleParams(**kw)
+    Hp, lam_max, kappa, c = co.calibrate(W.numpy(), H.numpy())
+    rl, rr = co.kkt_residuals(W.numpy(), d.L_star.cpu().numpy(), d.group_info["R_continuous"].cpu().numpy(), Hp, lam_max,
+                              kappa, c, prm)
+    assert rl <= 2e-2 and rr <= 3e-3, (rl, rr, d.solver_status, d.group_info["iterations"])
+    assert not d.group_info["rank_capped"] and 1 <= d.effective_rank <= k
