@@ -97,7 +97,7 @@ class _Slot:
     def __init__(self, device: torch.device, index: int):
         self.index = index
         self.stream = torch.cuda.Stream(device=device)
-        self.event = torch.cuda.Event()
+        self.event = torch.cuda.Event(blocking=True)    # the waiting thread sleeps (8 ranks share the host cores)
         self.arena: Optional[torch.Tensor] = None
         self.runners: Dict[tuple, object] = {}
         self.host_small: Optional[torch.Tensor] = None
