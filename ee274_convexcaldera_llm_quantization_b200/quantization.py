@@ -3,9 +3,10 @@
 Same names, constructor arguments, return conventions and exceptions as the reference's
 `LowMemoryQuantizer` / `QuantizerFactory` (quantization.py:18-37, 244-319).  The uniform
 method runs in the sm_100a kernels of csrc/quant.cu; the NormalFloat codebooks (nf4 / nf2,
-quantization.py:39-94) are available through the same class; the bitsandbytes-style methods
-(bbint4 / bbint2: outlier side tables and CSV logging, quantization.py:107-243) are outside the hot
-path and raise NotImplementedError at call time.
+quantization.py:39-94) and the bitsandbytes-style asymmetric methods with an outlier side table
+(bbint4 / bbint2, quantization.py:107-243; csrc/bbint.cu) are available through the same class
+(SURVEY.md section 8f rank 4).  The CSV log of outlier counts the reference appends to in the
+working directory (:126-137) is not written; `caldera()` itself accepts the uniform method only.
 """
 from __future__ import annotations
 
@@ -60,10 +61,57 @@ class LowMemoryQuantizer(AbstractQuantizer):
 
     # -- helpers -----------------------------------------------------------------
     def _check_method(self, what):
-        if self.method not in ("uniform", "nf4", "nf2"):
-            raise NotImplementedError(
-                f"{what} method '{self.method}' not implemented in the B200 path "
-                "(uniform is on the CALDERA hot path; nf4 / nf2 are available through this class).")
+        if self.method not in _QUANTIZER_METHODS:
+            raise NotImplementedError(f"{what} method '{self.method}' not implemented.")
+
+    def _quantize_bbint(self, weight: torch.Tensor, epsilon: float):
+        """quantization.py:107-154 / :175-221: (packed uint8 (numel/block, block*bits/8),
+        (block_min, scales, outlier_values, outlier_indices)).  bbint2 packs 2-bit codes whatever num_bits says,
+        like the reference (only bbint4 checks its bit width, :36-37)."""
+        lib = _lib.load()
+        bits = 4 if self.method == "bbint4" else 2
+        bs = int(self.block_size)
+        if bs < 2 or bs % (8 // bits) != 0:
+            raise ValueError(f"{self.method}: block size {bs} must be a multiple of {8 // bits} (whole packed bytes)")
+        w = (weight if weight.dtype == torch.float32 else weight.float()).contiguous()
+        total = w.numel()
+        nblk = total // bs
+        dev = w.device
+        packed = torch.empty((nblk, bs * bits // 8), dtype=torch.uint8, device=dev)
+        block_min = torch.empty((nblk, 1), dtype=torch.float32, device=dev)
+        scales = torch.empty((nblk, 1), dtype=torch.float32, device=dev)
+        counts = torch.empty(nblk, dtype=torch.int32, device=dev)
+        offsets = torch.empty(nblk + 1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.cb_quantize_bbint_f32(_lib.ptr(w), total, bs, bits, float(epsilon), _lib.ptr(packed),
+                                                 _lib.ptr(block_min), _lib.ptr(scales), _lib.ptr(counts), _lib.ptr(offsets),
+                                                 _lib.stream_ptr()), "quantize_block")
+            n_out = int(offsets[-1].item())                 # sizes the side table (the one host synchronisation)
+            values = torch.empty(n_out, dtype=torch.float32, device=dev)
+            indices = torch.empty((n_out, 2), dtype=torch.int64, device=dev)
+            if n_out > 0:
+                _lib.check(lib.cb_bbint_outliers_f32(_lib.ptr(w), total, bs, float(epsilon), _lib.ptr(counts), _lib.ptr(offsets),
+                                                     _lib.ptr(values), _lib.ptr(indices), _lib.stream_ptr()), "quantize_block")
+        return packed, (block_min, scales, values, indices)
+
+    def _dequantize_bbint(self, weight_packed: torch.Tensor, params, weight_shape):
+        """quantization.py:156-173 / :223-243."""
+        lib = _lib.load()
+        bits = 4 if self.method == "bbint4" else 2
+        block_min, scales, values, indices = params
+        q = weight_packed.contiguous()
+        numel = q.numel() * (8 // bits)
+        nblk = scales.numel()
+        out = torch.empty(numel, dtype=torch.float32, device=q.device)
+        values = values.to(q.device, torch.float32).contiguous()
+        indices = indices.to(q.device, torch.int64).contiguous()
+        with torch.cuda.device(q.device):
+            _lib.check(lib.cb_dequantize_bbint_f32(_lib.ptr(q), _lib.ptr(block_min.contiguous().float()),
+                                                   _lib.ptr(scales.contiguous().float()), numel, numel // nblk, bits,
+                                                   _lib.ptr(values) if values.numel() else None,
+                                                   _lib.ptr(indices) if values.numel() else None, values.numel(),
+                                                   _lib.ptr(out), _lib.stream_ptr()), "dequantize_block")
+        return out.reshape(tuple(weight_shape))
 
     def _quantize_nf(self, weight: torch.Tensor, epsilon: float):
         """quantization.py:270-279 with _quantize_nf (:68-88): uint8 level indices, fp32 block scales."""
@@ -112,6 +160,11 @@ class LowMemoryQuantizer(AbstractQuantizer):
             if return_packed:
                 raise NotImplementedError("return_packed is available for method='uniform' only")
             return self._quantize_nf(weight, epsilon)
+        if self.method in ("bbint4", "bbint2"):
+            if return_packed:
+                raise NotImplementedError("return_packed is available for method='uniform' only (bbint codes are always packed)")
+            weight_quant, weight_params = self._quantize_bbint(weight, epsilon)
+            return weight_quant, weight_params, weight.shape
         lib = _lib.load()
         w = weight if weight.dtype == torch.float32 else weight.float()
         nblk = total // self.block_size
@@ -137,6 +190,8 @@ class LowMemoryQuantizer(AbstractQuantizer):
         _lib.require_cuda(weight_quant, "weight_quant")
         if self.method in ("nf4", "nf2"):
             return self._dequantize_nf(weight_quant, weight_params, weight_shape)
+        if self.method in ("bbint4", "bbint2"):
+            return self._dequantize_bbint(weight_quant, weight_params, weight_shape)
         lib = _lib.load()
         numel = 1
         for s in weight_shape:

@@ -326,6 +326,24 @@ int cb_caldera_batch_supported(const cb_caldera_params* p, int64_t m, int64_t n,
 int cb_caldera_batch(const cb_caldera_params* p, int batch, int64_t stride_bytes, const float* W, int64_t m, int64_t n,
                      const float* h, int h_kind, const cb_caldera_out* out, void* ws, size_t ws_bytes, void* stream);
 
+/* bitsandbytes-style asymmetric block quantisers `bbint4` / `bbint2` of the QuantizerFactory surface
+ * (RCR/caldera/utils/quantization.py:107-243): per block of `block` consecutive elements mean / unbiased std,
+ * outliers (|x - mean| > 6 max(std, eps)) go to a side table and are replaced by the mean, then
+ * code = clamp(rint((x - min) / scale), 0, 2^bits - 1) with scale = max((max - min) / (2^bits - 1), eps), packed
+ * MSB-first (:152, :217-220).  cb_quantize_bbint_f32 writes the packed codes (numel * bits / 8 bytes), block_min and
+ * scales (numel / block floats), the outlier count of every block (counts) and its exclusive scan (offsets,
+ * numel / block + 1 entries, the last one the total).  cb_bbint_outliers_f32 then fills the side table (values and
+ * (block row, column) pairs in row-major order, the order of torch.nonzero) sized from that total.
+ * cb_dequantize_bbint_f32: code * scale + min, outliers restored (:156-173, :223-243).  The reference's CSV log of
+ * outlier counts (:126-137) is not written. */
+int cb_quantize_bbint_f32(const float* x, int64_t numel, int64_t block, int bits, float eps, uint8_t* packed,
+                          float* block_min, float* scales, int* counts, int64_t* offsets, void* stream);
+int cb_bbint_outliers_f32(const float* x, int64_t numel, int64_t block, float eps, const int* counts,
+                          const int64_t* offsets, float* values, int64_t* indices, void* stream);
+int cb_dequantize_bbint_f32(const uint8_t* packed, const float* block_min, const float* scales, int64_t numel,
+                            int64_t block, int bits, const float* outlier_values, const int64_t* outlier_indices,
+                            int64_t n_outliers, float* out, void* stream);
+
 /* ------------------------------------------------------------------------- Convex-CALDERA */
 
 /* out3[0] += sum x, out3[1] += sum x^2, out3[2] += sum (x - y)^2 (y may be NULL); device doubles the

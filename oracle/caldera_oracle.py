@@ -91,6 +91,50 @@ def dequantize_nf(idx: np.ndarray, scales: np.ndarray, shape, method: str) -> np
     return (NF_LEVELS[method][idx.astype(np.int64)] * scales).astype(F32).reshape(shape)
 
 
+def quantize_bbint(x: np.ndarray, method: str, block_size: int, eps: float = 1e-8):
+    """bitsandbytes-style asymmetric block quantiser (quantization.py:107-154 bbint4, :175-221 bbint2).  Per block:
+    outliers |x - mean| > 6 max(std_unbiased, eps) go to a side table (values, (row, col) in torch.nonzero order) and
+    are replaced by the mean; scale = max((max - min) / levels, eps); code = clip(rint((x - min) / scale), 0, levels),
+    packed MSB-first.  mean / std are accumulated in float64 and rounded to fp32 (torch accumulates in fp32 in an
+    order of its own: the two can differ in the last bit, which only matters for an element exactly on the outlier
+    threshold).  Returns (packed uint8 [nblk, bs*bits/8], (block_min, scales, outlier_values, outlier_indices), shape)."""
+    bits = 4 if method == "bbint4" else 2
+    levels = F32(2 ** bits - 1)
+    blocks = np.ascontiguousarray(x, dtype=F32).reshape(-1, int(block_size)).copy()
+    b64 = blocks.astype(np.float64)
+    mean = b64.mean(axis=1, keepdims=True).astype(F32)
+    std = np.sqrt(((b64 - mean.astype(np.float64)) ** 2).sum(axis=1, keepdims=True) / (blocks.shape[1] - 1)).astype(F32)
+    std = np.maximum(std, F32(eps))
+    mask = np.abs((blocks - mean).astype(F32)) > (F32(6.0) * std).astype(F32)
+    rows, cols = np.nonzero(mask)
+    values = blocks[rows, cols].astype(F32)
+    indices = np.stack([rows, cols], axis=1).astype(np.int64)
+    blocks = np.where(mask, mean, blocks).astype(F32)
+    bmin = blocks.min(axis=1, keepdims=True)
+    bmax = blocks.max(axis=1, keepdims=True)
+    scales = np.maximum(((bmax - bmin).astype(F32) / levels).astype(F32), F32(eps))
+    q = np.clip(np.rint(((blocks - bmin).astype(F32) / scales).astype(F32)), 0, levels).astype(np.uint8)
+    per = 8 // bits
+    packed = np.zeros((q.shape[0], q.shape[1] // per), dtype=np.uint8)
+    for e in range(per):                                     # element 0 of each group in the most significant bits
+        packed |= (q[:, e::per] << (bits * (per - 1 - e))).astype(np.uint8)
+    return packed, (bmin.astype(F32), scales, values, indices), tuple(x.shape)
+
+
+def dequantize_bbint(packed: np.ndarray, params, shape, method: str) -> np.ndarray:
+    """quantization.py:156-173 / :223-243: code * scale + min, then the outliers are put back."""
+    bits = 4 if method == "bbint4" else 2
+    per = 8 // bits
+    bmin, scales, values, indices = params
+    q = np.zeros((packed.shape[0], packed.shape[1] * per), dtype=F32)
+    for e in range(per):
+        q[:, e::per] = ((packed >> (bits * (per - 1 - e))) & (2 ** bits - 1)).astype(F32)
+    out = ((q * scales.astype(F32)).astype(F32) + bmin.astype(F32)).astype(F32)
+    if len(values):
+        out[indices[:, 0], indices[:, 1]] = values
+    return out.reshape(shape)
+
+
 def dequantize_uniform(codes: np.ndarray, scales: np.ndarray, shape, bits: int) -> np.ndarray:
     """x_hat = (float(code) / levels) * scale, reshaped (quantization.py:105, 295, 306)."""
     vals = (codes.astype(F32) / F32(uniform_levels(bits))) * scales.astype(F32)

@@ -114,7 +114,7 @@ def test_full_size_properties(bits, bs):
 
 
 def test_method_errors_on_gpu():
-    # the bitsandbytes-style methods are not built (nf4 / nf2 are: tests/test_nf_quantizer.py)
-    q = QuantizerFactory(method="bbint4", block_size=64).get_quantizer(4)
-    with pytest.raises(NotImplementedError):
-        q.quantize_block(torch.zeros(4, 64, device=DEV))
+    # (nf4 / nf2: tests/test_nf_quantizer.py; bbint4 / bbint2: tests/test_bbint_quantizer.py)
+    q = QuantizerFactory(method="bbint4", block_size=63).get_quantizer(4)
+    with pytest.raises(ValueError):
+        q.quantize_block(torch.zeros(4, 63, device=DEV))             # a block must pack into whole bytes

@@ -53,4 +53,4 @@ def test_gpu_nf_large_and_errors():
     with pytest.raises(ValueError):
         QuantizerFactory(method="nf4", block_size=64).get_quantizer(2)
     with pytest.raises(NotImplementedError):
-        QuantizerFactory(method="bbint4", block_size=64).get_quantizer(4).quantize_block(x.cuda())
+        QuantizerFactory(method="nf4", block_size=64).get_quantizer(4).quantize_block(x.cuda(), return_packed=True)
