@@ -662,9 +662,9 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
     ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
     ap.add_argument("--model-streams", type=int, default=48, help="layers in flight per GPU in the model-level job")
-    ap.add_argument("--slots", type=int, default=6, help="graph replays in flight per GPU")
+    ap.add_argument("--slots", type=int, default=5, help="graph replays in flight per GPU")
     ap.add_argument("--model-slots", type=int, default=3, help="graph replays in flight per GPU in the model-level job")
-    ap.add_argument("--batch", type=int, default=16, help="same-shape layers advancing in lock step per graph replay")
+    ap.add_argument("--batch", type=int, default=24, help="same-shape layers advancing in lock step per graph replay")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="execution mode written into cb_caldera_params.exec_mode (single-layer driver only)")
     args = ap.parse_args()

@@ -49,7 +49,11 @@ constexpr int G2_SQ = 4;                                   // depth of the tile-
 constexpr int G2_STAGES = 6;
 constexpr int G2_BAR_OFF = G2_STAGES * (G2_A_BYTES + G2_B_BYTES);
 constexpr int G2_NBAR = 2 * G2_STAGES + 4 + 2 * G2_SQ;     // full/empty ring, tmem full/empty x2, sched full/empty ring
-constexpr int G2_SMEM = G2_BAR_OFF + G2_NBAR * 8 + 16 + 4 * G2_SQ + 1024;
+constexpr int G2_EPI_OFF = G2_BAR_OFF + 1024;              // per epilogue warp: a 32 x 32 fp32 box (4 KiB, 128-byte swizzle) for TMA stores
+constexpr int G2_EPI_BYTES = 32 * 32 * 4;
+constexpr int G2_SMEM = G2_EPI_OFF + G2_EPI_WARPS * G2_EPI_BYTES + 1024;
+static_assert(G2_NBAR * 8 + 16 + 4 * G2_SQ <= 1024, "barrier block overlaps the epilogue staging buffers");
+static_assert(G2_SMEM <= 227 * 1024, "shared memory budget");
 
 struct Gemm2Args {
   int M, N, K, batch;
@@ -68,6 +72,7 @@ struct Gemm2Args {
   const float* rowscale; int64_t sRow;              // per output row, may be null
   int* error_flag; int64_t sFlag;
   int* tile_counter;             // 2 zeroed ints (next tile, clusters done; the kernel leaves them zero) or null = static
+  int c_tma;                     // fp32 C is the only output and is TMA-storable: staged per warp in shared memory
 };
 
 // 32 consecutive output columns of one row: scaling, then the fp32 / bf16 / transposed-bf16 stores asked for
@@ -161,12 +166,14 @@ __device__ __forceinline__ void g2_store_chunk(const Gemm2Args& a, int b, int ro
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
   // identical in both CTAs of the pair (same kernel, same dynamic shared memory window), which cta_group::2 relies on
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + G2_STAGES * G2_A_BYTES;
   const uint32_t bar_base = base + G2_BAR_OFF;
+  const uint32_t epi_base = base + G2_EPI_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
@@ -188,7 +195,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int b_rows = args.n_tile >> 1;                         // B rows held by each CTA
   const uint32_t stage_tx = 2u * (uint32_t)(G2_A_BYTES + b_rows * G2_BK * 2);   // bytes both CTAs deliver per stage
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (args.c_tma) tma_prefetch_desc(&tmC); }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -322,13 +329,40 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        g2_store_chunk(args, b, row, n_blk * args.n_tile + c * 32, rs, v);
+        const int col0 = n_blk * args.n_tile + c * 32;
+        if (args.c_tma) {
+          // fp32 output through a swizzled shared-memory box and one TMA store per 32 x 32 block: a direct store would
+          // cost the load/store unit 32 line transactions per instruction (every lane owns a different row)
+          const float* cs = boff(args.colscale, args.sCol * b);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] * args.alpha * rs;
+            if (cs != nullptr && col0 + j < args.N) x *= cs[col0 + j];
+            v[j] = x;
+          }
+          const uint32_t buf = epi_base + (uint32_t)(warp - 4) * G2_EPI_BYTES;
+          if (lane == 0) bulk_wait_group_read0();          // the previous store has read this buffer
+          __syncwarp();
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            st_shared_v4(buf + (uint32_t)lane * 128u + (uint32_t)((q4 ^ (lane & 7)) << 4), v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2],
+                         v[4 * q4 + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && col0 < args.N) {
+            tma_store_3d(&tmC, buf, col0, m_blk * 2 * G2_BM + (int)cta_rank * G2_BM + qd * 32, b);
+            bulk_commit_group();
+          }
+        } else {
+          g2_store_chunk(args, b, row, col0, rs, v);
+        }
       }
       // this warp has read its part of the accumulator: one arrival on the leader's tmem_empty barrier
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc), 0);
     }
+    if (args.c_tma && lane == 0) bulk_wait_group0();       // this warp's stores have landed
   }
   if (!ok && args.error_flag != nullptr) atomicExch(boff(args.error_flag, 0), 1);
   tc_fence_before();
@@ -358,6 +392,22 @@ static int make_tmap_bf16_batched(CUtensorMap* map, const void* ptr, int64_t row
   return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
 }
 
+// fp32 output, rows x cols per batch item, leading dimension ld (elements): 3-D map {cols, rows, batch}, box {32, 32, 1},
+// 128-byte swizzle (one box row = 32 floats = 128 bytes)
+static int make_tmap_f32_out(CUtensorMap* map, float* ptr, int64_t rows, int64_t cols, int64_t ld, int64_t batch, int64_t sbytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return CB_ERR_UNSUPPORTED;
+  if (batch <= 1) { batch = 1; sbytes = ((rows * ld * 4 + 15) / 16) * 16; }
+  if (sbytes % 16 != 0 || sbytes <= 0) return CB_ERR_ARG;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)sbytes};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CB_OK : CB_ERR_ARG;
+}
+
 bool gemm_tc2_supported(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb) {
   return M > 0 && N > 0 && K > 0 && M < (1ll << 30) && N < (1ll << 30) && K < (1ll << 30) && lda % 8 == 0 && ldb % 8 == 0 &&
          lda >= K && ldb >= K && aligned16(A) && aligned16(B);
@@ -381,16 +431,21 @@ int gemm_tc2(const Gemm2Batch& g, cudaStream_t st) {
   a.Cs = g.Cs; a.sCs = g.sCs; a.split_mode = g.split_mode;
   a.error_flag = g.error_flag; a.sFlag = 0;
   a.tile_counter = g.tile_counter;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   CB_TRY(make_tmap_bf16_batched(&ta, g.A, g.M, g.K, g.lda, g.batch, g.sA, G2_BM));
   CB_TRY(make_tmap_bf16_batched(&tb, g.B, g.N, g.K, g.ldb, g.batch, g.sB, a.n_tile / 2));
+  a.c_tma = 0;
+  tc = ta;                                              // (a valid descriptor when the fp32 store path is not taken)
+  if (g.C != nullptr && g.Cb == nullptr && g.Ct == nullptr && g.Cs == nullptr && aligned16(g.C) && g.ldc % 4 == 0 &&
+      (g.batch <= 1 || g.sC % 16 == 0) && make_tmap_f32_out(&tc, g.C, g.M, g.N, g.ldc, g.batch, g.sC) == CB_OK)
+    a.c_tma = 1;
   static PerDeviceOnce once;
   CB_TRY(opt_in_dynamic_smem(gemm_tc2_kernel, G2_SMEM, once));
   const int64_t total_tiles = (int64_t)a.batch * a.tiles_m * a.tiles_n;
   int clusters = g.max_clusters > 0 ? g.max_clusters : kNumSMs / 2;
   if (clusters > kNumSMs / 2) clusters = kNumSMs / 2;
   if (total_tiles < clusters) clusters = (int)total_tiles;
-  gemm_tc2_kernel<<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, a);
+  gemm_tc2_kernel<<<2 * clusters, G2_THREADS, G2_SMEM, st>>>(ta, tb, tc, a);
   CB_CHECK_LAUNCH();
   return CB_OK;
 }

@@ -405,3 +405,25 @@ def test_fullsize_golden_config3_quantised_factors(name, m, n, seed):
     np.testing.assert_allclose(float(d.L_scale), z["L_scale"], rtol=0.15)
     np.testing.assert_allclose(float(d.R_scale), z["R_scale"], rtol=0.35)
     assert d.L_idxs.shape == (1, m * 256) and d.R_idxs.shape == (1, 256 * n)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_after_first_in_one_process():
+    """kernel attribute opt-ins (> 48 KiB dynamic shared memory) are per device; a process that has already
+    used cuda:0 must be able to decompose on cuda:1 (single-layer and batched drivers, packed consumer)."""
+    from ee274_convexcaldera_llm_quantization_b200.alg import caldera_async
+    g = torch.Generator().manual_seed(77)
+    W = 0.02 * torch.randn(512, 768, generator=g)
+    h = 0.5 + torch.rand(768, generator=g)
+    fac = QuantizerFactory(method="uniform", block_size=64)
+    qp = CalderaParams(Q_bits=2, L_bits=4, R_bits=4, rank=32, iters=2, lplr_iters=2, update_order=["Q", "LR"],
+                       quant_factory_Q=fac, quant_factory_LR=fac)
+    out = {}
+    for dev in ("cuda:0", "cuda:1"):
+        d = caldera(qp, W, h, device=dev, use_tqdm=False, seed=3)
+        hs = [caldera_async(qp, W, h, device=dev, use_tqdm=False, seed=3, batch_hint=2) for _ in range(2)]
+        b = [x.result() for x in hs]
+        assert str(d.Q.device) == dev and str(b[0].L.device) == dev
+        out[dev] = (d.errors, b[0].errors, d.Q_idxs.cpu(), b[1].Q_idxs.cpu())
+    assert out["cuda:0"][0] == out["cuda:1"][0] and out["cuda:0"][1] == out["cuda:1"][1]
+    assert torch.equal(out["cuda:0"][2], out["cuda:1"][2]) and torch.equal(out["cuda:0"][3], out["cuda:1"][3])

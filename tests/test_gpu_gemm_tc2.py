@@ -94,3 +94,33 @@ def test_gemm_tc2_is_bitwise_reproducible():
         assert int(flag.item()) == 0
         outs.append(C)
     assert all(torch.equal(outs[0], o) for o in outs[1:])    # no dependence on the tile -> cluster map
+
+
+@pytest.mark.parametrize("batch,M,N,K,pad", [(1, 512, 512, 384, 0), (3, 1024, 1024, 96, 0), (2, 300, 100, 200, 0), (1, 37, 52, 32, 0),
+                                             (2, 1000, 332, 776, 0), (1, 256, 224, 512, 8), (4, 4096, 256, 384, 0)])
+def test_gemm_tc2_fp32_only_output_goes_through_tma_stores(batch, M, N, K, pad):
+    """fp32 C as the only output (the L R product of the batched driver): staged per warp in swizzled shared memory and
+    written with cp.async.bulk.tensor stores; ragged edges are clipped by the tensor map, padding columns of C (ldc >
+    N) and the rows of the next batch item must stay untouched."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(batch, M, (K + 7) // 8 * 8, generator=g, device=DEV).bfloat16()
+    B = torch.randn(batch, N, (K + 7) // 8 * 8, generator=g, device=DEV).bfloat16()
+    A[:, :, K:] = 0
+    B[:, :, K:] = 0
+    ldc = N + pad
+    C = torch.full((batch, M + 3, ldc), -777.0, device=DEV)                      # 3 guard rows per item, `pad` guard columns
+    cs = 0.5 + torch.rand(batch, N, generator=g, device=DEV)
+    rs = 0.5 + torch.rand(batch, M, generator=g, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    _lib.check(lib.cb_gemm_bf16_tn_batched(batch, M, N, K, 0.5, _lib.ptr(A), A.shape[2], A.stride(0) * 2, _lib.ptr(B), B.shape[2],
+                                           B.stride(0) * 2, _lib.ptr(C), ldc, C.stride(0) * 4, None, 0, 0, None, 0, 0,
+                                           _lib.ptr(cs), cs.stride(0) * 4, _lib.ptr(rs), rs.stride(0) * 4, 0, _lib.ptr(counter),
+                                           _lib.ptr(flag), _lib.stream_ptr()), "g2")
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0
+    ref = 0.5 * torch.bmm(A.double(), B.double().transpose(1, 2)) * rs.double()[:, :, None] * cs.double()[:, None, :]
+    err = float((C[:, :M, :N].double() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
+    assert bool((C[:, M:, :] == -777.0).all()) and bool((C[:, :, N:] == -777.0).all())
