@@ -23,6 +23,9 @@ input copies -- the host link then idles and the end-to-end rate drops by up to 
 inputs and hands full batches over; the slot's launcher replays, runs the `consume` hooks and records the slot's
 event (one thread per slot, so that a launch that blocks does not hold up the launches of the other slots).
 
+The first engine of a process also calls gc.freeze() (see _freeze_import_time_objects: full garbage collections of
+torch's import-time objects were the other source of 0.1-0.3 s stalls).
+
 Slots own a stream and one device arena that the graphs of every shape captured in that slot share (they are never in
 flight together), so device memory is slots x (largest batch footprint) whatever the number of distinct shapes; the
 arena is bounded by `CB_ENGINE_MAX_BYTES` (default 60 % of the device memory free at creation) through the batch size.
@@ -97,7 +100,8 @@ class _Slot:
     def __init__(self, device: torch.device, index: int):
         self.index = index
         self.stream = torch.cuda.Stream(device=device)
-        self.event = torch.cuda.Event(blocking=True)    # the waiting thread sleeps (8 ranks share the host cores)
+        # blocking: the waiting thread sleeps instead of spinning (8 ranks share the box's host cores)
+        self.event = torch.cuda.Event(blocking=os.environ.get("CB_ENGINE_SPIN_WAIT", "0") != "1")
         self.arena: Optional[torch.Tensor] = None
         self.runners: Dict[tuple, object] = {}
         self.host_small: Optional[torch.Tensor] = None
@@ -331,6 +335,23 @@ class LayerEngine:
 
 _ENGINES: Dict[int, LayerEngine] = {}
 _ENGINES_LOCK = threading.Lock()
+_GC_FROZEN = False
+
+
+def _freeze_import_time_objects() -> None:
+    """A process that has imported torch holds a few million long-lived Python objects, and a full (generation 2)
+    garbage collection walks all of them: 0.1-0.3 s, during which neither the submitting thread nor a slot's launcher
+    runs.  At ~650 layers/s the engine's per-layer handles, closures and records trigger one about every second
+    (measured: scripts/probe_e2e_trace.py, profiles/r2_e2e_trace.md -- a launcher stuck for 330 ms in its consume hooks,
+    end-to-end rate 560 instead of 660 matrices/s).  gc.freeze() moves what exists now to the permanent generation, so
+    later collections only look at what was allocated since.  Opt out with CB_ENGINE_GC_FREEZE=0."""
+    global _GC_FROZEN
+    if _GC_FROZEN or os.environ.get("CB_ENGINE_GC_FREEZE", "1") == "0":
+        return
+    import gc
+    gc.collect()
+    gc.freeze()
+    _GC_FROZEN = True
 
 
 def get_engine(device: torch.device, slots: Optional[int] = None, batch: Optional[int] = None) -> LayerEngine:
@@ -345,6 +366,7 @@ def get_engine(device: torch.device, slots: Optional[int] = None, batch: Optiona
             eng.release()
             eng = None
         if eng is None:
+            _freeze_import_time_objects()
             eng = _ENGINES[key] = LayerEngine(torch.device("cuda", key), want_slots, want_batch)
         return eng
 

@@ -71,9 +71,10 @@ def run(mode, count):
     return total, blocked, nblocked, steps
 
 
-for mode in a.modes.split(","):
-    run(mode, 2 * nstreams)
-    total, blocked, nblocked, steps = run(mode, a.steps * nstreams)
-    print(f"{a.slots}x{a.batch} {mode:7s}: {a.steps * nstreams / total:7.1f} matrices/s, total {total:.3f} s, submitting thread blocked "
-          f"{blocked:.3f} s in {nblocked} calls, submit-side step times {[round(s, 3) for s in steps]}", flush=True)
-release_engines()
+if __name__ == "__main__":
+    for mode in a.modes.split(","):
+        run(mode, 2 * nstreams)
+        total, blocked, nblocked, steps = run(mode, a.steps * nstreams)
+        print(f"{a.slots}x{a.batch} {mode:7s}: {a.steps * nstreams / total:7.1f} matrices/s, total {total:.3f} s, submitting thread blocked "
+              f"{blocked:.3f} s in {nblocked} calls, submit-side step times {[round(s, 3) for s in steps]}", flush=True)
+    release_engines()

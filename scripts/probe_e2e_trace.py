@@ -37,30 +37,45 @@ out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(
 engine = get_engine(dev, a.slots, a.batch)
 trace = []          # per batch: dict of events
 origin = torch.cuda.Event(enable_timing=True)
+issue_log = []      # (slot, t_begin, t_replayed, t_end) of every launcher-thread issue
 
-orig_launch = eng_mod.LayerEngine._launch
+orig_issue = eng_mod.LayerEngine._issue
+orig_replay = eng_mod.BatchRunner.replay
 
 
-def traced_launch(self, g):
-    if g.launched:
-        return
+def traced_replay(self, seeds):
+    t0 = time.perf_counter()
+    orig_replay(self, seeds)
+    self._t_replay = (t0, time.perf_counter())
+
+
+def traced_issue(self, g):
     rec = getattr(g, "_trace", None)
+    t0 = time.perf_counter()
     if rec is not None:
         rec["staged"] = torch.cuda.Event(enable_timing=True)
         rec["staged"].record(g.slot.stream)
-        rec["t_launch"] = time.perf_counter()
-    orig_launch(self, g)
+        rec["t_launch"] = t0
+    runner = g.runner
+    orig_issue(self, g)
+    t1 = time.perf_counter()
+    tr = getattr(runner, "_t_replay", (t0, t0))
+    issue_log.append((g.slot.index, t0, tr[0], tr[1], t1))
     if rec is not None:
-        rec["t_launched"] = time.perf_counter()
+        rec["t_launched"] = t1
         rec["done"] = torch.cuda.Event(enable_timing=True)
         rec["done"].record(g.slot.stream)
 
 
-eng_mod.LayerEngine._launch = traced_launch
+eng_mod.LayerEngine._issue = traced_issue
+eng_mod.BatchRunner.replay = traced_replay
 
 
 def run(count, keep):
     pending, calls = [], []
+    if os.environ.get("PROBE_NO_GC") == "1":
+        import gc
+        gc.disable()
     for i in range(count):
         W, h = host_layers[i % 3]
         dst = out_hosts[i % nstreams]
@@ -83,7 +98,7 @@ def run(count, keep):
         if len(pending) > nstreams:
             pending.pop(0).result()
         t2 = time.perf_counter()
-        calls.append((t1 - t0, t2 - t1))
+        calls.append((t1 - t0, t2 - t1, t0))
     engine.flush()
     for hd in pending:
         hd.result()
@@ -110,3 +125,17 @@ for k, rec in enumerate(trace):
     d = origin.elapsed_time(rec["done"])
     print(f"{k:4d} {rec['slot']:4d}  {f:10.1f} {s:10.1f} {d:10.1f}   {s - f:8.1f} {d - s:9.1f}   {(rec['t_launch'] - rec['t_first']) * 1e3:8.1f}   {(rec['t_first'] - t_begin) * 1e3:9.1f} {(rec['t_launched'] - rec['t_launch']) * 1e3:9.1f}")
 release_engines()
+
+print("\nhost-side events longer than 15 ms (ms since the start of the timed run):")
+events = []
+for sub, har, t0 in calls:
+    if sub > 0.015:
+        events.append((t0 - t_begin, f"submit thread: caldera_async() took {sub * 1e3:.1f} ms"))
+    if har > 0.015:
+        events.append((t0 + sub - t_begin, f"submit thread: result() took {har * 1e3:.1f} ms"))
+for slot, a0, r0, r1, a1 in issue_log:
+    if a0 >= t_begin and a1 - a0 > 0.015:
+        events.append((a0 - t_begin, f"launcher of slot {slot}: issue took {(a1 - a0) * 1e3:.1f} ms, of which graph replay call "
+                                     f"{(r1 - r0) * 1e3:.1f} ms, consume hooks + record {(a1 - r1) * 1e3:.1f} ms"))
+for t, msg in sorted(events):
+    print(f"  {t * 1e3:8.1f}  {msg}")
