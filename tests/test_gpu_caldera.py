@@ -80,7 +80,9 @@ def test_golden(path):
         assert got.shape == ref.shape and np.isfinite(got).all()
         ref_all.append(ref)
         got_all.append(got)
-        loose = 8e-2 if (quantised or p.rand_svd) else 5e-3
+        # (measured, scripts/golden_deviation.py: <= 4.3e-4 with fp32 factors; <= 4.5e-2 with re-quantised factors on
+        #  these 96 x 128 ... 512 x 384 matrices, where one flipped 4-bit code moves the trajectory; 1.3e-2 for rand_svd)
+        loose = 6e-2 if (quantised or p.rand_svd) else 5e-3
         np.testing.assert_allclose(got, ref, rtol=loose)
     ref_all, got_all = np.concatenate(ref_all), np.concatenate(got_all)
     # first sub-step: quantiser input (or SVD input) is bit-identical to the reference's
@@ -95,7 +97,9 @@ def test_golden(path):
     # north_star: within 1e-3 relative of the reference (one-sided: a lower error is never a failure;
     # the lower guard only catches a broken metric).  With re-quantised factors or rand_svd the
     # reference itself is only reproducible to a few percent.
-    tol = 1e-3 if not (quantised or p.rand_svd) else 8e-2
+    # (measured: <= 1.5e-5 with fp32 factors, <= 4.5e-3 with quantised factors; the LPLR iteration itself is pinned
+    #  stage by stage in tests/test_gpu_lplr_stage.py)
+    tol = 1e-3 if not (quantised or p.rand_svd) else 1e-2
     assert got_best <= ref_best * (1 + tol), (got_best, ref_best)
     assert got_best >= ref_best * (1 - max(10 * tol, 2e-2)), (got_best, ref_best)
     # ---- self consistency: the error reported for the returned iterate is the error of the returned tensors
