@@ -13,7 +13,6 @@ sub-modules have a 2-D `.weight` works, and `hessians` maps module names to the 
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
 

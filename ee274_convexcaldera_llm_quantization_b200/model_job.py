@@ -7,7 +7,7 @@ parameters.  Used by bench.py (the `full_7b_wall_s` keys) and scripts/decompose_
 from __future__ import annotations
 
 import time
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 

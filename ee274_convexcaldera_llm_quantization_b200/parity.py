@@ -10,7 +10,6 @@ from __future__ import annotations
 import hashlib
 import json
 import os
-from typing import Optional
 
 import numpy as np
 import torch
