@@ -146,7 +146,9 @@ class LowMemoryQuantizer(AbstractQuantizer):
 
     def quantize_block(self, weight: torch.Tensor, epsilon: float = 1e-8, return_packed: bool = False):
         """quantization.py:244-288.  With return_packed=True a fourth value, the packed
-        uint8 code stream (MSB-first, offset binary), is appended."""
+        uint8 code stream (MSB-first, offset binary), is appended.  return_packed="only" skips the int8 / int16 codes
+        altogether and returns (packed, scales, shape) -- the quantise + pack operation of the wire format, one pass at
+        4 + bits/8 + 4/block bytes per element; dequantize_block accepts the packed stream."""
         if len(weight.shape) != 2:
             raise ValueError(f"Support only for 2D matrix, but your input has {len(weight.shape)} dimensions.")
         total = weight.shape[0] * weight.shape[1]
@@ -169,7 +171,10 @@ class LowMemoryQuantizer(AbstractQuantizer):
         w = weight if weight.dtype == torch.float32 else weight.float()
         nblk = total // self.block_size
         cdtype = torch.int8 if self.num_bits <= 8 else torch.int16
-        codes = torch.empty((nblk, self.block_size), dtype=cdtype, device=w.device)
+        pack_only = isinstance(return_packed, str)
+        if pack_only and return_packed != "only":
+            raise ValueError('return_packed must be False, True or "only"')
+        codes = None if pack_only else torch.empty((nblk, self.block_size), dtype=cdtype, device=w.device)
         scales = torch.empty((nblk, 1), dtype=torch.float32, device=w.device)
         packed = None
         if return_packed:
@@ -179,6 +184,8 @@ class LowMemoryQuantizer(AbstractQuantizer):
                                      self.num_bits, self.block_size, float(epsilon), _lib.ptr(codes),
                                      _lib.ptr(packed), _lib.ptr(scales), None, _lib.stream_ptr())
         _lib.check(st, "quantize_block")
+        if pack_only:
+            return packed, scales, weight.shape
         if return_packed:
             return codes, scales, weight.shape, packed
         return codes, scales, weight.shape

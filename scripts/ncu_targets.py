@@ -16,7 +16,7 @@ from ee274_convexcaldera_llm_quantization_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 dev = "cuda"
-M, N, q, nb = 4096, 4096, 224, int(os.environ.get("CB_NCU_BATCH", "16"))
+M, N, q, nb = 4096, 4096, 224, int(os.environ.get("CB_NCU_BATCH", "24"))
 As = [(0.02 * torch.randn(nb, M, N, device=dev)).bfloat16() for _ in range(3)]
 B = torch.randn(nb, q, N, device=dev).bfloat16()
 Cb = torch.empty(nb, M, q, device=dev, dtype=torch.bfloat16)

@@ -9,7 +9,8 @@ lib = _lib.load()
 dev = "cuda"
 M, N, K = 4096, 224, 4096
 out = {}
-for batch in (1, 4, 16, 32, 37):
+BATCHES = tuple(int(a) for a in sys.argv[1:]) or (1, 4, 16, 32, 37)
+for batch in BATCHES:
     nrot = max(2, 256 // batch // 8 + 1) if batch < 16 else 2
     As = [torch.randn(batch, M, K, device=dev).bfloat16() for _ in range(nrot)]
     B = torch.randn(batch, N, K, device=dev).bfloat16()

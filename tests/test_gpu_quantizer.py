@@ -73,6 +73,64 @@ def test_oracle_bit_exact_seeded(bits, bs):
     np.testing.assert_array_equal(pack_codes(codes, bits).cpu().numpy(), packed.cpu().numpy())
 
 
+@pytest.mark.parametrize("bits,bs", [(2, 64), (4, 32), (8, 128), (16, 256), (2, 0)])
+def test_oracle_bit_exact_large_tensor(bits, bs):
+    """A large tensor (several tiles of 1024 elements per resident warp) against the numpy oracle, with zero blocks,
+    tiny values and heavy tails; the shared-memory-staged kernel itself is covered by test_pack_only_equals_oracle."""
+    rows, cols = 2048, 4096
+    g = torch.Generator().manual_seed(500 + bits)
+    x = torch.randn(rows, cols, generator=g) * torch.exp(torch.randn(rows, cols, generator=g))
+    x[5, :512] = 0.0
+    x[9, 3] = 1e-30
+    x[2047, 4095] = -77.0
+    block = rows * cols if bs == 0 else bs
+    q, (codes, scales, shape, packed) = _quant(x.to(DEV), bits, block)
+    c_ref, s_ref, _ = orc.quantize_uniform(x.numpy(), bits, block)
+    np.testing.assert_array_equal(codes.cpu().numpy(), c_ref)
+    np.testing.assert_array_equal(scales.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(packed.cpu().numpy(), orc.pack_codes(c_ref, bits))
+    deq = q.dequantize_block(packed, scales, shape)
+    np.testing.assert_array_equal(deq.cpu().numpy(), orc.dequantize_uniform(c_ref, s_ref, shape, bits))
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8])
+@pytest.mark.parametrize("bs", [32, 64, 128, 256, 0])
+@pytest.mark.parametrize("shape", [(96, 1024), (2048, 4096), (34, 1280)])
+def test_pack_only_equals_oracle(bits, bs, shape):
+    """return_packed="only" (no int8 codes: the lean instantiation of both quantiser kernels, with the branch-free 2- and
+    4-bit paths) against the numpy oracle: ties at exactly half a step, all-zero blocks (scale = epsilon), heavy tails,
+    a partial last tile (34 x 1280) and the shared-memory-staged kernel (2048 x 4096)."""
+    rows, cols = shape
+    g = torch.Generator().manual_seed(900 + bits + rows)
+    x = torch.randn(rows, cols, generator=g) * torch.exp(torch.randn(rows, cols, generator=g))
+    x[3, :256] = 0.0
+    x[4, :256] = torch.tensor([1.0, 0.5, -0.5, 0.25, -0.25, 0.75, -1.0, 0.5000001] * 32)   # ties for every bit width
+    x[5, 7] = 1e-30
+    block = rows * cols if bs == 0 else bs
+    q = QuantizerFactory(method="uniform", block_size=block).get_quantizer(bits)
+    packed, scales, shp = q.quantize_block(x.to(DEV), return_packed="only")
+    c_ref, s_ref, _ = orc.quantize_uniform(x.numpy(), bits, block)
+    np.testing.assert_array_equal(scales.cpu().numpy(), s_ref)
+    np.testing.assert_array_equal(packed.cpu().numpy(), orc.pack_codes(c_ref, bits))
+    np.testing.assert_array_equal(q.dequantize_block(packed, scales, shp).cpu().numpy(),
+                                  orc.dequantize_uniform(c_ref, s_ref, shp, bits))
+
+
+def test_pack_only_tiny_epsilon_takes_the_general_path():
+    """Scales below 1e-30 (possible only with a tiny epsilon) are outside the branch-free ternary path's validity range:
+    the warp vote must fall back to the IEEE-divide code."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(64, 1024, generator=g)
+    x[0, :128] = 0.0
+    x[1, :64] = 3e-36
+    for bits in (2, 4):
+        q = QuantizerFactory(method="uniform", block_size=64).get_quantizer(bits)
+        packed, scales, shp = q.quantize_block(x.to(DEV), epsilon=1e-37, return_packed="only")
+        c_ref, s_ref, _ = orc.quantize_uniform(x.numpy(), bits, 64, eps=1e-37)
+        np.testing.assert_array_equal(scales.cpu().numpy(), s_ref)
+        np.testing.assert_array_equal(packed.cpu().numpy(), orc.pack_codes(c_ref, bits))
+
+
 @pytest.mark.parametrize("shape,bs", [((37, 53), 37 * 53), ((3, 7), 7), ((1, 20), 4), ((129, 6), 2)])
 @pytest.mark.parametrize("bits", [2, 4, 8, 16])
 def test_ragged_shapes(shape, bs, bits):
