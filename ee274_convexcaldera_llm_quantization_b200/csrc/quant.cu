@@ -542,6 +542,8 @@ static QuantStreamPolicy quant_stream_policy(int bits, bool pack_only) {
   return p;
 }
 
+static bool bits_ok(int bits) { return bits == 2 || bits == 4 || bits == 8 || bits == 16; }
+
 template <int BITS>
 static int quantize_bits(const float* x, int64_t rows, int64_t cols, int64_t sr, int64_t sc, int64_t block,
                          float eps, void* codes, uint8_t* packed, float* scales, float* dequant,
