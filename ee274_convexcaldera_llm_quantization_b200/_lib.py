@@ -140,6 +140,8 @@ _MEASURE_SIGNATURES = {
     "cb_set_gemm_timing": (None, [C.c_void_p]),
     "cb_set_chol_timing": (None, [C.c_void_p]),
     "cb_probe_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cb_probe_err_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

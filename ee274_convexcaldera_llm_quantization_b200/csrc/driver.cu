@@ -1245,6 +1245,14 @@ extern "C" int cb_weighted_error(const float* W, int64_t m, int64_t n, const voi
   return CB_OK;
 }
 
+#ifdef CB_MEASURE
+extern "C" int cb_probe_err_pass(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR,
+                                 const float* w, int64_t m, int64_t n, double* num, float* amax_next, void* stream) {
+  if (Ws == nullptr || num == nullptr || m <= 0 || n <= 0) return CB_ERR_ARG;
+  return cb::err_accum(Ws, codes, bits, qscale, LR, w, m, n, num, (cudaStream_t)stream, amax_next);
+}
+#endif
+
 // ---------------------------------------------------------------- one LPLR iteration as a stage (C ABI)
 namespace cb {
 struct LplrStagePlan {

@@ -273,34 +273,77 @@ form_y_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, co
   }
 }
 
-template <int VEC, typename code_t>
-__global__ void __launch_bounds__(256)
+// The codes of one chunk as loaded (unpacked only where they are used, so that several chunks in flight cost one or
+// two registers each instead of VEC).
+template <int VEC, typename code_t> struct CodeWord;
+template <> struct CodeWord<4, int8_t> {
+  uint32_t w;
+  __device__ __forceinline__ void load(const int8_t* p) { w = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ int get(int k) const { return (int)(int8_t)((w >> (8 * k)) & 255u); }
+};
+template <> struct CodeWord<4, int16_t> {
+  uint2 w;
+  __device__ __forceinline__ void load(const int16_t* p) { w = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ int get(int k) const {
+    const uint32_t x = k < 2 ? w.x : w.y;
+    return (int)(int16_t)((k & 1) ? (x >> 16) : (x & 0xFFFFu));
+  }
+};
+template <typename code_t> struct CodeWord<1, code_t> {
+  code_t w;
+  __device__ __forceinline__ void load(const code_t* p) { w = p[0]; }
+  __device__ __forceinline__ int get(int) const { return (int)w; }
+};
+
+// U chunks per thread and iteration, every load of all of them issued before the first use (a lone chunk per
+// iteration leaves 36 bytes per thread in flight, which is not enough to cover the HBM latency at full bandwidth);
+// four CTAs per SM (<= 64 registers), i.e. ~110 KB of loads in flight per SM.
+// UNIT: the ternary grid (levels = 1), where code / levels * scale is code * scale and no division has to be emulated.
+template <int VEC, typename code_t, bool UNIT>
+__global__ void __launch_bounds__(256, 4)
 err_kernel(const float* __restrict__ Ws, const code_t* __restrict__ codes, const float* __restrict__ qscale,
            float lv, const float* __restrict__ LR, const float* __restrict__ wcol, int64_t numel, int64_t n,
            double* __restrict__ num, float* __restrict__ amax_next) {
+  constexpr int U = VEC == 4 ? 3 : 1;
   __shared__ double red[32];
   __shared__ float redf[32];
   const float s = codes != nullptr ? qscale[0] : 0.f;
   const ScaleRecip lvr = make_scale_recip(lv);
   double acc = 0.0;
   float amx = 0.f;   // max |Ws - LR|: the abs-max the next Q update would otherwise need a pass of its own for
-  CB_GRID_STRIDE_CHUNKS(VEC, numel) {
-    const int64_t i = ch__ * VEC;
-    const int64_t j = CB_CHUNK_COL(VEC, n);
-    FVec<VEC> w, p, hv;
-    w.load(Ws + i);
-    if (LR != nullptr) p.load_stream(LR + i);
-    if (wcol != nullptr) hv.load(wcol + j);
-    int c[VEC];
-    if (codes != nullptr) load_codes<VEC, code_t>(codes + i, c);
+  const int64_t nchunk = numel / VEC;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t chunks_per_row = (uint32_t)(n / VEC);
+  for (int64_t ch0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch0 < nchunk; ch0 += U * stride) {
+    FVec<VEC> w[U], p[U];
+    CodeWord<VEC, code_t> cw[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t ch = ch0 + u * stride;
+      ok[u] = ch < nchunk;
+      if (ok[u]) {
+        const int64_t i = ch * VEC;
+        w[u].load(Ws + i);
+        if (LR != nullptr) p[u].load_stream(LR + i);
+        if (codes != nullptr) cw[u].load(codes + i);
+      }
+    }
     float part = 0.f;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float e = w.v[k];
-      if (codes != nullptr) e -= dequant_val(c[k], s, lvr);
-      if (LR != nullptr) e -= p.v[k];
-      part = fmaf((wcol != nullptr ? hv.v[k] : 1.f) * e, e, part);
-      if (amax_next != nullptr) amx = fmaxf(amx, fabsf(LR != nullptr ? w.v[k] - p.v[k] : w.v[k]));
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
+        FVec<VEC> hv;        // column weights: a 4 n byte vector that lives in L1, fetched where it is used
+        if (wcol != nullptr) hv.load(wcol + (int64_t)((uint32_t)(ch0 + u * stride) % chunks_per_row) * VEC);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          float e = w[u].v[k];
+          if (codes != nullptr) e -= UNIT ? __fmul_rn((float)cw[u].get(k), s) : dequant_val(cw[u].get(k), s, lvr);
+          if (LR != nullptr) e -= p[u].v[k];
+          part = fmaf((wcol != nullptr ? hv.v[k] : 1.f) * e, e, part);
+          if (amax_next != nullptr) amx = fmaxf(amx, fabsf(LR != nullptr ? w[u].v[k] - p[u].v[k] : w[u].v[k]));
+        }
+      }
     }
     acc += (double)part;
   }
@@ -369,69 +412,116 @@ form_y_bf16_kernel(const float* __restrict__ Ws, const code_t* __restrict__ code
 // Y = (Ws - Q) (.) sqrt(h) as both bf16 operands (+ the fp32 residual for the LPLR loop).  Same element
 // arithmetic as quant_err_kernel followed by form_y_bf16_kernel, one read of Ws instead of two and no
 // read-back of the codes.
-template <typename code_t>
-__global__ void __launch_bounds__(256)
-quant_form_y_bf16_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, const float* __restrict__ h_err,
-                         const float* __restrict__ sqrt_h, int m, int n, const float* __restrict__ amax, float eps,
-                         float lv, code_t* __restrict__ codes, float* __restrict__ qscale, double* __restrict__ num,
-                         __nv_bfloat16* __restrict__ Yb, __nv_bfloat16* __restrict__ Ytb, float* __restrict__ RES) {
-  __shared__ __align__(16) __nv_bfloat16 tile[64][68];   // [col][row]
-  __shared__ double red[32];
-  const float s = fmaxf(amax[0], eps);
+// 1.0f / 0.0f comparison results (FSET.BF)
+__device__ __forceinline__ float fset_gt_f(float a, float b) {
+  float d;
+  asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fset_lt_f(float a, float b) {
+  float d;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
+// The 64 x 64 bf16 tile that turns Y into its transpose lives in shared memory as tile[col][row] with rows of 64
+// elements (16 units of 8 bytes) and the unit index XOR-ed with (col / 4) % 16: a thread writes one unit (4 consecutive
+// rows of one column) per column it owns and reads one unit per row of Ytb it writes, and both patterns touch every
+// bank pair exactly twice per warp instruction (the minimum for 256 bytes).
+__device__ __forceinline__ int tile_unit(int col, int unit) { return col * 16 + (unit ^ ((col >> 2) & 15)); }
+
+// TERN: the ternary grid with a scale inside the validity range of the compare-only code (common.cuh).  The code is
+// cf = (res > s/2) - (res < -s/2) as a float, so its dequantised value is the exact product cf * s (levels = 1: the
+// division by the level count is the identity) and neither the quantiser's nor the dequantiser's division is emulated.
+template <typename code_t, bool TERN>
+__device__ __forceinline__ void quant_form_y_body(const float* __restrict__ Ws, const float* __restrict__ LR,
+                                                  const float* __restrict__ h_err, const float* __restrict__ sqrt_h,
+                                                  const int m, const int n, const float s, const float lv,
+                                                  code_t* __restrict__ codes, double* __restrict__ num,
+                                                  __nv_bfloat16* __restrict__ Yb, __nv_bfloat16* __restrict__ Ytb,
+                                                  float* __restrict__ RES, uint2* tile, double* red) {
   const ScaleRecip sr = make_scale_recip(s), lvr = make_scale_recip(lv);
-  const bool tern = lv == 1.f && ternary_ok(s);      // 2-bit grid: exact codes from two compares (common.cuh)
-  const float hs = 0.5f * s;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) qscale[0] = s;
+  const float hs = 0.5f * s, nhs = -hs;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int col = blockIdx.x * 64 + 4 * tx;
+  const bool col_ok = col < n;
+  FVec<4> he, sh;
+  if (h_err != nullptr && col_ok) he.load(h_err + col);
+  if (sqrt_h != nullptr && col_ok) sh.load(sqrt_h + col);
   double acc = 0.0;
+  float y[4][4];                 // [row k of the thread's 4 consecutive rows][column j]
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int rl = ty + 16 * k, row = blockIdx.y * 64 + rl;
-    float y[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < m && col < n) {
+    const int row = blockIdx.y * 64 + 4 * ty + k;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[k][j] = 0.f;
+    if (row < m && col_ok) {
       const int64_t i = (int64_t)row * n + col;
-      FVec<4> w, p, he, sh;
+      FVec<4> w, p;
       w.load_stream(Ws + i);
       if (LR != nullptr) p.load_stream(LR + i);
-      if (h_err != nullptr) he.load(h_err + col);
-      if (sqrt_h != nullptr) sh.load(sqrt_h + col);
       int c[4];
       float part = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float res = LR != nullptr ? w.v[j] - p.v[j] : w.v[j];
-        c[j] = tern ? ternary_code(res, hs) : quant_code(res, sr, lv);
-        const float dq = dequant_val(c[j], s, lvr);
+        float dq;
+        if (TERN) {
+          const float cf = fset_gt_f(res, hs) - fset_lt_f(res, nhs);
+          c[j] = __float2int_rn(cf);
+          dq = __fmul_rn(cf, s);
+        } else {
+          c[j] = quant_code(res, sr, lv);
+          dq = dequant_val(c[j], s, lvr);
+        }
         const float e = res - dq;
         part = fmaf((h_err != nullptr ? he.v[j] : 1.f) * e, e, part);
         w.v[j] -= dq;                                      // Ws - Q
-        y[j] = sqrt_h != nullptr ? w.v[j] * sh.v[j] : w.v[j];
+        y[k][j] = sqrt_h != nullptr ? w.v[j] * sh.v[j] : w.v[j];
       }
       acc += (double)part;
       store_codes<4, code_t>(codes + i, c);
       if (RES != nullptr) w.store(RES + i);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0], y[1]), p1 = __floats2bfloat162_rn(y[2], y[3]);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(y[k][0], y[k][1]), p1 = __floats2bfloat162_rn(y[k][2], y[k][3]);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&p0);
       pk.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(Yb + i) = pk;
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tile[4 * tx + j][rl] = __float2bfloat16_rn(y[j]);
+  for (int j = 0; j < 4; ++j) {          // column 4 tx + j, rows 4 ty .. 4 ty + 3: one 8-byte unit
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(y[0][j], y[1][j]), p1 = __floats2bfloat162_rn(y[2][j], y[3][j]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0);
+    pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    tile[tile_unit(4 * tx + j, ty)] = pk;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int cl = ty + 16 * k;                 // column of the tile = row of Ytb
     const int gc = blockIdx.x * 64 + cl, gr = blockIdx.y * 64 + 4 * tx;
-    if (gc < n && gr < m) {
-      const uint2 pk = *reinterpret_cast<const uint2*>(&tile[cl][4 * tx]);
-      *reinterpret_cast<uint2*>(Ytb + (int64_t)gc * m + gr) = pk;
-    }
+    if (gc < n && gr < m) *reinterpret_cast<uint2*>(Ytb + (int64_t)gc * m + gr) = tile[tile_unit(cl, tx)];
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) atomicAdd(num, acc);
+}
+
+template <typename code_t>
+__global__ void __launch_bounds__(256)
+quant_form_y_bf16_kernel(const float* __restrict__ Ws, const float* __restrict__ LR, const float* __restrict__ h_err,
+                         const float* __restrict__ sqrt_h, int m, int n, const float* __restrict__ amax, float eps,
+                         float lv, code_t* __restrict__ codes, float* __restrict__ qscale, double* __restrict__ num,
+                         __nv_bfloat16* __restrict__ Yb, __nv_bfloat16* __restrict__ Ytb, float* __restrict__ RES) {
+  __shared__ __align__(16) uint2 tile[64 * 16];          // [col][unit of 4 rows], swizzled (tile_unit)
+  __shared__ double red[32];
+  const float s = fmaxf(amax[0], eps);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) qscale[0] = s;
+  if (lv == 1.f && ternary_ok(s))      // 2-bit grid: exact codes from two compares (common.cuh)
+    quant_form_y_body<code_t, true>(Ws, LR, h_err, sqrt_h, m, n, s, lv, codes, num, Yb, Ytb, RES, tile, red);
+  else
+    quant_form_y_body<code_t, false>(Ws, LR, h_err, sqrt_h, m, n, s, lv, codes, num, Yb, Ytb, RES, tile, red);
 }
 
 // ---------------------------------------------------------------- dense-Hessian helpers
@@ -919,10 +1009,13 @@ int err_accum(const float* Ws, const void* codes, int bits, const float* qscale,
   if (amax_next != nullptr) CB_CUDA(cudaMemsetAsync(amax_next, 0, sizeof(float), st));
   const float lv = (float)((1 << (bits - 1)) - 1);
   const bool v4 = can_vec4(n, {Ws, codes, LR, w});
-#define CB_ER(VEC, T, G) \
-  err_kernel<VEC, T><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num, amax_next)
-  if (bits <= 8) { if (v4) CB_ER(4, int8_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int8_t, grid_for(numel, 256 * 4, 8)); }
-  else { if (v4) CB_ER(4, int16_t, grid_for(numel / 4, 256 * 2, 8)); else CB_ER(1, int16_t, grid_for(numel, 256 * 4, 8)); }
+#define CB_ER(VEC, T, G)                                                                                                          \
+  do {                                                                                                                            \
+    if (lv == 1.f) err_kernel<VEC, T, true><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num, amax_next);  \
+    else err_kernel<VEC, T, false><<<G, 256, 0, st>>>(Ws, reinterpret_cast<const T*>(codes), qscale, lv, LR, w, numel, n, num, amax_next);           \
+  } while (0)
+  if (bits <= 8) { if (v4) CB_ER(4, int8_t, grid_for(numel / 4, 256 * 3, 4)); else CB_ER(1, int8_t, grid_for(numel, 256 * 4, 4)); }
+  else { if (v4) CB_ER(4, int16_t, grid_for(numel / 4, 256 * 3, 4)); else CB_ER(1, int16_t, grid_for(numel, 256 * 4, 4)); }
 #undef CB_ER
   CB_CHECK_LAUNCH();
   return CB_OK;

@@ -417,6 +417,10 @@ void cb_set_chol_timing(void* stamps_dev);
 /* Cycles that n_mma back-to-back tcgen05.mma (128 x bn x 16, bf16, operands resident in shared memory) take on an SM,
  * on a grid of `grid` CTAs.  out_cycles: two device int64 ([0] issue + drain, [1] issue only). */
 int cb_probe_mma_rate(int bn, int n_mma, int distinct_k, int grid, void* out_cycles, void* stream);
+/* The error pass of the outer loop alone (stages.cu: err_accum), with every optional operand: num += sum_ij w_j (Ws - Q -
+ * LR)_ij^2, *amax_next = max |Ws - LR|.  codes: int8 (bits <= 8) or int16; LR, w, amax_next may be NULL. */
+int cb_probe_err_pass(const float* Ws, const void* codes, int bits, const float* qscale, const float* LR, const float* w,
+                      int64_t m, int64_t n, double* num, float* amax_next, void* stream);
 #endif
 
 #ifdef __cplusplus
