@@ -464,6 +464,9 @@ def run_ours(args):
     # and the `consume` hook enqueues the D2H copies of the packed codes and the factors into pinned host buffers;
     # the ~100-byte result record (error trajectory, scales) follows.  `.result()` is called a batch later, so the
     # host never waits for the layer it has just submitted.
+    # the engine's arenas: slots x batch slabs of ~0.72 GiB (99 GiB at 6 x 23); the library's default cap is 60 % of
+    # the free memory, the bench owns the whole GPU
+    os.environ.setdefault("CB_ENGINE_MAX_BYTES", str(int(0.85 * torch.cuda.mem_get_info(dev)[0])))
     engine = get_engine(dev, nslots, nbatch)
     out_hosts = [{"Q_packed": torch.empty(M * N // 4, dtype=torch.uint8).pin_memory(),
                   "L": torch.empty(M, RANK).pin_memory(), "R": torch.empty(RANK, N).pin_memory()}
@@ -662,9 +665,11 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
     ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
     ap.add_argument("--model-streams", type=int, default=48, help="layers in flight per GPU in the model-level job")
-    ap.add_argument("--slots", type=int, default=5, help="graph replays in flight per GPU")
+    ap.add_argument("--slots", type=int, default=6, help="graph replays in flight per GPU")
     ap.add_argument("--model-slots", type=int, default=3, help="graph replays in flight per GPU in the model-level job")
-    ap.add_argument("--batch", type=int, default=24, help="same-shape layers advancing in lock step per graph replay")
+    ap.add_argument("--batch", type=int, default=23,
+                    help="same-shape layers advancing in lock step per graph replay (23 x 16 tiles of the sketch contraction "
+                         "= 4.97 waves of the 74 CTA pairs; 24 would be 5.19, i.e. a sixth, mostly empty wave)")
     ap.add_argument("--mode", default="throughput", choices=["throughput", "latency"],
                     help="execution mode written into cb_caldera_params.exec_mode (single-layer driver only)")
     args = ap.parse_args()

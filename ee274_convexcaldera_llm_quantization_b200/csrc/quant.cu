@@ -529,6 +529,11 @@ unpack_kernel(const uint8_t* __restrict__ packed, int64_t numel, void* __restric
 // latency, are faster there (15.1 against 16.2 us), so only the 2-bit packer takes the shared-memory-staged kernel.
 // The -DCB_MEASURE build reads CB_QS_WARPS / CB_QS_STAGES / CB_QS_PDL so that the probe can sweep them (warps = 0: never).
 struct QuantStreamPolicy { int warps, stages, pdl; };
+#ifdef CB_MEASURE
+constexpr bool kStreamEveryWidth = true;     // the probe may send any width through quant_stream_kernel
+#else
+constexpr bool kStreamEveryWidth = false;    // release: only the instantiations the policy below can select are compiled
+#endif
 constexpr int QS_MAX_SMEM = 216 * 1024;
 static QuantStreamPolicy quant_stream_policy(int bits, bool pack_only) {
   QuantStreamPolicy p = {(bits == 2 && pack_only) ? 16 : 0, 2, 1};
@@ -585,8 +590,9 @@ static int quantize_bits(const float* x, int64_t rows, int64_t cols, int64_t sr,
   } while (0)
 #define CB_QF_PO(LPB, PO)                                                                                         \
   do {                                                                                                            \
-    if (stream_path) CB_QF_STREAM(LPB, PO);                                                                       \
-    else if (full) quant_fast_kernel<BITS, LPB, true, PO><<<grid, 256, 0, st>>>(x, numel, eps, codes, packed, scales, dequant); \
+    if (stream_path) {                                                                                            \
+      if constexpr (kStreamEveryWidth || (BITS == 2 && (PO))) CB_QF_STREAM(LPB, PO);                              \
+    } else if (full) quant_fast_kernel<BITS, LPB, true, PO><<<grid, 256, 0, st>>>(x, numel, eps, codes, packed, scales, dequant); \
     else quant_fast_kernel<BITS, LPB, false, PO><<<grid, 256, 0, st>>>(x, numel, eps, codes, packed, scales, dequant);          \
   } while (0)
 #define CB_QF(LPB)                                                                                                \

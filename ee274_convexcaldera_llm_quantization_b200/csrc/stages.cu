@@ -1267,11 +1267,9 @@ fwht_rows_kernel(const float* __restrict__ src, int64_t src_rows, int64_t src_co
 static int fwht_rows(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, float* dst, int64_t nrows,
                      int64_t P, cudaStream_t st) {
   const size_t smem = (size_t)P * sizeof(float);
-  static size_t attr_bytes = 0;
-  if (smem > 48 * 1024 && smem > attr_bytes) {
-    CB_CUDA(cudaFuncSetAttribute(fwht_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
+  // the opt-in is a per-device attribute: always ask for the kernel's maximum (P <= 32768 rows of 4 bytes), once per device
+  static PerDeviceOnce once;
+  if (smem > 48 * 1024) CB_TRY(opt_in_dynamic_smem(fwht_rows_kernel, 32768 * (int)sizeof(float), once));
   fwht_rows_kernel<<<(unsigned)nrows, 256, smem, st>>>(src, src_rows, src_cols, src_ld, dst, P, 1.f / sqrtf((float)P));
   CB_CHECK_LAUNCH();
   return CB_OK;

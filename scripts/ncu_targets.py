@@ -2,7 +2,7 @@
 `ncu --set full --clock-control none --import-source on` capture (run plain first; it must exit 0):
 
   python scripts/ncu_targets.py
-  ncu --set full --clock-control none --import-source on -k regex:'gemm_tc2_kernel|quant_fast_kernel' -c 6 \
+  ncu --set full --clock-control none --import-source on -k regex:'gemm_tc2_kernel|quant_stream_kernel|quant_fast_kernel' -c 6 \
       -o gpurun_out/r2_targets python scripts/ncu_targets.py
 
 Operands are rotated so that no launch finds its input in L2."""
@@ -16,7 +16,7 @@ from ee274_convexcaldera_llm_quantization_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 dev = "cuda"
-M, N, q, nb = 4096, 4096, 224, int(os.environ.get("CB_NCU_BATCH", "24"))
+M, N, q, nb = 4096, 4096, 224, int(os.environ.get("CB_NCU_BATCH", "23"))
 As = [(0.02 * torch.randn(nb, M, N, device=dev)).bfloat16() for _ in range(3)]
 B = torch.randn(nb, q, N, device=dev).bfloat16()
 Cb = torch.empty(nb, M, q, device=dev, dtype=torch.bfloat16)
