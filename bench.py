@@ -562,26 +562,28 @@ def run_ours(args):
         full7b = {"layers": len(names), "params": sum(m * n for m, n in shapes), "rank": RANK, "iters": ITERS,
                   "streams": args.model_streams, "slots": args.model_slots, "inputs": "generated on the owning GPU before the clock (SURVEY 8e)",
                   "timed": "barrier -> all layers decomposed -> packed blobs gathered on rank 0 -> device synchronised; "
-                           "max over ranks; second pass (the first one captures the CUDA graphs)"}
+                           "max over ranks; median of three passes after a first one that captures the CUDA graphs"}
         shards = sch.shard_layout(params_for(16), shapes, world)[0]
         store = mj.synth_layers(shapes, shards[rank], dev)
         sch.warm_up_gather(dev, dst=0)
         for lbits in (16, 4):
             prm = params_for(lbits)
-            res = None
-            for attempt in range(2):
+            res, passes = None, []
+            for attempt in range(4):          # pass 0 captures the CUDA graphs; passes 1-3 are timed, the median is reported
+                res = None
                 res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams,
                                        slots=args.model_slots, barrier=barrier)
                 tt = torch.tensor([res["decompose_s"], res["gather_s"], res["wall_s"]], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                if attempt == 0:
-                    first_pass = float(tt[2])
-                    res = None
+                passes.append([float(x) for x in tt.tolist()] + [int(res["graphs_captured"])])
+            first_pass = passes[0][2]
+            med = sorted(passes[1:], key=lambda t_: t_[2])[1]
             key = f"lr{lbits}"
-            full7b[key] = {"wall_s": float(tt[2]), "decompose_s": float(tt[0]), "gather_s": float(tt[1]),
+            full7b[key] = {"wall_s": med[2], "decompose_s": med[0], "gather_s": med[1],
+                           "timed_passes_wall_s": [round(t_[2], 4) for t_ in passes[1:]],
                            "gathered_bytes": int(res["gathered_bytes"]), "first_pass_wall_s_incl_graph_capture": first_pass,
-                           "graphs_captured_in_timed_pass": int(res["graphs_captured"])}
+                           "graphs_captured_in_timed_pass": max(t_[3] for t_ in passes[1:])}
             if rank == 0:
                 parts = sch.split_gathered(res["arena"], res["shards"], res["sizes"])
                 first = sch.unpack_decomposition(parts[0])
@@ -664,9 +666,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity report against the stored reference run")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the informational reference-on-CUDA leg")
     ap.add_argument("--model-blocks", type=int, default=32, help="transformer blocks of the model-level job (32 = Llama-2-7B)")
-    ap.add_argument("--model-streams", type=int, default=48, help="layers in flight per GPU in the model-level job")
+    ap.add_argument("--model-streams", type=int, default=64, help="layers in flight per GPU in the model-level job")
     ap.add_argument("--slots", type=int, default=6, help="graph replays in flight per GPU")
-    ap.add_argument("--model-slots", type=int, default=3, help="graph replays in flight per GPU in the model-level job")
+    ap.add_argument("--model-slots", type=int, default=4, help="graph replays in flight per GPU in the model-level job")
     ap.add_argument("--batch", type=int, default=23,
                     help="same-shape layers advancing in lock step per graph replay (23 x 16 tiles of the sketch contraction "
                          "= 4.97 waves of the 74 CTA pairs; 24 would be 5.19, i.e. a sixth, mostly empty wave)")

@@ -71,6 +71,11 @@ void cb_note_launches(int64_t n);
  *   dequant  optional out, numel fp32 row-major: (code/levels)*scale
  * Per element: s = max(absmax(block), eps); code = rint((x / s) * levels)  (IEEE divide,
  * IEEE multiply, round-half-even) -- bit-exact with the reference.
+ * With only `packed` and `scales` requested (codes == NULL, dequant == NULL) the call is the quantise + pack pass of
+ * the wire format: one read of x, bits/8 + 4/block bytes written per element.  A contiguous 2-bit tensor of at least a
+ * few million elements is then staged through shared memory by bulk asynchronous copies and the launch carries the
+ * programmatic-stream-serialisation attribute (the kernel waits for its predecessor in the stream before it touches
+ * global memory, so ordering on `stream` is unchanged).
  */
 int cb_quantize_f32(const float* x, int64_t rows, int64_t cols, int64_t stride_r, int64_t stride_c,
                     int bits, int64_t block, float eps,
