@@ -562,26 +562,32 @@ def run_ours(args):
         full7b = {"layers": len(names), "params": sum(m * n for m, n in shapes), "rank": RANK, "iters": ITERS,
                   "streams": args.model_streams, "slots": args.model_slots, "inputs": "generated on the owning GPU before the clock (SURVEY 8e)",
                   "timed": "barrier -> all layers decomposed -> packed blobs gathered on rank 0 -> device synchronised; "
-                           "max over ranks; median of three passes after a first one that captures the CUDA graphs"}
+                           "max over ranks; median of five passes after a first one that captures the CUDA graphs"}
         shards = sch.shard_layout(params_for(16), shapes, world)[0]
         store = mj.synth_layers(shapes, shards[rank], dev)
         sch.warm_up_gather(dev, dst=0)
         for lbits in (16, 4):
             prm = params_for(lbits)
-            res, passes = None, []
-            for attempt in range(4):          # pass 0 captures the CUDA graphs; passes 1-3 are timed, the median is reported
+            res, passes, mallocs = None, [], []
+            for attempt in range(6):          # pass 0 captures the CUDA graphs; passes 1-5 are timed, the median is reported
                 res = None
+                ms0 = torch.cuda.memory_stats(dev)
                 res = mj.run_model_job(prm, names, shapes, store, rank, world, dev, streams=args.model_streams,
                                        slots=args.model_slots, barrier=barrier)
+                ms1 = torch.cuda.memory_stats(dev)
                 tt = torch.tensor([res["decompose_s"], res["gather_s"], res["wall_s"]], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 passes.append([float(x) for x in tt.tolist()] + [int(res["graphs_captured"])])
+                # cudaMalloc / cudaFree calls of torch's allocator during the pass (a cudaFree synchronises the device)
+                mallocs.append([int(ms1.get(k_, 0) - ms0.get(k_, 0)) for k_ in ("num_device_alloc", "num_device_free", "num_alloc_retries")])
             first_pass = passes[0][2]
-            med = sorted(passes[1:], key=lambda t_: t_[2])[1]
+            med = sorted(passes[1:], key=lambda t_: t_[2])[len(passes[1:]) // 2]
             key = f"lr{lbits}"
             full7b[key] = {"wall_s": med[2], "decompose_s": med[0], "gather_s": med[1],
                            "timed_passes_wall_s": [round(t_[2], 4) for t_ in passes[1:]],
+                           "best_pass_wall_s": min(t_[2] for t_ in passes[1:]),
+                           "allocator_device_alloc_free_retries_per_pass_rank0": mallocs,
                            "gathered_bytes": int(res["gathered_bytes"]), "first_pass_wall_s_incl_graph_capture": first_pass,
                            "graphs_captured_in_timed_pass": max(t_[3] for t_ in passes[1:])}
             if rank == 0:
