@@ -23,6 +23,12 @@ input copies -- the host link then idles and the end-to-end rate drops by up to 
 inputs and hands full batches over; the slot's launcher replays, runs the `consume` hooks and records the slot's
 event (one thread per slot, so that a launch that blocks does not hold up the launches of the other slots).
 
+Host inputs of every slot cross the link on ONE engine-wide copy stream, in submission order.  Copies enqueued on the
+slots' own streams are served side by side: when six slots are filled at once (the start of a job) all of them receive
+their last layer at about the same time, the first graph starts after the whole 9 GB instead of after its own 1.5 GB,
+and the slots then run -- and ask for their next inputs -- in lock step.  In FIFO order slot 0 starts after 28 ms and the
+slots stay staggered.  CB_ENGINE_COPY_FIFO=0 restores per-slot copies.
+
 The first engine of a process also calls gc.freeze() (see _freeze_import_time_objects: full garbage collections of
 torch's import-time objects were the other source of 0.1-0.3 s stalls).
 
@@ -92,6 +98,8 @@ class _Group:
         self.handles: List[LayerHandle] = []
         self.launched = False                    # handed to the launcher thread
         self.issued = threading.Event()          # the launcher has enqueued everything on the slot's stream
+        self.copy_done: Optional[torch.cuda.Event] = None    # host inputs staged on the engine's copy stream
+        self.fifo_inputs = False
         self.error: Optional[BaseException] = None
         self.host = None
 
@@ -121,6 +129,8 @@ class LayerEngine:
                 env = os.environ.get("CB_ENGINE_MAX_BYTES")
                 max_bytes = int(env) if env else int(0.6 * torch.cuda.mem_get_info(device)[0])
         self.max_bytes = int(max_bytes)
+        with torch.cuda.device(device):
+            self.copy_stream = torch.cuda.Stream(device=device) if os.environ.get("CB_ENGINE_COPY_FIFO", "1") != "0" else None
         self.free = list(reversed(self.slots))       # pop() hands out slot 0 first
         self.inflight: List[_Slot] = []              # launched, in launch order
         self.filling: Dict[tuple, _Group] = {}       # key -> group still collecting layers
@@ -219,8 +229,13 @@ class LayerEngine:
             idx = len(g.handles)
             handle = LayerHandle(g, idx, finish, consume, seed)
             caller = torch.cuda.current_stream()
-            g.slot.stream.wait_stream(caller)              # W / H may have been produced on the caller's stream
-            with torch.cuda.stream(g.slot.stream):
+            # host inputs: the engine-wide copy stream (FIFO over all slots, see the module docstring); the slot is free,
+            # i.e. its previous group was collected, so nothing on its own stream still reads the buffers written here
+            fifo = self.copy_stream is not None and not W.is_cuda
+            st = self.copy_stream if fifo else g.slot.stream
+            g.fifo_inputs = g.fifo_inputs or fifo
+            st.wait_stream(caller)                         # W / H may have been produced on the caller's stream
+            with torch.cuda.stream(st):
                 if isinstance(g.runner, BatchRunner):
                     g.runner.stage(idx, W, H)
                 else:
@@ -238,6 +253,9 @@ class LayerEngine:
             return
         g.launched = True
         self.filling.pop(g.key, None)
+        if g.fifo_inputs:
+            g.copy_done = torch.cuda.Event()
+            g.copy_done.record(self.copy_stream)
         self.inflight.append(g.slot)
         slot = g.slot
         if slot.launcher is None or not slot.launcher.is_alive():
@@ -262,6 +280,8 @@ class LayerEngine:
     def _issue(self, g: _Group) -> None:
         slot = g.slot
         with torch.cuda.device(self.device), torch.cuda.stream(slot.stream):
+            if g.copy_done is not None:
+                slot.stream.wait_event(g.copy_done)
             seeds = [h._seed for h in g.handles]
             if isinstance(g.runner, BatchRunner):
                 g.runner.replay(seeds)
