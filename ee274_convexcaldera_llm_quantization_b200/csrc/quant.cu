@@ -523,7 +523,7 @@ unpack_kernel(const uint8_t* __restrict__ packed, int64_t numel, void* __restric
 // Geometry of quant_stream_kernel: warps per CTA x ring stages per warp (4 KiB each) and whether the launch carries the
 // programmatic-stream-serialisation attribute (its CTAs are scheduled while the previous kernel of the stream drains
 // and wait in griddepcontrol.wait until that kernel has completed).  Measured at 4096 x 4096 on B200
-// (scripts/probe_quant_stream.py, gpurun_out/u3_quant_stream.log): 2-bit pack-only 13.5 us with 16 warps x 2 stages and
+// (scripts/probe_quant_stream.py, profiles/logs/u3_quant_stream.log): 2-bit pack-only 13.5 us with 16 warps x 2 stages and
 // the attribute (14.9 without it, 14.4 for the register-staged kernel); the 4- and 8-bit kernels, whose arithmetic
 // (correctly rounded reciprocal-multiply) needs the 32 resident warps of the register-staged kernel to hide its
 // latency, are faster there (15.1 against 16.2 us), so only the 2-bit packer takes the shared-memory-staged kernel.
